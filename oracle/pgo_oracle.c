@@ -311,6 +311,15 @@ og_graph *og_create(int64_t nv, const uint32_t *vid, const uint8_t *vkind, const
  * are kept as ids and resolved after the whole file is read, as the reference resolves them
  * lazily through the lut at use time (:312-313). */
 #define MAXTOK 40
+/* line[1].parse::<u32>()? (g2o.rs:55,80-81): digits only, optional '+', must fit 32 bits */
+static int parse_id(const char *t, uint32_t *out) {
+    if (*t == '+') t++;
+    if (!*t) return 0;
+    uint64_t a = 0;
+    for (; *t; t++) { if (*t < '0' || *t > '9') return 0; a = a * 10 + (uint64_t)(*t - '0'); if (a > 0xffffffffull) return 0; }
+    *out = (uint32_t)a;
+    return 1;
+}
 og_graph *og_parse_g2o(const char *path, char *err, int errlen) {
     FILE *f = fopen(path, "r");
     if (!f) { snprintf(err, errlen, "cannot open %s", path); return NULL; }
@@ -341,7 +350,8 @@ og_graph *og_parse_g2o(const char *path, char *err, int errlen) {
             if (nt < 2 || nn != KIND_NVAL[vk]) { snprintf(err, errlen, "line %ld: wrong field count", (long)lineno); bad = 1; break; }
             if (nv == cv) { cv *= 2; vid = realloc(vid, cv * 4); vkind = realloc(vkind, cv); }
             if (nvv + 8 > cvv) { cvv *= 2; vval = realloc(vval, cvv * 8); }
-            vid[nv] = (uint32_t)strtoul(tok[1], NULL, 10); vkind[nv] = (uint8_t)vk; nv++;
+            if (!parse_id(tok[1], &vid[nv])) { snprintf(err, errlen, "line %ld: bad vertex id", (long)lineno); bad = 1; break; }
+            vkind[nv] = (uint8_t)vk; nv++;
             memcpy(vval + nvv, num, nn * 8); nvv += nn;
         } else {
             int d = EKIND_DIM[ek], want = EKIND_NMEAS[ek] + d * (d + 1) / 2;
@@ -349,7 +359,7 @@ og_graph *og_parse_g2o(const char *path, char *err, int errlen) {
             if (ne == ce) { ce *= 2; efrom = realloc(efrom, ce * 4); eto = realloc(eto, ce * 4); ekind = realloc(ekind, ce); }
             if (nem + 8 > cem) { cem *= 2; emeas = realloc(emeas, cem * 8); }
             if (nei + 24 > cei) { cei *= 2; einfo = realloc(einfo, cei * 8); }
-            efrom[ne] = (uint32_t)strtoul(tok[1], NULL, 10); eto[ne] = (uint32_t)strtoul(tok[2], NULL, 10);
+            if (!parse_id(tok[1], &efrom[ne]) || !parse_id(tok[2], &eto[ne])) { snprintf(err, errlen, "line %ld: bad edge endpoint id", (long)lineno); bad = 1; break; }
             ekind[ne] = (uint8_t)ek; ne++;
             memcpy(emeas + nem, num, EKIND_NMEAS[ek] * 8); nem += EKIND_NMEAS[ek];
             memcpy(einfo + nei, num + EKIND_NMEAS[ek], (want - EKIND_NMEAS[ek]) * 8); nei += want - EKIND_NMEAS[ek];

@@ -1,0 +1,181 @@
+"""Host-side logic on CPU: C++ g2o loader/writer, C ABI surface, symbolic pass (bit-exact structure vs the
+oracle), synthetic generator.  No compute entry point is called (there is no GPU here)."""
+import ctypes as C
+import hashlib
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import KEYS, ROOT, SE2_GRAPHS, graph_of, load_golden
+import reference_kat as KAT
+from oracle.oracle import OraclePoseGraph
+
+
+def test_library_exports_every_header_symbol(built):
+    from rustrobotics_b200.mapping._lib import ABI_SYMBOLS
+    header = (ROOT / "include" / "pgo_b200.h").read_text()
+    declared = set(re.findall(r"\b(pgo_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(ABI_SYMBOLS)
+    for s in declared:
+        assert hasattr(built, s), f"libpgo_b200.so does not export {s}"
+    assert b"sm_100a" in built.pgo_version()
+
+
+@pytest.mark.parametrize("name", list(KAT.FROM_G2O))
+def test_parse_g2o_counts_and_roundtrip(g2o_files, name):      # g2o.rs:149-175
+    from rustrobotics_b200 import parse_g2o
+    ln, g = parse_g2o(g2o_files[name])
+    assert (len(g["vertex_id"]), len(g["edge_kind"]), ln) == KAT.FROM_G2O[name]
+    gold = load_golden(name)
+    for k in KEYS:                                              # %.17g text round trip is bit exact
+        assert np.array_equal(g[k], gold[k]), k
+    o = OraclePoseGraph.from_g2o(g2o_files[name])               # oracle's own parser agrees
+    oa = o.arrays()
+    for k in ("vertex_id", "vertex_kind", "edge_kind", "edge_from", "edge_to", "edge_info_upper"):
+        assert np.array_equal(g[k], oa[k]), k
+
+
+def test_parse_g2o_tolerates_double_and_trailing_spaces(tmp_path):   # g2o.rs:52
+    from rustrobotics_b200 import parse_g2o
+    p = tmp_path / "a.g2o"
+    p.write_text("VERTEX_SE2 0  0 0 0 \nVERTEX_SE2 1 1 0 0.5\r\nVERTEX_XY 7 2 2\n"
+                 "EDGE_SE2 0 1 1 0 0.5  1 0 0 1 0 1 \nEDGE_SE2_XY 1 7 1 2 1 0 1\n")
+    ln, g = parse_g2o(p)
+    assert ln == 8 and g["vertex_id"].tolist() == [0, 1, 7] and g["edge_kind"].tolist() == [0, 1]
+    assert g["edge_info_upper"].tolist() == [1, 0, 0, 1, 0, 1, 1, 0, 1]
+
+
+@pytest.mark.parametrize("text,what", [
+    ("VERTEX_SE2 0 0 0 0\n\nVERTEX_SE2 1 0 0 0\n", "blank line"),              # index panic, g2o.rs:53
+    ("VERTEX_SE2 0 0 0 0\nFIX 0\n", "not implemented"),                        # unimplemented!, :138
+    ("VERTEX_SE2 0 0 0\n", "wrong number"),                                    # todo!() arm, :56-58
+    ("VERTEX_SE2 a 0 0 0\n", "bad vertex id"),                                 # parse()? -> Err, :55
+    ("VERTEX_SE2 0 0 zero 0\n", "bad number"),                                 # unwrap panic, :30
+    ("VERTEX_SE2 0 0 0 0\nEDGE_SE2 0 1 1 0 0 1 0 0 1 0\n", "wrong number"),
+])
+def test_parse_g2o_errors(tmp_path, text, what):
+    from rustrobotics_b200 import parse_g2o
+    p = tmp_path / "bad.g2o"
+    p.write_text(text)
+    with pytest.raises(ValueError, match=what):
+        parse_g2o(p)
+    with pytest.raises(ValueError):
+        OraclePoseGraph.from_g2o(p)
+
+
+def test_missing_file_is_an_error(tmp_path, built):                # fs::read_to_string(...)? -> Err, g2o.rs:51
+    from rustrobotics_b200 import PgoError, PoseGraph, parse_g2o
+    with pytest.raises(ValueError):
+        parse_g2o(tmp_path / "nope.g2o")
+    with pytest.raises(PgoError):
+        PoseGraph(tmp_path / "nope.g2o")
+
+
+def _structure_handle(graph):
+    from rustrobotics_b200 import Options, PoseGraph
+    return PoseGraph(graph=graph, options=Options(device=-2))
+
+
+@pytest.mark.parametrize("name", SE2_GRAPHS)
+def test_pattern_bit_exact(built, name):
+    """the symbolic pass's scalar CSC pattern == the pattern the reference's COO puts turn into (oracle)"""
+    gold = load_golden(name)
+    pg = _structure_handle(graph_of(gold))
+    cp, ri = pg.pattern()
+    sls = OraclePoseGraph.from_arrays(**graph_of(gold)).build_linear_system()
+    assert np.array_equal(cp, sls.col_ptr) and np.array_equal(ri, sls.row_idx)
+    assert len(ri) == int(gold["nnz"])
+    h = hashlib.sha256(cp.tobytes() + ri.tobytes()).hexdigest()
+    assert h == str(gold["pattern_sha256"])
+
+
+@pytest.mark.parametrize("name", SE2_GRAPHS)
+def test_block_structure_and_slot_map(built, name):
+    """block CSR + edge->slot map against a direct restatement of update_linear_system's four set_matrix calls"""
+    gold = load_golden(name)
+    pg = _structure_handle(graph_of(gold))
+    rp, bc, es = pg.block_structure()
+    o = OraclePoseGraph.from_arrays(**graph_of(gold))
+    _, fi, ti = o.edge_endpoints()
+    nv = o.n_vertices
+    pairs = set(zip(fi.tolist(), ti.tolist())) | set(zip(ti.tolist(), fi.tolist())) | {(v, v) for v in range(nv)}
+    want = sorted(pairs)
+    got = [(r, int(c)) for r in range(nv) for c in bc[rp[r]:rp[r + 1]]]
+    assert got == want
+    assert len(bc) == nv + 2 * len(set(zip(np.minimum(fi, ti).tolist(), np.maximum(fi, ti).tolist())))
+    index = {rc: k for k, rc in enumerate(want)}
+    exp = np.array([[index[(a, a)], index[(a, b)], index[(b, a)], index[(b, b)]] for a, b in zip(fi.tolist(), ti.tolist())])
+    assert np.array_equal(es, exp)
+
+
+def test_anchor_is_first_pose_pose_edges_from(built):               # :330-336, SURVEY fact 6
+    for name, want_id in (("intel", 2), ("simulation-pose-landmark", 100), ("dlr", 0)):
+        gold = load_golden(name)
+        pg = _structure_handle(graph_of(gold))
+        assert int(gold["vertex_id"][pg.anchor()]) == want_id
+
+
+def test_create_rejects_malformed_graphs(built):
+    from rustrobotics_b200 import Options, PgoError, PoseGraph
+    g = graph_of(load_golden("simulation-pose-landmark"))
+    bad = dict(g); bad["edge_to"] = g["edge_to"].copy(); bad["edge_to"][0] = 99999
+    with pytest.raises(PgoError, match="unknown vertex id"):
+        PoseGraph(graph=bad, options=Options(device=-2))
+    bad = dict(g); bad["edge_kind"] = g["edge_kind"].copy(); bad["edge_kind"][1] = 0   # EDGE_SE2 onto a landmark
+    bad["edge_meas"] = np.concatenate([g["edge_meas"], [0.0]]); bad["edge_info_upper"] = np.concatenate([g["edge_info_upper"], [0.0] * 3])
+    with pytest.raises(PgoError, match="kinds"):
+        PoseGraph(graph=bad, options=Options(device=-2))
+    bad = dict(g); bad["vertex_id"] = g["vertex_id"].copy(); bad["vertex_id"][1] = bad["vertex_id"][0]
+    with pytest.raises(PgoError, match="duplicate"):
+        PoseGraph(graph=bad, options=Options(device=-2))
+
+
+def test_structure_only_handle_refuses_to_compute(built):
+    from rustrobotics_b200 import PgoError
+    pg = _structure_handle(graph_of(load_golden("simulation-pose-landmark")))
+    with pytest.raises(PgoError, match="no CPU fallback"):
+        pg.global_error()
+    with pytest.raises(PgoError):
+        pg.gn_step()
+
+
+def test_no_device_fails_loudly(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from rustrobotics_b200 import PgoError, PoseGraph
+    with pytest.raises(PgoError, match="no CPU fallback"):
+        PoseGraph(graph=graph_of(load_golden("simulation-pose-landmark")))
+
+
+def test_synthetic_manhattan_is_deterministic_and_well_formed():
+    from rustrobotics_b200.synthetic import manhattan_se2
+    a, b = manhattan_se2(5000), manhattan_se2(5000)
+    for k in KEYS:
+        assert np.array_equal(a[k], b[k])
+    c = manhattan_se2(5000, seed=7)
+    assert not np.array_equal(a["vertex_values"], c["vertex_values"])
+    f, t = a["edge_from"].astype(np.int64), a["edge_to"].astype(np.int64)
+    assert np.all(f < t)                                              # from < to always
+    assert len(set(zip(f.tolist(), t.tolist()))) == len(f)            # no duplicate pairs
+    odo = (t - f) == 1
+    assert odo.sum() == 5000 - 1 and np.all((t - f)[~odo] > 10)       # N-1 odometry edges, closures span > 10
+    assert 3.5 * 5000 <= len(f) <= 4 * 5000
+    g = manhattan_se2(20000)
+    assert len(g["edge_from"]) == 4 * 20000
+    # converges under the oracle in a handful of Gauss-Newton iterations
+    o = OraclePoseGraph.from_arrays(**manhattan_se2(2000))
+    errs = o.optimize(10)
+    assert errs[-1] < 0.2 * errs[0] and len(errs) <= 8
+
+
+def test_synthetic_sphere_is_well_formed():
+    from rustrobotics_b200.synthetic import sphere_se3
+    g = sphere_se3(20, 25)
+    n = 500
+    assert len(g["vertex_id"]) == n and len(g["vertex_values"]) == 7 * n
+    q = g["vertex_values"].reshape(n, 7)[:, 3:]
+    np.testing.assert_allclose(np.linalg.norm(q, axis=1), 1.0, atol=1e-12)
+    assert 3.8 * n <= len(g["edge_from"]) <= 4 * n

@@ -1,0 +1,81 @@
+"""Pins the CPU oracle (oracle/) against every known-answer value in the reference's own tests, through the
+committed fixtures (the reference datasets re-encoded, tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+from conftest import SE2_GRAPHS, graph_of, load_golden
+import reference_kat as KAT
+from oracle.oracle import OraclePoseGraph
+
+
+@pytest.fixture(scope="module")
+def graphs():
+    return {n: load_golden(n) for n in SE2_GRAPHS}
+
+
+@pytest.mark.parametrize("name", list(KAT.FROM_G2O))
+def test_from_g2o_counts(graphs, name):            # g2o.rs:149-175
+    g = OraclePoseGraph.from_arrays(**graph_of(graphs[name]))
+    assert (g.n_vertices, g.n_edges, g.len) == KAT.FROM_G2O[name]
+
+
+@pytest.mark.parametrize("name", list(KAT.INITIAL_ERROR))
+def test_initial_global_error(graphs, name):       # pose_graph_optimization.rs:580-598
+    g = OraclePoseGraph.from_arrays(**graph_of(graphs[name]))
+    want, eps = KAT.INITIAL_ERROR[name]
+    assert abs(g.global_error() - want) <= eps
+
+
+@pytest.mark.parametrize("name", list(KAT.FINAL_ERROR))
+def test_final_global_error(graphs, name):         # :600-631
+    g = OraclePoseGraph.from_arrays(**graph_of(graphs[name]))
+    errs = g.optimize(100)
+    want, eps = KAT.FINAL_ERROR[name]
+    assert abs(errs[-1] - want) <= eps
+    # and the committed oracle history is reproduced on this machine
+    gold = graphs[name]["chi2_history"]
+    assert len(errs) == len(gold)
+    np.testing.assert_allclose(errs, gold, rtol=1e-7)
+
+
+def test_jacobians(graphs):                        # :633-722
+    g = OraclePoseGraph.from_arrays(**graph_of(graphs["simulation-pose-landmark"]))
+    for k, (A_want, B_want) in KAT.POSE_POSE_JAC.items():
+        e, A, B = g.edge_linearize(k)
+        np.testing.assert_allclose(A, A_want, atol=1e-3)
+        np.testing.assert_allclose(B, B_want, atol=1e-3)
+        np.testing.assert_allclose(e, 0, atol=1e-3)
+    for k, (A_want, B_want) in KAT.POSE_LANDMARK_JAC.items():
+        e, A, B = g.edge_linearize(k)
+        assert A.shape == (2, 3) and B.shape == (2, 2)
+        np.testing.assert_allclose(A, A_want, atol=1e-3)
+        np.testing.assert_allclose(B, B_want, atol=1e-3)
+        np.testing.assert_allclose(e, 0, atol=1e-3)
+
+
+def test_linearize_and_solve(graphs):              # :724-739
+    g = OraclePoseGraph.from_arrays(**graph_of(graphs["simulation-pose-landmark"]))
+    dx = g.linearize_and_solve()
+    np.testing.assert_allclose(dx[:5], KAT.FIRST_DX, atol=1e-3)
+
+
+@pytest.mark.parametrize("name", SE2_GRAPHS)
+def test_put_count_identities(graphs, name):       # puts = 36 PP + 25 PL + 3 ; nnz = sum of block areas
+    gold = graphs[name]
+    g = OraclePoseGraph.from_arrays(**graph_of(gold))
+    sls = g.build_linear_system()
+    ek = gold["edge_kind"]
+    pp, pl = int(np.sum(ek == 0)), int(np.sum(ek == 1))
+    assert sls.puts == 36 * pp + 25 * pl + 3 == int(gold["puts"])
+    P, L = int(np.sum(gold["vertex_kind"] == 0)), int(np.sum(gold["vertex_kind"] == 1))
+    assert len(sls.row_idx) == 9 * P + 4 * L + 2 * (9 * pp + 6 * pl) == int(gold["nnz"])
+    # H as the reference assembles it is symmetric
+    H = sls.csc()
+    assert abs(H - H.T).max() <= 1e-9 * abs(H).max()
+
+
+def test_lm_bookkeeping(graphs):                   # :275-286: LM runs, error history is recorded even for rejected steps
+    g = OraclePoseGraph.from_arrays(**graph_of(graphs["simulation-pose-landmark"]), solver=OraclePoseGraph.LEVENBERG_MARQUARDT)
+    errs = g.optimize(20)
+    assert errs[0] == pytest.approx(3030.313, abs=1e-2)
+    assert min(errs) < 480.0
