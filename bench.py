@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the pose-graph-optimization hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--poses P]
+
+A "step" is ONE Gauss-Newton iteration (linearise + assemble + PCG solve + retract + chi2,
+reference pose_graph_optimization.rs:271-274) on BASELINE.json configs[3]: the synthetic
+Manhattan-world SE(2) graph with 1M poses / 4M edges (seed 42).  Every timed step starts from
+the same initial guess (device-side pose snapshot restored before the step), so all K steps
+do identical work.  The graph's working set (~2.4 GB) is far larger than the 126 MB L2, so no
+L2 flush is needed between steps.
+
+Prints ONE JSON line (rank 0).  value = edges processed per second by the whole job
+(|E| x GN iterations / s) with the graph resident in HBM, timed with CUDA events on the
+library's stream; e2e = the same metric through the public PoseGraph API with HOST buffers
+(pinned), i.e. set_poses (H2D) + gn_step + poses() (D2H) inside the timed region.
+
+--impl reference times the CPU restatement of the reference's own path (oracle/: sequential COO
+assembly in the reference's put order + COO->CSC + sparse LU + retract + chi2) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "gn_edges_per_sec"
+UNIT = "edges/s"
+CPU_SAMPLE_POSES = 100_000
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(self.device)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in Path(self.f.name).read_text().splitlines() if r.count(",") >= 8]
+        os.unlink(self.f.name)
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def measured_peak_hbm():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """per-launch DRAM bytes of the dominant kernel from the committed ncu --set full capture, if any"""
+    p = ROOT / "profiles" / "spmv_traffic.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text())
+        except Exception:
+            return None
+    return None
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(n_poses: int, steps: int, warmup: int):
+    """The reference's CPU path (oracle restatement) on a bounded sample: a Manhattan graph of `n_poses` poses.
+    Every step is one GN iteration from the same initial guess.  -> (edges/s, seconds per step, description, cores)"""
+    import numpy as np
+    from oracle.oracle import OraclePoseGraph
+    from rustrobotics_b200.synthetic import manhattan_se2
+    g = manhattan_se2(n_poses)
+    ne = len(g["edge_from"])
+    o = OraclePoseGraph.from_arrays(**g)
+    s0 = o.state().copy()
+    try:
+        from threadpoolctl import threadpool_info
+        blas_threads = max([t.get("num_threads", 1) for t in threadpool_info()] or [1])
+    except Exception:
+        blas_threads = 1
+    ts = []
+    for i in range(warmup + steps):
+        o.set_state(s0)
+        t = time.perf_counter()
+        dx = o.build_linear_system(0.0).solve()
+        o.update_nodes(dx)
+        float(np.linalg.norm(dx))
+        o.global_error()
+        dt = time.perf_counter() - t
+        if i >= warmup:
+            ts.append(dt)
+        log(f"[cpu] GN iteration {i}: {dt:.2f} s")
+    sec = sum(ts) / len(ts)
+    sample = (f"Manhattan SE2 {n_poses} poses / {ne} edges (seed 42), {steps} GN iteration(s) from the initial guess; "
+              f"oracle/ restatement: sequential COO assembly + COO->CSC + SciPy SuperLU (stand-in for UMFPACK) + retract + chi2; "
+              f"assembly single-threaded like the reference, BLAS threads available to SuperLU: {blas_threads}")
+    return ne / sec, sec, sample, 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    n = min(args.poses, CPU_SAMPLE_POSES)
+    val, sec, sample, cores = cpu_reference_run(n, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "gn_iterations_per_sec": 1.0 / sec,
+        "config": {"workload": f"synthetic Manhattan SE2, {args.poses} poses / {4 * args.poses} edges (BASELINE configs[3]); "
+                               f"CPU arm runs the bounded sample below", "sample_poses": n},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "host_cpus": os.cpu_count(),
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from rustrobotics_b200 import Options, PoseGraph, _build
+    from rustrobotics_b200.synthetic import manhattan_se2
+    _build.build()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    t0 = time.perf_counter()
+    g = manhattan_se2(args.poses)
+    n_poses, n_edges = len(g["vertex_id"]), len(g["edge_from"])
+    t_gen = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    pg = PoseGraph(graph=g, options=Options(device=local, pcg_rtol=args.pcg_rtol, preconditioner=args.preconditioner))
+    t_create = time.perf_counter() - t0
+    log(f"[rank {rank}] graph {n_poses} poses / {n_edges} edges generated in {t_gen:.1f}s, created in {t_create:.1f}s, {pg.stats()}")
+    chi2_0 = pg.global_error()
+    pg.snapshot_poses()
+
+    def one_step():
+        pg.restore_poses()
+        r = pg.gn_step(allow_not_converged=False)
+        t = pg.timings()
+        return r, t
+
+    for _ in range(args.warmup):
+        one_step()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    w0 = time.perf_counter()
+    dev_ms, launches, pcg_its, phases = 0.0, 0, [], {}
+    last = None
+    for _ in range(args.steps):
+        (nd, c2, it), t = one_step()
+        last = (nd, c2)
+        pcg_its.append(it)
+        for k, (ms, ln) in t.items():
+            if k == "spmv_fine":
+                continue
+            dev_ms += ms; launches += ln
+            phases[k] = phases.get(k, 0.0) + ms / args.steps
+    barrier()
+    wall_s = time.perf_counter() - w0
+    clocks = sampler.stop()
+
+    # ---- dominant kernel: fine-level BSR SpMV, timed live with CUDA events on the library's stream
+    spmv_ms = pg.time_spmv(50)
+    st = pg.stats()
+    nb = st["block_rows"] + st["offdiag_blocks"]          # blocks of H incl. diagonal
+    spmv_bytes = 76 * nb + 52 * st["block_rows"]          # 72B + 4B (col) + 4N (row ptr) + 24N (x) + 24N (y)
+    peak, peak_src = measured_peak_hbm()
+    achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9
+    tr = ncu_traffic()
+
+    # ---- e2e through the public API with host buffers (pinned)
+    init_host = torch.from_numpy(np.ascontiguousarray(g["vertex_values"])).pin_memory()
+    out_host = torch.empty_like(init_host).pin_memory()
+    init_np, out_np = init_host.numpy(), out_host.numpy()
+    from rustrobotics_b200.mapping._lib import lib, ptr
+    L = lib()
+    e2e_steps = max(1, min(args.steps, 3))
+
+    def e2e_step():
+        pg.set_poses(init_np)                                               # H2D: this step's input poses
+        r = pg.gn_step(allow_not_converged=False)                           # D2H: |dx|, chi2, PCG iterations
+        rc = L.pgo_get_poses(pg._h, ptr(out_np), len(out_np))               # D2H: the updated poses
+        assert rc == 0
+        return r
+    e2e_step()
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - e0) / e2e_steps
+
+    # ---- reduce over ranks: max time
+    step_ms = dev_ms / args.steps
+    tt = torch.tensor([step_ms, wall_s / args.steps * 1e3, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    step_ms, wall_ms, e2e_ms = tt.tolist()
+    total_edges = n_edges * world                                          # replicas: every rank solves its own graph
+    value = total_edges / (step_ms * 1e-3)
+
+    line = None
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            v, sec, sample, cores = cpu_reference_run(CPU_SAMPLE_POSES, 2, 0)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "s_per_gn_iteration": sec}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak" if world > 1 else "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"synthetic Manhattan-world SE2 pose graph, {n_poses} poses / {n_edges} edges, seed 42 "
+                                   f"(BASELINE configs[3]); 1 step = 1 Gauss-Newton iteration from the initial guess",
+                       "poses": n_poses, "edges": n_edges, "pcg_rtol": args.pcg_rtol,
+                       "preconditioner": "aggregation-AMG V-cycle" if args.preconditioner == 1 else "block-Jacobi",
+                       "parallelism": "single GPU" if world == 1 else f"{world} independent replicas",
+                       "l2": "working set 2.4 GB >> 126 MB L2, no flush needed"},
+            "gn_iterations_per_sec": world * 1e3 / step_ms, "pcg_iterations_per_step": sum(pcg_its) / len(pcg_its),
+            "wall_ms_per_step": wall_ms, "phase_ms": phases, "create_s": t_create,
+            "chi2": {"initial": chi2_0, "after_step": last[1], "norm_dx": last[0]},
+            "roofline": {"bound": "hbm", "kernel": "k_spmv<3,0> (fine-level BSR SpMV)", "achieved": achieved, "peak": peak,
+                         "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "ms_per_launch": spmv_ms,
+                         "algorithmic_bytes_per_launch": spmv_bytes,
+                         "traffic": (tr or {}).get("dram_bytes_per_launch")},
+            "cpu_baseline": cpu,
+            "e2e": {"value": total_edges / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(init_np.nbytes), "d2h_bytes_per_step": int(out_np.nbytes) + 20},
+            "gpu_launches": int(launches), "clocks": clocks, "host_cpus": os.cpu_count(),
+        }
+        print(json.dumps(line), flush=True)
+    pg.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--poses", type=int, default=1_000_000)
+    ap.add_argument("--pcg-rtol", type=float, default=1e-8)
+    ap.add_argument("--preconditioner", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -100,6 +100,10 @@ int pgo_undo_last_step(pgo_handle *h);
 /* poses in the layout of pgo_create's vertex_values (theta = atan2(im, re) of the stored unit complex) */
 int pgo_get_poses(pgo_handle *h, double *vertex_values_out, int64_t n_values);
 int pgo_set_poses(pgo_handle *h, const double *vertex_values, int64_t n_values);
+/* device-side checkpoint of the poses (the reference's "call optimize again from the current nodes" state, :157-160):
+ * snapshot copies the current poses to a second HBM buffer, restore copies them back.  No host traffic. */
+int pgo_snapshot_poses(pgo_handle *h);
+int pgo_restore_poses(pgo_handle *h);
 /* the dx of the last pgo_gn_step / pgo_linearize_and_solve, length len, lut (scalar-offset) order */
 int pgo_get_dx(pgo_handle *h, double *dx_out, int64_t len);
 

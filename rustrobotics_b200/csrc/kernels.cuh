@@ -409,8 +409,18 @@ __global__ void __launch_bounds__(128) k_invert_diag3(LevelDev L) {
     double a[9], o[9];
 #pragma unroll
     for (int q = 0; q < 9; q++) a[q] = L.diag[(int64_t)q * L.n_pad + row];
-    if (row < L.n) inv3(a, o);
-    else {
+    if (row < L.n) {
+        // an aggregate made of landmarks that all sit on its centroid (e.g. a single landmark) has no
+        // rotational unknown: P^T H P is exactly singular in theta.  Decouple that unknown (its restricted
+        // residual is always 0) so that the level stays SPD.
+        if (!(a[8] > 1e-14 * (a[0] + a[4]))) {
+            a[2] = a[5] = a[6] = a[7] = 0.0; a[8] = 1.0;
+            L.diag[(int64_t)2 * L.n_pad + row] = 0.0; L.diag[(int64_t)5 * L.n_pad + row] = 0.0;
+            L.diag[(int64_t)6 * L.n_pad + row] = 0.0; L.diag[(int64_t)7 * L.n_pad + row] = 0.0;
+            L.diag[(int64_t)8 * L.n_pad + row] = 1.0;
+        }
+        inv3(a, o);
+    } else {
 #pragma unroll
         for (int q = 0; q < 9; q++) o[q] = 0.0;
     }
@@ -682,6 +692,29 @@ __global__ void __launch_bounds__(256) k_retract_se2(LevelDev L, double *__restr
     }
     double total;
     if (block_sum_last<256>(n2, partials, &S->counter[FIN_NORM], total)) finalize(FIN_NORM, S, total);
+}
+
+// pgo_set_poses / pgo_get_poses: g2o-layout vertex values (x y theta | x y, lut order, packed) <-> the
+// 32-byte device pose records (x, y, cos, sin) in storage order.  iso2 (g2o.rs:14-16) on the way in,
+// atan2(im, re) on the way out.
+__global__ void __launch_bounds__(256) k_import_poses(int64_t n, const int64_t *__restrict__ row_valofs, const uint8_t *__restrict__ vkind,
+                                                       const double *__restrict__ values, double *__restrict__ poses) {
+    const int64_t row = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (row >= n) return;
+    const double *v = values + row_valofs[row];
+    double p[4] = {v[0], v[1], 1.0, 0.0};
+    if (vkind[row] == 0) sincos(v[2], &p[3], &p[2]);
+    st_vec<4>(poses + row * 4, p);
+}
+__global__ void __launch_bounds__(256) k_export_poses(int64_t n, const int64_t *__restrict__ row_valofs, const uint8_t *__restrict__ vkind,
+                                                       const double *__restrict__ poses, double *__restrict__ values) {
+    const int64_t row = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (row >= n) return;
+    double p[4];
+    ld_vec<4>(poses + row * 4, p);
+    double *v = values + row_valofs[row];
+    v[0] = p[0]; v[1] = p[1];
+    if (vkind[row] == 0) v[2] = atan2(p[3], p[2]);
 }
 
 } // namespace pgo

@@ -53,7 +53,9 @@ struct pgo_handle {
     std::vector<void *> allocs;
     size_t device_bytes = 0;
     // level-0 state
-    double *poses = nullptr, *hz = nullptr, *ed = nullptr;
+    double *poses = nullptr, *poses_saved = nullptr, *hz = nullptr, *ed = nullptr;
+    double *vstage = nullptr;          // g2o-layout vertex values (n_values) for set/get_poses
+    int64_t *row_valofs = nullptr;     // [n] offset of each storage row's values in vstage
     int2 *ends = nullptr;
     double *x = nullptr, *r = nullptr, *p = nullptr, *q = nullptr, *z = nullptr;
     Scalars *S = nullptr, *hS = nullptr;   // device / pinned host (2 slots)
@@ -427,19 +429,17 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
     const int64_t n = S.n, n_pad = S.levels[0].n_pad;
     {
         std::vector<uint8_t> vk(n_pad, 0);
-        std::vector<double> ps((size_t)4 * n_pad, 0.0);
-        for (int64_t r = 0; r < n; r++) {
-            const int64_t v = S.perm[r];
-            vk[r] = S.vkind[v];
-            const double *val = vval + S.vvalofs[v];
-            ps[4 * r] = val[0]; ps[4 * r + 1] = val[1];
-            if (S.vkind[v] == 0) { ps[4 * r + 2] = std::cos(val[2]); ps[4 * r + 3] = std::sin(val[2]); }   // iso2, g2o.rs:14-16
-            else { ps[4 * r + 2] = 1.0; ps[4 * r + 3] = 0.0; }
-        }
+        std::vector<int64_t> rvo(n_pad, 0);
+        for (int64_t r = 0; r < n; r++) { const int64_t v = S.perm[r]; vk[r] = S.vkind[v]; rvo[r] = S.vvalofs[v]; }
         uint8_t *dvk;
         CKC(upload(h, &dvk, vk));
         h->lv[0].d.vkind = dvk;
-        CKC(upload(h, &h->poses, ps));
+        CKC(upload(h, &h->row_valofs, rvo));
+        CKC(dalloc(h, &h->poses, (size_t)4 * n_pad));
+        CKC(dalloc(h, &h->vstage, (size_t)S.n_values));
+        CKU(cudaMemcpyAsync(h->vstage, vval, S.n_values * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        k_import_poses<<<grid_for(n, 256), 256, 0, h->stream>>>(n, h->row_valofs, dvk, h->vstage, h->poses);
+        CKU(cudaGetLastError());
     }
     h->anchor_row = S.anchor >= 0 ? S.iperm[S.anchor] : -1;
     // ---- measurements: per-edge packed offsets
@@ -579,15 +579,11 @@ int pgo_get_poses(pgo_handle *h, double *out, int64_t n_values) {
     NEED_DEVICE(h);
     const Symbolic &S = h->sym;
     if (n_values != S.n_values) { h->err = "pgo_get_poses: wrong buffer length"; return PGO_ERR_ARG; }
-    std::vector<double> ps((size_t)4 * S.n);
-    CK(cudaMemcpyAsync(ps.data(), h->poses, ps.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    k_export_poses<<<grid_for(S.n, 256), 256, 0, h->stream>>>(S.n, h->row_valofs, h->lv[0].d.vkind, h->poses, h->vstage);
+    h->launch_count += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, h->vstage, S.n_values * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    for (int64_t r = 0; r < S.n; r++) {
-        const int64_t v = S.perm[r];
-        double *o = out + S.vvalofs[v];
-        o[0] = ps[4 * r]; o[1] = ps[4 * r + 1];
-        if (S.vkind[v] == 0) o[2] = std::atan2(ps[4 * r + 3], ps[4 * r + 2]);
-    }
     return PGO_OK;
 }
 
@@ -596,15 +592,30 @@ int pgo_set_poses(pgo_handle *h, const double *in, int64_t n_values) {
     NEED_DEVICE(h);
     const Symbolic &S = h->sym;
     if (n_values != S.n_values) { h->err = "pgo_set_poses: wrong buffer length"; return PGO_ERR_ARG; }
-    std::vector<double> ps((size_t)4 * S.n);
-    for (int64_t r = 0; r < S.n; r++) {
-        const int64_t v = S.perm[r];
-        const double *val = in + S.vvalofs[v];
-        ps[4 * r] = val[0]; ps[4 * r + 1] = val[1];
-        if (S.vkind[v] == 0) { ps[4 * r + 2] = std::cos(val[2]); ps[4 * r + 3] = std::sin(val[2]); }
-        else { ps[4 * r + 2] = 1.0; ps[4 * r + 3] = 0.0; }
-    }
-    CK(cudaMemcpyAsync(h->poses, ps.data(), ps.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->vstage, in, S.n_values * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    k_import_poses<<<grid_for(S.n, 256), 256, 0, h->stream>>>(S.n, h->row_valofs, h->lv[0].d.vkind, h->vstage, h->poses);
+    h->launch_count += 1;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));   // `in` is borrowed for the duration of the call only
+    h->have_step = false;
+    return PGO_OK;
+}
+
+int pgo_snapshot_poses(pgo_handle *h) {
+    if (!h) return PGO_ERR_ARG;
+    NEED_DEVICE(h);
+    const size_t cnt = (size_t)4 * h->sym.levels[0].n_pad;
+    if (!h->poses_saved) { int rc = dalloc(h, &h->poses_saved, cnt, false); if (rc) return rc; }
+    CK(cudaMemcpyAsync(h->poses_saved, h->poses, cnt * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return PGO_OK;
+}
+
+int pgo_restore_poses(pgo_handle *h) {
+    if (!h) return PGO_ERR_ARG;
+    NEED_DEVICE(h);
+    if (!h->poses_saved) { h->err = "pgo_restore_poses: no snapshot"; return PGO_ERR_ARG; }
+    CK(cudaMemcpyAsync(h->poses, h->poses_saved, (size_t)4 * h->sym.levels[0].n_pad * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->have_step = false;
     return PGO_OK;

@@ -13,7 +13,7 @@ ABI_SYMBOLS = [
     "pgo_default_options", "pgo_create", "pgo_destroy", "pgo_last_error", "pgo_get_sizes", "pgo_chi2", "pgo_gn_step",
     "pgo_undo_last_step", "pgo_get_poses", "pgo_set_poses", "pgo_get_dx", "pgo_linearize_and_solve", "pgo_get_pattern",
     "pgo_get_block_structure", "pgo_get_anchor", "pgo_get_system", "pgo_get_timings", "pgo_time_spmv", "pgo_get_stats",
-    "pgo_version",
+    "pgo_version", "pgo_snapshot_poses", "pgo_restore_poses",
 ]
 
 
@@ -50,6 +50,8 @@ def lib():
     L.pgo_get_poses.argtypes = [P, P, i64]
     L.pgo_set_poses.argtypes = [P, P, i64]
     L.pgo_get_dx.argtypes = [P, P, i64]
+    L.pgo_snapshot_poses.argtypes = [P]
+    L.pgo_restore_poses.argtypes = [P]
     L.pgo_linearize_and_solve.argtypes = [P, C.POINTER(i32)]
     L.pgo_get_pattern.argtypes = [P, C.POINTER(i64), C.POINTER(i64), P, P]
     L.pgo_get_block_structure.argtypes = [P, C.POINTER(i64), P, P, P]

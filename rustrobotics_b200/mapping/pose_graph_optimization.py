@@ -130,6 +130,12 @@ class PoseGraph:
         v = np.ascontiguousarray(values, np.float64)
         self._check(lib().pgo_set_poses(self._h, ptr(v), len(v)), "pgo_set_poses")
 
+    def snapshot_poses(self):
+        self._check(lib().pgo_snapshot_poses(self._h), "pgo_snapshot_poses")
+
+    def restore_poses(self):
+        self._check(lib().pgo_restore_poses(self._h), "pgo_restore_poses")
+
     def gn_step(self, lam=0.0, add_lambda=False, allow_not_converged=True):
         nd, c2, it = C.c_double(), C.c_double(), C.c_int32()
         rc = lib().pgo_gn_step(self._h, lam, int(add_lambda), C.byref(nd), C.byref(c2), C.byref(it))

@@ -1,0 +1,269 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  Every compute call goes through the C ABI of
+libpgo_b200.so (include/pgo_b200.h), either directly (pgo_*) or through the C++ host mirror (pg_*), and is
+compared with the CPU oracle (oracle/, a restatement of the reference pinned by tests/test_oracle_kat.py) and with
+the committed golden fixtures (tests/golden/*.npz, generated from the reference's datasets by make_golden.py).
+
+Stated tolerances (BASELINE.json north_star): sparsity pattern / slot map bit-exact; chi2 per Gauss-Newton
+iteration 1e-6 relative; final poses 1e-6 m / 1e-6 rad.  Assembled H and b are compared at 1e-12 relative to the
+largest entry (fp64 sums in a different association order).
+"""
+import numpy as np
+import pytest
+
+from conftest import SE2_GRAPHS, graph_of, load_golden
+import reference_kat as KAT
+
+pytestmark = pytest.mark.gpu
+
+CHI2_RTOL = 1e-6
+POSE_ATOL = 1e-6
+BJ, AMG = 0, 1
+
+
+def _oracle(graph, solver=0):
+    from oracle.oracle import OraclePoseGraph
+    return OraclePoseGraph.from_arrays(**graph, solver=solver)
+
+
+def _pg(graph, **opt):
+    from rustrobotics_b200 import Options, PoseGraph
+    solver = opt.pop("solver", 0)
+    return PoseGraph(graph=graph, solver=solver, options=Options(**opt))
+
+
+def _angle_diff(a, b):
+    d = a - b
+    return np.abs(np.arctan2(np.sin(d), np.cos(d)))
+
+
+def _pose_diff(graph, got, want):
+    """max |dx|,|dy| and max wrapped |dtheta| between two packed vertex-value arrays"""
+    kind = graph["vertex_kind"]
+    ofs = np.concatenate([[0], np.cumsum(np.where(kind == 0, 3, 2))])[:-1]
+    xy = np.concatenate([ofs, ofs + 1])
+    th = ofs[kind == 0] + 2
+    return float(np.abs(got[xy] - want[xy]).max()), float(_angle_diff(got[th], want[th]).max())
+
+
+def test_library_is_the_cuda_build(built):
+    import torch
+    assert torch.cuda.is_available()
+    assert b"sm_100a" in built.pgo_version()
+
+
+# ---- reference known-answer tests, run through the GPU path (pose_graph_optimization.rs:580-739) -------------
+@pytest.mark.parametrize("name", list(KAT.INITIAL_ERROR))
+def test_initial_global_error(built, name):            # :580-598
+    pg = _pg(graph_of(load_golden(name)))
+    want, eps = KAT.INITIAL_ERROR[name]
+    assert abs(pg.global_error() - want) <= eps
+
+
+@pytest.mark.parametrize("precond", [BJ, AMG])
+@pytest.mark.parametrize("name", list(KAT.FINAL_ERROR))
+def test_final_global_error(built, name, precond):     # :600-631, optimize(100) with Gauss-Newton
+    gold = load_golden(name)
+    pg = _pg(graph_of(gold), preconditioner=precond)
+    errs = pg.optimize(100)
+    want, eps = KAT.FINAL_ERROR[name]
+    assert abs(errs[-1] - want) <= eps
+    # per-iteration chi2 history and the stop iteration against the oracle's committed history
+    hist = gold["chi2_history"]
+    assert len(errs) == len(hist)
+    np.testing.assert_allclose(errs, hist, rtol=CHI2_RTOL)
+    np.testing.assert_allclose(pg.norms, gold["norm_history"], rtol=1e-5, atol=1e-9)
+    dxy, dth = _pose_diff(gold, pg.poses(), gold["final_values"])
+    assert dxy < POSE_ATOL and dth < POSE_ATOL
+
+
+@pytest.mark.parametrize("precond", [BJ, AMG])
+def test_linearize_and_solve(built, precond):          # :724-739
+    gold = load_golden("simulation-pose-landmark")
+    pg = _pg(graph_of(gold), preconditioner=precond)
+    dx, its = pg.linearize_and_solve()
+    np.testing.assert_allclose(dx[:5], KAT.FIRST_DX, atol=1e-3)
+    np.testing.assert_allclose(dx, gold["dx0"], rtol=0, atol=1e-8 * np.abs(gold["dx0"]).max())
+    assert its > 0
+
+
+# ---- assembled system against the oracle's COO->CSC (pattern bit-exact, values 1e-12) -------------------------
+@pytest.mark.parametrize("name", SE2_GRAPHS)
+def test_assembled_system_matches_oracle(built, name):
+    gold = load_golden(name)
+    pg = _pg(graph_of(gold))
+    sls = _oracle(graph_of(gold)).build_linear_system()
+    cp, ri, vals, b = pg.system()
+    assert np.array_equal(cp, sls.col_ptr) and np.array_equal(ri, sls.row_idx)          # bit-exact
+    assert np.abs(vals - sls.vals).max() <= 1e-12 * np.abs(sls.vals).max()
+    assert np.abs(b - sls.b).max() <= 1e-12 * np.abs(sls.b).max()
+    # LM: lambda on every diagonal (:362-366)
+    o = _oracle(graph_of(gold), solver=1)
+    sl = o.build_linear_system(0.37)
+    _, _, v2, _ = pg.system(0.37, True)
+    assert np.abs(v2 - sl.vals).max() <= 1e-12 * np.abs(sl.vals).max()
+
+
+@pytest.mark.parametrize("name", SE2_GRAPHS)
+def test_chi2_and_retract_match_oracle(built, name):
+    """global_error (:537-574) and update_nodes (:229-245) in isolation: apply the same dx on both sides"""
+    gold = load_golden(name)
+    g = graph_of(gold)
+    pg, o = _pg(g), _oracle(g)
+    c_o = o.global_error()
+    assert abs(pg.global_error() - c_o) <= 1e-12 * c_o
+    dx, _ = pg.linearize_and_solve()
+    pg.gn_step()
+    o.update_nodes(dx)
+    _, _, _, vo = o.vertices()
+    dxy, dth = _pose_diff(g, pg.poses(), vo)
+    assert dxy < 1e-12 * max(1.0, np.abs(vo).max()) and dth < 1e-12
+    c_o = o.global_error()
+    assert abs(pg.global_error() - c_o) <= 1e-10 * c_o
+    # undo (LM rejection, :277) restores the poses
+    pg.undo_last_step()
+    dxy, dth = _pose_diff(g, pg.poses(), g["vertex_values"])
+    assert dxy < 1e-9 and dth < 1e-9
+
+
+def test_set_get_poses_roundtrip_and_snapshot(built):
+    gold = load_golden("dlr")
+    g = graph_of(gold)
+    pg = _pg(g)
+    dxy, dth = _pose_diff(g, pg.poses(), g["vertex_values"])
+    assert dxy == 0.0 and dth < 1e-15
+    pg.snapshot_poses()
+    c0 = pg.global_error()
+    pg.set_poses(gold["final_values"])
+    assert abs(pg.global_error() - gold["chi2_history"][-1]) <= 1e-6 * gold["chi2_history"][-1]
+    pg.restore_poses()
+    assert pg.global_error() == c0
+
+
+def test_levenberg_marquardt_matches_oracle(built):    # :275-286 incl. the rejected-error quirk
+    g = graph_of(load_golden("simulation-pose-landmark"))
+    errs_o = _oracle(g, solver=1).optimize(20)
+    pg = _pg(g, solver=1)
+    errs_g = pg.optimize(20)
+    assert len(errs_g) == len(errs_o)
+    np.testing.assert_allclose(errs_g, errs_o, rtol=CHI2_RTOL)
+
+
+def test_lm_on_a_graph_where_steps_get_rejected(built):
+    g = graph_of(load_golden("dlr"))                     # GN is non-monotone here, so LM rejects steps
+    errs_o = _oracle(g, solver=1).optimize(6)
+    errs_g = _pg(g, solver=1).optimize(6)
+    np.testing.assert_allclose(errs_g, errs_o, rtol=1e-5)
+
+
+def test_optimize_continues_from_current_poses(built):  # state persists across optimize calls (:157-160, 270)
+    g = graph_of(load_golden("intel"))
+    a = _pg(g)
+    e1 = a.optimize(2)
+    e2 = a.optimize(2)
+    b = _pg(g)
+    e = b.optimize(4)
+    assert e2[0] == e1[-1]
+    np.testing.assert_allclose(e1 + e2[1:], e, rtol=1e-9)
+
+
+def test_g2o_file_entry_point(built, g2o_files):       # PoseGraph::new(path, solver), :215
+    from rustrobotics_b200 import PoseGraph, PoseGraphSolver
+    pg = PoseGraph.new(g2o_files["intel"], PoseGraphSolver.GaussNewton)
+    assert (pg.num_nodes, pg.num_edges, pg.len) == KAT.FROM_G2O["intel"]
+    errs = pg.optimize(10)
+    np.testing.assert_allclose(errs, load_golden("intel")["chi2_history"], rtol=CHI2_RTOL)
+
+
+# ---- edge cases ------------------------------------------------------------------------------------------------
+def test_graph_without_pose_pose_edge_reports_breakdown(built):
+    """no EDGE_SE2 => no anchor (:330 is inside the SE2_SE2 arm) => H singular: UMFPACK errors in the reference, PCG
+    reports a status here; nothing aborts"""
+    from rustrobotics_b200 import PgoError
+    g = dict(vertex_id=np.array([0, 1], np.uint32), vertex_kind=np.array([0, 1], np.uint8),
+             vertex_values=np.array([0.0, 0, 0, 1, 1]), edge_kind=np.array([1], np.uint8), edge_from=np.array([0], np.uint32),
+             edge_to=np.array([1], np.uint32), edge_meas=np.array([1.0, 0.5]), edge_info_upper=np.array([1.0, 0, 1]))
+    pg = _pg(g, preconditioner=BJ, pcg_max_iterations=50)
+    assert pg.anchor() == -1
+    assert pg.global_error() == pytest.approx(0.25)
+    with pytest.raises(PgoError):
+        pg.gn_step(allow_not_converged=False)
+
+
+def test_two_pose_graph_and_duplicate_edges(built):
+    """smallest graph, and two edges between the same pair (their blocks sum into one BSR block like duplicate COO
+    puts sum in the reference's COO->CSC)"""
+    g = dict(vertex_id=np.array([7, 3], np.uint32), vertex_kind=np.zeros(2, np.uint8),
+             vertex_values=np.array([0.0, 0, 0, 1.2, 0.1, 0.3]), edge_kind=np.zeros(2, np.uint8),
+             edge_from=np.array([7, 3], np.uint32), edge_to=np.array([3, 7], np.uint32),
+             edge_meas=np.array([1.0, 0, 0.2, -1.0, 0.1, -0.2]), edge_info_upper=np.array([10.0, 1, 0, 20, 0, 30, 5, 0, 0, 5, 0, 8]))
+    for pc in (BJ, AMG):
+        pg, o = _pg(g, preconditioner=pc), _oracle(g)
+        sls = o.build_linear_system()
+        cp, ri, vals, b = pg.system()
+        assert np.array_equal(cp, sls.col_ptr) and np.array_equal(ri, sls.row_idx)
+        assert np.abs(vals - sls.vals).max() <= 1e-12 * np.abs(sls.vals).max()
+        np.testing.assert_allclose(pg.optimize(10), o.optimize(10), rtol=CHI2_RTOL)
+
+
+def test_ragged_sizes_around_the_slice_width(built):
+    """row counts around multiples of the 32-row slice / 128-thread CTA (padding rows must stay inert)"""
+    from rustrobotics_b200.synthetic import manhattan_se2
+    for n in (31, 32, 33, 127, 129, 1000):
+        g = manhattan_se2(n)
+        o = _oracle(g)
+        pg = _pg(g)
+        c = o.global_error()
+        assert abs(pg.global_error() - c) <= 1e-12 * c
+        np.testing.assert_allclose(pg.optimize(4), o.optimize(4), rtol=CHI2_RTOL)
+
+
+@pytest.mark.parametrize("precond", [BJ, AMG])
+def test_synthetic_manhattan_10k_matches_oracle(built, precond):
+    from rustrobotics_b200.synthetic import manhattan_se2
+    g = manhattan_se2(10000)
+    o = _oracle(g)
+    pg = _pg(g, preconditioner=precond)
+    errs_o, errs_g = o.optimize(6), pg.optimize(6)
+    assert len(errs_o) == len(errs_g)
+    np.testing.assert_allclose(errs_g, errs_o, rtol=CHI2_RTOL)
+    _, _, _, vo = o.vertices()
+    dxy, dth = _pose_diff(g, pg.poses(), vo)
+    assert dxy < POSE_ATOL and dth < POSE_ATOL
+
+
+def test_config3_manhattan_100k_vs_direct_solve(built):
+    """BASELINE config 3: 100k poses / 400k edges, PCG (AMG) vs the oracle's direct solve, 3 GN iterations"""
+    from rustrobotics_b200.synthetic import manhattan_se2
+    g = manhattan_se2(100000)
+    o = _oracle(g)
+    pg = _pg(g)
+    errs_o, errs_g = o.optimize(3), pg.optimize(3)
+    np.testing.assert_allclose(errs_g, errs_o, rtol=CHI2_RTOL)
+    _, _, _, vo = o.vertices()
+    dxy, dth = _pose_diff(g, pg.poses(), vo)
+    assert dxy < POSE_ATOL and dth < POSE_ATOL
+
+
+def test_config4_full_size_properties(built):
+    """BASELINE config 4 (1M poses / 4M edges) is beyond what the oracle solves in seconds: size-independent
+    properties instead.  (1) chi2 equals the oracle's chi2 (one cheap CPU pass); (2) the solved dx satisfies the
+    assembled system: the step drives the gradient to ~0 -- a second linearisation at x+dx gives |dx2| << |dx1|
+    (quadratic convergence of Gauss-Newton near the optimum); (3) chi2 decreases monotonically and stagnates;
+    (4) snapshot/restore + repeat reproduces the step (the AMG Galerkin product uses fp64 atomics, so to 1e-9)."""
+    from rustrobotics_b200.synthetic import manhattan_se2
+    g = manhattan_se2(1000000)
+    assert len(g["edge_from"]) == 4000000
+    pg = _pg(g, pcg_rtol=1e-8)
+    c0 = pg.global_error()
+    c_o = _oracle(g).global_error()
+    assert abs(c0 - c_o) <= 1e-10 * c_o
+    pg.snapshot_poses()
+    n1, c1, it1 = pg.gn_step(allow_not_converged=False)
+    n2, c2, it2 = pg.gn_step(allow_not_converged=False)
+    n3, c3, it3 = pg.gn_step(allow_not_converged=False)
+    assert c1 < 0.1 * c0 and c2 <= c1 and c3 <= c2 * (1 + 1e-9)
+    assert n2 < 0.1 * n1 and n3 < 0.1 * n2
+    pg.restore_poses()
+    assert pg.global_error() == c0
+    m1, d1, jt1 = pg.gn_step(allow_not_converged=False)
+    assert abs(m1 - n1) <= 1e-7 * n1 and abs(d1 - c1) <= 1e-9 * c1 and abs(jt1 - it1) <= 0.05 * it1
