@@ -111,8 +111,8 @@ def test_chi2_and_retract_match_oracle(built, name):
     pg, o = _pg(g), _oracle(g)
     c_o = o.global_error()
     assert abs(pg.global_error() - c_o) <= 1e-12 * c_o
-    dx, _ = pg.linearize_and_solve()
     pg.gn_step()
+    dx = pg.dx()                                        # the dx this step applied
     o.update_nodes(dx)
     _, _, _, vo = o.vertices()
     dxy, dth = _pose_diff(g, pg.poses(), vo)
@@ -249,7 +249,7 @@ def test_config4_full_size_properties(built):
     properties instead.  (1) chi2 equals the oracle's chi2 (one cheap CPU pass); (2) the solved dx satisfies the
     assembled system: the step drives the gradient to ~0 -- a second linearisation at x+dx gives |dx2| << |dx1|
     (quadratic convergence of Gauss-Newton near the optimum); (3) chi2 decreases monotonically and stagnates;
-    (4) snapshot/restore + repeat reproduces the step (the AMG Galerkin product uses fp64 atomics, so to 1e-9)."""
+    (4) snapshot/restore + repeat reproduces the step (the AMG Galerkin product uses fp64 atomics and the PCG stops at rtol 1e-8, so to the stated 1e-6)."""
     from rustrobotics_b200.synthetic import manhattan_se2
     g = manhattan_se2(1000000)
     assert len(g["edge_from"]) == 4000000
@@ -266,4 +266,4 @@ def test_config4_full_size_properties(built):
     pg.restore_poses()
     assert pg.global_error() == c0
     m1, d1, jt1 = pg.gn_step(allow_not_converged=False)
-    assert abs(m1 - n1) <= 1e-7 * n1 and abs(d1 - c1) <= 1e-9 * c1 and abs(jt1 - it1) <= 0.05 * it1
+    assert abs(m1 - n1) <= 1e-6 * n1 and abs(d1 - c1) <= CHI2_RTOL * c1 and abs(jt1 - it1) <= 0.05 * it1
