@@ -55,10 +55,14 @@ typedef struct {
     int32_t sort_window;       /* rows per degree-sorting window of the sliced storage (multiple of 32; 0 = default) */
     int32_t amg_max_levels;    /* 0 = default */
     int32_t device;            /* CUDA device ordinal, -1 = current; -2 = structure-only handle (symbolic-pass queries, no device) */
-    int32_t reserved;
+    int32_t world;             /* number of ranks (one process per GPU) sharing the graph; 1 = single GPU */
+    int32_t rank;              /* this process' rank, 0 .. world-1: it owns a contiguous vertex range */
+    int32_t amg_dense_max;     /* a level with at most this many block rows is solved directly (explicit inverse); 0 = default */
+    int32_t amg_aggregate_size;/* upper bound on the members of an aggregate; 0 = default */
+    int32_t amg_kcycle;        /* 1 = K-cycle (two Krylov-accelerated coarse solves per level), 0 = V-cycle */
 } pgo_options;
 
-/* fills *opt with the defaults (anchor 1e7, rtol 1e-10, max 200000 iterations, AMG) */
+/* fills *opt with the defaults (anchor 1e7, rtol 1e-10, max 200000 iterations, AMG K-cycle, single GPU) */
 void pgo_default_options(pgo_options *opt);
 
 /*
@@ -77,6 +81,20 @@ int pgo_create(pgo_handle **out, const pgo_options *opt,
                const double *edge_information_upper);
 void pgo_destroy(pgo_handle *h);
 const char *pgo_last_error(const pgo_handle *h);
+
+/* --- sharded handles (world > 1): one process per GPU, every rank passes the WHOLE graph to pgo_create and keeps the
+ * block rows of its contiguous vertex range.  Neighbour rows on other ranks are read straight from peer HBM over
+ * NVLink, so the ranks must exchange one CUDA IPC handle each before the first computing call: every rank exports
+ * pgo_shard_handle_bytes() bytes, the caller all-gathers them in rank order (e.g. torch.distributed.all_gather) and
+ * hands the concatenation to pgo_shard_connect.  All computing entry points are then COLLECTIVE: every rank must
+ * make the same calls in the same order.  Scalars (chi2, |dx|, iterations) come back identical on every rank;
+ * pgo_get_poses / pgo_get_dx / pgo_get_system fill only the part the rank owns (a contiguous span). */
+int pgo_shard_handle_bytes(void);
+int pgo_shard_export(pgo_handle *h, void *buf, int64_t capacity);
+int pgo_shard_connect(pgo_handle *h, const void *all_handles, int64_t n_handles);
+/* partition: vertex_range[world + 1] (lut order), n_remote_blocks[world] = off-diagonal blocks of H whose column
+ * vertex lives on another rank (the halo the SpMV reads over NVLink).  Any argument may be NULL. */
+int pgo_get_partition(const pgo_handle *h, int32_t *world, int32_t *rank, int64_t *vertex_range, int64_t *n_remote_blocks);
 
 /* sizes: len = total scalar dimension returned by parse_g2o (g2o.rs:142) */
 int pgo_get_sizes(const pgo_handle *h, int64_t *n_vertices, int64_t *n_edges, int64_t *len,
@@ -140,6 +158,9 @@ int pgo_time_spmv(pgo_handle *h, int32_t repeats, double *avg_ms);
 /* structure statistics for the roofline accounting: block rows, off-diagonal blocks, stored slots */
 int pgo_get_stats(const pgo_handle *h, int64_t *n_block_rows, int64_t *n_offdiag_blocks,
                   int64_t *n_levels, int64_t *device_bytes);
+
+/* rows and stored off-diagonal blocks of every level of the hierarchy; returns the number of levels */
+int pgo_get_level_sizes(const pgo_handle *h, int32_t max_levels, int64_t *rows, int64_t *blocks);
 
 /* library / device identification, e.g. "pgo_b200 0.1 sm_100a" */
 const char *pgo_version(void);

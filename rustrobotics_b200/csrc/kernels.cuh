@@ -1,37 +1,56 @@
 // CUDA kernels (sm_100a, fp64) of the pose-graph-optimization hot path.
 //
-// All of this is HBM-bound 3x3 / 6x6 block work: no tensor cores (a 3x3 block product is not a
-// dense contraction).  The design rules that matter: one thread per block row, one warp per
-// 32-row slice streaming ONE contiguous blob of matrix data front to back with fully coalesced
-// loads (sliced jagged storage, pgo_internal.h), 32-byte pose / vector records so a gather is
-// exactly one sector, no atomics on the Gauss-Newton system (every block has a single writer),
-// deterministic two-stage reductions ("last block finalises"), and no host in the PCG loop.
+// All of this is HBM-bound 3x3 block work: no tensor cores (a 3x3 block product is not a dense contraction).
+// Design rules: level 0 (the Gauss-Newton system, far larger than L2) is streamed by one thread per block row, one
+// warp per 32-row slice reading ONE contiguous blob front to back with coalesced loads (sliced jagged storage,
+// pgo_internal.h); coarse AMG levels (L2-resident, latency-bound) use one warp per block row over block CSR; 32-byte
+// pose / vector records so a gather is exactly one sector; neighbour rows are addressed as (owner rank, local row)
+// through a table of peer pointers (XRef), so that the same kernels run sharded over NVLink peer memory; no atomics on
+// the Gauss-Newton system (every block has a single writer); deterministic two-stage reductions ("last block
+// finalises") with all PCG / K-cycle scalars resident on the device; no host in the PCG loop.
 #pragma once
 #include <cstdint>
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include "pgo_internal.h"
 
 namespace pgo {
+namespace cg = cooperative_groups;
 
 // ------------------------------------------------------------------------------------------------
+constexpr int MAX_LEVELS = 12;
+struct KScal { double alpha, coef1, coef2, rho1, a1; };
 struct Scalars {
     double rz, rz0, pq, alpha, beta, tol2;
     double norm2_dx, chi2;
     int iters, max_iters, done, status;
-    unsigned counter[8];
+    unsigned counter[8];            // everything from here on survives the per-solve reset
+    int world, pad_;
+    unsigned long long epoch;       // cross-rank barrier epoch (peer.cuh)
+    KScal k[MAX_LEVELS];
+    double loc[4];                  // sharded mode: this rank's partial sums, reduced across ranks by k_xreduce
 };
-enum { ST_OK = 0, ST_BREAKDOWN = 1, ST_MAXIT = 2 };
-enum { FIN_NONE = 0, FIN_PQ = 1, FIN_RZ = 2, FIN_RZ_INIT = 3, FIN_NORM = 4, FIN_CHI2 = 5 };
+enum { ST_OK = 0, ST_BREAKDOWN = 1, ST_MAXIT = 2, ST_COMM = 3 };
+enum { FIN_NONE = 0, FIN_PQ = 1, FIN_RZ = 2, FIN_RZ_INIT = 3, FIN_NORM = 4, FIN_CHI2 = 5, FIN_K1 = 6, FIN_K2 = 7 };
+__host__ __device__ constexpr int fin_ndot(int FIN) { return FIN == FIN_K2 ? 3 : (FIN == FIN_RZ || FIN == FIN_K1) ? 2 : FIN == FIN_NONE ? 0 : 1; }
+
+// one vector (or pose / lever-arm array) as seen from this rank: p[k] = base of rank k's segment
+struct XRef { const double *p[MAX_RANKS]; };
+template <int STRIDE> __device__ __forceinline__ const double *xgather(const XRef &x, uint32_t colword) {
+    return x.p[(colword >> COL_OWNER_SHIFT) & (MAX_RANKS - 1)] + (int64_t)(colword & COL_LOCAL_MASK) * STRIDE;
+}
 
 struct LevelDev {
-    int64_t n, n_pad, n_slices, n_slots;
-    const int64_t *slice_ptr; const int32_t *deg; const uint32_t *col;
+    int64_t n, n_pad, n_slices, n_slots;      // local to this rank
+    const int64_t *slice_ptr;                 // JDS: [n_slices + 1] ; CSR: row_ptr [n_pad + 1]
+    const int32_t *deg; const uint32_t *col;
     double *val, *diag, *dinv;
     double *pos;                 // [2][n_pad] planes: position of each row (centroid on coarse levels)
+    double *lev;                 // [n_pad][2]: lever arm of each row about its aggregate's centroid (peer-visible)
     const uint8_t *vkind;        // level 0 only (nullptr on coarse levels)
-    const int32_t *agg; const int64_t *ctgt; const int32_t *cstr;   // towards the coarser level
-    const int64_t *mem_ptr; const int32_t *mem_idx;                 // members in the finer level
+    const int32_t *agg; const int32_t *ctgt;                        // towards the coarser level (local indices)
+    const int64_t *mem_ptr; const int32_t *mem_idx;                 // members in the finer level (local rows)
 };
 
 template <int D> struct VecStride { static constexpr int value = (D == 3) ? 4 : D; };
@@ -53,19 +72,25 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// Block-level sum of v; the block writes its partial, the LAST block to arrive sums all partials in a
+// Block-level sum of NV values; the block writes its partials, the LAST block to arrive sums all partials in a
 // fixed order (deterministic) and returns true in thread 0 with `total` set.  counter wraps to 0.
-template <int NT> __device__ bool block_sum_last(double v, double *partials, unsigned *counter, double &total) {
-    __shared__ double sm[NT / 32];
+template <int NT, int NV> __device__ bool block_sum_last(const double *v, double *partials, unsigned *counter, double *total) {
+    __shared__ double sm[NV][NT / 32];
     __shared__ bool is_last;
-    v = warp_sum(v);
-    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+        double w = warp_sum(v[k]);
+        if ((threadIdx.x & 31) == 0) sm[k][threadIdx.x >> 5] = w;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
-        double s = 0;
 #pragma unroll
-        for (int w = 0; w < NT / 32; w++) s += sm[w];
-        partials[blockIdx.x] = s;
+        for (int k = 0; k < NV; k++) {
+            double s = 0;
+#pragma unroll
+            for (int w = 0; w < NT / 32; w++) s += sm[k][w];
+            partials[(size_t)blockIdx.x * NV + k] = s;
+        }
         __threadfence();
         unsigned t = atomicInc(counter, gridDim.x - 1);
         is_last = (t == gridDim.x - 1);
@@ -73,56 +98,97 @@ template <int NT> __device__ bool block_sum_last(double v, double *partials, uns
     __syncthreads();
     if (!is_last) return false;
     __threadfence();
-    double s = 0;
-    for (unsigned i = threadIdx.x; i < gridDim.x; i += NT) s += __ldcg(partials + i);
-    s = warp_sum(s);
+    double s[NV];
+#pragma unroll
+    for (int k = 0; k < NV; k++) s[k] = 0;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += NT)
+#pragma unroll
+        for (int k = 0; k < NV; k++) s[k] += __ldcg(partials + (size_t)i * NV + k);
     __syncthreads();
-    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+        double w = warp_sum(s[k]);
+        if ((threadIdx.x & 31) == 0) sm[k][threadIdx.x >> 5] = w;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
-        double t = 0;
 #pragma unroll
-        for (int w = 0; w < NT / 32; w++) t += sm[w];
-        total = t;
+        for (int k = 0; k < NV; k++) {
+            double t = 0;
+#pragma unroll
+            for (int w = 0; w < NT / 32; w++) t += sm[k][w];
+            total[k] = t;
+        }
         return true;
     }
     return false;
 }
 
-__device__ __forceinline__ void finalize(int FIN, Scalars *S, double total) {
+// what the owner of a global sum does with it (PCG / flexible-CG / K-cycle scalar recurrences)
+__device__ __forceinline__ void finalize(int FIN, Scalars *S, const double *t, int lvl) {
     if (FIN == FIN_PQ) {
-        S->pq = total;
-        if (!(total > 0.0)) { S->status = ST_BREAKDOWN; S->done = 1; S->alpha = 0.0; }
-        else S->alpha = S->rz / total;
+        S->pq = t[0];
+        if (!(t[0] > 0.0)) { S->status = ST_BREAKDOWN; S->done = 1; S->alpha = 0.0; }
+        else S->alpha = S->rz / t[0];
     } else if (FIN == FIN_RZ) {
-        double rz = S->rz;
-        S->beta = total / rz;
-        S->rz = total;
+        // flexible CG (the K-cycle preconditioner is a variable operator): beta = -(z.q)/(p.q); t = {r.z, z.q}
+        S->beta = -t[1] / S->pq;
+        S->rz = t[0];
         int it = S->iters + 1;
         S->iters = it;
-        if (!(total >= 0.0)) { S->status = ST_BREAKDOWN; S->done = 1; }
-        else if (total <= S->tol2 * S->rz0) S->done = 1;
+        if (!(t[0] >= 0.0)) { S->status = ST_BREAKDOWN; S->done = 1; }
+        else if (t[0] <= S->tol2 * S->rz0) S->done = 1;
         else if (it >= S->max_iters) { S->status = ST_MAXIT; S->done = 1; }
     } else if (FIN == FIN_RZ_INIT) {
-        S->rz = total; S->rz0 = total; S->beta = 0.0;
-        if (!(total >= 0.0)) { S->status = ST_BREAKDOWN; S->done = 1; }
-        else if (total == 0.0) S->done = 1;
+        S->rz = t[0]; S->rz0 = t[0]; S->beta = 0.0;
+        if (!(t[0] >= 0.0)) { S->status = ST_BREAKDOWN; S->done = 1; }
+        else if (t[0] == 0.0) S->done = 1;
     } else if (FIN == FIN_NORM) {
-        S->norm2_dx = total;
+        S->norm2_dx = t[0];
     } else if (FIN == FIN_CHI2) {
-        S->chi2 = total;
+        S->chi2 = t[0];
+    } else if (FIN == FIN_K1) {
+        // first inner FCG step of the K-cycle at level lvl: t = {c1.v1, c1.rhs}
+        KScal &K = S->k[lvl];
+        K.rho1 = t[0]; K.a1 = t[1];
+        K.alpha = (t[0] > 0.0) ? t[1] / t[0] : 0.0;
+    } else if (FIN == FIN_K2) {
+        // second step: t = {c2.v1, c2.v2, c2.r1}; x = coef1 c1 + coef2 c2 (Notay's K-cycle, two FCG steps)
+        KScal &K = S->k[lvl];
+        const double rho1 = K.rho1, a1 = K.a1, gam = t[0], beta = t[1], a2 = t[2];
+        const double rho2 = beta - gam * gam / rho1;
+        if (rho1 > 0.0 && rho2 > 1e-12 * beta && rho2 == rho2) {
+            K.coef1 = a1 / rho1 - gam * a2 / (rho1 * rho2);
+            K.coef2 = a2 / rho2;
+        } else {
+            K.coef1 = K.alpha; K.coef2 = 0.0;
+        }
     }
     __threadfence();
 }
 
+template <int NT, int FIN> __device__ __forceinline__ void reduce_and_finalize(const double *dots, Scalars *S, double *partials, int lvl) {
+    if (FIN == FIN_NONE) return;
+    constexpr int NV = fin_ndot(FIN) > 0 ? fin_ndot(FIN) : 1;
+    double total[NV];
+    if (block_sum_last<NT, NV>(dots, partials, &S->counter[FIN], total)) {
+        if (S->world > 1) {
+#pragma unroll
+            for (int k = 0; k < NV; k++) S->loc[k] = total[k];
+            __threadfence();
+        } else finalize(FIN, S, total, lvl);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
-// BSR SpMV over the sliced jagged storage, one thread per block row.
-//   MODE 0: y = H x                      (+ partial x.y  -> FIN_PQ)
+// Level 0: BSR SpMV over the sliced jagged storage, one thread per block row.
+//   MODE 0: y = H x                      (+ x.y  -> FIN_PQ)
 //   MODE 1: y = r - H x                  (residual)
-//   MODE 2: y = x + omega Dinv (r - H x) (damped block-Jacobi sweep; + partial r.y -> FIN_RZ*)
+//   MODE 2: y = x + omega Dinv (r - H x) (damped block-Jacobi sweep; + r.y -> FIN_RZ_INIT, + {r.y, y.u1} -> FIN_RZ)
 template <int D, int MODE, int FIN>
-__global__ void __launch_bounds__(128) k_spmv(LevelDev L, const double *__restrict__ x, const double *__restrict__ r,
-                                               double *__restrict__ y, double omega, Scalars *S, double *partials, int check_done) {
+__global__ void __launch_bounds__(128) k_spmv(LevelDev L, XRef xr, const double *__restrict__ x, const double *__restrict__ r,
+                                               double *__restrict__ y, double omega, const double *__restrict__ u1,
+                                               Scalars *S, double *partials, int check_done) {
     if (check_done && ld_done(S)) return;
     constexpr int DD = D * D, VS = VecStride<D>::value;
     const int64_t row = (int64_t)blockIdx.x * 128 + threadIdx.x;
@@ -149,9 +215,9 @@ __global__ void __launch_bounds__(128) k_spmv(LevelDev L, const double *__restri
             const bool active = k < mydeg;
             const int cnt = __popc(__ballot_sync(0xffffffffu, active));
             if (active) {
-                const uint32_t c = __ldg(L.col + base + off + lane) & COL_MASK;
+                const uint32_t c = __ldg(L.col + base + off + lane);
                 double xj[VS];
-                ld_vec<VS>(x + (int64_t)c * VS, xj);
+                ld_vec<VS>(xgather<VS>(xr, c), xj);
                 const double *v = L.val + (base + off) * DD + lane;
                 double h[DD];
 #pragma unroll
@@ -164,14 +230,14 @@ __global__ void __launch_bounds__(128) k_spmv(LevelDev L, const double *__restri
             off += cnt;
         }
     }
-    double dot = 0.0;
+    double dots[2] = {0.0, 0.0};
     if (live) {
         double out[VS];
 #pragma unroll
         for (int a = 0; a < VS; a++) out[a] = 0.0;
         if (MODE == 0) {
 #pragma unroll
-            for (int a = 0; a < D; a++) { out[a] = acc[a]; dot = fma(xi[a], acc[a], dot); }
+            for (int a = 0; a < D; a++) { out[a] = acc[a]; dots[0] = fma(xi[a], acc[a], dots[0]); }
         } else {
             double ri[VS];
             ld_vec<VS>(r + row * VS, ri);
@@ -189,26 +255,100 @@ __global__ void __launch_bounds__(128) k_spmv(LevelDev L, const double *__restri
 #pragma unroll
                     for (int b = 0; b < D; b++) s = fma(__ldg(di + (int64_t)(a * D + b) * L.n_pad), t[b], s);
                     out[a] = fma(omega, s, xi[a]);
-                    dot = fma(ri[a], out[a], dot);
+                    dots[0] = fma(ri[a], out[a], dots[0]);
+                }
+                if (FIN == FIN_RZ) {
+                    double ui[VS];
+                    ld_vec<VS>(u1 + row * VS, ui);
+#pragma unroll
+                    for (int a = 0; a < D; a++) dots[1] = fma(ui[a], out[a], dots[1]);
                 }
             }
         }
         st_vec<VS>(y + row * VS, out);
     }
-    if (FIN != FIN_NONE) {
-        double total;
-        if (block_sum_last<128>(dot, partials, &S->counter[FIN], total)) finalize(FIN, S, total);
-    }
+    reduce_and_finalize<128, FIN>(dots, S, partials, 0);
 }
 
-// x = omega Dinv r  (first half of the V-cycle pre-smoothing; with FIN: block-Jacobi z = Dinv r and r.z)
+// Coarse levels: block CSR, one warp per block row (8 rows per CTA).  Same modes; K-cycle dots:
+//   FIN_K1: {x.y, x.u1}    FIN_K2: {x.u1, x.y, x.u2}      (x = c, y = H c)
+template <int MODE, int FIN>
+__global__ void __launch_bounds__(256) k_spmv_csr(LevelDev L, XRef xr, const double *__restrict__ x, const double *__restrict__ r,
+                                                   double *__restrict__ y, double omega, const double *__restrict__ u1,
+                                                   const double *__restrict__ u2, Scalars *S, double *partials, int lvl, int check_done) {
+    if (check_done && ld_done(S)) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    double dots[3] = {0.0, 0.0, 0.0};
+    if (row < L.n) {
+        double a0 = 0, a1 = 0, a2 = 0;
+        const int64_t b = L.slice_ptr[row], e = L.slice_ptr[row + 1];
+        for (int64_t s = b + lane; s < e; s += 32) {
+            const uint32_t c = __ldg(L.col + s);
+            double xj[4];
+            ld_vec<4>(xgather<4>(xr, c), xj);
+            const double *v = L.val + s * 9;
+            a0 = fma(v[0], xj[0], fma(v[1], xj[1], fma(v[2], xj[2], a0)));
+            a1 = fma(v[3], xj[0], fma(v[4], xj[1], fma(v[5], xj[2], a1)));
+            a2 = fma(v[6], xj[0], fma(v[7], xj[1], fma(v[8], xj[2], a2)));
+        }
+        a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+        if (lane == 0) {
+            double xi[4], out[4] = {0, 0, 0, 0};
+            ld_vec<4>(x + row * 4, xi);
+            const double *dg = L.diag + row;
+            double acc[3] = {a0, a1, a2};
+#pragma unroll
+            for (int a = 0; a < 3; a++)
+#pragma unroll
+                for (int q = 0; q < 3; q++) acc[a] = fma(dg[(int64_t)(a * 3 + q) * L.n_pad], xi[q], acc[a]);
+            if (MODE == 0) {
+#pragma unroll
+                for (int a = 0; a < 3; a++) out[a] = acc[a];
+                if (FIN == FIN_K1) {
+                    double ui[4];
+                    ld_vec<4>(u1 + row * 4, ui);
+#pragma unroll
+                    for (int a = 0; a < 3; a++) { dots[0] = fma(xi[a], acc[a], dots[0]); dots[1] = fma(xi[a], ui[a], dots[1]); }
+                } else if (FIN == FIN_K2) {
+                    double ui[4], wi[4];
+                    ld_vec<4>(u1 + row * 4, ui);
+                    ld_vec<4>(u2 + row * 4, wi);
+#pragma unroll
+                    for (int a = 0; a < 3; a++) { dots[0] = fma(xi[a], ui[a], dots[0]); dots[1] = fma(xi[a], acc[a], dots[1]); dots[2] = fma(xi[a], wi[a], dots[2]); }
+                }
+            } else {
+                double ri[4];
+                ld_vec<4>(r + row * 4, ri);
+                if (MODE == 1) {
+#pragma unroll
+                    for (int a = 0; a < 3; a++) out[a] = ri[a] - acc[a];
+                } else {
+                    const double *di = L.dinv + row;
+                    double t[3] = {ri[0] - acc[0], ri[1] - acc[1], ri[2] - acc[2]};
+#pragma unroll
+                    for (int a = 0; a < 3; a++) {
+                        double s = 0.0;
+#pragma unroll
+                        for (int q = 0; q < 3; q++) s = fma(di[(int64_t)(a * 3 + q) * L.n_pad], t[q], s);
+                        out[a] = fma(omega, s, xi[a]);
+                    }
+                }
+            }
+            st_vec<4>(y + row * 4, out);
+        }
+    }
+    reduce_and_finalize<256, FIN>(dots, S, partials, lvl);
+}
+
+// x = omega Dinv r  (pre-smoothing from a zero guess; with FIN: block-Jacobi z = Dinv r and r.z (, z.u1))
 template <int D, int FIN>
 __global__ void __launch_bounds__(128) k_dinv_apply(LevelDev L, const double *__restrict__ r, double *__restrict__ x, double omega,
-                                                     Scalars *S, double *partials, int check_done) {
+                                                     const double *__restrict__ u1, Scalars *S, double *partials, int check_done) {
     if (check_done && ld_done(S)) return;
     constexpr int VS = VecStride<D>::value;
     const int64_t row = (int64_t)blockIdx.x * 128 + threadIdx.x;
-    double dot = 0.0;
+    double dots[2] = {0.0, 0.0};
     if (row < L.n_pad) {
         double ri[VS], out[VS];
         ld_vec<VS>(r + row * VS, ri);
@@ -221,14 +361,17 @@ __global__ void __launch_bounds__(128) k_dinv_apply(LevelDev L, const double *__
 #pragma unroll
             for (int b = 0; b < D; b++) s = fma(__ldg(di + (int64_t)(a * D + b) * L.n_pad), ri[b], s);
             out[a] = omega * s;
-            dot = fma(ri[a], out[a], dot);
+            dots[0] = fma(ri[a], out[a], dots[0]);
+        }
+        if (FIN == FIN_RZ) {
+            double ui[VS];
+            ld_vec<VS>(u1 + row * VS, ui);
+#pragma unroll
+            for (int a = 0; a < D; a++) dots[1] = fma(ui[a], out[a], dots[1]);
         }
         st_vec<VS>(x + row * VS, out);
     }
-    if (FIN != FIN_NONE) {
-        double total;
-        if (block_sum_last<128>(dot, partials, &S->counter[FIN], total)) finalize(FIN, S, total);
-    }
+    reduce_and_finalize<128, FIN>(dots, S, partials, 0);
 }
 
 // x += alpha p ; r -= alpha q
@@ -262,44 +405,55 @@ __global__ void __launch_bounds__(256) k_update_p(int64_t n_pad, double *__restr
     *reinterpret_cast<double2 *>(p + i) = pv;
 }
 
-__global__ void k_fill(double *p, int64_t n, double v) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
+// K-cycle vector updates at level lvl:  WHICH 0: out = a - alpha_l b      WHICH 1: out = coef1_l a + coef2_l b
+template <int WHICH>
+__global__ void __launch_bounds__(256) k_kcombine(int64_t n_pad, const double *__restrict__ a, const double *__restrict__ b,
+                                                   double *__restrict__ out, const Scalars *S, int lvl) {
+    if (ld_done(S)) return;
+    const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 2;
+    if (i >= n_pad * 4) return;
+    const double2 av = *reinterpret_cast<const double2 *>(a + i), bv = *reinterpret_cast<const double2 *>(b + i);
+    double2 o;
+    if (WHICH == 0) { const double al = S->k[lvl].alpha; o.x = fma(-al, bv.x, av.x); o.y = fma(-al, bv.y, av.y); }
+    else { const double c1 = S->k[lvl].coef1, c2 = S->k[lvl].coef2; o.x = fma(c1, av.x, c2 * bv.x); o.y = fma(c1, av.y, c2 * bv.y); }
+    *reinterpret_cast<double2 *>(out + i) = o;
 }
 
 // ------------------------------------------------------------------------------------------------
 // Aggregation AMG transfer operators (D = 3).  The coarse unknown of an aggregate is a rigid motion
-// (tx, ty, theta) of its members about the aggregate centroid c:  P_i = [[1,0,-dy],[0,1,dx],[0,0,pz]],
-// d = pos_i - c ; pz = 0 for landmark rows (their third, padding, unknown stays decoupled).
-// Global rigid motions -- the near-null space of H that the 1e7 anchor barely pins -- are
+// (tx, ty, theta) of its members about the aggregate centroid c:  P_i = [[1,0,-ly],[0,1,lx],[0,0,pz]],
+// l = pos_i - c (the row's lever arm) ; pz = 0 for landmark rows (their third, padding, unknown stays
+// decoupled).  Global rigid motions -- the near-null space of H that the 1e7 anchor barely pins -- are
 // represented exactly on every level.
 __device__ __forceinline__ double row_pz(const LevelDev &L, int64_t row) { return (L.vkind && L.vkind[row] == 1) ? 0.0 : 1.0; }
 
-// rc_I = sum_{i in I} P_i^T res_i   (one thread per coarse row; deterministic)
-__global__ void __launch_bounds__(128) k_restrict3(LevelDev F, LevelDev C, const double *__restrict__ res, double *__restrict__ rc,
+// rc_I = sum_{i in I} P_i^T res_i   (one warp per coarse row; fixed summation order => deterministic)
+__global__ void __launch_bounds__(256) k_restrict3(LevelDev F, LevelDev C, const double *__restrict__ res, double *__restrict__ rc,
                                                     const Scalars *S) {
     if (ld_done(S)) return;
-    const int64_t I = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int64_t I = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (I >= C.n_pad) return;
     double s0 = 0, s1 = 0, s2 = 0;
     if (I < C.n) {
-        const double cx = C.pos[I], cy = C.pos[C.n_pad + I];
-        for (int64_t m = C.mem_ptr[I]; m < C.mem_ptr[I + 1]; m++) {
+        for (int64_t m = C.mem_ptr[I] + lane; m < C.mem_ptr[I + 1]; m += 32) {
             const int64_t i = C.mem_idx[m];
             double r[4];
             ld_vec<4>(res + i * 4, r);
-            const double dx = F.pos[i] - cx, dy = F.pos[F.n_pad + i] - cy;
+            const double2 l = *reinterpret_cast<const double2 *>(F.lev + i * 2);
             s0 += r[0]; s1 += r[1];
-            s2 += fma(-dy, r[0], fma(dx, r[1], row_pz(F, i) * r[2]));
+            s2 += fma(-l.y, r[0], fma(l.x, r[1], row_pz(F, i) * r[2]));
         }
+        s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
     }
-    double out[4] = {s0, s1, s2, 0.0};
-    st_vec<4>(rc + I * 4, out);
+    if (lane == 0) {
+        double out[4] = {s0, s1, s2, 0.0};
+        st_vec<4>(rc + I * 4, out);
+    }
 }
 
 // x_i += P_i e_{agg(i)}
-__global__ void __launch_bounds__(128) k_prolong3(LevelDev F, LevelDev C, const double *__restrict__ ec, double *__restrict__ x,
-                                                   const Scalars *S) {
+__global__ void __launch_bounds__(128) k_prolong3(LevelDev F, const double *__restrict__ ec, double *__restrict__ x, const Scalars *S) {
     if (ld_done(S)) return;
     const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
     if (i >= F.n) return;
@@ -307,24 +461,34 @@ __global__ void __launch_bounds__(128) k_prolong3(LevelDev F, LevelDev C, const 
     double e[4], xi[4];
     ld_vec<4>(ec + I * 4, e);
     ld_vec<4>(x + i * 4, xi);
-    const double dx = F.pos[i] - C.pos[I], dy = F.pos[F.n_pad + i] - C.pos[C.n_pad + I];
-    xi[0] += fma(-dy, e[2], e[0]);
-    xi[1] += fma(dx, e[2], e[1]);
+    const double2 l = *reinterpret_cast<const double2 *>(F.lev + i * 2);
+    xi[0] += fma(-l.y, e[2], e[0]);
+    xi[1] += fma(l.x, e[2], e[1]);
     xi[2] += row_pz(F, i) * e[2];
     st_vec<4>(x + i * 4, xi);
 }
 
-// centroid of the members
-__global__ void __launch_bounds__(128) k_coarse_pos(LevelDev F, LevelDev C) {
-    const int64_t I = (int64_t)blockIdx.x * 128 + threadIdx.x;
+// centroid of the members (one warp per coarse row)
+__global__ void __launch_bounds__(256) k_coarse_pos(LevelDev F, LevelDev C) {
+    const int lane = threadIdx.x & 31;
+    const int64_t I = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (I >= C.n_pad) return;
     double sx = 0, sy = 0;
     if (I < C.n) {
         const int64_t b = C.mem_ptr[I], e = C.mem_ptr[I + 1];
-        for (int64_t m = b; m < e; m++) { const int64_t i = C.mem_idx[m]; sx += F.pos[i]; sy += F.pos[F.n_pad + i]; }
-        sx /= (double)(e - b); sy /= (double)(e - b);
+        for (int64_t m = b + lane; m < e; m += 32) { const int64_t i = C.mem_idx[m]; sx += F.pos[i]; sy += F.pos[F.n_pad + i]; }
+        sx = warp_sum(sx) / (double)(e - b); sy = warp_sum(sy) / (double)(e - b);
     }
-    C.pos[I] = sx; C.pos[C.n_pad + I] = sy;
+    if (lane == 0) { C.pos[I] = sx; C.pos[C.n_pad + I] = sy; }
+}
+
+// lever arm of every fine row about its aggregate's centroid
+__global__ void __launch_bounds__(128) k_lever(LevelDev F, LevelDev C) {
+    const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (i >= F.n_pad) return;
+    double2 l = make_double2(0.0, 0.0);
+    if (i < F.n) { const int64_t I = F.agg[i]; l.x = F.pos[i] - C.pos[I]; l.y = F.pos[F.n_pad + i] - C.pos[C.n_pad + I]; }
+    *reinterpret_cast<double2 *>(F.lev + i * 2) = l;
 }
 
 // G = P_i^T H P_j for 3x3 blocks
@@ -344,10 +508,22 @@ __device__ __forceinline__ void ptap3(const double *h, double dxi, double dyi, d
     }
 }
 
-// Galerkin product Hc = P^T H P: every fine block adds P_i^T H_ij P_j into the coarse block of
-// (agg i, agg j).  Several fine blocks share a coarse block, hence atomics (coarse levels only;
-// the Gauss-Newton system itself is assembled without atomics).
-__global__ void __launch_bounds__(128) k_galerkin3(LevelDev F, LevelDev C) {
+__device__ __forceinline__ void galerkin_scatter(const LevelDev &C, int32_t tgt, const double *g) {
+    if (tgt < 0) {
+        double *dst = C.diag + (int64_t)(-1 - tgt);
+#pragma unroll
+        for (int q = 0; q < 9; q++) atomicAdd(dst + (int64_t)q * C.n_pad, g[q]);
+    } else {
+        double *dst = C.val + (int64_t)tgt * 9;
+#pragma unroll
+        for (int q = 0; q < 9; q++) atomicAdd(dst + q, g[q]);
+    }
+}
+
+// Galerkin product Hc = P^T H P: every fine block adds P_i^T H_ij P_j into the coarse block of (agg i, agg j), which
+// lives in a row this rank owns.  Several fine blocks share a coarse block, hence atomics (coarse levels only; the
+// Gauss-Newton system itself is assembled without atomics).  Level-0 source (JDS): one thread per row.
+__global__ void __launch_bounds__(128) k_galerkin3_jds(LevelDev F, LevelDev C, XRef levr) {
     const int64_t row = (int64_t)blockIdx.x * 128 + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int64_t slice = row >> 5;
@@ -355,17 +531,16 @@ __global__ void __launch_bounds__(128) k_galerkin3(LevelDev F, LevelDev C) {
     const int mydeg = F.deg[row];
     const int maxdeg = __shfl_sync(0xffffffffu, mydeg, 0);
     const bool real = row < F.n;
-    int64_t I = 0; double dxi = 0, dyi = 0, pzi = 1;
+    double dxi = 0, dyi = 0, pzi = 1;
     if (real) {
-        I = F.agg[row];
-        dxi = F.pos[row] - C.pos[I]; dyi = F.pos[F.n_pad + row] - C.pos[C.n_pad + I];
+        const double2 l = *reinterpret_cast<const double2 *>(F.lev + row * 2);
+        dxi = l.x; dyi = l.y;
         pzi = row_pz(F, row);
         double h[9], g[9];
 #pragma unroll
         for (int q = 0; q < 9; q++) h[q] = F.diag[(int64_t)q * F.n_pad + row];
         ptap3(h, dxi, dyi, pzi, dxi, dyi, pzi, g);
-#pragma unroll
-        for (int q = 0; q < 9; q++) atomicAdd(C.diag + (int64_t)q * C.n_pad + I, g[q]);
+        galerkin_scatter(C, -1 - F.agg[row], g);
     }
     const int64_t base = F.slice_ptr[slice];
     int64_t off = 0;
@@ -374,22 +549,42 @@ __global__ void __launch_bounds__(128) k_galerkin3(LevelDev F, LevelDev C) {
         const int cnt = __popc(__ballot_sync(0xffffffffu, active));
         if (active) {
             const int64_t slot = base + off + lane;
-            const int64_t j = F.col[slot] & COL_MASK;
-            const int64_t J = F.agg[j];
-            const double dxj = F.pos[j] - C.pos[J], dyj = F.pos[F.n_pad + j] - C.pos[C.n_pad + J];
+            const uint32_t cw = F.col[slot];
+            const double2 lj = *reinterpret_cast<const double2 *>(xgather<2>(levr, cw));
             const double *v = F.val + (base + off) * 9 + lane;
             double h[9], g[9];
 #pragma unroll
             for (int q = 0; q < 9; q++) h[q] = v[(int64_t)q * cnt];
-            ptap3(h, dxi, dyi, pzi, dxj, dyj, row_pz(F, j), g);
-            const int64_t t = F.ctgt[slot];
-            double *dst; int64_t str;
-            if (t & CTGT_DIAG) { dst = C.diag + (t & ~CTGT_DIAG); str = C.n_pad; }
-            else { dst = C.val + t; str = F.cstr[slot]; }
-#pragma unroll
-            for (int q = 0; q < 9; q++) atomicAdd(dst + (int64_t)q * str, g[q]);
+            // the neighbour is a landmark iff this is a pose-landmark edge seen from its pose (`from`) side
+            const double pzj = ((cw & COL_EDGE_XY) && !(cw & COL_ROLE_TO)) ? 0.0 : 1.0;
+            ptap3(h, dxi, dyi, pzi, lj.x, lj.y, pzj, g);
+            galerkin_scatter(C, F.ctgt[slot], g);
         }
         off += cnt;
+    }
+}
+
+// coarse source (block CSR): one warp per row
+__global__ void __launch_bounds__(256) k_galerkin3_csr(LevelDev F, LevelDev C, XRef levr) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= F.n) return;
+    const double2 l = *reinterpret_cast<const double2 *>(F.lev + row * 2);
+    if (lane == 0) {
+        double h[9], g[9];
+#pragma unroll
+        for (int q = 0; q < 9; q++) h[q] = F.diag[(int64_t)q * F.n_pad + row];
+        ptap3(h, l.x, l.y, 1.0, l.x, l.y, 1.0, g);
+        galerkin_scatter(C, -1 - F.agg[row], g);
+    }
+    for (int64_t s = F.slice_ptr[row] + lane; s < F.slice_ptr[row + 1]; s += 32) {
+        const double2 lj = *reinterpret_cast<const double2 *>(xgather<2>(levr, F.col[s]));
+        const double *v = F.val + s * 9;
+        double h[9], g[9];
+#pragma unroll
+        for (int q = 0; q < 9; q++) h[q] = v[q];
+        ptap3(h, l.x, l.y, 1.0, lj.x, lj.y, 1.0, g);
+        galerkin_scatter(C, F.ctgt[s], g);
     }
 }
 
@@ -428,73 +623,108 @@ __global__ void __launch_bounds__(128) k_invert_diag3(LevelDev L) {
     for (int q = 0; q < 9; q++) L.dinv[(int64_t)q * L.n_pad + row] = o[q];
 }
 
-// Coarsest level: explicit dense inverse (m = D n <= 150 unknowns) by Gauss-Jordan in shared memory.
-// H_c is SPD, so no pivoting.  One CTA.
-template <int D>
-__global__ void __launch_bounds__(256) k_dense_invert(LevelDev L, double *__restrict__ Ainv) {
-    extern __shared__ double sA[];
-    constexpr int DD = D * D;
-    const int m = (int)L.n * D;
-    for (int i = threadIdx.x; i < m * m; i += 256) sA[i] = 0.0;
-    __syncthreads();
-    for (int row = threadIdx.x; row < (int)L.n; row += 256) {
-        for (int a = 0; a < D; a++)
-            for (int b = 0; b < D; b++) sA[(row * D + a) * m + row * D + b] = L.diag[(int64_t)(a * D + b) * L.n_pad + row];
-        // walk this row's slots
-        const int slice = row >> 5, lane = row & 31;
+// ------------------------------------------------------------------------------------------------
+// Coarsest level: explicit dense inverse.  The level's rows are numbered densely across ranks:
+// dense index of (rank k, local row i) = dense_off[k] + i ; m = 3 * sum of real rows.
+struct DenseMap { int32_t off[MAX_RANKS + 1]; };
+
+__device__ __forceinline__ int dense_col(const DenseMap &dm, uint32_t colword) {
+    return dm.off[(colword >> COL_OWNER_SHIFT) & (MAX_RANKS - 1)] + (int)(colword & COL_LOCAL_MASK);
+}
+
+// scatter this rank's block rows into rows [3*dense_off[rank], ...) of the (pre-zeroed) dense matrix A (m x m, row-major)
+template <bool JDS>
+__global__ void __launch_bounds__(128) k_dense_assemble(LevelDev L, DenseMap dm, int rank, int m, double *__restrict__ A) {
+    const int64_t row = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (row >= L.n) return;
+    const int gi = dm.off[rank] + (int)row;
+    for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3; b++) A[(int64_t)(gi * 3 + a) * m + gi * 3 + b] = L.diag[(int64_t)(a * 3 + b) * L.n_pad + row];
+    if (JDS) {
+        const int64_t slice = row >> 5; const int lane = (int)(row & 31);
         const int64_t base = L.slice_ptr[slice];
-        int64_t off = 0;
         const int mydeg = L.deg[row];
+        int64_t off = 0;
         for (int k = 0; k < mydeg; k++) {
             int cnt = 0;
             while (cnt < 32 && L.deg[slice * 32 + cnt] > k) cnt++;
-            const int j = (int)(L.col[base + off + lane] & COL_MASK);
-            const double *v = L.val + (base + off) * DD + lane;
-            for (int a = 0; a < D; a++)
-                for (int b = 0; b < D; b++) sA[(row * D + a) * m + j * D + b] += v[(int64_t)(a * D + b) * cnt];
+            const int gj = dense_col(dm, L.col[base + off + lane]);
+            const double *v = L.val + (base + off) * 9 + lane;
+            for (int a = 0; a < 3; a++)
+                for (int b = 0; b < 3; b++) A[(int64_t)(gi * 3 + a) * m + gj * 3 + b] += v[(int64_t)(a * 3 + b) * cnt];   // duplicate edges sum
             off += cnt;
         }
-    }
-    __syncthreads();
-    // in-place Gauss-Jordan: for pivot p, A[i][j] -= A[i][p] A[p][j] / A[p][p] (i,j != p),
-    // A[i][p] = -A[i][p] / A[p][p], A[p][j] /= A[p][p], A[p][p] = 1 / A[p][p]
-    __shared__ double colp[256];
-    for (int p = 0; p < m; p++) {
-        if ((int)threadIdx.x < m) colp[threadIdx.x] = sA[threadIdx.x * m + p];
-        __syncthreads();
-        const double ip = 1.0 / colp[p];
-        for (int idx = threadIdx.x; idx < m * m; idx += 256) {
-            const int i = idx / m, j = idx - i * m;
-            if (i != p && j != p) sA[idx] = fma(-colp[i] * ip, sA[p * m + j], sA[idx]);
+    } else {
+        for (int64_t s = L.slice_ptr[row]; s < L.slice_ptr[row + 1]; s++) {
+            const int gj = dense_col(dm, L.col[s]);
+            const double *v = L.val + s * 9;
+            for (int a = 0; a < 3; a++)
+                for (int b = 0; b < 3; b++) A[(int64_t)(gi * 3 + a) * m + gj * 3 + b] = v[a * 3 + b];
         }
-        __syncthreads();
-        for (int j = threadIdx.x; j < m; j += 256) {
-            if (j == p) continue;
-            sA[p * m + j] *= ip;
-            sA[j * m + p] = -colp[j] * ip;
-        }
-        if (threadIdx.x == 0) sA[p * m + p] = ip;
-        __syncthreads();
     }
-    for (int i = threadIdx.x; i < m * m; i += 256) Ainv[i] = sA[i];
 }
 
-// x = Ainv r on the coarsest level (Ainv symmetric: column reads are coalesced)
-template <int D>
-__global__ void __launch_bounds__(256) k_dense_apply(LevelDev L, const double *__restrict__ Ainv, const double *__restrict__ r,
-                                                      double *__restrict__ x, const Scalars *S) {
-    if (ld_done(S)) return;
-    constexpr int VS = VecStride<D>::value;
-    __shared__ double sr[256];
-    const int m = (int)L.n * D;
-    const int t = threadIdx.x;
-    if (t < m) sr[t] = r[(t / D) * VS + (t % D)];
-    __syncthreads();
-    if (t < m) {
-        double s = 0.0;
-        for (int j = 0; j < m; j++) s = fma(__ldg(Ainv + (int64_t)j * m + t), sr[j], s);
-        x[(t / D) * VS + (t % D)] = s;
+// In-place block Gauss-Jordan inversion of the SPD matrix A (m x m, m = 3 nb), no pivoting; cooperative launch.
+// Sweep of pivot block p:  A_pp <- A_pp^-1 ; A_pj <- A_pp^-1 A_pj ; A_ip <- -A_ip A_pp^-1 ; A_ij <- A_ij - A_ip A_pp^-1 A_pj.
+// R (3 x m) and Cp (m x 3) are scratch panels.
+__global__ void __launch_bounds__(256) k_dense_invert(int m, double *__restrict__ A, double *__restrict__ R, double *__restrict__ Cp) {
+    cg::grid_group grid = cg::this_grid();
+    const int nb = m / 3;
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+    for (int pb = 0; pb < nb; pb++) {
+        const int p0 = 3 * pb;
+        double P[9], Pi[9];
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int b = 0; b < 3; b++) P[a * 3 + b] = __ldcg(A + (int64_t)(p0 + a) * m + p0 + b);
+        inv3(P, Pi);
+        for (int j = gtid; j < m; j += gsize) {
+            const double a0 = __ldcg(A + (int64_t)p0 * m + j), a1 = __ldcg(A + (int64_t)(p0 + 1) * m + j), a2 = __ldcg(A + (int64_t)(p0 + 2) * m + j);
+#pragma unroll
+            for (int a = 0; a < 3; a++) R[(int64_t)a * m + j] = Pi[a * 3] * a0 + Pi[a * 3 + 1] * a1 + Pi[a * 3 + 2] * a2;
+#pragma unroll
+            for (int b = 0; b < 3; b++) Cp[(int64_t)j * 3 + b] = __ldcg(A + (int64_t)j * m + p0 + b);
+        }
+        grid.sync();
+        for (int i = blockIdx.x; i < m; i += gridDim.x) {
+            const double c0 = __ldcg(Cp + (int64_t)i * 3), c1 = __ldcg(Cp + (int64_t)i * 3 + 1), c2 = __ldcg(Cp + (int64_t)i * 3 + 2);
+            const bool inP = i >= p0 && i < p0 + 3;
+            double *Ai = A + (int64_t)i * m;
+            for (int j = threadIdx.x; j < m; j += blockDim.x) {
+                const bool jin = j >= p0 && j < p0 + 3;
+                double v;
+                if (inP && jin) v = Pi[(i - p0) * 3 + (j - p0)];
+                else if (inP) v = __ldcg(R + (int64_t)(i - p0) * m + j);
+                else if (jin) v = -(c0 * Pi[j - p0] + c1 * Pi[3 + j - p0] + c2 * Pi[6 + j - p0]);
+                else v = __ldcg(Ai + j) - (c0 * __ldcg(R + j) + c1 * __ldcg(R + m + j) + c2 * __ldcg(R + 2 * (int64_t)m + j));
+                Ai[j] = v;
+            }
+        }
+        grid.sync();
     }
+}
+
+// x_own = Ainv[own rows, :] r  on the coarsest level; r is gathered from all ranks.  One warp per scalar row.
+__global__ void __launch_bounds__(256) k_dense_apply(int64_t n_local, DenseMap dm, int rank, int world, int m, const double *__restrict__ Ainv,
+                                                      XRef rr, double *__restrict__ x, const Scalars *S) {
+    if (ld_done(S)) return;
+    extern __shared__ double sr[];
+    for (int t = threadIdx.x; t < m; t += 256) {
+        const int g = t / 3, c = t - 3 * g;
+        int k = 0;
+        while (k + 1 < world && g >= dm.off[k + 1]) k++;
+        sr[t] = rr.p[k][(int64_t)(g - dm.off[k]) * 4 + c];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t srow = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);      // local scalar row
+    if (srow >= n_local * 3) return;
+    const double *a = Ainv + ((int64_t)dm.off[rank] * 3 + srow) * m;
+    double s = 0.0;
+    for (int j = lane; j < m; j += 32) s = fma(__ldg(a + j), sr[j], s);
+    s = warp_sum(s);
+    if (lane == 0) x[(srow / 3) * 4 + (srow % 3)] = s;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -542,7 +772,7 @@ __device__ __forceinline__ void xtwy3(const double *X, const double *w, const do
 // diagonal block and gradient in registers, streams the off-diagonal block into the slice blob, and
 // finally writes diag, its inverse (the block-Jacobi preconditioner), r = b = -g and the row position.
 // hz: measurement stream laid out like val with 10 components (z: x y cos sin ; Omega upper 6).
-__global__ void __launch_bounds__(128) k_assemble_se2(LevelDev L, const double *__restrict__ poses, const double *__restrict__ hz,
+__global__ void __launch_bounds__(128) k_assemble_se2(LevelDev L, XRef posr, const double *__restrict__ poses, const double *__restrict__ hz,
                                                        double *__restrict__ rvec, int64_t anchor_row, double anchor_w, double lambda) {
     const int64_t row = (int64_t)blockIdx.x * 128 + threadIdx.x;
     const int lane = threadIdx.x & 31;
@@ -565,7 +795,7 @@ __global__ void __launch_bounds__(128) k_assemble_se2(LevelDev L, const double *
             const uint32_t cw = __ldg(L.col + base + off + lane);
             const bool to_side = (cw & COL_ROLE_TO) != 0;
             double xj[4], z[4], w[6];
-            ld_vec<4>(poses + (int64_t)(cw & COL_MASK) * 4, xj);
+            ld_vec<4>(xgather<4>(posr, cw), xj);
             const double *m = hz + (base + off) * 10 + lane;
 #pragma unroll
             for (int q = 0; q < 4; q++) z[q] = __ldg(m + (int64_t)q * cnt);
@@ -638,18 +868,20 @@ __global__ void __launch_bounds__(128) k_assemble_se2(LevelDev L, const double *
     L.pos[row] = xi[0]; L.pos[L.n_pad + row] = xi[1];
 }
 
-// global_error (:537-574): one thread per edge, edge-ordered SoA copy of the measurements.
+// global_error (:537-574): one thread per edge this rank owns (edges whose `from` vertex it owns),
+// edge-ordered SoA copy of the measurements.
 // ed: [10][n_edges] planes (z: x y cos sin ; Omega upper 6 -- for XY edges w11 w12 w22 in the first three)
-__global__ void __launch_bounds__(256) k_chi2_se2(int64_t n_edges, const int2 *__restrict__ ends, const double *__restrict__ ed,
-                                                   const double *__restrict__ poses, Scalars *S, double *partials) {
+// ends: .x = local row of `from`, .y = column word of `to` (COL_EDGE_XY marks a pose-landmark edge)
+__global__ void __launch_bounds__(256) k_chi2_se2(int64_t n_edges, const uint2 *__restrict__ ends, const double *__restrict__ ed,
+                                                   const double *__restrict__ poses, XRef posr, Scalars *S, double *partials) {
     const int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x;
     double c = 0.0;
     if (k < n_edges) {
-        const int2 en = ends[k];
+        const uint2 en = ends[k];
         double x1[4], x2[4], z[4], w[6];
-        const bool xy = en.y < 0;
+        const bool xy = (en.y & COL_EDGE_XY) != 0;
         ld_vec<4>(poses + (int64_t)en.x * 4, x1);
-        ld_vec<4>(poses + (int64_t)(xy ? ~en.y : en.y) * 4, x2);
+        ld_vec<4>(xgather<4>(posr, en.y), x2);
 #pragma unroll
         for (int q = 0; q < 4; q++) z[q] = __ldg(ed + (int64_t)q * n_edges + k);
 #pragma unroll
@@ -665,8 +897,7 @@ __global__ void __launch_bounds__(256) k_chi2_se2(int64_t n_edges, const int2 *_
             c = e0 * (w[0] * e0 + w[1] * e1) + e1 * (w[1] * e0 + w[2] * e1);
         }
     }
-    double total;
-    if (block_sum_last<256>(c, partials, &S->counter[FIN_CHI2], total)) finalize(FIN_CHI2, S, total);
+    reduce_and_finalize<256, FIN_CHI2>(&c, S, partials, 0);
 }
 
 // update_nodes (:229-245): t += dx.xy (global frame), r <- r * (cos dth, sin dth) without
@@ -690,13 +921,12 @@ __global__ void __launch_bounds__(256) k_retract_se2(LevelDev L, double *__restr
         }
         st_vec<4>(poses + row * 4, p);
     }
-    double total;
-    if (block_sum_last<256>(n2, partials, &S->counter[FIN_NORM], total)) finalize(FIN_NORM, S, total);
+    reduce_and_finalize<256, FIN_NORM>(&n2, S, partials, 0);
 }
 
 // pgo_set_poses / pgo_get_poses: g2o-layout vertex values (x y theta | x y, lut order, packed) <-> the
 // 32-byte device pose records (x, y, cos, sin) in storage order.  iso2 (g2o.rs:14-16) on the way in,
-// atan2(im, re) on the way out.
+// atan2(im, re) on the way out.  row_valofs is relative to the first value this rank owns.
 __global__ void __launch_bounds__(256) k_import_poses(int64_t n, const int64_t *__restrict__ row_valofs, const uint8_t *__restrict__ vkind,
                                                        const double *__restrict__ values, double *__restrict__ poses) {
     const int64_t row = (int64_t)blockIdx.x * 256 + threadIdx.x;

@@ -2,9 +2,14 @@
 //
 // One pgo_gn_step = the body of the reference's optimisation loop
 // (pose_graph_optimization.rs:271-274): build_linear_system + solve + update_nodes + global_error,
-// with the UMFPACK factorisation replaced by a preconditioned conjugate gradient that runs entirely
+// with the UMFPACK factorisation replaced by a preconditioned (flexible) conjugate gradient that runs entirely
 // on the GPU: the PCG iterations are captured once into a CUDA graph; every kernel tests a device
 // `done` flag, so the host only polls a pinned copy of the scalars once per graph launch.
+// Preconditioner: block-Jacobi, or an aggregation-AMG K-cycle (two Krylov-accelerated coarse solves per level,
+// Notay) over rigid-motion coarse spaces with an explicit dense inverse on the coarsest level.
+// Sharded mode (world > 1): every rank owns a contiguous vertex range of every level; neighbour rows are read
+// directly from peer HBM over NVLink (CUDA IPC), dot products and stage barriers are one tiny kernel that
+// exchanges partial sums through peer memory.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -14,6 +19,7 @@
 
 #include "../../include/pgo_b200.h"
 #include "kernels.cuh"
+#include "peer.cuh"
 
 using namespace pgo;
 
@@ -24,6 +30,7 @@ thread_local std::string g_create_error;
 #define NEED_DEVICE(h)                                                                             \
     do {                                                                                           \
         if (!(h)->stream) { (h)->err = "structure-only handle: no device state (there is no CPU fallback)"; return PGO_ERR_CUDA; } \
+        if ((h)->world > 1 && !(h)->connected) { (h)->err = "sharded handle: call pgo_shard_connect first"; return PGO_ERR_ARG; } \
     } while (0)
 
 #define CK(call)                                                                                   \
@@ -37,31 +44,47 @@ thread_local std::string g_create_error;
 
 struct LevelBuf {
     LevelDev d{};
-    double *r = nullptr, *xa = nullptr, *res = nullptr, *e = nullptr;  // V-cycle work vectors
+    bool jds = false, kcycle = false;
+    double *rhs = nullptr, *sol = nullptr, *xa = nullptr, *res = nullptr;      // cycle work vectors
+    double *c1 = nullptr, *c2 = nullptr, *v1 = nullptr, *v2 = nullptr, *r1 = nullptr;   // K-cycle work vectors
     double omega = 0.6;
-    int grid128 = 0;
+    int grid128 = 0, gridw = 0, gridv = 0;
 };
+
+struct ArenaReq { double **p; size_t count; };
 
 } // namespace
 
 struct pgo_handle {
     Symbolic sym;
     pgo_options opt{};
-    int device = 0;
+    int device = 0, world = 1, rank = 0;
+    bool connected = false;
     cudaStream_t stream = nullptr;
     std::vector<LevelBuf> lv;
     std::vector<void *> allocs;
     size_t device_bytes = 0;
-    // level-0 state
+    // peer-visible arena: identical layout on every rank
+    char *arena = nullptr;
+    size_t arena_bytes = 0;
+    char *peer_base[MAX_RANKS]{};
+    std::vector<ArenaReq> arena_reqs;
+    Comm *comm = nullptr;
+    CommRef comm_ref{};
+    // level-0 state (local rows)
+    int64_t n_loc = 0, n_pad_loc = 0, n_edges_loc = 0, row0 = 0;
     double *poses = nullptr, *poses_saved = nullptr, *hz = nullptr, *ed = nullptr;
     double *vstage = nullptr;          // g2o-layout vertex values (n_values) for set/get_poses
-    int64_t *row_valofs = nullptr;     // [n] offset of each storage row's values in vstage
-    int2 *ends = nullptr;
+    int64_t *row_valofs = nullptr;     // [n_loc] offset of each local row's values in vstage
+    uint2 *ends = nullptr;
     double *x = nullptr, *r = nullptr, *p = nullptr, *q = nullptr, *z = nullptr;
     Scalars *S = nullptr, *hS = nullptr;   // device / pinned host (2 slots)
     double *partials = nullptr;
-    double *Ainv = nullptr;
-    bool dense_coarsest = false, use_amg = false, omega_ready = false;
+    double *Ainv = nullptr, *panelR = nullptr, *panelC = nullptr;
+    double *Arows = nullptr;           // peer-visible copy of this rank's rows of the coarsest dense matrix
+    DenseMap dmap{};
+    int dense_m = 0, invert_grid = 0;
+    bool use_amg = false, omega_ready = false;
     int64_t anchor_row = -1;
     cudaGraphExec_t pcg_graph = nullptr;
     int chunk = 8;
@@ -91,59 +114,145 @@ template <typename T> int upload(pgo_handle *h, T **p, const std::vector<T> &v) 
     return PGO_OK;
 }
 
-inline int grid_for(int64_t n, int bs) { return (int)((n + bs - 1) / bs); }
+inline int grid_for(int64_t n, int bs) { return (int)std::max<int64_t>(1, (n + bs - 1) / bs); }
 
-// ---- V-cycle: z = M^-1 r, all launches on h->stream.  FINK: finalize kind of the last kernel on level 0.
-template <int FINK> void launch_post(pgo_handle *h, int l, const double *r_l, double *out) {
-    LevelBuf &B = h->lv[l];
-    k_spmv<3, 2, FINK><<<B.grid128, 128, 0, h->stream>>>(B.d, B.xa, r_l, out, B.omega, h->S, h->partials, 1);
+// peer-visible vectors are carved from one arena whose layout is identical on every rank (sizes use the
+// largest partition of the level), so that rank k's copy of a vector is peer_base[k] + the same offset
+inline void arena_request(pgo_handle *h, double **p, size_t count) { h->arena_reqs.push_back({p, count}); }
+
+int arena_commit(pgo_handle *h) {
+    size_t off = (sizeof(Comm) + 255) / 256 * 256;
+    std::vector<size_t> offs;
+    for (auto &rq : h->arena_reqs) { offs.push_back(off); off += (rq.count * sizeof(double) + 255) / 256 * 256; }
+    h->arena_bytes = off;
+    CK(cudaMalloc((void **)&h->arena, off));
+    h->allocs.push_back(h->arena);
+    h->device_bytes += off;
+    CK(cudaMemsetAsync(h->arena, 0, off, h->stream));
+    for (size_t i = 0; i < offs.size(); i++) *h->arena_reqs[i].p = (double *)(h->arena + offs[i]);
+    h->comm = (Comm *)h->arena;
+    for (int k = 0; k < MAX_RANKS; k++) h->peer_base[k] = nullptr;
+    h->peer_base[h->rank] = h->arena;
+    return PGO_OK;
 }
 
-template <int FINK> void vcycle(pgo_handle *h, int l, const double *r_l, double *out) {
+// the same vector on every rank
+XRef xref(const pgo_handle *h, const double *local) {
+    XRef x{};
+    const size_t off = (const char *)local - h->arena;
+    for (int k = 0; k < h->world; k++) x.p[k] = (const double *)(h->peer_base[k] + off);
+    for (int k = h->world; k < MAX_RANKS; k++) x.p[k] = local;
+    return x;
+}
+
+// ---- cross-rank stage barrier / all-reduce of the partial sums a kernel left in S->loc (world > 1 only)
+template <int FIN> void xreduce(pgo_handle *h, int lvl, int check_done) {
+    if (h->world == 1) return;
+    k_xreduce<FIN><<<1, 32, 0, h->stream>>>(h->comm, h->comm_ref, h->rank, h->world, h->S, lvl, check_done);
+    h->launch_count += 1;
+}
+inline void xbarrier(pgo_handle *h, int check_done = 1) { xreduce<FIN_NONE>(h, 0, check_done); }
+
+// ---- SpMV launchers
+template <int MODE, int FIN> void spmv0(pgo_handle *h, const double *x, const double *r, double *y, double omega, const double *u1, int check) {
+    LevelBuf &B = h->lv[0];
+    k_spmv<3, MODE, FIN><<<B.grid128, 128, 0, h->stream>>>(B.d, xref(h, x), x, r, y, omega, u1, h->S, h->partials, check);
+    h->launch_count += 1;
+    xreduce<FIN>(h, 0, check);
+}
+template <int MODE, int FIN> void spmvc(pgo_handle *h, int l, const double *x, const double *r, double *y, double omega,
+                                        const double *u1, const double *u2, int check) {
+    LevelBuf &B = h->lv[l];
+    k_spmv_csr<MODE, FIN><<<B.gridw, 256, 0, h->stream>>>(B.d, xref(h, x), x, r, y, omega, u1, u2, h->S, h->partials, l, check);
+    h->launch_count += 1;
+    xreduce<FIN>(h, l, check);
+}
+template <int MODE> void spmv_any(pgo_handle *h, int l, const double *x, const double *r, double *y, double omega, int check) {
+    if (h->lv[l].jds) spmv0<MODE, FIN_NONE>(h, x, r, y, omega, nullptr, check);
+    else spmvc<MODE, FIN_NONE>(h, l, x, r, y, omega, nullptr, nullptr, check);
+}
+
+void coarse_solve(pgo_handle *h, int l, const double *rhs, double *out);
+
+void dense_apply(pgo_handle *h, int l, const double *rhs, double *out) {
+    LevelBuf &B = h->lv[l];
+    xbarrier(h);                                     // every rank's rhs segment is complete
+    k_dense_apply<<<grid_for(B.d.n * 3, 8), 256, sizeof(double) * h->dense_m, h->stream>>>(B.d.n, h->dmap, h->rank, h->world, h->dense_m,
+                                                                                          h->Ainv, xref(h, rhs), out, h->S);
+    h->launch_count += 1;
+}
+
+// ---- one multigrid cycle at level l: out = M_l(rhs).  FINK: dots fused into the last kernel (level 0 only).
+template <int FINK> void cycle(pgo_handle *h, int l, const double *rhs, double *out) {
     LevelBuf &B = h->lv[l];
     const int last = (int)h->lv.size() - 1;
     if (l == last) {
-        if (h->dense_coarsest) {
-            k_dense_apply<3><<<1, 256, 0, h->stream>>>(B.d, h->Ainv, r_l, out, h->S);
+        if (h->sym.dense_coarsest) dense_apply(h, l, rhs, out);
+        else {
+            // no direct solve possible: a few damped block-Jacobi sweeps
+            k_dinv_apply<3, FIN_NONE><<<B.grid128, 128, 0, h->stream>>>(B.d, rhs, B.xa, B.omega, nullptr, h->S, h->partials, 1);
             h->launch_count += 1;
-        } else {
-            // no dense solve possible: a few damped block-Jacobi sweeps
-            k_dinv_apply<3, FIN_NONE><<<B.grid128, 128, 0, h->stream>>>(B.d, r_l, B.xa, B.omega, h->S, h->partials, 1);
-            k_spmv<3, 2, FIN_NONE><<<B.grid128, 128, 0, h->stream>>>(B.d, B.xa, r_l, B.res, B.omega, h->S, h->partials, 1);
-            k_spmv<3, 2, FIN_NONE><<<B.grid128, 128, 0, h->stream>>>(B.d, B.res, r_l, out, B.omega, h->S, h->partials, 1);
-            h->launch_count += 3;
+            xbarrier(h);
+            spmv_any<2>(h, l, B.xa, rhs, B.res, B.omega, 1);
+            xbarrier(h);
+            spmv_any<2>(h, l, B.res, rhs, out, B.omega, 1);
+            xbarrier(h);
         }
         return;
     }
     LevelBuf &C = h->lv[l + 1];
-    k_dinv_apply<3, FIN_NONE><<<B.grid128, 128, 0, h->stream>>>(B.d, r_l, B.xa, B.omega, h->S, h->partials, 1);
-    k_spmv<3, 1, FIN_NONE><<<B.grid128, 128, 0, h->stream>>>(B.d, B.xa, r_l, B.res, 0.0, h->S, h->partials, 1);
-    k_restrict3<<<C.grid128, 128, 0, h->stream>>>(B.d, C.d, B.res, C.r, h->S);
-    vcycle<FIN_NONE>(h, l + 1, C.r, C.e);
-    k_prolong3<<<B.grid128, 128, 0, h->stream>>>(B.d, C.d, C.e, B.xa, h->S);
-    if (l == 0) launch_post<FINK>(h, l, r_l, out);
-    else launch_post<FIN_NONE>(h, l, r_l, out);
-    h->launch_count += 5;
+    k_dinv_apply<3, FIN_NONE><<<B.grid128, 128, 0, h->stream>>>(B.d, rhs, B.xa, B.omega, nullptr, h->S, h->partials, 1);
+    h->launch_count += 1;
+    xbarrier(h);
+    spmv_any<1>(h, l, B.xa, rhs, B.res, 0.0, 1);
+    k_restrict3<<<C.gridw, 256, 0, h->stream>>>(B.d, C.d, B.res, C.rhs, h->S);
+    h->launch_count += 1;
+    coarse_solve(h, l + 1, C.rhs, C.sol);
+    k_prolong3<<<B.grid128, 128, 0, h->stream>>>(B.d, C.sol, B.xa, h->S);
+    h->launch_count += 1;
+    xbarrier(h);
+    if (l == 0) spmv0<2, FINK>(h, B.xa, rhs, out, B.omega, FINK == FIN_RZ ? h->q : nullptr, 1);
+    else spmvc<2, FIN_NONE>(h, l, B.xa, rhs, out, B.omega, nullptr, nullptr, 1);
+    if (FINK == FIN_NONE) xbarrier(h);               // FINK != NONE: the all-reduce is the barrier
 }
 
-template <int FINK> void precondition(pgo_handle *h) {   // z = M^-1 r (+ r.z)
-    if (h->use_amg && h->lv.size() > 1) vcycle<FINK>(h, 0, h->r, h->z);
-    else {
-        LevelBuf &B = h->lv[0];
-        k_dinv_apply<3, FINK><<<B.grid128, 128, 0, h->stream>>>(B.d, h->r, h->z, 1.0, h->S, h->partials, 1);
+// K-cycle: the coarse system of level l is solved by two flexible-CG steps preconditioned by the cycle of level l
+void coarse_solve(pgo_handle *h, int l, const double *rhs, double *out) {
+    LevelBuf &B = h->lv[l];
+    const int last = (int)h->lv.size() - 1;
+    if (l == last || !B.kcycle) { cycle<FIN_NONE>(h, l, rhs, out); return; }
+    cycle<FIN_NONE>(h, l, rhs, B.c1);
+    spmvc<0, FIN_K1>(h, l, B.c1, nullptr, B.v1, 0.0, rhs, nullptr, 1);
+    k_kcombine<0><<<B.gridv, 256, 0, h->stream>>>(B.d.n_pad, rhs, B.v1, B.r1, h->S, l);
+    cycle<FIN_NONE>(h, l, B.r1, B.c2);
+    spmvc<0, FIN_K2>(h, l, B.c2, nullptr, B.v2, 0.0, B.v1, B.r1, 1);
+    k_kcombine<1><<<B.gridv, 256, 0, h->stream>>>(B.d.n_pad, B.c1, B.c2, out, h->S, l);
+    h->launch_count += 2;
+}
+
+template <int FINK> void precondition(pgo_handle *h) {   // z = M^-1 r (+ r.z, z.q)
+    LevelBuf &B = h->lv[0];
+    if (h->use_amg && h->lv.size() > 1) cycle<FINK>(h, 0, h->r, h->z);
+    else if (h->use_amg && h->sym.dense_coarsest) {      // the whole system fits the direct solve
+        dense_apply(h, 0, h->r, h->z);
+        k_dots<FINK><<<B.grid128, 128, 0, h->stream>>>(B.d.n_pad, h->r, h->z, h->q, h->S, h->partials);
         h->launch_count += 1;
+        xreduce<FINK>(h, 0, 1);
+    } else {
+        k_dinv_apply<3, FINK><<<B.grid128, 128, 0, h->stream>>>(B.d, h->r, h->z, 1.0, h->q, h->S, h->partials, 1);
+        h->launch_count += 1;
+        xreduce<FINK>(h, 0, 1);
     }
 }
 
 void pcg_iteration(pgo_handle *h) {
     LevelBuf &B = h->lv[0];
-    const int64_t nd = B.d.n_pad * 4;
-    const int g256 = grid_for(nd / 2, 256);
-    k_spmv<3, 0, FIN_PQ><<<B.grid128, 128, 0, h->stream>>>(B.d, h->p, nullptr, h->q, 0.0, h->S, h->partials, 1);
-    k_update_xr<3><<<g256, 256, 0, h->stream>>>(B.d.n_pad, h->x, h->r, h->p, h->q, h->S);
+    spmv0<0, FIN_PQ>(h, h->p, nullptr, h->q, 0.0, nullptr, 1);
+    k_update_xr<3><<<B.gridv, 256, 0, h->stream>>>(B.d.n_pad, h->x, h->r, h->p, h->q, h->S);
     precondition<FIN_RZ>(h);
-    k_update_p<3><<<g256, 256, 0, h->stream>>>(B.d.n_pad, h->p, h->z, h->S);
-    h->launch_count += 3;
+    k_update_p<3><<<B.gridv, 256, 0, h->stream>>>(B.d.n_pad, h->p, h->z, h->S);
+    h->launch_count += 2;
+    xbarrier(h);                                     // p complete on every rank before the next SpMV reads it
 }
 
 int build_pcg_graph(pgo_handle *h) {
@@ -163,14 +272,16 @@ int build_pcg_graph(pgo_handle *h) {
 // ---- assemble the Gauss-Newton system at the current poses (H in lv[0], b in h->r)
 int assemble(pgo_handle *h, double lambda, int add_lambda) {
     LevelBuf &B = h->lv[0];
-    k_assemble_se2<<<B.grid128, 128, 0, h->stream>>>(B.d, h->poses, h->hz, h->r, h->anchor_row, h->opt.anchor_weight,
+    xbarrier(h, 0);                                  // every rank's poses are final
+    k_assemble_se2<<<B.grid128, 128, 0, h->stream>>>(B.d, xref(h, h->poses), h->poses, h->hz, h->r, h->anchor_row, h->opt.anchor_weight,
                                                       add_lambda ? lambda : 0.0);
     h->launch_count += 1;
     CK(cudaGetLastError());
     return PGO_OK;
 }
 
-// power iteration for rho(Dinv H) on one level -> damping of the block-Jacobi smoother
+// power iteration for rho(Dinv H) on one level -> damping of the block-Jacobi smoother (the norm is taken over the
+// local rows only: an estimate is all that is needed)
 int estimate_omega(pgo_handle *h, int l) {
     LevelBuf &B = h->lv[l];
     const int64_t nd = B.d.n_pad * 4;
@@ -178,55 +289,78 @@ int estimate_omega(pgo_handle *h, int l) {
     uint64_t s = 0x9E3779B97F4A7C15ull;
     for (int64_t i = 0; i < B.d.n; i++)
         for (int c = 0; c < 3; c++) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; v[i * 4 + c] = (double)(s >> 11) / 9007199254740992.0 - 0.5; }
-    if (B.d.vkind) {   // keep the landmark padding unknown out of it
-        for (int64_t i = 0; i < B.d.n; i++) if (h->sym.vkind[h->sym.perm[i]] == 1) v[i * 4 + 2] = 0.0;
+    if (l == 0) {   // keep the landmark padding unknown out of it
+        for (int64_t i = 0; i < B.d.n; i++) if (h->sym.vkind[h->sym.perm[h->row0 + i]] == 1) v[i * 4 + 2] = 0.0;
     }
     double *a = B.xa, *b = B.res;
     CK(cudaMemcpyAsync(a, v.data(), nd * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     double rho = 1.0;
-    for (int it = 0; it < 12; it++) {
+    for (int it = 0; it < 10; it++) {
         // b = H a ; a' = Dinv b ; rho ~ |a'| / |a|
-        k_spmv<3, 0, FIN_NONE><<<B.grid128, 128, 0, h->stream>>>(B.d, a, nullptr, b, 0.0, h->S, h->partials, 0);
-        k_dinv_apply<3, FIN_NONE><<<B.grid128, 128, 0, h->stream>>>(B.d, b, a, 1.0, h->S, h->partials, 0);
+        xbarrier(h, 0);
+        spmv_any<0>(h, l, a, nullptr, b, 0.0, 0);
+        xbarrier(h, 0);
+        k_dinv_apply<3, FIN_NONE><<<B.grid128, 128, 0, h->stream>>>(B.d, b, a, 1.0, nullptr, h->S, h->partials, 0);
         CK(cudaMemcpyAsync(v.data(), a, nd * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
         double nrm = 0.0;
         for (double t : v) nrm += t * t;
         nrm = std::sqrt(nrm);
-        if (!(nrm > 0.0) || !std::isfinite(nrm)) { rho = 2.0; break; }
-        rho = nrm;                       // |a| was normalised to 1
+        if (!(nrm > 0.0) || !std::isfinite(nrm)) { rho = 2.0; nrm = 1.0; }
+        else rho = nrm;                  // |a| was normalised to 1
         for (double &t : v) t /= nrm;
         CK(cudaMemcpyAsync(a, v.data(), nd * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     }
-    // first iterate is not normalised: rho from the last step only
-    B.omega = 4.0 / (3.0 * 1.1 * rho);
+    B.omega = 4.0 / (3.0 * 1.1 * std::max(rho, 1.0));
     if (B.omega > 1.0) B.omega = 1.0;
     return PGO_OK;
 }
 
 // numeric setup of the hierarchy for the current H: coarse positions, Galerkin products, inverses
 int amg_setup(pgo_handle *h) {
-    if (!h->use_amg || h->lv.size() < 2) return PGO_OK;
+    if (!h->use_amg) return PGO_OK;
     const int last = (int)h->lv.size() - 1;
     for (int l = 0; l < last; l++) {
         LevelBuf &F = h->lv[l], &C = h->lv[l + 1];
-        k_coarse_pos<<<C.grid128, 128, 0, h->stream>>>(F.d, C.d);
-        CK(cudaMemsetAsync(C.d.val, 0, sizeof(double) * 9 * C.d.n_slots, h->stream));
+        k_coarse_pos<<<C.gridw, 256, 0, h->stream>>>(F.d, C.d);
+        k_lever<<<F.grid128, 128, 0, h->stream>>>(F.d, C.d);
+        CK(cudaMemsetAsync(C.d.val, 0, sizeof(double) * 9 * std::max<int64_t>(C.d.n_slots, 1), h->stream));
         CK(cudaMemsetAsync(C.d.diag, 0, sizeof(double) * 9 * C.d.n_pad, h->stream));
-        k_galerkin3<<<F.grid128, 128, 0, h->stream>>>(F.d, C.d);
+        xbarrier(h, 0);                              // lever arms of neighbour rows on other ranks
+        if (F.jds) k_galerkin3_jds<<<F.grid128, 128, 0, h->stream>>>(F.d, C.d, xref(h, F.d.lev));
+        else k_galerkin3_csr<<<F.gridw, 256, 0, h->stream>>>(F.d, C.d, xref(h, F.d.lev));
         k_invert_diag3<<<C.grid128, 128, 0, h->stream>>>(C.d);
-        h->launch_count += 3;
+        h->launch_count += 4;
     }
-    if (h->dense_coarsest) {
+    if (h->sym.dense_coarsest) {
         LevelBuf &C = h->lv[last];
-        const int m = (int)C.d.n * 3;
-        k_dense_invert<3><<<1, 256, sizeof(double) * m * m, h->stream>>>(C.d, h->Ainv);
+        const int m = h->dense_m;
+        CK(cudaMemsetAsync(h->Ainv, 0, sizeof(double) * (size_t)m * m, h->stream));
+        if (C.jds) k_dense_assemble<true><<<C.grid128, 128, 0, h->stream>>>(C.d, h->dmap, h->rank, m, h->Ainv);
+        else k_dense_assemble<false><<<C.grid128, 128, 0, h->stream>>>(C.d, h->dmap, h->rank, m, h->Ainv);
+        h->launch_count += 1;
+        if (h->world > 1) {
+            // publish this rank's rows, then collect everybody else's
+            const size_t row_bytes = sizeof(double) * (size_t)m;
+            const int r0 = h->dmap.off[h->rank] * 3, nr = (h->dmap.off[h->rank + 1] - h->dmap.off[h->rank]) * 3;
+            if (nr > 0) CK(cudaMemcpyAsync(h->Arows, h->Ainv + (size_t)r0 * m, row_bytes * nr, cudaMemcpyDeviceToDevice, h->stream));
+            xbarrier(h, 0);
+            XRef ar = xref(h, h->Arows);
+            for (int k = 0; k < h->world; k++) {
+                if (k == h->rank) continue;
+                const int k0 = h->dmap.off[k] * 3, kn = (h->dmap.off[k + 1] - h->dmap.off[k]) * 3;
+                if (kn > 0) CK(cudaMemcpyAsync(h->Ainv + (size_t)k0 * m, ar.p[k], row_bytes * kn, cudaMemcpyDeviceToDevice, h->stream));
+            }
+            xbarrier(h, 0);
+        }
+        void *args[] = {(void *)&h->dense_m, (void *)&h->Ainv, (void *)&h->panelR, (void *)&h->panelC};
+        CK(cudaLaunchCooperativeKernel((void *)k_dense_invert, dim3(h->invert_grid), dim3(256), args, 0, h->stream));
         h->launch_count += 1;
     }
     CK(cudaGetLastError());
     if (!h->omega_ready) {
         for (int l = 0; l < (int)h->lv.size(); l++) {
-            if (l == last && h->dense_coarsest) continue;
+            if (l == last && h->sym.dense_coarsest) continue;
             int rc = estimate_omega(h, l);
             if (rc) return rc;
         }
@@ -240,8 +374,13 @@ int reset_scalars(pgo_handle *h) {
     Scalars s{};
     s.tol2 = h->opt.pcg_rtol * h->opt.pcg_rtol;
     s.max_iters = h->opt.pcg_max_iterations;
-    // counters must survive (they are always 0 between kernels); everything else is re-initialised
+    // counters / epoch / world must survive (they are always consistent between kernels); everything before them is re-initialised
     CK(cudaMemcpyAsync(h->S, &s, offsetof(Scalars, counter), cudaMemcpyHostToDevice, h->stream));
+    return PGO_OK;
+}
+
+int comm_status(pgo_handle *h, const Scalars &s) {
+    if (s.status == ST_COMM) { h->err = "peer synchronisation timed out (a rank is missing or out of step)"; return PGO_ERR_NCCL; }
     return PGO_OK;
 }
 
@@ -256,6 +395,7 @@ int solve(pgo_handle *h, int32_t *iters_out) {
     CK(cudaMemsetAsync(h->x, 0, nd * sizeof(double), h->stream));
     precondition<FIN_RZ_INIT>(h);
     CK(cudaMemcpyAsync(h->p, h->z, nd * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    xbarrier(h);
     // keep two graph launches in flight; poll the pinned scalars of the older one
     int slot = 0, inflight = 0;
     int64_t launched = 0;
@@ -280,6 +420,7 @@ int solve(pgo_handle *h, int32_t *iters_out) {
     CK(cudaMemcpyAsync(&h->hS[0], h->S, sizeof(Scalars), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     if (iters_out) *iters_out = h->hS[0].iters;
+    if ((rc = comm_status(h, h->hS[0]))) return rc;
     if (h->hS[0].status == ST_BREAKDOWN) {
         h->err = "PCG breakdown: H is not positive definite (isolated vertex, or graph without a pose-pose edge to anchor)";
         return PGO_ERR_SOLVER;
@@ -292,13 +433,16 @@ int retract(pgo_handle *h, double sign) {
     LevelBuf &B = h->lv[0];
     k_retract_se2<<<grid_for(B.d.n, 256), 256, 0, h->stream>>>(B.d, h->poses, h->x, sign, h->S, h->partials);
     h->launch_count += 1;
+    xreduce<FIN_NORM>(h, 0, 0);                      // also: every rank's poses are updated before anyone reads them
     CK(cudaGetLastError());
     return PGO_OK;
 }
 
 int chi2_launch(pgo_handle *h) {
-    k_chi2_se2<<<std::max(1, grid_for(h->sym.n_edges, 256)), 256, 0, h->stream>>>(h->sym.n_edges, h->ends, h->ed, h->poses, h->S, h->partials);
+    xbarrier(h, 0);
+    k_chi2_se2<<<grid_for(h->n_edges_loc, 256), 256, 0, h->stream>>>(h->n_edges_loc, h->ends, h->ed, h->poses, xref(h, h->poses), h->S, h->partials);
     h->launch_count += 1;
+    xreduce<FIN_CHI2>(h, 0, 0);
     CK(cudaGetLastError());
     return PGO_OK;
 }
@@ -314,7 +458,7 @@ int fail_create(pgo_handle *h, int rc, const std::string &msg) {
 // ================================================================================================
 extern "C" {
 
-const char *pgo_version(void) { return "pgo_b200 0.1 (sm_100a, fp64)"; }
+const char *pgo_version(void) { return "pgo_b200 0.2 (sm_100a, fp64)"; }
 
 void pgo_default_options(pgo_options *o) {
     if (!o) return;
@@ -326,6 +470,11 @@ void pgo_default_options(pgo_options *o) {
     o->sort_window = 2048;
     o->amg_max_levels = 12;
     o->device = -1;
+    o->world = 1;
+    o->rank = 0;
+    o->amg_dense_max = 640;
+    o->amg_aggregate_size = 16;
+    o->amg_kcycle = 1;
 }
 
 const char *pgo_last_error(const pgo_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -334,6 +483,8 @@ void pgo_destroy(pgo_handle *h) {
     if (!h) return;
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->pcg_graph) cudaGraphExecDestroy(h->pcg_graph);
+    for (int k = 0; k < MAX_RANKS; k++)
+        if (h->peer_base[k] && k != h->rank) cudaIpcCloseMemHandle(h->peer_base[k]);
     for (void *p : h->allocs) cudaFree(p);
     if (h->hS) cudaFreeHost(h->hS);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
@@ -354,17 +505,27 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
     }
     pgo_handle *h = new pgo_handle();
     if (opt_in) h->opt = *opt_in; else pgo_default_options(&h->opt);
-    if (h->opt.pcg_rtol <= 0) h->opt.pcg_rtol = 1e-10;
-    if (h->opt.pcg_max_iterations <= 0) h->opt.pcg_max_iterations = 200000;
-    if (h->opt.sort_window <= 0) h->opt.sort_window = 2048;
-    if (h->opt.amg_max_levels <= 0) h->opt.amg_max_levels = 12;
-    if (h->opt.anchor_weight == 0) h->opt.anchor_weight = 1e7;
+    pgo_options dflt; pgo_default_options(&dflt);
+    if (h->opt.pcg_rtol <= 0) h->opt.pcg_rtol = dflt.pcg_rtol;
+    if (h->opt.pcg_max_iterations <= 0) h->opt.pcg_max_iterations = dflt.pcg_max_iterations;
+    if (h->opt.sort_window <= 0) h->opt.sort_window = dflt.sort_window;
+    if (h->opt.amg_max_levels <= 0) h->opt.amg_max_levels = dflt.amg_max_levels;
+    if (h->opt.amg_max_levels > MAX_LEVELS) h->opt.amg_max_levels = MAX_LEVELS;
+    if (h->opt.anchor_weight == 0) h->opt.anchor_weight = dflt.anchor_weight;
+    if (h->opt.world <= 0) h->opt.world = 1;
+    if (h->opt.amg_dense_max <= 0) h->opt.amg_dense_max = dflt.amg_dense_max;
+    if (h->opt.amg_dense_max > 1024) h->opt.amg_dense_max = 1024;
+    if (h->opt.amg_aggregate_size <= 1) h->opt.amg_aggregate_size = dflt.amg_aggregate_size;
     h->use_amg = h->opt.preconditioner == PGO_PRECOND_AMG;
+    h->world = h->opt.world; h->rank = h->opt.rank;
+    if (h->rank < 0 || h->rank >= h->world) return fail_create(h, PGO_ERR_ARG, "pgo_create: rank out of range");
 
     SymbolicOptions so;
+    so.world = h->world;
     so.sort_window = h->opt.sort_window;
-    so.amg_max_levels = h->opt.amg_max_levels;
-    so.coarsest_max = 48;
+    so.max_levels = h->opt.amg_max_levels;
+    so.agg_size = h->opt.amg_aggregate_size;
+    so.dense_max = h->opt.amg_dense_max;
     so.build_amg = h->use_amg;
     if (!build_symbolic(h->sym, so, nv, vid, vkind, ne, ekind, efrom, eto)) return fail_create(h, PGO_ERR_ARG, h->sym.error);
     Symbolic &S = h->sym;
@@ -383,65 +544,134 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
     CKU(cudaHostAlloc((void **)&h->hS, 2 * sizeof(Scalars), cudaHostAllocDefault));
     std::memset(h->hS, 0, 2 * sizeof(Scalars));
 
-    // ---- level structures
+    const int rank = h->rank, world = h->world;
     const int nl = (int)S.levels.size();
     h->lv.resize(nl);
     int64_t max_grid = 1;
+    // ---- pass 1: local structure of every level + arena requests (sizes from the largest partition: same layout on all ranks)
     for (int l = 0; l < nl; l++) {
         HostLevel &H = S.levels[l];
         LevelBuf &B = h->lv[l];
         LevelDev &d = B.d;
-        d.n = H.n; d.n_pad = H.n_pad; d.n_slices = H.n_slices; d.n_slots = H.n_slots;
-        B.grid128 = grid_for(H.n_pad, 128);
-        max_grid = std::max<int64_t>(max_grid, B.grid128);
-        int64_t *sp; int32_t *dg; uint32_t *cl;
-        CKC(upload(h, &sp, H.slice_ptr)); CKC(upload(h, &dg, H.deg)); CKC(upload(h, &cl, H.col));
-        d.slice_ptr = sp; d.deg = dg; d.col = cl;
-        CKC(dalloc(h, &d.val, (size_t)9 * H.n_slots));
-        CKC(dalloc(h, &d.diag, (size_t)9 * H.n_pad));
-        CKC(dalloc(h, &d.dinv, (size_t)9 * H.n_pad));
-        CKC(dalloc(h, &d.pos, (size_t)2 * H.n_pad));
+        const int64_t r0 = H.part_off[rank], r1 = H.part_off[rank + 1];
+        const int64_t s0 = H.part_slot[rank], s1 = H.part_slot[rank + 1];
+        B.jds = H.jds;
+        d.n = H.part_real[rank]; d.n_pad = r1 - r0; d.n_slots = s1 - s0; d.n_slices = H.jds ? d.n_pad / 32 : 0;
+        int64_t max_pad = 32;
+        for (int k = 0; k < world; k++) max_pad = std::max(max_pad, H.part_off[k + 1] - H.part_off[k]);
+        B.grid128 = grid_for(d.n_pad, 128);
+        B.gridw = grid_for(d.n_pad, 8);
+        B.gridv = grid_for(d.n_pad * 2, 256);
+        max_grid = std::max<int64_t>(max_grid, std::max(B.grid128, B.gridw));
+        // row pointers
+        std::vector<int64_t> rp;
+        if (H.jds) { rp.resize(d.n_slices + 1); for (int64_t i = 0; i <= d.n_slices; i++) rp[i] = H.slice_ptr[r0 / 32 + i] - s0; }
+        else { rp.resize(d.n_pad + 1); for (int64_t i = 0; i <= d.n_pad; i++) rp[i] = H.adj_ptr[r0 + i] - s0; }
+        std::vector<int32_t> dg(d.n_pad, 0);
+        std::vector<uint32_t> cl(std::max<int64_t>(d.n_slots, 1), 0);
+        for (int64_t r = r0; r < r1; r++) {
+            dg[r - r0] = (int32_t)(H.adj_ptr[r + 1] - H.adj_ptr[r]);
+            for (int64_t q = H.adj_ptr[r]; q < H.adj_ptr[r + 1]; q++) {
+                const int64_t nb = H.adj_nbr[q];
+                const int ow = H.part_of(nb);
+                cl[H.adj_slot[q] - s0] = ((uint32_t)ow << COL_OWNER_SHIFT) | (uint32_t)(nb - H.part_off[ow]) | (H.adj_flags.empty() ? 0u : H.adj_flags[q]);
+            }
+        }
+        int64_t *drp; int32_t *ddg; uint32_t *dcl;
+        CKC(upload(h, &drp, rp)); CKC(upload(h, &ddg, dg)); CKC(upload(h, &dcl, cl));
+        d.slice_ptr = drp; d.deg = ddg; d.col = dcl;
+        CKC(dalloc(h, &d.val, (size_t)9 * std::max<int64_t>(d.n_slots, 1)));
+        CKC(dalloc(h, &d.diag, (size_t)9 * d.n_pad));
+        CKC(dalloc(h, &d.dinv, (size_t)9 * d.n_pad));
+        CKC(dalloc(h, &d.pos, (size_t)2 * d.n_pad));
         if (!H.agg.empty()) {
-            int32_t *ag; int64_t *ct; int32_t *cs;
-            CKC(upload(h, &ag, H.agg)); CKC(upload(h, &ct, H.ctgt)); CKC(upload(h, &cs, H.cstr));
-            d.agg = ag; d.ctgt = ct; d.cstr = cs;
+            HostLevel &Cn = S.levels[l + 1];
+            std::vector<int32_t> ag(d.n_pad, -1);
+            for (int64_t r = r0; r < r1; r++) if (H.agg[r] >= 0) ag[r - r0] = (int32_t)(H.agg[r] - Cn.part_off[rank]);
+            std::vector<int32_t> ct(H.ctgt.begin() + s0, H.ctgt.begin() + s1);
+            if (ct.empty()) ct.push_back(0);
+            int32_t *dag, *dct;
+            CKC(upload(h, &dag, ag)); CKC(upload(h, &dct, ct));
+            d.agg = dag; d.ctgt = dct;
         }
         if (!H.mem_ptr.empty()) {
-            int64_t *mp; int32_t *mi;
-            CKC(upload(h, &mp, H.mem_ptr)); CKC(upload(h, &mi, H.mem_idx));
-            d.mem_ptr = mp; d.mem_idx = mi;
+            HostLevel &Fn = S.levels[l - 1];
+            std::vector<int64_t> mp(d.n_pad + 1);
+            const int64_t m0 = H.mem_ptr[r0];
+            for (int64_t i = 0; i <= d.n_pad; i++) mp[i] = H.mem_ptr[r0 + i] - m0;
+            std::vector<int32_t> mi(H.mem_idx.begin() + m0, H.mem_idx.begin() + H.mem_ptr[r1]);
+            for (auto &v : mi) v -= (int32_t)Fn.part_off[rank];
+            if (mi.empty()) mi.push_back(0);
+            int64_t *dmp; int32_t *dmi;
+            CKC(upload(h, &dmp, mp)); CKC(upload(h, &dmi, mi));
+            d.mem_ptr = dmp; d.mem_idx = dmi;
         }
-        if (h->use_amg && nl > 1) {
-            CKC(dalloc(h, &B.xa, (size_t)4 * H.n_pad)); CKC(dalloc(h, &B.res, (size_t)4 * H.n_pad));
-            if (l > 0) { CKC(dalloc(h, &B.r, (size_t)4 * H.n_pad)); CKC(dalloc(h, &B.e, (size_t)4 * H.n_pad)); }
+        // peer-visible vectors of this level
+        const size_t vec = (size_t)4 * max_pad;
+        arena_request(h, &d.lev, (size_t)2 * max_pad);
+        if (h->use_amg) {
+            arena_request(h, &B.xa, vec); arena_request(h, &B.res, vec);
+            if (l > 0) {
+                arena_request(h, &B.rhs, vec); arena_request(h, &B.sol, vec);
+                arena_request(h, &B.c1, vec); arena_request(h, &B.c2, vec); arena_request(h, &B.v1, vec);
+                arena_request(h, &B.v2, vec); arena_request(h, &B.r1, vec);
+            }
         }
+        B.kcycle = h->opt.amg_kcycle != 0 && l > 0;
     }
-    max_grid = std::max<int64_t>(max_grid, grid_for(std::max<int64_t>(ne, 1), 256));
-    h->dense_coarsest = h->use_amg && nl > 1 && S.levels[nl - 1].n * 3 <= 150;
-    if (h->dense_coarsest) {
-        const int m = (int)S.levels[nl - 1].n * 3;
-        CKC(dalloc(h, &h->Ainv, (size_t)m * m));
-        CKU(cudaFuncSetAttribute(k_dense_invert<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 150 * 150)));
-    }
-    h->chunk = (h->use_amg && nl > 1) ? 4 : 16;
-
-    // ---- level-0 vertex data in storage order
-    const int64_t n = S.n, n_pad = S.levels[0].n_pad;
     {
-        std::vector<uint8_t> vk(n_pad, 0);
-        std::vector<int64_t> rvo(n_pad, 0);
-        for (int64_t r = 0; r < n; r++) { const int64_t v = S.perm[r]; vk[r] = S.vkind[v]; rvo[r] = S.vvalofs[v]; }
+        const HostLevel &H0 = S.levels[0];
+        int64_t max_pad = 32;
+        for (int k = 0; k < world; k++) max_pad = std::max(max_pad, H0.part_off[k + 1] - H0.part_off[k]);
+        const size_t vec = (size_t)4 * max_pad;
+        arena_request(h, &h->poses, vec);
+        arena_request(h, &h->x, vec); arena_request(h, &h->r, vec); arena_request(h, &h->p, vec);
+        arena_request(h, &h->q, vec); arena_request(h, &h->z, vec);
+    }
+    if (h->use_amg && S.dense_coarsest) {
+        const HostLevel &HL = S.levels[nl - 1];
+        h->dmap.off[0] = 0;
+        int64_t max_real = 1;
+        for (int k = 0; k < world; k++) { h->dmap.off[k + 1] = h->dmap.off[k] + (int32_t)HL.part_real[k]; max_real = std::max(max_real, HL.part_real[k]); }
+        for (int k = world; k < MAX_RANKS; k++) h->dmap.off[k + 1] = h->dmap.off[world];
+        h->dense_m = (int)HL.n * 3;
+        if (world > 1) arena_request(h, &h->Arows, (size_t)3 * max_real * h->dense_m);
+    }
+    CKC(arena_commit(h));
+    if (h->use_amg && S.dense_coarsest) {
+        const int m = h->dense_m;
+        CKC(dalloc(h, &h->Ainv, (size_t)m * m));
+        CKC(dalloc(h, &h->panelR, (size_t)3 * m));
+        CKC(dalloc(h, &h->panelC, (size_t)3 * m));
+        int per_sm = 0, sms = 0;
+        CKU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dense_invert, 256, 0));
+        CKU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+        h->invert_grid = std::max(1, std::min(per_sm, 2) * sms);
+        CKU(cudaFuncSetAttribute(k_dense_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 3 * 1024)));
+    }
+    h->chunk = h->use_amg ? 4 : 16;
+
+    // ---- level-0 vertex data of the owned rows, in storage order
+    const HostLevel &H0 = S.levels[0];
+    const int64_t r0 = H0.part_off[rank], r1 = H0.part_off[rank + 1], s0 = H0.part_slot[rank], s1 = H0.part_slot[rank + 1];
+    h->row0 = r0; h->n_loc = H0.part_real[rank]; h->n_pad_loc = r1 - r0;
+    {
+        std::vector<uint8_t> vk(h->n_pad_loc, 0);
+        std::vector<int64_t> rvo(h->n_pad_loc, 0);
+        for (int64_t r = r0; r < r0 + h->n_loc; r++) { const int64_t v = S.perm[r]; vk[r - r0] = S.vkind[v]; rvo[r - r0] = S.vvalofs[v]; }
         uint8_t *dvk;
         CKC(upload(h, &dvk, vk));
         h->lv[0].d.vkind = dvk;
         CKC(upload(h, &h->row_valofs, rvo));
-        CKC(dalloc(h, &h->poses, (size_t)4 * n_pad));
         CKC(dalloc(h, &h->vstage, (size_t)S.n_values));
         CKU(cudaMemcpyAsync(h->vstage, vval, S.n_values * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        k_import_poses<<<grid_for(n, 256), 256, 0, h->stream>>>(n, h->row_valofs, dvk, h->vstage, h->poses);
+        k_import_poses<<<grid_for(h->n_loc, 256), 256, 0, h->stream>>>(h->n_loc, h->row_valofs, dvk, h->vstage, h->poses);
         CKU(cudaGetLastError());
     }
-    h->anchor_row = S.anchor >= 0 ? S.iperm[S.anchor] : -1;
+    {
+        const int64_t ag = S.anchor >= 0 ? S.iperm[S.anchor] : -1;
+        h->anchor_row = (ag >= r0 && ag < r1) ? ag - r0 : -1;
+    }
     // ---- measurements: per-edge packed offsets
     std::vector<int64_t> mofs(ne + 1, 0), iofs(ne + 1, 0);
     for (int64_t k = 0; k < ne; k++) { mofs[k + 1] = mofs[k] + (ekind[k] == 0 ? 3 : 2); iofs[k + 1] = iofs[k] + (ekind[k] == 0 ? 6 : 3); }
@@ -453,46 +683,99 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
         else { for (int c = 0; c < 3; c++) o[4 + c] = w[c]; }
     };
     {   // half-edge stream, laid out like val with 10 components
-        HostLevel &H = S.levels[0];
-        std::vector<double> hz((size_t)10 * H.n_slots, 0.0);
+        std::vector<double> hz((size_t)10 * std::max<int64_t>(s1 - s0, 1), 0.0);
         double rec[10];
-        for (int64_t r = 0; r < n; r++) {
+        for (int64_t r = r0; r < r0 + h->n_loc; r++) {
             const int lane = (int)(r & 31);
-            for (int64_t qi = H.adj_ptr[r]; qi < H.adj_ptr[r + 1]; qi++) {
-                const int64_t slot = H.adj_slot[qi];
-                const int64_t cnt = H.adj_cnt[qi];
-                edge_rec(S.slot_edge[slot], rec);
+            for (int64_t qi = H0.adj_ptr[r]; qi < H0.adj_ptr[r + 1]; qi++) {
+                const int64_t slot = H0.adj_slot[qi] - s0;
+                const int64_t cnt = H0.adj_cnt[qi];
+                edge_rec(S.slot_edge[H0.adj_slot[qi]], rec);
                 double *dst = hz.data() + (slot - lane) * 10 + lane;
                 for (int c = 0; c < 10; c++) dst[c * cnt] = rec[c];
             }
         }
         CKC(upload(h, &h->hz, hz));
     }
-    {   // edge-ordered copy for chi2
-        std::vector<int2> ends(std::max<int64_t>(ne, 1));
-        std::vector<double> ed((size_t)10 * std::max<int64_t>(ne, 1), 0.0);
+    {   // edge-ordered copy of the edges this rank owns (owner = the rank of `from`) for chi2
+        std::vector<int64_t> mine;
+        for (int64_t k = 0; k < ne; k++) { const int64_t a = S.iperm[S.efrom[k]]; if (a >= r0 && a < r1) mine.push_back(k); }
+        const int64_t nm = (int64_t)mine.size();
+        h->n_edges_loc = nm;
+        std::vector<uint2> ends(std::max<int64_t>(nm, 1));
+        std::vector<double> ed((size_t)10 * std::max<int64_t>(nm, 1), 0.0);
         double rec[10];
-        for (int64_t k = 0; k < ne; k++) {
-            const int a = S.iperm[S.efrom[k]], b = S.iperm[S.eto[k]];
-            ends[k] = make_int2(a, ekind[k] == 1 ? ~b : b);
+        for (int64_t i = 0; i < nm; i++) {
+            const int64_t k = mine[i];
+            const int64_t a = S.iperm[S.efrom[k]], b = S.iperm[S.eto[k]];
+            const int ow = H0.part_of(b);
+            ends[i] = make_uint2((uint32_t)(a - r0), ((uint32_t)ow << COL_OWNER_SHIFT) | (uint32_t)(b - H0.part_off[ow]) | (ekind[k] == 1 ? COL_EDGE_XY : 0u));
             edge_rec(k, rec);
-            for (int c = 0; c < 10; c++) ed[(size_t)c * ne + k] = rec[c];
+            for (int c = 0; c < 10; c++) ed[(size_t)c * nm + i] = rec[c];
         }
         CKC(upload(h, &h->ends, ends));
         CKC(upload(h, &h->ed, ed));
+        max_grid = std::max<int64_t>(max_grid, grid_for(nm, 256));
     }
-    // ---- solver vectors
-    CKC(dalloc(h, &h->x, (size_t)4 * n_pad)); CKC(dalloc(h, &h->r, (size_t)4 * n_pad)); CKC(dalloc(h, &h->p, (size_t)4 * n_pad));
-    CKC(dalloc(h, &h->q, (size_t)4 * n_pad)); CKC(dalloc(h, &h->z, (size_t)4 * n_pad));
     CKC(dalloc(h, &h->S, 1));
-    CKC(dalloc(h, &h->partials, (size_t)max_grid + 8));
+    CKC(dalloc(h, &h->partials, (size_t)3 * max_grid + 8));
+    {
+        Scalars s{};
+        s.world = world;
+        CKU(cudaMemcpyAsync(h->S, &s, sizeof(Scalars), cudaMemcpyHostToDevice, h->stream));
+    }
     CKU(cudaStreamSynchronize(h->stream));
 #undef CKC
 #undef CKU
-    // host copies only needed for the structure queries stay in h->sym; drop the big transient ones
-    S.levels[0].ctgt.clear(); S.levels[0].ctgt.shrink_to_fit();
-    S.levels[0].cstr.clear(); S.levels[0].cstr.shrink_to_fit();
+    // the big transient host arrays are not needed any more
+    for (auto &L : S.levels) { L.ctgt.clear(); L.ctgt.shrink_to_fit(); }
     *out = h;
+    return PGO_OK;
+}
+
+// ---- sharded handles: exchange of the peer-memory handles (the caller moves the bytes, e.g. with torch.distributed.all_gather)
+int pgo_shard_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+
+int pgo_shard_export(pgo_handle *h, void *buf, int64_t cap) {
+    if (!h || !buf || cap < (int64_t)sizeof(cudaIpcMemHandle_t)) return PGO_ERR_ARG;
+    if (!h->stream) { h->err = "structure-only handle"; return PGO_ERR_CUDA; }
+    cudaIpcMemHandle_t mh;
+    CK(cudaIpcGetMemHandle(&mh, h->arena));
+    std::memcpy(buf, &mh, sizeof(mh));
+    return PGO_OK;
+}
+
+int pgo_shard_connect(pgo_handle *h, const void *all_handles, int64_t n_handles) {
+    if (!h || !all_handles || n_handles != h->world) return PGO_ERR_ARG;
+    if (!h->stream) { h->err = "structure-only handle"; return PGO_ERR_CUDA; }
+    for (int k = 0; k < h->world; k++) {
+        if (k == h->rank) continue;
+        cudaIpcMemHandle_t mh;
+        std::memcpy(&mh, (const char *)all_handles + (size_t)k * sizeof(mh), sizeof(mh));
+        void *p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+        h->peer_base[k] = (char *)p;
+    }
+    for (int k = 0; k < MAX_RANKS; k++) h->comm_ref.p[k] = (Comm *)h->peer_base[k < h->world ? k : h->rank];
+    h->connected = true;
+    return PGO_OK;
+}
+
+int pgo_get_partition(const pgo_handle *h, int32_t *world, int32_t *rank, int64_t *vertex_range, int64_t *n_remote_blocks) {
+    if (!h) return PGO_ERR_ARG;
+    const Symbolic &S = h->sym;
+    if (world) *world = S.world;
+    if (rank) *rank = h->rank;
+    if (vertex_range) for (int k = 0; k <= S.world; k++) vertex_range[k] = S.vrange[k];
+    if (n_remote_blocks) {
+        const HostLevel &H = S.levels[0];
+        for (int k = 0; k < S.world; k++) {
+            int64_t c = 0;
+            for (int64_t r = H.part_off[k]; r < H.part_off[k + 1]; r++)
+                for (int64_t q = H.adj_ptr[r]; q < H.adj_ptr[r + 1]; q++) c += H.part_of(H.adj_nbr[q]) != k;
+            n_remote_blocks[k] = c;
+        }
+    }
     return PGO_OK;
 }
 
@@ -512,6 +795,7 @@ int pgo_chi2(pgo_handle *h, double *chi2) {
     if (rc) return rc;
     CK(cudaMemcpyAsync(&h->hS[0], h->S, sizeof(Scalars), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if ((rc = comm_status(h, h->hS[0]))) return rc;
     *chi2 = h->hS[0].chi2;
     return PGO_OK;
 }
@@ -519,7 +803,6 @@ int pgo_chi2(pgo_handle *h, double *chi2) {
 int pgo_gn_step(pgo_handle *h, double lambda, int add_lambda, double *norm_dx, double *chi2, int32_t *pcg_iterations) {
     if (!h) return PGO_ERR_ARG;
     NEED_DEVICE(h);
-    int64_t l0 = h->launch_count;
     auto mark = [&](int i) { cudaEventRecord(h->ev[i], h->stream); };
     int64_t lc[6];
     mark(0); lc[0] = h->launch_count;
@@ -546,8 +829,8 @@ int pgo_gn_step(pgo_handle *h, double lambda, int add_lambda, double *norm_dx, d
         cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]);
         h->ms[i] = ms; h->launches[i] = lc[i + 1] - lc[i];
     }
-    (void)l0;
     h->have_step = true;
+    if ((rc = comm_status(h, h->hS[0]))) return rc;
     if (norm_dx) *norm_dx = std::sqrt(h->hS[0].norm2_dx);
     if (chi2) *chi2 = h->hS[0].chi2;
     if (pcg_iterations) *pcg_iterations = iters;
@@ -574,15 +857,24 @@ int pgo_linearize_and_solve(pgo_handle *h, int32_t *pcg_iterations) {
     return solve(h, pcg_iterations);
 }
 
+// vertex values of the rows this rank owns are a contiguous span of the packed array (contiguous vertex ranges)
+static void owned_span(const pgo_handle *h, int64_t *o0, int64_t *o1) {
+    const Symbolic &S = h->sym;
+    const int64_t a = S.vrange[h->rank], b = S.vrange[h->rank + 1];
+    *o0 = S.vvalofs[a]; *o1 = b < S.n ? S.vvalofs[b] : S.n_values;
+}
+
 int pgo_get_poses(pgo_handle *h, double *out, int64_t n_values) {
     if (!h || !out) return PGO_ERR_ARG;
     NEED_DEVICE(h);
     const Symbolic &S = h->sym;
     if (n_values != S.n_values) { h->err = "pgo_get_poses: wrong buffer length"; return PGO_ERR_ARG; }
-    k_export_poses<<<grid_for(S.n, 256), 256, 0, h->stream>>>(S.n, h->row_valofs, h->lv[0].d.vkind, h->poses, h->vstage);
+    int64_t o0, o1;
+    owned_span(h, &o0, &o1);
+    k_export_poses<<<grid_for(h->n_loc, 256), 256, 0, h->stream>>>(h->n_loc, h->row_valofs, h->lv[0].d.vkind, h->poses, h->vstage);
     h->launch_count += 1;
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(out, h->vstage, S.n_values * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(out + o0, h->vstage + o0, (o1 - o0) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return PGO_OK;
 }
@@ -592,8 +884,10 @@ int pgo_set_poses(pgo_handle *h, const double *in, int64_t n_values) {
     NEED_DEVICE(h);
     const Symbolic &S = h->sym;
     if (n_values != S.n_values) { h->err = "pgo_set_poses: wrong buffer length"; return PGO_ERR_ARG; }
-    CK(cudaMemcpyAsync(h->vstage, in, S.n_values * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    k_import_poses<<<grid_for(S.n, 256), 256, 0, h->stream>>>(S.n, h->row_valofs, h->lv[0].d.vkind, h->vstage, h->poses);
+    int64_t o0, o1;
+    owned_span(h, &o0, &o1);
+    CK(cudaMemcpyAsync(h->vstage + o0, in + o0, (o1 - o0) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    k_import_poses<<<grid_for(h->n_loc, 256), 256, 0, h->stream>>>(h->n_loc, h->row_valofs, h->lv[0].d.vkind, h->vstage, h->poses);
     h->launch_count += 1;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));   // `in` is borrowed for the duration of the call only
@@ -604,7 +898,7 @@ int pgo_set_poses(pgo_handle *h, const double *in, int64_t n_values) {
 int pgo_snapshot_poses(pgo_handle *h) {
     if (!h) return PGO_ERR_ARG;
     NEED_DEVICE(h);
-    const size_t cnt = (size_t)4 * h->sym.levels[0].n_pad;
+    const size_t cnt = (size_t)4 * h->n_pad_loc;
     if (!h->poses_saved) { int rc = dalloc(h, &h->poses_saved, cnt, false); if (rc) return rc; }
     CK(cudaMemcpyAsync(h->poses_saved, h->poses, cnt * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -615,7 +909,7 @@ int pgo_restore_poses(pgo_handle *h) {
     if (!h) return PGO_ERR_ARG;
     NEED_DEVICE(h);
     if (!h->poses_saved) { h->err = "pgo_restore_poses: no snapshot"; return PGO_ERR_ARG; }
-    CK(cudaMemcpyAsync(h->poses, h->poses_saved, (size_t)4 * h->sym.levels[0].n_pad * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->poses, h->poses_saved, (size_t)4 * h->n_pad_loc * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->have_step = false;
     return PGO_OK;
@@ -626,11 +920,11 @@ int pgo_get_dx(pgo_handle *h, double *out, int64_t len) {
     NEED_DEVICE(h);
     const Symbolic &S = h->sym;
     if (len != S.len) { h->err = "pgo_get_dx: wrong buffer length"; return PGO_ERR_ARG; }
-    std::vector<double> xs((size_t)4 * S.n);
+    std::vector<double> xs((size_t)4 * h->n_pad_loc);
     CK(cudaMemcpyAsync(xs.data(), h->x, xs.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    for (int64_t r = 0; r < S.n; r++) {
-        const int64_t v = S.perm[r];
+    for (int64_t r = 0; r < h->n_loc; r++) {
+        const int64_t v = S.perm[h->row0 + r];
         const int d = S.vkind[v] == 0 ? 3 : 2;
         for (int c = 0; c < d; c++) out[S.voffset[v] + c] = xs[4 * r + c];
     }
@@ -665,6 +959,8 @@ int pgo_get_anchor(const pgo_handle *h, int64_t *v) {
     return PGO_OK;
 }
 
+// Sharded handles return the block rows they own: entries of other ranks' block rows are left untouched,
+// so the caller can merge the ranks' outputs (they are disjoint).
 int pgo_get_system(pgo_handle *h, double lambda, int add_lambda, double *csc_values, double *b) {
     if (!h) return PGO_ERR_ARG;
     NEED_DEVICE(h);
@@ -673,24 +969,25 @@ int pgo_get_system(pgo_handle *h, double lambda, int add_lambda, double *csc_val
     int rc = assemble(h, lambda, add_lambda);
     if (rc) return rc;
     HostLevel &H = S.levels[0];
-    std::vector<double> val((size_t)9 * H.n_slots), diag((size_t)9 * H.n_pad), rv((size_t)4 * H.n_pad);
+    const int64_t r0 = h->row0, s0 = H.part_slot[h->rank], s1 = H.part_slot[h->rank + 1], npl = h->n_pad_loc;
+    std::vector<double> val((size_t)9 * std::max<int64_t>(s1 - s0, 1)), diag((size_t)9 * npl), rv((size_t)4 * npl);
     CK(cudaMemcpyAsync(val.data(), h->lv[0].d.val, val.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(diag.data(), h->lv[0].d.diag, diag.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(rv.data(), h->r, rv.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    // canonical block values (duplicate edges between a vertex pair sum into one block)
+    // canonical block values of the owned block rows (duplicate edges between a vertex pair sum into one block)
     std::vector<double> blk((size_t)9 * S.bcol.size(), 0.0);
     auto find = [&](int32_t rr, int32_t cc) -> int64_t {
         auto bb = S.bcol.begin() + S.brow_ptr[rr], ee = S.bcol.begin() + S.brow_ptr[rr + 1];
         return std::lower_bound(bb, ee, cc) - S.bcol.begin();
     };
-    for (int64_t r = 0; r < S.n; r++) {
-        const int32_t u = S.perm[r];
+    for (int64_t r = 0; r < h->n_loc; r++) {
+        const int32_t u = S.perm[r0 + r];
         const int lane = (int)(r & 31);
         double *d = &blk[9 * find(u, u)];
-        for (int c = 0; c < 9; c++) d[c] += diag[(size_t)c * H.n_pad + r];
-        for (int64_t qi = H.adj_ptr[r]; qi < H.adj_ptr[r + 1]; qi++) {
-            const int64_t slot = H.adj_slot[qi], cnt = H.adj_cnt[qi];
+        for (int c = 0; c < 9; c++) d[c] += diag[(size_t)c * npl + r];
+        for (int64_t qi = H.adj_ptr[r0 + r]; qi < H.adj_ptr[r0 + r + 1]; qi++) {
+            const int64_t slot = H.adj_slot[qi] - s0, cnt = H.adj_cnt[qi];
             const int32_t v = S.perm[H.adj_nbr[qi]];
             double *o = &blk[9 * find(u, v)];
             const double *src = val.data() + (slot - lane) * 9 + lane;
@@ -705,14 +1002,17 @@ int pgo_get_system(pgo_handle *h, double lambda, int add_lambda, double *csc_val
                 for (int64_t pp = S.brow_ptr[v]; pp < S.brow_ptr[v + 1]; pp++) {
                     const int32_t u = S.bcol[pp];
                     const int du = S.vkind[u] == 0 ? 3 : 2;
-                    const int64_t bi = find(u, (int32_t)v);                    // block (row u, col v)
-                    for (int rr = 0; rr < du; rr++) csc_values[o++] = blk[9 * bi + 3 * rr + c];
+                    if (u >= S.vrange[h->rank] && u < S.vrange[h->rank + 1]) {
+                        const int64_t bi = find(u, (int32_t)v);                    // block (row u, col v)
+                        for (int rr = 0; rr < du; rr++) csc_values[o + rr] = blk[9 * bi + 3 * rr + c];
+                    }
+                    o += du;
                 }
         }
     }
     if (b) {
-        for (int64_t r = 0; r < S.n; r++) {
-            const int64_t v = S.perm[r];
+        for (int64_t r = 0; r < h->n_loc; r++) {
+            const int64_t v = S.perm[r0 + r];
             const int d = S.vkind[v] == 0 ? 3 : 2;
             for (int c = 0; c < d; c++) b[S.voffset[v] + c] = rv[4 * r + c];
         }
@@ -733,10 +1033,11 @@ int pgo_time_spmv(pgo_handle *h, int32_t repeats, double *avg_ms) {
     if (!h || !avg_ms || repeats <= 0) return PGO_ERR_ARG;
     NEED_DEVICE(h);
     LevelBuf &B = h->lv[0];
-    // p -> q with the PCG SpMV; done-flag test disabled so the launches always do the work
-    for (int i = 0; i < 3; i++) k_spmv<3, 0, FIN_NONE><<<B.grid128, 128, 0, h->stream>>>(B.d, h->p, nullptr, h->q, 0.0, h->S, h->partials, 0);
+    // p -> q with the PCG SpMV; done-flag test disabled so the launches always do the work, no cross-rank reduction
+    XRef xr = xref(h, h->p);
+    for (int i = 0; i < 3; i++) k_spmv<3, 0, FIN_NONE><<<B.grid128, 128, 0, h->stream>>>(B.d, xr, h->p, nullptr, h->q, 0.0, nullptr, h->S, h->partials, 0);
     CK(cudaEventRecord(h->ev[PGO_NUM_PHASES], h->stream));
-    for (int i = 0; i < repeats; i++) k_spmv<3, 0, FIN_NONE><<<B.grid128, 128, 0, h->stream>>>(B.d, h->p, nullptr, h->q, 0.0, h->S, h->partials, 0);
+    for (int i = 0; i < repeats; i++) k_spmv<3, 0, FIN_NONE><<<B.grid128, 128, 0, h->stream>>>(B.d, xr, h->p, nullptr, h->q, 0.0, nullptr, h->S, h->partials, 0);
     CK(cudaEventRecord(h->ev[PGO_NUM_PHASES + 1], h->stream));
     CK(cudaStreamSynchronize(h->stream));
     float ms = 0;
@@ -749,11 +1050,24 @@ int pgo_time_spmv(pgo_handle *h, int32_t repeats, double *avg_ms) {
 
 int pgo_get_stats(const pgo_handle *h, int64_t *rows, int64_t *offdiag, int64_t *levels, int64_t *bytes) {
     if (!h) return PGO_ERR_ARG;
-    if (rows) *rows = h->sym.n;
-    if (offdiag) *offdiag = 2 * h->sym.n_edges;
-    if (levels) *levels = (int64_t)h->lv.size();
+    if (rows) *rows = h->stream ? h->n_loc : h->sym.n;
+    if (offdiag) {
+        const HostLevel &H = h->sym.levels[0];
+        *offdiag = h->stream ? H.adj_ptr[H.part_off[h->rank + 1]] - H.adj_ptr[H.part_off[h->rank]] : 2 * h->sym.n_edges;
+    }
+    if (levels) *levels = (int64_t)h->sym.levels.size();
     if (bytes) *bytes = (int64_t)h->device_bytes;
     return PGO_OK;
+}
+
+int pgo_get_level_sizes(const pgo_handle *h, int32_t max_levels, int64_t *rows, int64_t *blocks) {
+    if (!h) return PGO_ERR_ARG;
+    const int nl = (int)h->sym.levels.size();
+    for (int l = 0; l < nl && l < max_levels; l++) {
+        if (rows) rows[l] = h->sym.levels[l].n;
+        if (blocks) blocks[l] = h->sym.levels[l].adj_ptr[h->sym.levels[l].n_pad];
+    }
+    return nl;
 }
 
 } // extern "C"

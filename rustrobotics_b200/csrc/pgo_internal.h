@@ -7,41 +7,60 @@
 
 namespace pgo {
 
-constexpr uint32_t COL_MASK = 0x3FFFFFFFu;   // neighbour row index
-constexpr uint32_t COL_ROLE_TO = 0x80000000u; // own row is the edge's `to` vertex
-constexpr uint32_t COL_EDGE_XY = 0x40000000u; // pose-landmark edge (EDGE_SE2_XY)
+constexpr int MAX_RANKS = 8;
+// column word of a stored block: [31] own row is the edge's `to` vertex, [30] pose-landmark edge (level 0 only),
+// [29:27] owner rank of the neighbour row, [26:0] the neighbour's row index local to its owner.
+constexpr uint32_t COL_ROLE_TO = 0x80000000u;
+constexpr uint32_t COL_EDGE_XY = 0x40000000u;
+constexpr int COL_OWNER_SHIFT = 27;
+constexpr uint32_t COL_LOCAL_MASK = (1u << COL_OWNER_SHIFT) - 1u;
+constexpr uint32_t COL_FLAG_MASK = COL_ROLE_TO | COL_EDGE_XY;
 
-// Sliced jagged storage ("slice-contiguous JDS") of one block-sparse level.
-// Rows are grouped in slices of 32 (one warp, one thread per block row); inside a slice the rows
-// are ordered by decreasing off-diagonal count, so in "column" k of the slice the active rows are
-// lanes 0..cnt_k-1 and their entries are stored densely:  slot(k, lane) = slice_ptr[s] + off_k + lane,
-// off_k = sum_{k'<k} cnt_k'.  Values of a column are component-major,
-//   val[(slice_ptr[s] + off_k) * DD + c * cnt_k + lane],
+// One level of the block-sparse hierarchy, in GLOBAL PADDED row numbering: the rows of partition (rank) k are
+// [part_off[k], part_off[k+1]) with part_real[k] real rows first and padding rows (deg 0) behind them, so that every
+// partition starts on a 32-row slice boundary.  A rank's device arrays are contiguous sub-ranges of these.
+//
+// Level 0 is stored as sliced jagged storage ("slice-contiguous JDS"): rows in slices of 32 (one warp, one thread per
+// block row); inside a slice the rows are ordered by decreasing off-diagonal count, so in "column" k of the slice the
+// active rows are lanes 0..cnt_k-1 and their entries are stored densely:  slot(k, lane) = slice_ptr[s] + off_k + lane,
+// off_k = sum_{k'<k} cnt_k'.  Values of a column are component-major, val[(slice_ptr[s] + off_k) * DD + c * cnt_k + lane],
 // so a whole slice is ONE contiguous blob that a warp streams front to back with coalesced loads.
+// Coarse levels (small, L2-resident, latency-bound) are plain block CSR, one warp per row: slot = adj_ptr[row] + k,
+// val[slot * DD + c].
 struct HostLevel {
-    int64_t n = 0, n_pad = 0, n_slices = 0, n_slots = 0;
+    bool jds = false;
+    int64_t n = 0;                    // real rows (all partitions)
+    int64_t n_pad = 0;                // global padded rows
+    int64_t n_slots = 0;
+    std::vector<int64_t> part_off;    // [world + 1], multiples of 32
+    std::vector<int64_t> part_real;   // [world]
+    std::vector<int64_t> part_slot;   // [world + 1] slot range of each partition
+    std::vector<uint8_t> real;        // [n_pad] 1 for real rows
+    // JDS only
+    int64_t n_slices = 0;
     std::vector<int64_t> slice_ptr;   // [n_slices + 1]
     std::vector<int32_t> deg;         // [n_pad]
-    std::vector<uint32_t> col;        // [n_slots]  neighbour row | flags (level 0 only)
-    // adjacency in storage order, for host-side bookkeeping
-    std::vector<int64_t> adj_ptr;     // [n + 1]
+    // adjacency in storage order (both formats); for CSR levels slot == position
+    std::vector<int64_t> adj_ptr;     // [n_pad + 1]
     std::vector<int64_t> adj_slot;    // slot index of each entry
-    std::vector<int32_t> adj_cnt;     // cnt_k (component stride) of each entry
-    std::vector<int32_t> adj_nbr;     // neighbour row
+    std::vector<int32_t> adj_cnt;     // JDS: cnt_k (component stride) of each entry; CSR: 1
+    std::vector<int32_t> adj_nbr;     // neighbour global padded row
+    std::vector<uint32_t> adj_flags;  // level 0: COL_ROLE_TO / COL_EDGE_XY
     // aggregation towards the next coarser level (empty on the coarsest)
-    std::vector<int32_t> agg;         // [n_pad] coarse row of each row (-1 for padding rows)
-    std::vector<int64_t> ctgt;        // [n_slots] Galerkin target: component-0 offset in coarse val, or
-                                      //           (coarse row | DIAG_FLAG) when both ends share the aggregate
-    std::vector<int32_t> cstr;        // [n_slots] component stride at the target (cnt_k of the coarse column)
-    // this level seen as the coarse side of the finer level: members of each row
-    std::vector<int64_t> mem_ptr;     // [n + 1]
-    std::vector<int32_t> mem_idx;     // finer-level rows
+    std::vector<int32_t> agg;         // [n_pad] coarse global padded row of each row (-1 for padding rows)
+    std::vector<int32_t> ctgt;        // [n_slots] Galerkin target of each stored block, LOCAL to the owning partition:
+                                      //   >= 0: slot of the coarse level ; < 0: diagonal of coarse row (-1 - row)
+    // this level seen as the coarse side of the finer level: members (finer global padded rows) of each row
+    std::vector<int64_t> mem_ptr;     // [n_pad + 1]
+    std::vector<int32_t> mem_idx;
+
+    int part_of(int64_t row) const { int k = 0; while (row >= part_off[k + 1]) k++; return k; }
 };
-constexpr int64_t CTGT_DIAG = int64_t(1) << 62;
 
 // Output of the one-time symbolic pass over the graph.
 struct Symbolic {
     int D = 3;                         // block dimension (3: SE2/XY, 6: SE3)
+    int world = 1;
     int64_t n = 0, n_edges = 0, len = 0, n_values = 0;
     std::vector<uint8_t> vkind;        // lut order
     std::vector<int64_t> voffset;      // lut: scalar offset of each vertex (g2o.rs:60,67,76)
@@ -49,18 +68,27 @@ struct Symbolic {
     std::vector<int32_t> efrom, eto;   // edge endpoints as vertex indices (lut order)
     std::vector<uint8_t> ekind;
     int64_t anchor = -1;               // lut index of the anchored vertex (:330-336)
+    std::vector<int64_t> vrange;       // [world + 1] contiguous vertex (lut) range of each rank
     // canonical block CSR (lut order) + edge -> block slots + scalar CSC pattern
     std::vector<int64_t> brow_ptr; std::vector<int32_t> bcol; std::vector<int64_t> edge_slots;
     std::vector<int32_t> csc_ptr, csc_row;
-    // internal ordering
-    std::vector<int32_t> perm, iperm;  // perm[internal row] = lut index ; iperm = inverse
+    // internal ordering of level 0
+    std::vector<int32_t> perm;         // [levels[0].n_pad] global padded row -> lut index (-1 for padding rows)
+    std::vector<int32_t> iperm;        // [n] lut index -> global padded row
     std::vector<HostLevel> levels;     // levels[0] = the Gauss-Newton system
-    // per stored slot of level 0: the edge it comes from (measurement scatter at create time)
-    std::vector<int32_t> slot_edge;
+    std::vector<int32_t> slot_edge;    // per stored slot of level 0: the edge it comes from
+    bool dense_coarsest = false;       // the last level is solved directly (explicit inverse)
     std::string error;
 };
 
-struct SymbolicOptions { int sort_window = 4096; int amg_max_levels = 12; int coarsest_max = 64; bool build_amg = true; };
+struct SymbolicOptions {
+    int world = 1;
+    int sort_window = 2048;
+    int max_levels = 12;
+    int agg_size = 16;
+    int dense_max = 640;               // a level with at most this many rows is solved directly
+    bool build_amg = true;
+};
 
 // Builds everything above. Returns false and sets sym.error on malformed input.
 bool build_symbolic(Symbolic &sym, const SymbolicOptions &opt,

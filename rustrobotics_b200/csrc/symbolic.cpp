@@ -1,8 +1,9 @@
-// One-time symbolic pass (host): block structure of H, edge -> slot map, sliced jagged storage
-// and the structure of the aggregation-AMG hierarchy.  The reference never materialises this
-// structure explicitly -- it is implied by the 36 (pose-pose) / 25 (pose-landmark) `put` calls
-// per edge of update_linear_system / set_matrix (pose_graph_optimization.rs:165-206), re-derived
-// inside russell_sparse's COO->CSC conversion on every iteration.  Here it is computed once.
+// One-time symbolic pass (host): block structure of H, edge -> slot map, sliced jagged storage of the
+// Gauss-Newton system, contiguous vertex-range partition across ranks, and the structure of the
+// aggregation-AMG hierarchy.  The reference never materialises this structure explicitly -- it is implied
+// by the 36 (pose-pose) / 25 (pose-landmark) `put` calls per edge of update_linear_system / set_matrix
+// (pose_graph_optimization.rs:165-206), re-derived inside russell_sparse's COO->CSC conversion on every
+// iteration.  Here it is computed once.
 #include "pgo_internal.h"
 
 #include <algorithm>
@@ -14,45 +15,44 @@ namespace pgo {
 static const int KIND_DIM[3] = {3, 2, 6};   // lut stride, g2o.rs:61,68,77
 static const int KIND_NVAL[3] = {3, 2, 7};
 
-// ------------------------------------------------------------------------------------------------
-// row ordering: inside windows of `window` rows (multiple of 32) sort by decreasing degree (stable)
-static void order_rows(const std::vector<int32_t> &deg, int64_t n, int window, std::vector<int32_t> &perm) {
-    perm.resize(n);
-    std::iota(perm.begin(), perm.end(), 0);
-    if (window < 32) window = 32;
-    window = (window / 32) * 32;
-    for (int64_t w = 0; w < n; w += window) {
-        int64_t e = std::min<int64_t>(n, w + window);
-        std::stable_sort(perm.begin() + w, perm.begin() + e, [&](int32_t a, int32_t b) { return deg[a] > deg[b]; });
-    }
+static inline int64_t pad32(int64_t x) { return (x + 31) / 32 * 32; }
+
+// partitions laid out back to back, each padded to a multiple of 32 rows
+static void layout_partitions(HostLevel &L, const std::vector<int64_t> &counts) {
+    const int world = (int)counts.size();
+    L.part_real = counts;
+    L.part_off.assign(world + 1, 0);
+    L.n = 0;
+    for (int k = 0; k < world; k++) { L.part_off[k + 1] = L.part_off[k] + pad32(counts[k]); L.n += counts[k]; }
+    if (L.part_off[world] == 0) L.part_off[world] = 32;
+    L.n_pad = L.part_off[world];
+    L.real.assign(L.n_pad, 0);
+    for (int k = 0; k < world; k++) std::fill(L.real.begin() + L.part_off[k], L.real.begin() + L.part_off[k] + counts[k], 1);
 }
 
-// sliced jagged storage from per-row entry counts (rows already in storage order)
-static void build_jds(HostLevel &L, int64_t n, const std::vector<int64_t> &ptr) {
-    L.n = n;
-    L.n_pad = (n + 31) / 32 * 32;
-    if (L.n_pad == 0) L.n_pad = 32;
+// sliced jagged storage from L.adj_ptr (rows of a slice already ordered by decreasing entry count)
+static void build_jds(HostLevel &L) {
+    L.jds = true;
     L.n_slices = L.n_pad / 32;
     L.deg.assign(L.n_pad, 0);
-    for (int64_t r = 0; r < n; r++) L.deg[r] = (int32_t)(ptr[r + 1] - ptr[r]);
+    for (int64_t r = 0; r < L.n_pad; r++) L.deg[r] = (int32_t)(L.adj_ptr[r + 1] - L.adj_ptr[r]);
     L.slice_ptr.assign(L.n_slices + 1, 0);
-    L.adj_ptr = ptr;
-    int64_t nent = ptr[n];
+    const int64_t nent = L.adj_ptr[L.n_pad];
     L.adj_slot.assign(nent, 0);
     L.adj_cnt.assign(nent, 0);
     int64_t base = 0;
     for (int64_t s = 0; s < L.n_slices; s++) {
         L.slice_ptr[s] = base;
         const int32_t *d = &L.deg[32 * s];
-        int maxdeg = d[0];
+        const int maxdeg = d[0];
         int64_t off = 0;
         for (int k = 0; k < maxdeg; k++) {
             int cnt = 0;
-            while (cnt < 32 && d[cnt] > k) cnt++;         // rows are sorted by decreasing degree
+            while (cnt < 32 && d[cnt] > k) cnt++;
             for (int l = 0; l < cnt; l++) {
-                int64_t row = 32 * s + l;
-                L.adj_slot[ptr[row] + k] = base + off + l;
-                L.adj_cnt[ptr[row] + k] = cnt;
+                const int64_t row = 32 * s + l;
+                L.adj_slot[L.adj_ptr[row] + k] = base + off + l;
+                L.adj_cnt[L.adj_ptr[row] + k] = cnt;
             }
             off += cnt;
         }
@@ -60,6 +60,19 @@ static void build_jds(HostLevel &L, int64_t n, const std::vector<int64_t> &ptr) 
     }
     L.slice_ptr[L.n_slices] = base;
     L.n_slots = base;
+    L.part_slot.assign(L.part_off.size(), 0);
+    for (size_t k = 0; k < L.part_off.size(); k++) L.part_slot[k] = L.slice_ptr[L.part_off[k] / 32];
+}
+
+static void build_csr(HostLevel &L) {
+    L.jds = false;
+    const int64_t nent = L.adj_ptr[L.n_pad];
+    L.adj_slot.resize(nent);
+    std::iota(L.adj_slot.begin(), L.adj_slot.end(), int64_t(0));
+    L.adj_cnt.assign(nent, 1);
+    L.n_slots = nent;
+    L.part_slot.assign(L.part_off.size(), 0);
+    for (size_t k = 0; k < L.part_off.size(); k++) L.part_slot[k] = L.adj_ptr[L.part_off[k]];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -122,24 +135,26 @@ bool build_csc_pattern(Symbolic &S) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// unique-neighbour adjacency of a level (storage order), from its stored entries
-static void unique_adjacency(const HostLevel &L, std::vector<int64_t> &ptr, std::vector<int32_t> &nbr) {
-    ptr.assign(L.n + 1, 0);
-    nbr.clear();
-    nbr.reserve(L.adj_nbr.size());
-    for (int64_t r = 0; r < L.n; r++) {
-        size_t start = nbr.size();
-        for (int64_t p = L.adj_ptr[r]; p < L.adj_ptr[r + 1]; p++) nbr.push_back(L.adj_nbr[p]);
+// Root + neighbours aggregation (Vanek-style, three passes) of the rows of ONE partition of a level, restricted to
+// edges inside the partition (aggregates never straddle ranks, so restriction, prolongation and the Galerkin
+// product need no communication).  agg[row - r0] = aggregate id in creation order.
+static int32_t aggregate_partition(const HostLevel &F, int k, int max_size, std::vector<int32_t> &agg) {
+    const int64_t r0 = F.part_off[k], n = F.part_real[k];
+    agg.assign(n, -1);
+    if (n == 0) return 0;
+    std::vector<int64_t> ptr(n + 1, 0);
+    std::vector<int32_t> nbr;
+    nbr.reserve(F.adj_ptr[r0 + n] - F.adj_ptr[r0]);
+    for (int64_t i = 0; i < n; i++) {
+        const size_t start = nbr.size();
+        for (int64_t p = F.adj_ptr[r0 + i]; p < F.adj_ptr[r0 + i + 1]; p++) {
+            const int64_t j = F.adj_nbr[p] - r0;
+            if (j >= 0 && j < n && j != i) nbr.push_back((int32_t)j);
+        }
         std::sort(nbr.begin() + start, nbr.end());
         nbr.erase(std::unique(nbr.begin() + start, nbr.end()), nbr.end());
-        ptr[r + 1] = (int64_t)nbr.size();
+        ptr[i + 1] = (int64_t)nbr.size();
     }
-}
-
-// root + neighbours aggregation (Vanek-style, three passes) on a unique-neighbour adjacency
-static int32_t aggregate_graph(int64_t n, const std::vector<int64_t> &ptr, const std::vector<int32_t> &nbr,
-                               int max_size, std::vector<int32_t> &agg) {
-    agg.assign(n, -1);
     int32_t nc = 0;
     for (int64_t i = 0; i < n; i++) {
         if (agg[i] >= 0) continue;
@@ -151,8 +166,7 @@ static int32_t aggregate_graph(int64_t n, const std::vector<int64_t> &ptr, const
         for (int64_t p = ptr[i]; p < ptr[i + 1] && sz < max_size; p++) { agg[nbr[p]] = nc; sz++; }
         nc++;
     }
-    std::vector<int32_t> snap(agg);
-    std::vector<int32_t> cand;
+    std::vector<int32_t> snap(agg), cand;
     for (int64_t i = 0; i < n; i++) {
         if (agg[i] >= 0) continue;
         cand.clear();
@@ -176,117 +190,64 @@ static int32_t aggregate_graph(int64_t n, const std::vector<int64_t> &ptr, const
     return nc;
 }
 
-// Level 0: runs of up to `run` consecutive (lut-order) vertices that are chained by edges -- a short
-// odometry segment moves almost rigidly, which is exactly what the coarse basis can represent.
-// Vertices left alone (landmarks, chain breaks) join the neighbouring aggregate they touch most.
-static int32_t aggregate_chain(const Symbolic &S, const HostLevel &L, const std::vector<int64_t> &ptr,
-                               const std::vector<int32_t> &nbr, int run, int max_size, std::vector<int32_t> &agg) {
-    const int64_t n = L.n;
-    agg.assign(n, -1);
-    std::vector<int32_t> size;
-    int32_t nc = 0; int cur = 0;
-    auto adjacent = [&](int32_t a, int32_t b) {            // internal rows
-        return std::binary_search(nbr.begin() + ptr[a], nbr.begin() + ptr[a + 1], b);
-    };
-    for (int64_t v = 0; v < n; v++) {                       // lut order
-        int32_t r = S.iperm[v];
-        bool join = v > 0 && cur > 0 && cur < run && adjacent(r, S.iperm[v - 1]) && agg[S.iperm[v - 1]] == nc - 1;
-        if (join) { agg[r] = nc - 1; cur++; size[nc - 1]++; }
-        else { agg[r] = nc++; cur = 1; size.push_back(1); }
-    }
-    // merge singletons into the most-connected neighbouring aggregate with room
-    std::vector<int32_t> cand;
-    for (int64_t r = 0; r < n; r++) {
-        if (size[agg[r]] != 1) continue;
-        cand.clear();
-        for (int64_t p = ptr[r]; p < ptr[r + 1]; p++) { int32_t a = agg[nbr[p]]; if (a != agg[r] && size[a] < max_size && size[a] > 1) cand.push_back(a); }
-        if (cand.empty()) continue;
-        std::sort(cand.begin(), cand.end());
-        int32_t best = cand[0]; int bc = 0, rn = 0;
-        for (size_t q = 0; q < cand.size(); q++) { rn = (q > 0 && cand[q] == cand[q - 1]) ? rn + 1 : 1; if (rn > bc) { bc = rn; best = cand[q]; } }
-        size[agg[r]] = 0; agg[r] = best; size[best]++;
-    }
-    // compact ids
-    std::vector<int32_t> remap(nc, -1);
-    int32_t m = 0;
-    for (int64_t v = 0; v < n; v++) { int32_t &a = agg[S.iperm[v]]; if (remap[a] < 0) remap[a] = m++; a = remap[a]; }
-    return m;
-}
-
-// Given a fine level and an aggregation (ids 0..nc-1 in creation order), build the coarse level
-// (storage-ordered), relabel agg to coarse storage rows, and fill the Galerkin targets.
-static void build_coarse_level(HostLevel &F, HostLevel &C, std::vector<int32_t> &agg, int32_t nc, int window, int DD) {
-    const int64_t n = F.n;
-    // coarse unique adjacency in creation ids
-    std::vector<int64_t> cnt(nc + 1, 0);
-    for (int64_t r = 0; r < n; r++) cnt[agg[r] + 1] += F.adj_ptr[r + 1] - F.adj_ptr[r];
-    for (int32_t a = 0; a < nc; a++) cnt[a + 1] += cnt[a];
-    std::vector<int32_t> tmp(cnt[nc]);
-    std::vector<int64_t> pos(cnt.begin(), cnt.end() - 1);
-    for (int64_t r = 0; r < n; r++)
-        for (int64_t p = F.adj_ptr[r]; p < F.adj_ptr[r + 1]; p++) tmp[pos[agg[r]]++] = agg[F.adj_nbr[p]];
-    std::vector<int64_t> cptr(nc + 1, 0);
-    std::vector<int32_t> cnbr;
-    cnbr.reserve(tmp.size() / 2);
-    std::vector<int32_t> cdeg(nc);
-    for (int32_t a = 0; a < nc; a++) {
-        auto b = tmp.begin() + cnt[a], e = tmp.begin() + cnt[a + 1];
-        std::sort(b, e);
-        e = std::unique(b, e);
-        for (auto it = b; it != e; ++it) if (*it != a) cnbr.push_back(*it);
-        cptr[a + 1] = (int64_t)cnbr.size();
-        cdeg[a] = (int32_t)(cptr[a + 1] - cptr[a]);
-    }
-    // storage order of the coarse level
-    std::vector<int32_t> cperm, ciperm(nc);
-    order_rows(cdeg, nc, window, cperm);
-    for (int32_t s = 0; s < nc; s++) ciperm[cperm[s]] = s;
-    std::vector<int64_t> sptr(nc + 1, 0);
-    for (int32_t s = 0; s < nc; s++) sptr[s + 1] = sptr[s] + cdeg[cperm[s]];
-    build_jds(C, nc, sptr);
-    C.adj_nbr.resize(sptr[nc]);
-    C.col.assign(C.n_slots, 0);
-    for (int32_t s = 0; s < nc; s++) {
-        int32_t a = cperm[s];
-        int64_t o = sptr[s];
-        for (int64_t p = cptr[a]; p < cptr[a + 1]; p++) C.adj_nbr[o++] = ciperm[cnbr[p]];
-        std::sort(C.adj_nbr.begin() + sptr[s], C.adj_nbr.begin() + sptr[s + 1]);
-        for (int64_t q = sptr[s]; q < sptr[s + 1]; q++) C.col[C.adj_slot[q]] = (uint32_t)C.adj_nbr[q];
-    }
-    // relabel agg to storage rows; padding rows -> -1
+// Build the coarse level (block CSR, global padded numbering) from per-partition aggregate ids; fills F.agg, F.ctgt.
+static void build_coarse_level(HostLevel &F, HostLevel &C, const std::vector<std::vector<int32_t>> &pagg,
+                               const std::vector<int64_t> &pnc) {
+    const int world = (int)pnc.size();
+    layout_partitions(C, pnc);
     F.agg.assign(F.n_pad, -1);
-    for (int64_t r = 0; r < n; r++) F.agg[r] = ciperm[agg[r]];
-    // members
-    C.mem_ptr.assign(nc + 1, 0);
-    for (int64_t r = 0; r < n; r++) C.mem_ptr[F.agg[r] + 1]++;
-    for (int32_t s = 0; s < nc; s++) C.mem_ptr[s + 1] += C.mem_ptr[s];
-    C.mem_idx.resize(n);
-    std::vector<int64_t> mp(C.mem_ptr.begin(), C.mem_ptr.end() - 1);
-    for (int64_t r = 0; r < n; r++) C.mem_idx[mp[F.agg[r]]++] = (int32_t)r;
-    // Galerkin targets of every fine slot
-    F.ctgt.assign(F.n_slots, CTGT_DIAG);
-    F.cstr.assign(F.n_slots, 0);
-    for (int64_t r = 0; r < n; r++) {
-        int32_t I = F.agg[r];
-        for (int64_t p = F.adj_ptr[r]; p < F.adj_ptr[r + 1]; p++) {
-            int32_t J = F.agg[F.adj_nbr[p]];
-            int64_t slot = F.adj_slot[p];
-            if (I == J) { F.ctgt[slot] = CTGT_DIAG | I; F.cstr[slot] = (int32_t)C.n_pad; continue; }
-            auto b = C.adj_nbr.begin() + C.adj_ptr[I], e = C.adj_nbr.begin() + C.adj_ptr[I + 1];
-            int64_t q = std::lower_bound(b, e, J) - C.adj_nbr.begin();
-            int64_t cs = C.adj_slot[q];
-            int lane = I & 31;
-            F.ctgt[slot] = (cs - lane) * DD + lane;
-            F.cstr[slot] = C.adj_cnt[q];
-        }
+    for (int k = 0; k < world; k++)
+        for (int64_t i = 0; i < F.part_real[k]; i++) F.agg[F.part_off[k] + i] = (int32_t)(C.part_off[k] + pagg[k][i]);
+    // members of every coarse row
+    C.mem_ptr.assign(C.n_pad + 1, 0);
+    for (int64_t r = 0; r < F.n_pad; r++) if (F.agg[r] >= 0) C.mem_ptr[F.agg[r] + 1]++;
+    for (int64_t I = 0; I < C.n_pad; I++) C.mem_ptr[I + 1] += C.mem_ptr[I];
+    C.mem_idx.resize(C.mem_ptr[C.n_pad]);
+    {
+        std::vector<int64_t> mp(C.mem_ptr.begin(), C.mem_ptr.end() - 1);
+        for (int64_t r = 0; r < F.n_pad; r++) if (F.agg[r] >= 0) C.mem_idx[mp[F.agg[r]]++] = (int32_t)r;
     }
+    // coarse adjacency: I ~ J when any member of I has a stored block towards a member of J
+    C.adj_ptr.assign(C.n_pad + 1, 0);
+    C.adj_nbr.clear();
+    std::vector<int32_t> tmp;
+    for (int64_t I = 0; I < C.n_pad; I++) {
+        tmp.clear();
+        for (int64_t m = C.mem_ptr[I]; m < C.mem_ptr[I + 1]; m++) {
+            const int64_t r = C.mem_idx[m];
+            for (int64_t p = F.adj_ptr[r]; p < F.adj_ptr[r + 1]; p++) { const int32_t J = F.agg[F.adj_nbr[p]]; if (J != I) tmp.push_back(J); }
+        }
+        std::sort(tmp.begin(), tmp.end());
+        tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+        C.adj_nbr.insert(C.adj_nbr.end(), tmp.begin(), tmp.end());
+        C.adj_ptr[I + 1] = (int64_t)C.adj_nbr.size();
+    }
+    build_csr(C);
+    // Galerkin targets of every fine block, local to the owning partition
+    F.ctgt.assign(F.n_slots, 0);
+    for (int k = 0; k < world; k++)
+        for (int64_t r = F.part_off[k]; r < F.part_off[k] + F.part_real[k]; r++) {
+            const int32_t I = F.agg[r];
+            for (int64_t p = F.adj_ptr[r]; p < F.adj_ptr[r + 1]; p++) {
+                const int32_t J = F.agg[F.adj_nbr[p]];
+                const int64_t slot = F.adj_slot[p];
+                if (I == J) { F.ctgt[slot] = (int32_t)(-1 - (I - C.part_off[k])); continue; }
+                auto b = C.adj_nbr.begin() + C.adj_ptr[I], e = C.adj_nbr.begin() + C.adj_ptr[I + 1];
+                const int64_t q = std::lower_bound(b, e, J) - C.adj_nbr.begin();
+                F.ctgt[slot] = (int32_t)(q - C.part_slot[k]);
+            }
+        }
 }
 
 // ------------------------------------------------------------------------------------------------
 bool build_symbolic(Symbolic &S, const SymbolicOptions &opt,
                     int64_t nv, const uint32_t *vid, const uint8_t *vkind,
                     int64_t ne, const uint8_t *ekind, const uint32_t *efrom, const uint32_t *eto) {
-    if (nv <= 0 || nv > 0x3fffffffll || ne < 0 || ne > 0x7fffffffll) { S.error = "vertex/edge count out of range"; return false; }
+    if (nv <= 0 || nv > (int64_t)COL_LOCAL_MASK || ne < 0 || ne > 0x7fffffffll) { S.error = "vertex/edge count out of range"; return false; }
+    const int world = opt.world;
+    if (world < 1 || world > MAX_RANKS) { S.error = "world size must be 1.." + std::to_string(MAX_RANKS); return false; }
+    if (world > 1 && nv < 64 * world) { S.error = "graph too small to shard: needs at least 64 vertices per rank"; return false; }
+    S.world = world;
     S.n = nv; S.n_edges = ne;
     S.vkind.assign(vkind, vkind + nv);
     S.voffset.resize(nv); S.vvalofs.resize(nv);
@@ -322,61 +283,87 @@ bool build_symbolic(Symbolic &S, const SymbolicOptions &opt,
         S.efrom[k] = i; S.eto[k] = j;
         if (S.anchor < 0 && ekind[k] != 1) S.anchor = i;   // first pose-pose edge's `from` (:330-336)
     }
-    // degrees, storage order
     std::vector<int32_t> deg(nv, 0);
     for (int64_t k = 0; k < ne; k++) { deg[S.efrom[k]]++; deg[S.eto[k]]++; }
-    order_rows(deg, nv, opt.sort_window, S.perm);
-    S.iperm.resize(nv);
-    for (int64_t r = 0; r < nv; r++) S.iperm[S.perm[r]] = (int32_t)r;
-    // half edges per storage row, sorted by neighbour row
-    std::vector<int64_t> ptr(nv + 1, 0);
-    for (int64_t r = 0; r < nv; r++) ptr[r + 1] = ptr[r] + deg[S.perm[r]];
-    struct HE { int32_t nbr, edge; uint32_t flags; };
-    std::vector<HE> he(ptr[nv]);
-    {
-        std::vector<int64_t> pos(ptr.begin(), ptr.end() - 1);
-        for (int64_t k = 0; k < ne; k++) {
-            int32_t ri = S.iperm[S.efrom[k]], rj = S.iperm[S.eto[k]];
-            uint32_t xy = ekind[k] == 1 ? COL_EDGE_XY : 0u;
-            he[pos[ri]++] = {rj, (int32_t)k, xy};
-            he[pos[rj]++] = {ri, (int32_t)k, xy | COL_ROLE_TO};
+
+    // ---- contiguous vertex (lut) ranges per rank, boundaries on multiples of 32, balanced by stored blocks
+    S.vrange.assign(world + 1, 0);
+    S.vrange[world] = nv;
+    if (world > 1) {
+        std::vector<int64_t> pre(nv + 1, 0);
+        for (int64_t v = 0; v < nv; v++) pre[v + 1] = pre[v] + 1 + deg[v];
+        for (int k = 1; k < world; k++) {
+            const int64_t target = pre[nv] * k / world;
+            int64_t v = std::lower_bound(pre.begin(), pre.end(), target) - pre.begin();
+            v = (v + 16) / 32 * 32;
+            v = std::max(v, S.vrange[k - 1] + 32);
+            v = std::min(v, (nv - 32 * (int64_t)(world - k)) / 32 * 32);
+            S.vrange[k] = v;
         }
-        for (int64_t r = 0; r < nv; r++)
-            std::sort(he.begin() + ptr[r], he.begin() + ptr[r + 1], [](const HE &a, const HE &b) { return a.nbr != b.nbr ? a.nbr < b.nbr : a.edge < b.edge; });
     }
+    // ---- storage order: inside every rank's range, windows of `sort_window` rows sorted by decreasing degree (stable)
     S.levels.clear();
     S.levels.emplace_back();
-    HostLevel &L0 = S.levels[0];
-    build_jds(L0, nv, ptr);
-    L0.col.assign(L0.n_slots, 0);
-    L0.adj_nbr.resize(ptr[nv]);
-    S.slot_edge.assign(L0.n_slots, -1);
-    for (int64_t q = 0; q < ptr[nv]; q++) {
-        L0.adj_nbr[q] = he[q].nbr;
-        L0.col[L0.adj_slot[q]] = (uint32_t)he[q].nbr | he[q].flags;
-        S.slot_edge[L0.adj_slot[q]] = he[q].edge;
+    {
+        HostLevel &L0 = S.levels[0];
+        std::vector<int64_t> counts(world);
+        for (int k = 0; k < world; k++) counts[k] = S.vrange[k + 1] - S.vrange[k];
+        layout_partitions(L0, counts);
+        S.perm.assign(L0.n_pad, -1);
+        S.iperm.assign(nv, -1);
+        int window = std::max(32, opt.sort_window / 32 * 32);
+        std::vector<int32_t> idv;
+        for (int k = 0; k < world; k++) {
+            idv.resize(counts[k]);
+            std::iota(idv.begin(), idv.end(), (int32_t)S.vrange[k]);
+            for (int64_t w = 0; w < counts[k]; w += window) {
+                const int64_t e = std::min<int64_t>(counts[k], w + window);
+                std::stable_sort(idv.begin() + w, idv.begin() + e, [&](int32_t a, int32_t b) { return deg[a] > deg[b]; });
+            }
+            for (int64_t i = 0; i < counts[k]; i++) { S.perm[L0.part_off[k] + i] = idv[i]; S.iperm[idv[i]] = (int32_t)(L0.part_off[k] + i); }
+        }
+        // half edges per storage row, sorted by neighbour row
+        L0.adj_ptr.assign(L0.n_pad + 1, 0);
+        for (int64_t r = 0; r < L0.n_pad; r++) L0.adj_ptr[r + 1] = L0.adj_ptr[r] + (S.perm[r] >= 0 ? deg[S.perm[r]] : 0);
+        struct HE { int32_t nbr, edge; uint32_t flags; };
+        std::vector<HE> he(L0.adj_ptr[L0.n_pad]);
+        {
+            std::vector<int64_t> pos(L0.adj_ptr.begin(), L0.adj_ptr.end() - 1);
+            for (int64_t k = 0; k < ne; k++) {
+                const int32_t ri = S.iperm[S.efrom[k]], rj = S.iperm[S.eto[k]];
+                const uint32_t xy = ekind[k] == 1 ? COL_EDGE_XY : 0u;
+                he[pos[ri]++] = {rj, (int32_t)k, xy};
+                he[pos[rj]++] = {ri, (int32_t)k, xy | COL_ROLE_TO};
+            }
+            for (int64_t r = 0; r < L0.n_pad; r++)
+                std::sort(he.begin() + L0.adj_ptr[r], he.begin() + L0.adj_ptr[r + 1],
+                          [](const HE &a, const HE &b) { return a.nbr != b.nbr ? a.nbr < b.nbr : a.edge < b.edge; });
+        }
+        build_jds(L0);
+        const int64_t nent = L0.adj_ptr[L0.n_pad];
+        L0.adj_nbr.resize(nent); L0.adj_flags.resize(nent);
+        S.slot_edge.assign(L0.n_slots, -1);
+        for (int64_t q = 0; q < nent; q++) {
+            L0.adj_nbr[q] = he[q].nbr;
+            L0.adj_flags[q] = he[q].flags;
+            S.slot_edge[L0.adj_slot[q]] = he[q].edge;
+        }
     }
-    he.clear(); he.shrink_to_fit();
+    S.dense_coarsest = false;
     if (!opt.build_amg) return true;
 
     // ---- aggregation hierarchy
-    const int DD = S.D * S.D;
-    for (int lvl = 0; lvl + 1 < opt.amg_max_levels; lvl++) {
-        HostLevel &F = S.levels[lvl];
-        if (F.n <= opt.coarsest_max) break;
-        std::vector<int64_t> uptr; std::vector<int32_t> unbr;
-        unique_adjacency(F, uptr, unbr);
-        std::vector<int32_t> agg;
-        int32_t nc = 0;
-        if (lvl == 0) {
-            nc = aggregate_chain(S, F, uptr, unbr, 4, 8, agg);
-            if (nc > 0.6 * F.n) nc = aggregate_graph(F.n, uptr, unbr, 16, agg);
-        } else {
-            nc = aggregate_graph(F.n, uptr, unbr, 16, agg);
-        }
-        if (nc >= F.n || nc > 0.9 * F.n) break;                 // coarsening stalled
+    while (true) {
+        const size_t lvl = S.levels.size() - 1;
+        if (S.levels[lvl].n <= opt.dense_max) { S.dense_coarsest = true; break; }
+        if ((int)S.levels.size() >= opt.max_levels) break;
+        std::vector<std::vector<int32_t>> pagg(world);
+        std::vector<int64_t> pnc(world, 0);
+        int64_t nc = 0;
+        for (int k = 0; k < world; k++) { pnc[k] = aggregate_partition(S.levels[lvl], k, opt.agg_size, pagg[k]); nc += pnc[k]; }
+        if (nc > 0.8 * S.levels[lvl].n) break;                   // coarsening stalled
         S.levels.emplace_back();
-        build_coarse_level(S.levels[lvl], S.levels[lvl + 1], agg, nc, opt.sort_window, DD);
+        build_coarse_level(S.levels[lvl], S.levels[lvl + 1], pagg, pnc);
     }
     return true;
 }

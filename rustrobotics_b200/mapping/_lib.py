@@ -13,14 +13,16 @@ ABI_SYMBOLS = [
     "pgo_default_options", "pgo_create", "pgo_destroy", "pgo_last_error", "pgo_get_sizes", "pgo_chi2", "pgo_gn_step",
     "pgo_undo_last_step", "pgo_get_poses", "pgo_set_poses", "pgo_get_dx", "pgo_linearize_and_solve", "pgo_get_pattern",
     "pgo_get_block_structure", "pgo_get_anchor", "pgo_get_system", "pgo_get_timings", "pgo_time_spmv", "pgo_get_stats",
-    "pgo_version", "pgo_snapshot_poses", "pgo_restore_poses",
+    "pgo_version", "pgo_snapshot_poses", "pgo_restore_poses", "pgo_shard_handle_bytes", "pgo_shard_export",
+    "pgo_shard_connect", "pgo_get_partition", "pgo_get_level_sizes",
 ]
 
 
 class pgo_options(C.Structure):
     _fields_ = [("anchor_weight", C.c_double), ("pcg_rtol", C.c_double), ("pcg_max_iterations", C.c_int32),
                 ("preconditioner", C.c_int32), ("sort_window", C.c_int32), ("amg_max_levels", C.c_int32),
-                ("device", C.c_int32), ("reserved", C.c_int32)]
+                ("device", C.c_int32), ("world", C.c_int32), ("rank", C.c_int32), ("amg_dense_max", C.c_int32),
+                ("amg_aggregate_size", C.c_int32), ("amg_kcycle", C.c_int32)]
 
 
 def lib_path() -> Path:
@@ -51,6 +53,10 @@ def lib():
     L.pgo_set_poses.argtypes = [P, P, i64]
     L.pgo_get_dx.argtypes = [P, P, i64]
     L.pgo_snapshot_poses.argtypes = [P]
+    L.pgo_shard_export.argtypes = [P, P, i64]
+    L.pgo_shard_connect.argtypes = [P, P, i64]
+    L.pgo_get_partition.argtypes = [P, C.POINTER(i32), C.POINTER(i32), P, P]
+    L.pgo_get_level_sizes.argtypes = [P, i32, P, P]
     L.pgo_restore_poses.argtypes = [P]
     L.pgo_linearize_and_solve.argtypes = [P, C.POINTER(i32)]
     L.pgo_get_pattern.argtypes = [P, C.POINTER(i64), C.POINTER(i64), P, P]

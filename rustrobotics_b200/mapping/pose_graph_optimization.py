@@ -32,7 +32,8 @@ BLOCK_JACOBI, AMG = 0, 1
 
 def Options(**kw) -> pgo_options:
     """pgo_options with the library defaults, overridden by keyword (anchor_weight, pcg_rtol,
-    pcg_max_iterations, preconditioner, sort_window, amg_max_levels, device)."""
+    pcg_max_iterations, preconditioner, sort_window, amg_max_levels, device, world, rank, amg_dense_max,
+    amg_aggregate_size, amg_kcycle)."""
     o = pgo_options()
     lib().pgo_default_options(C.byref(o))
     for k, v in kw.items():
@@ -194,6 +195,18 @@ class PoseGraph:
         v = C.c_double()
         self._check(lib().pgo_time_spmv(self._h, repeats, C.byref(v)), "pgo_time_spmv")
         return v.value
+
+    def level_sizes(self):
+        rows = np.zeros(16, np.int64); blocks = np.zeros(16, np.int64)
+        nl = lib().pgo_get_level_sizes(self._h, 16, ptr(rows), ptr(blocks))
+        return rows[:nl].tolist(), blocks[:nl].tolist()
+
+    def partition(self):
+        w, r = C.c_int32(), C.c_int32()
+        lib().pgo_get_partition(self._h, C.byref(w), C.byref(r), None, None)
+        vr = np.zeros(w.value + 1, np.int64); rb = np.zeros(w.value, np.int64)
+        lib().pgo_get_partition(self._h, C.byref(w), C.byref(r), ptr(vr), ptr(rb))
+        return dict(world=w.value, rank=r.value, vertex_range=vr.tolist(), remote_blocks=rb.tolist())
 
     def stats(self):
         s = [C.c_int64() for _ in range(4)]

@@ -19,7 +19,7 @@ def check_graph(name, graph, precond, its=30, rtol=1e-10, full=True):
     o = OraclePoseGraph.from_arrays(**graph)
     t = time.time()
     pg = PoseGraph(graph=graph, options=Options(preconditioner=precond, pcg_rtol=rtol))
-    print(f"  create {time.time()-t:.2f}s stats {pg.stats()}")
+    print(f"  create {time.time()-t:.2f}s stats {pg.stats()} levels {pg.level_sizes()}")
     c_g, c_o = pg.global_error(), o.global_error()
     print(f"  chi2 gpu {c_g:.10g} oracle {c_o:.10g} rel {abs(c_g-c_o)/c_o:.2e}")
     if full:
@@ -64,7 +64,7 @@ def main():
         try:
             t = time.time()
             pg = PoseGraph(graph=g, options=Options(preconditioner=1, pcg_rtol=1e-8))
-            print(f"=== manhattan 1M create {time.time()-t:.1f}s {pg.stats()}")
+            print(f"=== manhattan 1M create {time.time()-t:.1f}s {pg.stats()} levels {pg.level_sizes()}")
             print("  chi2", pg.global_error())
             for i in range(4):
                 t = time.time(); r = pg.gn_step(); print(f"  step {i}: {r} {time.time()-t:.3f}s {pg.timings()}", flush=True)
