@@ -59,7 +59,8 @@ typedef struct {
     int32_t rank;              /* this process' rank, 0 .. world-1: it owns a contiguous vertex range */
     int32_t amg_dense_max;     /* a level with at most this many block rows is solved directly (explicit inverse); 0 = default */
     int32_t amg_aggregate_size;/* upper bound on the members of an aggregate; 0 = default */
-    int32_t amg_kcycle;        /* 1 = K-cycle (two Krylov-accelerated coarse solves per level), 0 = V-cycle */
+    int32_t amg_kcycle;        /* coarse levels 1..amg_kcycle are solved by a K-cycle (two Krylov-accelerated cycles per
+                                * visit, Notay), deeper ones by a V-cycle; 0 = plain V-cycle; default: all levels */
 } pgo_options;
 
 /* fills *opt with the defaults (anchor 1e7, rtol 1e-10, max 200000 iterations, AMG K-cycle, single GPU) */

@@ -185,8 +185,8 @@ template <int NT, int FIN> __device__ __forceinline__ void reduce_and_finalize(c
 //   MODE 0: y = H x                      (+ x.y  -> FIN_PQ)
 //   MODE 1: y = r - H x                  (residual)
 //   MODE 2: y = x + omega Dinv (r - H x) (damped block-Jacobi sweep; + r.y -> FIN_RZ_INIT, + {r.y, y.u1} -> FIN_RZ)
-template <int D, int MODE, int FIN>
-__global__ void __launch_bounds__(128) k_spmv(LevelDev L, XRef xr, const double *__restrict__ x, const double *__restrict__ r,
+template <int D, int MODE, int FIN, bool PEER>
+__global__ void __launch_bounds__(128) k_spmv(LevelDev L, const __grid_constant__ XRef xr, const double *__restrict__ x, const double *__restrict__ r,
                                                double *__restrict__ y, double omega, const double *__restrict__ u1,
                                                Scalars *S, double *partials, int check_done) {
     if (check_done && ld_done(S)) return;
@@ -210,24 +210,38 @@ __global__ void __launch_bounds__(128) k_spmv(LevelDev L, XRef xr, const double 
 #pragma unroll
             for (int b = 0; b < D; b++) acc[a] = fma(__ldg(dg + (int64_t)(a * D + b) * L.n_pad), xi[b], acc[a]);
         const int64_t base = L.slice_ptr[slice];
+        // software pipeline: the column word and the gathered x record of entry k+1 are requested while the block of
+        // entry k is multiplied, so the dependent chain col -> gather never sits on the critical path of an iteration
         int64_t off = 0;
+        uint32_t c_nxt = 0;
+        double xn[VS];
+#pragma unroll
+        for (int a = 0; a < VS; a++) xn[a] = 0.0;
+        if (mydeg > 0) {
+            c_nxt = __ldg(L.col + base + lane);
+            ld_vec<VS>(PEER ? xgather<VS>(xr, c_nxt) : x + (int64_t)(c_nxt & COL_LOCAL_MASK) * VS, xn);
+        }
+        int cnt = __popc(__ballot_sync(0xffffffffu, 0 < mydeg));
         for (int k = 0; k < maxdeg; k++) {
             const bool active = k < mydeg;
-            const int cnt = __popc(__ballot_sync(0xffffffffu, active));
+            const int cnt_nxt = __popc(__ballot_sync(0xffffffffu, k + 1 < mydeg));
+            double xj[VS];
+#pragma unroll
+            for (int a = 0; a < VS; a++) xj[a] = xn[a];
+            if (k + 1 < mydeg) c_nxt = __ldg(L.col + base + off + cnt + lane);
             if (active) {
-                const uint32_t c = __ldg(L.col + base + off + lane);
-                double xj[VS];
-                ld_vec<VS>(xgather<VS>(xr, c), xj);
                 const double *v = L.val + (base + off) * DD + lane;
                 double h[DD];
 #pragma unroll
                 for (int q = 0; q < DD; q++) h[q] = __ldg(v + (int64_t)q * cnt);
+                if (k + 1 < mydeg) ld_vec<VS>(PEER ? xgather<VS>(xr, c_nxt) : x + (int64_t)(c_nxt & COL_LOCAL_MASK) * VS, xn);
 #pragma unroll
                 for (int a = 0; a < D; a++)
 #pragma unroll
                     for (int b = 0; b < D; b++) acc[a] = fma(h[a * D + b], xj[b], acc[a]);
             }
             off += cnt;
+            cnt = cnt_nxt;
         }
     }
     double dots[2] = {0.0, 0.0};
@@ -272,8 +286,8 @@ __global__ void __launch_bounds__(128) k_spmv(LevelDev L, XRef xr, const double 
 
 // Coarse levels: block CSR, one warp per block row (8 rows per CTA).  Same modes; K-cycle dots:
 //   FIN_K1: {x.y, x.u1}    FIN_K2: {x.u1, x.y, x.u2}      (x = c, y = H c)
-template <int MODE, int FIN>
-__global__ void __launch_bounds__(256) k_spmv_csr(LevelDev L, XRef xr, const double *__restrict__ x, const double *__restrict__ r,
+template <int MODE, int FIN, bool PEER>
+__global__ void __launch_bounds__(256) k_spmv_csr(LevelDev L, const __grid_constant__ XRef xr, const double *__restrict__ x, const double *__restrict__ r,
                                                    double *__restrict__ y, double omega, const double *__restrict__ u1,
                                                    const double *__restrict__ u2, Scalars *S, double *partials, int lvl, int check_done) {
     if (check_done && ld_done(S)) return;
@@ -286,7 +300,7 @@ __global__ void __launch_bounds__(256) k_spmv_csr(LevelDev L, XRef xr, const dou
         for (int64_t s = b + lane; s < e; s += 32) {
             const uint32_t c = __ldg(L.col + s);
             double xj[4];
-            ld_vec<4>(xgather<4>(xr, c), xj);
+            ld_vec<4>(PEER ? xgather<4>(xr, c) : x + (int64_t)(c & COL_LOCAL_MASK) * 4, xj);
             const double *v = L.val + s * 9;
             a0 = fma(v[0], xj[0], fma(v[1], xj[1], fma(v[2], xj[2], a0)));
             a1 = fma(v[3], xj[0], fma(v[4], xj[1], fma(v[5], xj[2], a1)));
@@ -523,7 +537,7 @@ __device__ __forceinline__ void galerkin_scatter(const LevelDev &C, int32_t tgt,
 // Galerkin product Hc = P^T H P: every fine block adds P_i^T H_ij P_j into the coarse block of (agg i, agg j), which
 // lives in a row this rank owns.  Several fine blocks share a coarse block, hence atomics (coarse levels only; the
 // Gauss-Newton system itself is assembled without atomics).  Level-0 source (JDS): one thread per row.
-__global__ void __launch_bounds__(128) k_galerkin3_jds(LevelDev F, LevelDev C, XRef levr) {
+__global__ void __launch_bounds__(128) k_galerkin3_jds(LevelDev F, LevelDev C, const __grid_constant__ XRef levr) {
     const int64_t row = (int64_t)blockIdx.x * 128 + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int64_t slice = row >> 5;
@@ -565,7 +579,7 @@ __global__ void __launch_bounds__(128) k_galerkin3_jds(LevelDev F, LevelDev C, X
 }
 
 // coarse source (block CSR): one warp per row
-__global__ void __launch_bounds__(256) k_galerkin3_csr(LevelDev F, LevelDev C, XRef levr) {
+__global__ void __launch_bounds__(256) k_galerkin3_csr(LevelDev F, LevelDev C, const __grid_constant__ XRef levr) {
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= F.n) return;
@@ -664,41 +678,83 @@ __global__ void __launch_bounds__(128) k_dense_assemble(LevelDev L, DenseMap dm,
     }
 }
 
-// In-place block Gauss-Jordan inversion of the SPD matrix A (m x m, m = 3 nb), no pivoting; cooperative launch.
-// Sweep of pivot block p:  A_pp <- A_pp^-1 ; A_pj <- A_pp^-1 A_pj ; A_ip <- -A_ip A_pp^-1 ; A_ij <- A_ij - A_ip A_pp^-1 A_pj.
-// R (3 x m) and Cp (m x 3) are scratch panels.
+// In-place blocked Gauss-Jordan inversion of the SPD matrix A (m x m, row-major), no pivoting; cooperative launch.
+// Panels of GJ_W = 24 scalars (8 block rows): per panel p (two grid syncs)
+//   phase 0  every CTA inverts the pivot block A_pp in shared memory (redundantly: cheaper than a third sync)
+//   phase 1  R = A_pp^-1 A_p: (w x m) and Cp = A_:p (m x w) go to scratch
+//   phase 2  A_pp <- A_pp^-1 ; A_pj <- R_j ; A_ip <- -Cp_i A_pp^-1 ; A_ij <- A_ij - Cp_i R_j   (tiles of 8 rows x 256 columns)
+constexpr int GJ_W = 24;
 __global__ void __launch_bounds__(256) k_dense_invert(int m, double *__restrict__ A, double *__restrict__ R, double *__restrict__ Cp) {
     cg::grid_group grid = cg::this_grid();
-    const int nb = m / 3;
-    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
-    for (int pb = 0; pb < nb; pb++) {
-        const int p0 = 3 * pb;
-        double P[9], Pi[9];
-#pragma unroll
-        for (int a = 0; a < 3; a++)
-#pragma unroll
-            for (int b = 0; b < 3; b++) P[a * 3 + b] = __ldcg(A + (int64_t)(p0 + a) * m + p0 + b);
-        inv3(P, Pi);
+    __shared__ double P[GJ_W][GJ_W + 1];
+    __shared__ double Cs[8][GJ_W];
+    const int tid = threadIdx.x;
+    const int gtid = blockIdx.x * 256 + tid, gsize = gridDim.x * 256;
+    const int n_rg = (m + 7) / 8, n_cc = (m + 255) / 256;
+    for (int p0 = 0; p0 < m; p0 += GJ_W) {
+        const int w = min(GJ_W, m - p0);
+        // ---- phase 0
+        for (int t = tid; t < w * w; t += 256) P[t / w][t % w] = __ldcg(A + (int64_t)(p0 + t / w) * m + p0 + t % w);
+        __syncthreads();
+        for (int k = 0; k < w; k++) {
+            double nv[3]; int ne = 0;
+            const double ikk = 1.0 / P[k][k];
+            for (int t = tid; t < w * w; t += 256, ne++) {
+                const int i = t / w, j = t % w;
+                double v;
+                if (i == k && j == k) v = ikk;
+                else if (i == k) v = P[k][j] * ikk;
+                else if (j == k) v = -P[i][k] * ikk;
+                else v = P[i][j] - P[i][k] * P[k][j] * ikk;
+                nv[ne] = v;
+            }
+            __syncthreads();
+            ne = 0;
+            for (int t = tid; t < w * w; t += 256, ne++) P[t / w][t % w] = nv[ne];
+            __syncthreads();
+        }
+        // ---- phase 1
         for (int j = gtid; j < m; j += gsize) {
-            const double a0 = __ldcg(A + (int64_t)p0 * m + j), a1 = __ldcg(A + (int64_t)(p0 + 1) * m + j), a2 = __ldcg(A + (int64_t)(p0 + 2) * m + j);
+            double a[GJ_W];
 #pragma unroll
-            for (int a = 0; a < 3; a++) R[(int64_t)a * m + j] = Pi[a * 3] * a0 + Pi[a * 3 + 1] * a1 + Pi[a * 3 + 2] * a2;
+            for (int l = 0; l < GJ_W; l++) a[l] = l < w ? __ldcg(A + (int64_t)(p0 + l) * m + j) : 0.0;
+            for (int k = 0; k < w; k++) {
+                double s = 0.0;
 #pragma unroll
-            for (int b = 0; b < 3; b++) Cp[(int64_t)j * 3 + b] = __ldcg(A + (int64_t)j * m + p0 + b);
+                for (int l = 0; l < GJ_W; l++) s = fma(P[k][l < w ? l : 0], a[l], s);   // a[l] = 0 beyond w
+                R[(int64_t)k * m + j] = s;
+            }
+            for (int k = 0; k < w; k++) Cp[(int64_t)j * GJ_W + k] = __ldcg(A + (int64_t)j * m + p0 + k);
         }
         grid.sync();
-        for (int i = blockIdx.x; i < m; i += gridDim.x) {
-            const double c0 = __ldcg(Cp + (int64_t)i * 3), c1 = __ldcg(Cp + (int64_t)i * 3 + 1), c2 = __ldcg(Cp + (int64_t)i * 3 + 2);
-            const bool inP = i >= p0 && i < p0 + 3;
-            double *Ai = A + (int64_t)i * m;
-            for (int j = threadIdx.x; j < m; j += blockDim.x) {
-                const bool jin = j >= p0 && j < p0 + 3;
+        // ---- phase 2
+        for (int tile = blockIdx.x; tile < n_rg * n_cc; tile += gridDim.x) {
+            const int i0 = (tile / n_cc) * 8, j = (tile % n_cc) * 256 + tid;
+            __syncthreads();
+            if (tid < 8 * GJ_W) { const int i = i0 + tid / GJ_W; Cs[tid / GJ_W][tid % GJ_W] = (i < m && tid % GJ_W < w) ? __ldcg(Cp + (int64_t)i * GJ_W + tid % GJ_W) : 0.0; }
+            __syncthreads();
+            if (j >= m) continue;
+            const bool jin = j >= p0 && j < p0 + w;
+            double r[GJ_W];
+#pragma unroll
+            for (int k = 0; k < GJ_W; k++) r[k] = (k < w && !jin) ? __ldcg(R + (int64_t)k * m + j) : 0.0;
+#pragma unroll
+            for (int ii = 0; ii < 8; ii++) {
+                const int i = i0 + ii;
+                if (i >= m) break;
+                const bool iin = i >= p0 && i < p0 + w;
                 double v;
-                if (inP && jin) v = Pi[(i - p0) * 3 + (j - p0)];
-                else if (inP) v = __ldcg(R + (int64_t)(i - p0) * m + j);
-                else if (jin) v = -(c0 * Pi[j - p0] + c1 * Pi[3 + j - p0] + c2 * Pi[6 + j - p0]);
-                else v = __ldcg(Ai + j) - (c0 * __ldcg(R + j) + c1 * __ldcg(R + m + j) + c2 * __ldcg(R + 2 * (int64_t)m + j));
-                Ai[j] = v;
+                if (iin && jin) v = P[i - p0][j - p0];
+                else if (iin) v = __ldcg(R + (int64_t)(i - p0) * m + j);
+                else if (jin) {
+                    v = 0.0;
+                    for (int l = 0; l < w; l++) v = fma(-Cs[ii][l], P[l][j - p0], v);
+                } else {
+                    v = __ldcg(A + (int64_t)i * m + j);
+#pragma unroll
+                    for (int k = 0; k < GJ_W; k++) v = fma(-Cs[ii][k], r[k], v);
+                }
+                A[(int64_t)i * m + j] = v;
             }
         }
         grid.sync();
@@ -707,7 +763,7 @@ __global__ void __launch_bounds__(256) k_dense_invert(int m, double *__restrict_
 
 // x_own = Ainv[own rows, :] r  on the coarsest level; r is gathered from all ranks.  One warp per scalar row.
 __global__ void __launch_bounds__(256) k_dense_apply(int64_t n_local, DenseMap dm, int rank, int world, int m, const double *__restrict__ Ainv,
-                                                      XRef rr, double *__restrict__ x, const Scalars *S) {
+                                                      const __grid_constant__ XRef rr, double *__restrict__ x, const Scalars *S) {
     if (ld_done(S)) return;
     extern __shared__ double sr[];
     for (int t = threadIdx.x; t < m; t += 256) {
@@ -772,7 +828,7 @@ __device__ __forceinline__ void xtwy3(const double *X, const double *w, const do
 // diagonal block and gradient in registers, streams the off-diagonal block into the slice blob, and
 // finally writes diag, its inverse (the block-Jacobi preconditioner), r = b = -g and the row position.
 // hz: measurement stream laid out like val with 10 components (z: x y cos sin ; Omega upper 6).
-__global__ void __launch_bounds__(128) k_assemble_se2(LevelDev L, XRef posr, const double *__restrict__ poses, const double *__restrict__ hz,
+__global__ void __launch_bounds__(128) k_assemble_se2(LevelDev L, const __grid_constant__ XRef posr, const double *__restrict__ poses, const double *__restrict__ hz,
                                                        double *__restrict__ rvec, int64_t anchor_row, double anchor_w, double lambda) {
     const int64_t row = (int64_t)blockIdx.x * 128 + threadIdx.x;
     const int lane = threadIdx.x & 31;
@@ -873,7 +929,7 @@ __global__ void __launch_bounds__(128) k_assemble_se2(LevelDev L, XRef posr, con
 // ed: [10][n_edges] planes (z: x y cos sin ; Omega upper 6 -- for XY edges w11 w12 w22 in the first three)
 // ends: .x = local row of `from`, .y = column word of `to` (COL_EDGE_XY marks a pose-landmark edge)
 __global__ void __launch_bounds__(256) k_chi2_se2(int64_t n_edges, const uint2 *__restrict__ ends, const double *__restrict__ ed,
-                                                   const double *__restrict__ poses, XRef posr, Scalars *S, double *partials) {
+                                                   const double *__restrict__ poses, const __grid_constant__ XRef posr, Scalars *S, double *partials) {
     const int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x;
     double c = 0.0;
     if (k < n_edges) {

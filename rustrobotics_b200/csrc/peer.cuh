@@ -6,7 +6,7 @@
 // (ld.acquire.sys); thread 0 adds the partials in rank order (identical bits on every rank) and runs the same scalar
 // recurrence a single GPU runs in the "last block finalises" step.  Because kernels of one stream run in order, every
 // kernel launched after it sees all peers' earlier writes, and no peer can be more than one epoch ahead (values are
-// double-buffered by epoch parity).  A spin that exceeds ~2 s sets ST_COMM and ends the solve instead of hanging.
+// double-buffered by epoch parity).  A spin that exceeds ~20 s sets ST_COMM and ends the solve instead of hanging.
 #pragma once
 #include "kernels.cuh"
 
@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(32) k_xreduce(Comm *mine, CommRef peers, int r
         unsigned long long v;
         do {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(&mine->flags[t]) : "memory");
-            if (v < epoch && clock64() - t0 > 4000000000ll) { bad = 1; break; }
+            if (v < epoch && clock64() - t0 > 40000000000ll) { bad = 1; break; }
         } while (v < epoch);
     }
     __syncthreads();

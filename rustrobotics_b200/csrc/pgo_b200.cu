@@ -156,14 +156,16 @@ inline void xbarrier(pgo_handle *h, int check_done = 1) { xreduce<FIN_NONE>(h, 0
 // ---- SpMV launchers
 template <int MODE, int FIN> void spmv0(pgo_handle *h, const double *x, const double *r, double *y, double omega, const double *u1, int check) {
     LevelBuf &B = h->lv[0];
-    k_spmv<3, MODE, FIN><<<B.grid128, 128, 0, h->stream>>>(B.d, xref(h, x), x, r, y, omega, u1, h->S, h->partials, check);
+    if (h->world > 1) k_spmv<3, MODE, FIN, true><<<B.grid128, 128, 0, h->stream>>>(B.d, xref(h, x), x, r, y, omega, u1, h->S, h->partials, check);
+    else k_spmv<3, MODE, FIN, false><<<B.grid128, 128, 0, h->stream>>>(B.d, xref(h, x), x, r, y, omega, u1, h->S, h->partials, check);
     h->launch_count += 1;
     xreduce<FIN>(h, 0, check);
 }
 template <int MODE, int FIN> void spmvc(pgo_handle *h, int l, const double *x, const double *r, double *y, double omega,
                                         const double *u1, const double *u2, int check) {
     LevelBuf &B = h->lv[l];
-    k_spmv_csr<MODE, FIN><<<B.gridw, 256, 0, h->stream>>>(B.d, xref(h, x), x, r, y, omega, u1, u2, h->S, h->partials, l, check);
+    if (h->world > 1) k_spmv_csr<MODE, FIN, true><<<B.gridw, 256, 0, h->stream>>>(B.d, xref(h, x), x, r, y, omega, u1, u2, h->S, h->partials, l, check);
+    else k_spmv_csr<MODE, FIN, false><<<B.gridw, 256, 0, h->stream>>>(B.d, xref(h, x), x, r, y, omega, u1, u2, h->S, h->partials, l, check);
     h->launch_count += 1;
     xreduce<FIN>(h, l, check);
 }
@@ -474,7 +476,7 @@ void pgo_default_options(pgo_options *o) {
     o->rank = 0;
     o->amg_dense_max = 640;
     o->amg_aggregate_size = 16;
-    o->amg_kcycle = 1;
+    o->amg_kcycle = MAX_LEVELS;
 }
 
 const char *pgo_last_error(const pgo_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -617,7 +619,7 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
                 arena_request(h, &B.v2, vec); arena_request(h, &B.r1, vec);
             }
         }
-        B.kcycle = h->opt.amg_kcycle != 0 && l > 0;
+        B.kcycle = l > 0 && l <= h->opt.amg_kcycle;
     }
     {
         const HostLevel &H0 = S.levels[0];
@@ -641,12 +643,13 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
     if (h->use_amg && S.dense_coarsest) {
         const int m = h->dense_m;
         CKC(dalloc(h, &h->Ainv, (size_t)m * m));
-        CKC(dalloc(h, &h->panelR, (size_t)3 * m));
-        CKC(dalloc(h, &h->panelC, (size_t)3 * m));
+        CKC(dalloc(h, &h->panelR, (size_t)GJ_W * m));
+        CKC(dalloc(h, &h->panelC, (size_t)GJ_W * m));
         int per_sm = 0, sms = 0;
         CKU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dense_invert, 256, 0));
         CKU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
         h->invert_grid = std::max(1, std::min(per_sm, 2) * sms);
+        h->invert_grid = std::min(h->invert_grid, std::max(sms, ((m + 7) / 8) * ((m + 255) / 256)));
         CKU(cudaFuncSetAttribute(k_dense_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 3 * 1024)));
     }
     h->chunk = h->use_amg ? 4 : 16;
@@ -1035,9 +1038,13 @@ int pgo_time_spmv(pgo_handle *h, int32_t repeats, double *avg_ms) {
     LevelBuf &B = h->lv[0];
     // p -> q with the PCG SpMV; done-flag test disabled so the launches always do the work, no cross-rank reduction
     XRef xr = xref(h, h->p);
-    for (int i = 0; i < 3; i++) k_spmv<3, 0, FIN_NONE><<<B.grid128, 128, 0, h->stream>>>(B.d, xr, h->p, nullptr, h->q, 0.0, nullptr, h->S, h->partials, 0);
+    auto launch = [&]() {
+        if (h->world > 1) k_spmv<3, 0, FIN_NONE, true><<<B.grid128, 128, 0, h->stream>>>(B.d, xr, h->p, nullptr, h->q, 0.0, nullptr, h->S, h->partials, 0);
+        else k_spmv<3, 0, FIN_NONE, false><<<B.grid128, 128, 0, h->stream>>>(B.d, xr, h->p, nullptr, h->q, 0.0, nullptr, h->S, h->partials, 0);
+    };
+    for (int i = 0; i < 3; i++) launch();
     CK(cudaEventRecord(h->ev[PGO_NUM_PHASES], h->stream));
-    for (int i = 0; i < repeats; i++) k_spmv<3, 0, FIN_NONE><<<B.grid128, 128, 0, h->stream>>>(B.d, xr, h->p, nullptr, h->q, 0.0, nullptr, h->S, h->partials, 0);
+    for (int i = 0; i < repeats; i++) launch();
     CK(cudaEventRecord(h->ev[PGO_NUM_PHASES + 1], h->stream));
     CK(cudaStreamSynchronize(h->stream));
     float ms = 0;

@@ -53,6 +53,7 @@ def lib():
     L.pgo_set_poses.argtypes = [P, P, i64]
     L.pgo_get_dx.argtypes = [P, P, i64]
     L.pgo_snapshot_poses.argtypes = [P]
+    L.pgo_shard_handle_bytes.restype = C.c_int
     L.pgo_shard_export.argtypes = [P, P, i64]
     L.pgo_shard_connect.argtypes = [P, P, i64]
     L.pgo_get_partition.argtypes = [P, C.POINTER(i32), C.POINTER(i32), P, P]

@@ -43,8 +43,19 @@ def Options(**kw) -> pgo_options:
     return o
 
 
+def gather_handles(mine: bytes, world: int, group=None) -> bytes:
+    """all-gather one fixed-size byte string per rank, concatenated in rank order"""
+    import torch.distributed as dist
+    parts = [None] * world
+    dist.all_gather_object(parts, bytes(mine), group=group)
+    if any(p is None or len(p) != len(mine) for p in parts):
+        raise PgoError("shard handle exchange failed")
+    return b"".join(parts)
+
+
 class PoseGraph:
-    def __init__(self, file_path=None, solver=PoseGraphSolver.GaussNewton, *, graph=None, name="graph", options=None):
+    def __init__(self, file_path=None, solver=PoseGraphSolver.GaussNewton, *, graph=None, name="graph", options=None,
+                 process_group=None):
         L = lib()
         self._pg = None
         self.solver = PoseGraphSolver(solver)
@@ -66,6 +77,11 @@ class PoseGraph:
         self._h = L.pg_handle(self._pg)
         self.norms: list[float] = []
         self.pcg_iterations: list[int] = []
+        self.world = int(options.world) if options is not None else 1
+        self.rank = int(options.rank) if options is not None else 0
+        self._group = process_group
+        if self.world > 1 and options.device != -2:
+            self.connect_shards()
 
     @classmethod
     def new(cls, file_path, solver=PoseGraphSolver.GaussNewton, **kw):
@@ -82,6 +98,34 @@ class PoseGraph:
             self.close()
         except Exception:
             pass
+
+    # ---- sharded handles (one process per GPU) ------------------------------------------
+    def connect_shards(self):
+        """Exchange the ranks' peer-memory handles (torch.distributed is only the plumbing: one all-gather of
+        64 bytes per rank at start-up) and connect the shards.  Afterwards every computing call is collective."""
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise PgoError("sharded PoseGraph (options.world > 1) needs an initialised torch.distributed process group")
+        if dist.get_world_size(self._group) != self.world or dist.get_rank(self._group) != self.rank:
+            raise PgoError("options.world / options.rank do not match the process group")
+        n = lib().pgo_shard_handle_bytes()
+        buf = C.create_string_buffer(n)
+        self._check(lib().pgo_shard_export(self._h, buf, n), "pgo_shard_export")
+        blob = gather_handles(buf.raw, self.world, self._group)
+        self._check(lib().pgo_shard_connect(self._h, blob, self.world), "pgo_shard_connect")
+        dist.barrier(self._group)      # every rank has opened every arena before the first peer read
+
+    def _merge_owned(self, out):
+        """sharded getters fill the span this rank owns: sum the (disjoint, zero elsewhere) spans over ranks"""
+        if self.world == 1:
+            return out
+        import torch
+        import torch.distributed as dist
+        t = torch.from_numpy(out)
+        if dist.get_backend(self._group) == "nccl":
+            t = t.cuda()
+        dist.all_reduce(t, group=self._group)
+        return t.cpu().numpy()
 
     # ---- reference API ----------------------------------------------------------------------
     def optimize(self, num_iterations, log=False, plot=False):
@@ -123,9 +167,9 @@ class PoseGraph:
 
     def poses(self):
         """vertex values in the input packing (x y theta | x y), lut order."""
-        out = np.empty(self.sizes()[3])
+        out = np.zeros(self.sizes()[3])
         self._check(lib().pgo_get_poses(self._h, ptr(out), len(out)), "pgo_get_poses")
-        return out
+        return self._merge_owned(out)
 
     def set_poses(self, values):
         v = np.ascontiguousarray(values, np.float64)
@@ -150,14 +194,12 @@ class PoseGraph:
     def linearize_and_solve(self):
         it = C.c_int32()
         self._check(lib().pgo_linearize_and_solve(self._h, C.byref(it)), "pgo_linearize_and_solve")
-        dx = np.empty(self.len)
-        self._check(lib().pgo_get_dx(self._h, ptr(dx), len(dx)), "pgo_get_dx")
-        return dx, it.value
+        return self.dx(), it.value
 
     def dx(self):
-        dx = np.empty(self.len)
+        dx = np.zeros(self.len)
         self._check(lib().pgo_get_dx(self._h, ptr(dx), len(dx)), "pgo_get_dx")
-        return dx
+        return self._merge_owned(dx)
 
     def pattern(self):
         n, nnz = C.c_int64(), C.c_int64()
@@ -181,9 +223,9 @@ class PoseGraph:
 
     def system(self, lam=0.0, add_lambda=False):
         cp, ri = self.pattern()
-        vals = np.empty(len(ri)); b = np.empty(self.len)
+        vals = np.zeros(len(ri)); b = np.zeros(self.len)
         self._check(lib().pgo_get_system(self._h, lam, int(add_lambda), ptr(vals), ptr(b)), "pgo_get_system")
-        return cp, ri, vals, b
+        return cp, ri, self._merge_owned(vals), self._merge_owned(b)
 
     def timings(self):
         ms = np.zeros(6); ln = np.zeros(6, np.int64)

@@ -9,6 +9,5 @@ timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_$tag.json 2>
 cat gpurun_out/bench_$tag.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_$tag.csv \
     python tools/profile_step.py --pcg-iters 16 > gpurun_out/ncu_launches_$tag.log 2>&1; echo "ncu list rc=$?"
-timeout 600 ncu --set full --clock-control none --import-source on -k "regex:^k_spmv$" -s 12 -c 3 -f -o gpurun_out/prof_spmv_$tag \
-    python tools/profile_step.py --pcg-iters 16 > gpurun_out/ncu_full_$tag.log 2>&1; echo "ncu full rc=$?"
+bash tools/gpu_ncu_spmv.sh $tag
 ls -la gpurun_out | tail -12
