@@ -49,7 +49,7 @@ struct LevelDev {
     double *pos;                 // [2][n_pad] planes: position of each row (centroid on coarse levels)
     double *lev;                 // [n_pad][2]: lever arm of each row about its aggregate's centroid (peer-visible)
     const uint8_t *vkind;        // level 0 only (nullptr on coarse levels)
-    const int32_t *agg; const int32_t *ctgt;                        // towards the coarser level (local indices)
+    const int32_t *agg; const int32_t *ctgt; const int32_t *cstr;   // towards the coarser level (local indices)
     const int64_t *mem_ptr; const int32_t *mem_idx;                 // members in the finer level (local rows)
 };
 
@@ -185,10 +185,11 @@ template <int NT, int FIN> __device__ __forceinline__ void reduce_and_finalize(c
 //   MODE 0: y = H x                      (+ x.y  -> FIN_PQ)
 //   MODE 1: y = r - H x                  (residual)
 //   MODE 2: y = x + omega Dinv (r - H x) (damped block-Jacobi sweep; + r.y -> FIN_RZ_INIT, + {r.y, y.u1} -> FIN_RZ)
+// Large coarse levels use the same kernel (K-cycle dots FIN_K1 / FIN_K2 as in k_spmv_csr).
 template <int D, int MODE, int FIN, bool PEER>
 __global__ void __launch_bounds__(128) k_spmv(LevelDev L, const __grid_constant__ XRef xr, const double *__restrict__ x, const double *__restrict__ r,
-                                               double *__restrict__ y, double omega, const double *__restrict__ u1,
-                                               Scalars *S, double *partials, int check_done) {
+                                               double *__restrict__ y, double omega, const double *__restrict__ u1, const double *__restrict__ u2,
+                                               Scalars *S, double *partials, int lvl, int check_done) {
     if (check_done && ld_done(S)) return;
     constexpr int DD = D * D, VS = VecStride<D>::value;
     const int64_t row = (int64_t)blockIdx.x * 128 + threadIdx.x;
@@ -244,14 +245,29 @@ __global__ void __launch_bounds__(128) k_spmv(LevelDev L, const __grid_constant_
             cnt = cnt_nxt;
         }
     }
-    double dots[2] = {0.0, 0.0};
+    double dots[3] = {0.0, 0.0, 0.0};
     if (live) {
         double out[VS];
 #pragma unroll
         for (int a = 0; a < VS; a++) out[a] = 0.0;
         if (MODE == 0) {
 #pragma unroll
-            for (int a = 0; a < D; a++) { out[a] = acc[a]; dots[0] = fma(xi[a], acc[a], dots[0]); }
+            for (int a = 0; a < D; a++) out[a] = acc[a];
+            if (FIN == FIN_K1) {
+                double ui[VS];
+                ld_vec<VS>(u1 + row * VS, ui);
+#pragma unroll
+                for (int a = 0; a < D; a++) { dots[0] = fma(xi[a], acc[a], dots[0]); dots[1] = fma(xi[a], ui[a], dots[1]); }
+            } else if (FIN == FIN_K2) {
+                double ui[VS], wi[VS];
+                ld_vec<VS>(u1 + row * VS, ui);
+                ld_vec<VS>(u2 + row * VS, wi);
+#pragma unroll
+                for (int a = 0; a < D; a++) { dots[0] = fma(xi[a], ui[a], dots[0]); dots[1] = fma(xi[a], acc[a], dots[1]); dots[2] = fma(xi[a], wi[a], dots[2]); }
+            } else {
+#pragma unroll
+                for (int a = 0; a < D; a++) dots[0] = fma(xi[a], acc[a], dots[0]);
+            }
         } else {
             double ri[VS];
             ld_vec<VS>(r + row * VS, ri);
@@ -281,23 +297,26 @@ __global__ void __launch_bounds__(128) k_spmv(LevelDev L, const __grid_constant_
         }
         st_vec<VS>(y + row * VS, out);
     }
-    reduce_and_finalize<128, FIN>(dots, S, partials, 0);
+    reduce_and_finalize<128, FIN>(dots, S, partials, lvl);
 }
 
-// Coarse levels: block CSR, one warp per block row (8 rows per CTA).  Same modes; K-cycle dots:
+// Coarse levels (L2-resident, latency-bound): block CSR, LPR lanes per block row (8 when rows are short, else a full
+// warp), 256 / LPR rows per CTA.  Same modes; K-cycle dots:
 //   FIN_K1: {x.y, x.u1}    FIN_K2: {x.u1, x.y, x.u2}      (x = c, y = H c)
-template <int MODE, int FIN, bool PEER>
+template <int MODE, int FIN, bool PEER, int LPR>
 __global__ void __launch_bounds__(256) k_spmv_csr(LevelDev L, const __grid_constant__ XRef xr, const double *__restrict__ x, const double *__restrict__ r,
                                                    double *__restrict__ y, double omega, const double *__restrict__ u1,
                                                    const double *__restrict__ u2, Scalars *S, double *partials, int lvl, int check_done) {
     if (check_done && ld_done(S)) return;
-    const int lane = threadIdx.x & 31;
-    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int sub = threadIdx.x & (LPR - 1);
+    const int64_t row = (int64_t)blockIdx.x * (256 / LPR) + threadIdx.x / LPR;
     double dots[3] = {0.0, 0.0, 0.0};
-    if (row < L.n) {
-        double a0 = 0, a1 = 0, a2 = 0;
+    // whole warps take the branch together (LPR divides 32 and rows beyond n only occur at the tail)
+    const bool live = row < L.n;
+    double a0 = 0, a1 = 0, a2 = 0;
+    if (live) {
         const int64_t b = L.slice_ptr[row], e = L.slice_ptr[row + 1];
-        for (int64_t s = b + lane; s < e; s += 32) {
+        for (int64_t s = b + sub; s < e; s += LPR) {
             const uint32_t c = __ldg(L.col + s);
             double xj[4];
             ld_vec<4>(PEER ? xgather<4>(xr, c) : x + (int64_t)(c & COL_LOCAL_MASK) * 4, xj);
@@ -306,51 +325,54 @@ __global__ void __launch_bounds__(256) k_spmv_csr(LevelDev L, const __grid_const
             a1 = fma(v[3], xj[0], fma(v[4], xj[1], fma(v[5], xj[2], a1)));
             a2 = fma(v[6], xj[0], fma(v[7], xj[1], fma(v[8], xj[2], a2)));
         }
-        a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
-        if (lane == 0) {
-            double xi[4], out[4] = {0, 0, 0, 0};
-            ld_vec<4>(x + row * 4, xi);
-            const double *dg = L.diag + row;
-            double acc[3] = {a0, a1, a2};
+    }
 #pragma unroll
-            for (int a = 0; a < 3; a++)
+    for (int o = LPR / 2; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    if (live && sub == 0) {
+        double xi[4], out[4] = {0, 0, 0, 0};
+        ld_vec<4>(x + row * 4, xi);
+        const double *dg = L.diag + row;
+        double acc[3] = {a0, a1, a2};
 #pragma unroll
-                for (int q = 0; q < 3; q++) acc[a] = fma(dg[(int64_t)(a * 3 + q) * L.n_pad], xi[q], acc[a]);
-            if (MODE == 0) {
+        for (int a = 0; a < 3; a++)
 #pragma unroll
-                for (int a = 0; a < 3; a++) out[a] = acc[a];
-                if (FIN == FIN_K1) {
-                    double ui[4];
-                    ld_vec<4>(u1 + row * 4, ui);
+            for (int q = 0; q < 3; q++) acc[a] = fma(dg[(int64_t)(a * 3 + q) * L.n_pad], xi[q], acc[a]);
+        if (MODE == 0) {
 #pragma unroll
-                    for (int a = 0; a < 3; a++) { dots[0] = fma(xi[a], acc[a], dots[0]); dots[1] = fma(xi[a], ui[a], dots[1]); }
-                } else if (FIN == FIN_K2) {
-                    double ui[4], wi[4];
-                    ld_vec<4>(u1 + row * 4, ui);
-                    ld_vec<4>(u2 + row * 4, wi);
+            for (int a = 0; a < 3; a++) out[a] = acc[a];
+            if (FIN == FIN_K1) {
+                double ui[4];
+                ld_vec<4>(u1 + row * 4, ui);
 #pragma unroll
-                    for (int a = 0; a < 3; a++) { dots[0] = fma(xi[a], ui[a], dots[0]); dots[1] = fma(xi[a], acc[a], dots[1]); dots[2] = fma(xi[a], wi[a], dots[2]); }
-                }
+                for (int a = 0; a < 3; a++) { dots[0] = fma(xi[a], acc[a], dots[0]); dots[1] = fma(xi[a], ui[a], dots[1]); }
+            } else if (FIN == FIN_K2) {
+                double ui[4], wi[4];
+                ld_vec<4>(u1 + row * 4, ui);
+                ld_vec<4>(u2 + row * 4, wi);
+#pragma unroll
+                for (int a = 0; a < 3; a++) { dots[0] = fma(xi[a], ui[a], dots[0]); dots[1] = fma(xi[a], acc[a], dots[1]); dots[2] = fma(xi[a], wi[a], dots[2]); }
+            }
+        } else {
+            double ri[4];
+            ld_vec<4>(r + row * 4, ri);
+            if (MODE == 1) {
+#pragma unroll
+                for (int a = 0; a < 3; a++) out[a] = ri[a] - acc[a];
             } else {
-                double ri[4];
-                ld_vec<4>(r + row * 4, ri);
-                if (MODE == 1) {
+                const double *di = L.dinv + row;
+                double t[3] = {ri[0] - acc[0], ri[1] - acc[1], ri[2] - acc[2]};
 #pragma unroll
-                    for (int a = 0; a < 3; a++) out[a] = ri[a] - acc[a];
-                } else {
-                    const double *di = L.dinv + row;
-                    double t[3] = {ri[0] - acc[0], ri[1] - acc[1], ri[2] - acc[2]};
+                for (int a = 0; a < 3; a++) {
+                    double s = 0.0;
 #pragma unroll
-                    for (int a = 0; a < 3; a++) {
-                        double s = 0.0;
-#pragma unroll
-                        for (int q = 0; q < 3; q++) s = fma(di[(int64_t)(a * 3 + q) * L.n_pad], t[q], s);
-                        out[a] = fma(omega, s, xi[a]);
-                    }
+                    for (int q = 0; q < 3; q++) s = fma(di[(int64_t)(a * 3 + q) * L.n_pad], t[q], s);
+                    out[a] = fma(omega, s, xi[a]);
                 }
             }
-            st_vec<4>(y + row * 4, out);
         }
+        st_vec<4>(y + row * 4, out);
     }
     reduce_and_finalize<256, FIN>(dots, S, partials, lvl);
 }
@@ -522,16 +544,11 @@ __device__ __forceinline__ void ptap3(const double *h, double dxi, double dyi, d
     }
 }
 
-__device__ __forceinline__ void galerkin_scatter(const LevelDev &C, int32_t tgt, const double *g) {
-    if (tgt < 0) {
-        double *dst = C.diag + (int64_t)(-1 - tgt);
+__device__ __forceinline__ void galerkin_scatter(const LevelDev &C, int32_t tgt, int32_t stride, const double *g) {
+    double *dst = tgt < 0 ? C.diag + (int64_t)(-1 - tgt) : C.val + (int64_t)tgt;
+    const int64_t st = tgt < 0 ? C.n_pad : (int64_t)stride;
 #pragma unroll
-        for (int q = 0; q < 9; q++) atomicAdd(dst + (int64_t)q * C.n_pad, g[q]);
-    } else {
-        double *dst = C.val + (int64_t)tgt * 9;
-#pragma unroll
-        for (int q = 0; q < 9; q++) atomicAdd(dst + q, g[q]);
-    }
+    for (int q = 0; q < 9; q++) atomicAdd(dst + (int64_t)q * st, g[q]);
 }
 
 // Galerkin product Hc = P^T H P: every fine block adds P_i^T H_ij P_j into the coarse block of (agg i, agg j), which
@@ -554,7 +571,7 @@ __global__ void __launch_bounds__(128) k_galerkin3_jds(LevelDev F, LevelDev C, c
 #pragma unroll
         for (int q = 0; q < 9; q++) h[q] = F.diag[(int64_t)q * F.n_pad + row];
         ptap3(h, dxi, dyi, pzi, dxi, dyi, pzi, g);
-        galerkin_scatter(C, -1 - F.agg[row], g);
+        galerkin_scatter(C, -1 - F.agg[row], 0, g);
     }
     const int64_t base = F.slice_ptr[slice];
     int64_t off = 0;
@@ -572,7 +589,7 @@ __global__ void __launch_bounds__(128) k_galerkin3_jds(LevelDev F, LevelDev C, c
             // the neighbour is a landmark iff this is a pose-landmark edge seen from its pose (`from`) side
             const double pzj = ((cw & COL_EDGE_XY) && !(cw & COL_ROLE_TO)) ? 0.0 : 1.0;
             ptap3(h, dxi, dyi, pzi, lj.x, lj.y, pzj, g);
-            galerkin_scatter(C, F.ctgt[slot], g);
+            galerkin_scatter(C, F.ctgt[slot], F.cstr[slot], g);
         }
         off += cnt;
     }
@@ -589,7 +606,7 @@ __global__ void __launch_bounds__(256) k_galerkin3_csr(LevelDev F, LevelDev C, c
 #pragma unroll
         for (int q = 0; q < 9; q++) h[q] = F.diag[(int64_t)q * F.n_pad + row];
         ptap3(h, l.x, l.y, 1.0, l.x, l.y, 1.0, g);
-        galerkin_scatter(C, -1 - F.agg[row], g);
+        galerkin_scatter(C, -1 - F.agg[row], 0, g);
     }
     for (int64_t s = F.slice_ptr[row] + lane; s < F.slice_ptr[row + 1]; s += 32) {
         const double2 lj = *reinterpret_cast<const double2 *>(xgather<2>(levr, F.col[s]));
@@ -598,7 +615,7 @@ __global__ void __launch_bounds__(256) k_galerkin3_csr(LevelDev F, LevelDev C, c
 #pragma unroll
         for (int q = 0; q < 9; q++) h[q] = v[q];
         ptap3(h, l.x, l.y, 1.0, lj.x, lj.y, 1.0, g);
-        galerkin_scatter(C, F.ctgt[s], g);
+        galerkin_scatter(C, F.ctgt[s], F.cstr[s], g);
     }
 }
 

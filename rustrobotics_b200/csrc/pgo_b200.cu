@@ -48,7 +48,7 @@ struct LevelBuf {
     double *rhs = nullptr, *sol = nullptr, *xa = nullptr, *res = nullptr;      // cycle work vectors
     double *c1 = nullptr, *c2 = nullptr, *v1 = nullptr, *v2 = nullptr, *r1 = nullptr;   // K-cycle work vectors
     double omega = 0.6;
-    int grid128 = 0, gridw = 0, gridv = 0;
+    int grid128 = 0, gridw = 0, gridv = 0, grid8 = 0, lpr = 32;
 };
 
 struct ArenaReq { double **p; size_t count; };
@@ -153,25 +153,28 @@ template <int FIN> void xreduce(pgo_handle *h, int lvl, int check_done) {
 }
 inline void xbarrier(pgo_handle *h, int check_done = 1) { xreduce<FIN_NONE>(h, 0, check_done); }
 
-// ---- SpMV launchers
-template <int MODE, int FIN> void spmv0(pgo_handle *h, const double *x, const double *r, double *y, double omega, const double *u1, int check) {
-    LevelBuf &B = h->lv[0];
-    if (h->world > 1) k_spmv<3, MODE, FIN, true><<<B.grid128, 128, 0, h->stream>>>(B.d, xref(h, x), x, r, y, omega, u1, h->S, h->partials, check);
-    else k_spmv<3, MODE, FIN, false><<<B.grid128, 128, 0, h->stream>>>(B.d, xref(h, x), x, r, y, omega, u1, h->S, h->partials, check);
-    h->launch_count += 1;
-    xreduce<FIN>(h, 0, check);
-}
-template <int MODE, int FIN> void spmvc(pgo_handle *h, int l, const double *x, const double *r, double *y, double omega,
-                                        const double *u1, const double *u2, int check) {
+// ---- SpMV launcher: sliced storage (level 0 and large coarse levels) or block CSR
+template <int MODE, int FIN> void spmv(pgo_handle *h, int l, const double *x, const double *r, double *y, double omega,
+                                       const double *u1, const double *u2, int check) {
     LevelBuf &B = h->lv[l];
-    if (h->world > 1) k_spmv_csr<MODE, FIN, true><<<B.gridw, 256, 0, h->stream>>>(B.d, xref(h, x), x, r, y, omega, u1, u2, h->S, h->partials, l, check);
-    else k_spmv_csr<MODE, FIN, false><<<B.gridw, 256, 0, h->stream>>>(B.d, xref(h, x), x, r, y, omega, u1, u2, h->S, h->partials, l, check);
+    const XRef xr = xref(h, x);
+    if (B.jds) {
+        if (h->world > 1) k_spmv<3, MODE, FIN, true><<<B.grid128, 128, 0, h->stream>>>(B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
+        else k_spmv<3, MODE, FIN, false><<<B.grid128, 128, 0, h->stream>>>(B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
+    } else {
+        if (B.lpr == 8) {
+            if (h->world > 1) k_spmv_csr<MODE, FIN, true, 8><<<B.grid8, 256, 0, h->stream>>>(B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
+            else k_spmv_csr<MODE, FIN, false, 8><<<B.grid8, 256, 0, h->stream>>>(B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
+        } else {
+            if (h->world > 1) k_spmv_csr<MODE, FIN, true, 32><<<B.gridw, 256, 0, h->stream>>>(B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
+            else k_spmv_csr<MODE, FIN, false, 32><<<B.gridw, 256, 0, h->stream>>>(B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
+        }
+    }
     h->launch_count += 1;
     xreduce<FIN>(h, l, check);
 }
 template <int MODE> void spmv_any(pgo_handle *h, int l, const double *x, const double *r, double *y, double omega, int check) {
-    if (h->lv[l].jds) spmv0<MODE, FIN_NONE>(h, x, r, y, omega, nullptr, check);
-    else spmvc<MODE, FIN_NONE>(h, l, x, r, y, omega, nullptr, nullptr, check);
+    spmv<MODE, FIN_NONE>(h, l, x, r, y, omega, nullptr, nullptr, check);
 }
 
 void coarse_solve(pgo_handle *h, int l, const double *rhs, double *out);
@@ -213,8 +216,7 @@ template <int FINK> void cycle(pgo_handle *h, int l, const double *rhs, double *
     k_prolong3<<<B.grid128, 128, 0, h->stream>>>(B.d, C.sol, B.xa, h->S);
     h->launch_count += 1;
     xbarrier(h);
-    if (l == 0) spmv0<2, FINK>(h, B.xa, rhs, out, B.omega, FINK == FIN_RZ ? h->q : nullptr, 1);
-    else spmvc<2, FIN_NONE>(h, l, B.xa, rhs, out, B.omega, nullptr, nullptr, 1);
+    spmv<2, FINK>(h, l, B.xa, rhs, out, B.omega, FINK == FIN_RZ ? h->q : nullptr, nullptr, 1);
     if (FINK == FIN_NONE) xbarrier(h);               // FINK != NONE: the all-reduce is the barrier
 }
 
@@ -224,10 +226,10 @@ void coarse_solve(pgo_handle *h, int l, const double *rhs, double *out) {
     const int last = (int)h->lv.size() - 1;
     if (l == last || !B.kcycle) { cycle<FIN_NONE>(h, l, rhs, out); return; }
     cycle<FIN_NONE>(h, l, rhs, B.c1);
-    spmvc<0, FIN_K1>(h, l, B.c1, nullptr, B.v1, 0.0, rhs, nullptr, 1);
+    spmv<0, FIN_K1>(h, l, B.c1, nullptr, B.v1, 0.0, rhs, nullptr, 1);
     k_kcombine<0><<<B.gridv, 256, 0, h->stream>>>(B.d.n_pad, rhs, B.v1, B.r1, h->S, l);
     cycle<FIN_NONE>(h, l, B.r1, B.c2);
-    spmvc<0, FIN_K2>(h, l, B.c2, nullptr, B.v2, 0.0, B.v1, B.r1, 1);
+    spmv<0, FIN_K2>(h, l, B.c2, nullptr, B.v2, 0.0, B.v1, B.r1, 1);
     k_kcombine<1><<<B.gridv, 256, 0, h->stream>>>(B.d.n_pad, B.c1, B.c2, out, h->S, l);
     h->launch_count += 2;
 }
@@ -249,7 +251,7 @@ template <int FINK> void precondition(pgo_handle *h) {   // z = M^-1 r (+ r.z, z
 
 void pcg_iteration(pgo_handle *h) {
     LevelBuf &B = h->lv[0];
-    spmv0<0, FIN_PQ>(h, h->p, nullptr, h->q, 0.0, nullptr, 1);
+    spmv<0, FIN_PQ>(h, 0, h->p, nullptr, h->q, 0.0, nullptr, nullptr, 1);
     k_update_xr<3><<<B.gridv, 256, 0, h->stream>>>(B.d.n_pad, h->x, h->r, h->p, h->q, h->S);
     precondition<FIN_RZ>(h);
     k_update_p<3><<<B.gridv, 256, 0, h->stream>>>(B.d.n_pad, h->p, h->z, h->S);
@@ -563,6 +565,8 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
         for (int k = 0; k < world; k++) max_pad = std::max(max_pad, H.part_off[k + 1] - H.part_off[k]);
         B.grid128 = grid_for(d.n_pad, 128);
         B.gridw = grid_for(d.n_pad, 8);
+        B.grid8 = grid_for(d.n_pad, 32);
+        B.lpr = (!H.jds && d.n > 0 && d.n_slots <= 12 * d.n) ? 8 : 32;     // short rows: 8 lanes per row
         B.gridv = grid_for(d.n_pad * 2, 256);
         max_grid = std::max<int64_t>(max_grid, std::max(B.grid128, B.gridw));
         // row pointers
@@ -590,11 +594,11 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
             HostLevel &Cn = S.levels[l + 1];
             std::vector<int32_t> ag(d.n_pad, -1);
             for (int64_t r = r0; r < r1; r++) if (H.agg[r] >= 0) ag[r - r0] = (int32_t)(H.agg[r] - Cn.part_off[rank]);
-            std::vector<int32_t> ct(H.ctgt.begin() + s0, H.ctgt.begin() + s1);
-            if (ct.empty()) ct.push_back(0);
-            int32_t *dag, *dct;
-            CKC(upload(h, &dag, ag)); CKC(upload(h, &dct, ct));
-            d.agg = dag; d.ctgt = dct;
+            std::vector<int32_t> ct(H.ctgt.begin() + s0, H.ctgt.begin() + s1), cs(H.cstr.begin() + s0, H.cstr.begin() + s1);
+            if (ct.empty()) { ct.push_back(0); cs.push_back(1); }
+            int32_t *dag, *dct, *dcs;
+            CKC(upload(h, &dag, ag)); CKC(upload(h, &dct, ct)); CKC(upload(h, &dcs, cs));
+            d.agg = dag; d.ctgt = dct; d.cstr = dcs;
         }
         if (!H.mem_ptr.empty()) {
             HostLevel &Fn = S.levels[l - 1];
@@ -731,7 +735,7 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
 #undef CKC
 #undef CKU
     // the big transient host arrays are not needed any more
-    for (auto &L : S.levels) { L.ctgt.clear(); L.ctgt.shrink_to_fit(); }
+    for (auto &L : S.levels) { L.ctgt.clear(); L.ctgt.shrink_to_fit(); L.cstr.clear(); L.cstr.shrink_to_fit(); }
     *out = h;
     return PGO_OK;
 }
@@ -1039,8 +1043,8 @@ int pgo_time_spmv(pgo_handle *h, int32_t repeats, double *avg_ms) {
     // p -> q with the PCG SpMV; done-flag test disabled so the launches always do the work, no cross-rank reduction
     XRef xr = xref(h, h->p);
     auto launch = [&]() {
-        if (h->world > 1) k_spmv<3, 0, FIN_NONE, true><<<B.grid128, 128, 0, h->stream>>>(B.d, xr, h->p, nullptr, h->q, 0.0, nullptr, h->S, h->partials, 0);
-        else k_spmv<3, 0, FIN_NONE, false><<<B.grid128, 128, 0, h->stream>>>(B.d, xr, h->p, nullptr, h->q, 0.0, nullptr, h->S, h->partials, 0);
+        if (h->world > 1) k_spmv<3, 0, FIN_NONE, true><<<B.grid128, 128, 0, h->stream>>>(B.d, xr, h->p, nullptr, h->q, 0.0, nullptr, nullptr, h->S, h->partials, 0, 0);
+        else k_spmv<3, 0, FIN_NONE, false><<<B.grid128, 128, 0, h->stream>>>(B.d, xr, h->p, nullptr, h->q, 0.0, nullptr, nullptr, h->S, h->partials, 0, 0);
     };
     for (int i = 0; i < 3; i++) launch();
     CK(cudaEventRecord(h->ev[PGO_NUM_PHASES], h->stream));

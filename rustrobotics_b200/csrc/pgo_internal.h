@@ -49,7 +49,8 @@ struct HostLevel {
     // aggregation towards the next coarser level (empty on the coarsest)
     std::vector<int32_t> agg;         // [n_pad] coarse global padded row of each row (-1 for padding rows)
     std::vector<int32_t> ctgt;        // [n_slots] Galerkin target of each stored block, LOCAL to the owning partition:
-                                      //   >= 0: slot of the coarse level ; < 0: diagonal of coarse row (-1 - row)
+                                      //   >= 0: element offset of component 0 in the coarse val array ; < 0: diagonal of coarse row (-1 - row)
+    std::vector<int32_t> cstr;        // [n_slots] stride between the 9 components of that target (1: CSR ; cnt: sliced storage)
     // this level seen as the coarse side of the finer level: members (finer global padded rows) of each row
     std::vector<int64_t> mem_ptr;     // [n_pad + 1]
     std::vector<int32_t> mem_idx;
@@ -87,6 +88,7 @@ struct SymbolicOptions {
     int max_levels = 12;
     int agg_size = 16;
     int dense_max = 640;               // a level with at most this many rows is solved directly
+    int64_t jds_min_rows = INT64_MAX;     // coarse levels at least this large use the sliced storage (thread per row), smaller ones block CSR
     bool build_amg = true;
 };
 

@@ -192,7 +192,7 @@ static int32_t aggregate_partition(const HostLevel &F, int k, int max_size, std:
 
 // Build the coarse level (block CSR, global padded numbering) from per-partition aggregate ids; fills F.agg, F.ctgt.
 static void build_coarse_level(HostLevel &F, HostLevel &C, const std::vector<std::vector<int32_t>> &pagg,
-                               const std::vector<int64_t> &pnc) {
+                               const std::vector<int64_t> &pnc, bool jds) {
     const int world = (int)pnc.size();
     layout_partitions(C, pnc);
     F.agg.assign(F.n_pad, -1);
@@ -222,9 +222,11 @@ static void build_coarse_level(HostLevel &F, HostLevel &C, const std::vector<std
         C.adj_nbr.insert(C.adj_nbr.end(), tmp.begin(), tmp.end());
         C.adj_ptr[I + 1] = (int64_t)C.adj_nbr.size();
     }
-    build_csr(C);
-    // Galerkin targets of every fine block, local to the owning partition
+    if (jds) build_jds(C); else build_csr(C);
+    // Galerkin targets of every fine block, local to the owning partition: element offset of component 0 of the coarse
+    // block inside the partition's val array + the stride between components (CSR: 9 s, 1 ; JDS: component-major)
     F.ctgt.assign(F.n_slots, 0);
+    F.cstr.assign(F.n_slots, 1);
     for (int k = 0; k < world; k++)
         for (int64_t r = F.part_off[k]; r < F.part_off[k] + F.part_real[k]; r++) {
             const int32_t I = F.agg[r];
@@ -234,9 +236,32 @@ static void build_coarse_level(HostLevel &F, HostLevel &C, const std::vector<std
                 if (I == J) { F.ctgt[slot] = (int32_t)(-1 - (I - C.part_off[k])); continue; }
                 auto b = C.adj_nbr.begin() + C.adj_ptr[I], e = C.adj_nbr.begin() + C.adj_ptr[I + 1];
                 const int64_t q = std::lower_bound(b, e, J) - C.adj_nbr.begin();
-                F.ctgt[slot] = (int32_t)(q - C.part_slot[k]);
+                const int64_t cs = C.adj_slot[q] - C.part_slot[k];
+                if (jds) {
+                    const int64_t lane = I & 31;
+                    F.ctgt[slot] = (int32_t)((cs - lane) * 9 + lane);
+                    F.cstr[slot] = C.adj_cnt[q];
+                } else F.ctgt[slot] = (int32_t)(cs * 9);
             }
         }
+}
+
+// renumber the aggregates of every partition by decreasing coarse degree inside windows (what the sliced storage needs)
+static void sort_aggregates_by_degree(const HostLevel &C, std::vector<std::vector<int32_t>> &pagg, const std::vector<int64_t> &pnc, int window) {
+    const int world = (int)pnc.size();
+    for (int k = 0; k < world; k++) {
+        const int64_t n = pnc[k], r0 = C.part_off[k];
+        std::vector<int32_t> order(n), newid(n);
+        std::iota(order.begin(), order.end(), 0);
+        for (int64_t w = 0; w < n; w += window) {
+            const int64_t e = std::min<int64_t>(n, w + window);
+            std::stable_sort(order.begin() + w, order.begin() + e, [&](int32_t a, int32_t b) {
+                return C.adj_ptr[r0 + a + 1] - C.adj_ptr[r0 + a] > C.adj_ptr[r0 + b + 1] - C.adj_ptr[r0 + b];
+            });
+        }
+        for (int64_t i = 0; i < n; i++) newid[order[i]] = (int32_t)i;
+        for (auto &a : pagg[k]) a = newid[a];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -363,7 +388,14 @@ bool build_symbolic(Symbolic &S, const SymbolicOptions &opt,
         for (int k = 0; k < world; k++) { pnc[k] = aggregate_partition(S.levels[lvl], k, opt.agg_size, pagg[k]); nc += pnc[k]; }
         if (nc > 0.8 * S.levels[lvl].n) break;                   // coarsening stalled
         S.levels.emplace_back();
-        build_coarse_level(S.levels[lvl], S.levels[lvl + 1], pagg, pnc);
+        build_coarse_level(S.levels[lvl], S.levels[lvl + 1], pagg, pnc, false);
+        if (nc >= opt.jds_min_rows) {
+            // a large coarse level is streamed like level 0: one thread per row over the sliced storage
+            sort_aggregates_by_degree(S.levels[lvl + 1], pagg, pnc, std::max(32, opt.sort_window / 32 * 32));
+            S.levels[lvl + 1] = HostLevel();
+            build_coarse_level(S.levels[lvl], S.levels[lvl + 1], pagg, pnc, true);
+        }
+        if (S.levels[lvl + 1].n_slots * 9 > 0x7fffffffll) { S.error = "coarse level exceeds 32-bit Galerkin targets"; return false; }
     }
     return true;
 }
