@@ -26,7 +26,7 @@ struct Scalars {
     double norm2_dx, chi2;
     int iters, max_iters, done, status;
     unsigned counter[8];            // everything from here on survives the per-solve reset
-    int world, pad_;
+    int world, repl_from;           // sharded handles: levels >= repl_from are replicated (their sums are already global)
     unsigned long long epoch;       // cross-rank barrier epoch (peer.cuh)
     KScal k[MAX_LEVELS];
     double loc[4];                  // sharded mode: this rank's partial sums, reduced across ranks by k_xreduce
@@ -40,6 +40,9 @@ struct XRef { const double *p[MAX_RANKS]; };
 template <int STRIDE> __device__ __forceinline__ const double *xgather(const XRef &x, uint32_t colword) {
     return x.p[(colword >> COL_OWNER_SHIFT) & (MAX_RANKS - 1)] + (int64_t)(colword & COL_LOCAL_MASK) * STRIDE;
 }
+
+// element ranges (rows or stored blocks) produced by each rank on the first replicated level
+struct SegMap { int64_t off[MAX_RANKS + 1]; };
 
 struct LevelDev {
     int64_t n, n_pad, n_slices, n_slots;      // local to this rank
@@ -172,7 +175,7 @@ template <int NT, int FIN> __device__ __forceinline__ void reduce_and_finalize(c
     constexpr int NV = fin_ndot(FIN) > 0 ? fin_ndot(FIN) : 1;
     double total[NV];
     if (block_sum_last<NT, NV>(dots, partials, &S->counter[FIN], total)) {
-        if (S->world > 1) {
+        if (S->world > 1 && lvl < S->repl_from) {
 #pragma unroll
             for (int k = 0; k < NV; k++) S->loc[k] = total[k];
             __threadfence();
@@ -513,7 +516,8 @@ __global__ void __launch_bounds__(256) k_coarse_pos(LevelDev F, LevelDev C) {
     if (I < C.n) {
         const int64_t b = C.mem_ptr[I], e = C.mem_ptr[I + 1];
         for (int64_t m = b + lane; m < e; m += 32) { const int64_t i = C.mem_idx[m]; sx += F.pos[i]; sy += F.pos[F.n_pad + i]; }
-        sx = warp_sum(sx) / (double)(e - b); sy = warp_sum(sy) / (double)(e - b);
+        const double inv = e > b ? 1.0 / (double)(e - b) : 0.0;     // rows built by another rank have no members here
+        sx = warp_sum(sx) * inv; sy = warp_sum(sy) * inv;
     }
     if (lane == 0) { C.pos[I] = sx; C.pos[C.n_pad + I] = sy; }
 }
@@ -798,6 +802,35 @@ __global__ void __launch_bounds__(256) k_dense_apply(int64_t n_local, DenseMap d
     for (int j = lane; j < m; j += 32) s = fma(__ldg(a + j), sr[j], s);
     s = warp_sum(s);
     if (lane == 0) x[(srow / 3) * 4 + (srow % 3)] = s;
+}
+
+// Halo exchange: v[(n_pad + i) * STRIDE ...] <- the record of row halo_src[i] in its owner's copy of v (peer HBM, NVLink).
+// One thread per halo row: independent remote reads, so the NVLink latency is paid once per exchange, not per gather.
+template <int STRIDE>
+__global__ void __launch_bounds__(128) k_halo_pull(double *__restrict__ v, const __grid_constant__ XRef peers, const uint32_t *__restrict__ halo_src,
+                                                    int64_t n_halo, int64_t n_pad, const Scalars *S, int check_done) {
+    if (check_done && ld_done(S)) return;
+    const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (i >= n_halo) return;
+    const double *src = xgather<STRIDE>(peers, halo_src[i]);
+    double *dst = v + (n_pad + i) * STRIDE;
+#pragma unroll
+    for (int c = 0; c < STRIDE; c += 2) *reinterpret_cast<double2 *>(dst + c) = *reinterpret_cast<const double2 *>(src + c);
+}
+
+// First replicated level of a sharded handle: copy the element ranges the OTHER ranks produced from their (identically
+// laid out) arrays in peer HBM.  v has n_planes planes of plane_stride doubles; inside a plane the elements of rank k
+// are [seg.off[k] * comps, seg.off[k+1] * comps).
+__global__ void __launch_bounds__(256) k_gather_peer(double *__restrict__ v, const __grid_constant__ XRef src, const __grid_constant__ SegMap seg,
+                                                      int rank, int world, int comps, int n_planes, int64_t plane_stride,
+                                                      const Scalars *S, int check_done) {
+    if (check_done && ld_done(S)) return;
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= seg.off[world] * comps) return;
+    int k = 0;
+    while (k + 1 < world && i >= seg.off[k + 1] * comps) k++;
+    if (k == rank) return;
+    for (int q = 0; q < n_planes; q++) v[q * plane_stride + i] = src.p[k][q * plane_stride + i];
 }
 
 // ------------------------------------------------------------------------------------------------

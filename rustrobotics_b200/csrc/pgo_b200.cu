@@ -45,6 +45,14 @@ thread_local std::string g_create_error;
 struct LevelBuf {
     LevelDev d{};
     bool jds = false, kcycle = false;
+    bool repl = false;                 // sharded handle: this level is replicated on every rank (no peer traffic inside it)
+    bool first_repl = false;           // ... and the finer level is sharded: rhs / val / diag / pos rows are gathered from the peers
+    SegMap src_rows{}, src_slots{};    // first_repl: row / stored-block ranges produced by each rank
+    // sharded level: rows of other ranks that this rank's blocks reference (the halo).  Their vector records are pulled
+    // from peer HBM into slots n_pad .. n_pad + n_halo of the local vector before a kernel gathers from it.
+    uint32_t *halo_src = nullptr;      // [n_halo] (owner rank << COL_OWNER_SHIFT) | row local to the owner
+    int64_t n_halo = 0;
+    int64_t vec_rows = 0;              // rows (own, padded to the largest partition, + halo) every vector of the level has room for
     double *rhs = nullptr, *sol = nullptr, *xa = nullptr, *res = nullptr;      // cycle work vectors
     double *c1 = nullptr, *c2 = nullptr, *v1 = nullptr, *v2 = nullptr, *r1 = nullptr;   // K-cycle work vectors
     double omega = 0.6;
@@ -63,6 +71,7 @@ struct pgo_handle {
     cudaStream_t stream = nullptr;
     std::vector<LevelBuf> lv;
     std::vector<void *> allocs;
+    std::vector<uint32_t> to_index;    // transient (pgo_create): index of every owned edge's `to` pose in the halo-extended pose array
     size_t device_bytes = 0;
     // peer-visible arena: identical layout on every rank
     char *arena = nullptr;
@@ -81,7 +90,6 @@ struct pgo_handle {
     Scalars *S = nullptr, *hS = nullptr;   // device / pinned host (2 slots)
     double *partials = nullptr;
     double *Ainv = nullptr, *panelR = nullptr, *panelC = nullptr;
-    double *Arows = nullptr;           // peer-visible copy of this rank's rows of the coarsest dense matrix
     DenseMap dmap{};
     int dense_m = 0, invert_grid = 0;
     bool use_amg = false, omega_ready = false;
@@ -136,40 +144,51 @@ int arena_commit(pgo_handle *h) {
     return PGO_OK;
 }
 
-// the same vector on every rank
-XRef xref(const pgo_handle *h, const double *local) {
+// the same vector on every rank (a vector of a replicated level is only ever read locally)
+XRef xref(const pgo_handle *h, const double *local, bool repl = false) {
     XRef x{};
     const size_t off = (const char *)local - h->arena;
-    for (int k = 0; k < h->world; k++) x.p[k] = (const double *)(h->peer_base[k] + off);
-    for (int k = h->world; k < MAX_RANKS; k++) x.p[k] = local;
+    for (int k = 0; k < MAX_RANKS; k++) x.p[k] = (k < h->world && !repl) ? (const double *)(h->peer_base[k] + off) : local;
     return x;
 }
 
 // ---- cross-rank stage barrier / all-reduce of the partial sums a kernel left in S->loc (world > 1 only)
 template <int FIN> void xreduce(pgo_handle *h, int lvl, int check_done) {
-    if (h->world == 1) return;
+    if (h->world == 1 || h->lv[lvl].repl) return;
     k_xreduce<FIN><<<1, 32, 0, h->stream>>>(h->comm, h->comm_ref, h->rank, h->world, h->S, lvl, check_done);
     h->launch_count += 1;
 }
 inline void xbarrier(pgo_handle *h, int check_done = 1) { xreduce<FIN_NONE>(h, 0, check_done); }
+inline void lbarrier(pgo_handle *h, int lvl, int check_done = 1) { xreduce<FIN_NONE>(h, lvl, check_done); }   // no-op on replicated levels
+
+// halo exchange of a sharded level's vector (stride doubles per row): ONE bulk kernel of independent peer reads over NVLink
+// (latency-tolerant), after which every gather of the following kernel is local
+void halo_pull(pgo_handle *h, int l, const double *v, int stride, int check_done) {
+    LevelBuf &B = h->lv[l];
+    if (h->world == 1 || B.repl || B.n_halo == 0) return;
+    double *w = const_cast<double *>(v);
+    if (stride == 4) k_halo_pull<4><<<grid_for(B.n_halo, 128), 128, 0, h->stream>>>(w, xref(h, v), B.halo_src, B.n_halo, B.d.n_pad, h->S, check_done);
+    else k_halo_pull<2><<<grid_for(B.n_halo, 128), 128, 0, h->stream>>>(w, xref(h, v), B.halo_src, B.n_halo, B.d.n_pad, h->S, check_done);
+    h->launch_count += 1;
+}
+
+// first replicated level: pull the rows the other ranks produced (planes of `stride` doubles, `comps` doubles per row/slot)
+void gather_rows(pgo_handle *h, double *v, const SegMap &seg, int comps, int n_planes, int64_t plane_stride, int check_done) {
+    const int64_t total = (int64_t)seg.off[h->world] * comps;
+    if (total == 0) return;
+    k_gather_peer<<<grid_for(total, 256), 256, 0, h->stream>>>(v, xref(h, v), seg, h->rank, h->world, comps, n_planes, plane_stride, h->S, check_done);
+    h->launch_count += 1;
+}
 
 // ---- SpMV launcher: sliced storage (level 0 and large coarse levels) or block CSR
 template <int MODE, int FIN> void spmv(pgo_handle *h, int l, const double *x, const double *r, double *y, double omega,
                                        const double *u1, const double *u2, int check) {
     LevelBuf &B = h->lv[l];
-    const XRef xr = xref(h, x);
-    if (B.jds) {
-        if (h->world > 1) k_spmv<3, MODE, FIN, true><<<B.grid128, 128, 0, h->stream>>>(B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
-        else k_spmv<3, MODE, FIN, false><<<B.grid128, 128, 0, h->stream>>>(B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
-    } else {
-        if (B.lpr == 8) {
-            if (h->world > 1) k_spmv_csr<MODE, FIN, true, 8><<<B.grid8, 256, 0, h->stream>>>(B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
-            else k_spmv_csr<MODE, FIN, false, 8><<<B.grid8, 256, 0, h->stream>>>(B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
-        } else {
-            if (h->world > 1) k_spmv_csr<MODE, FIN, true, 32><<<B.gridw, 256, 0, h->stream>>>(B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
-            else k_spmv_csr<MODE, FIN, false, 32><<<B.gridw, 256, 0, h->stream>>>(B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
-        }
-    }
+    halo_pull(h, l, x, 4, check);                    // the caller's barrier made the peers' x final
+    const XRef xr = xref(h, x, true);
+    if (B.jds) k_spmv<3, MODE, FIN, false><<<B.grid128, 128, 0, h->stream>>>(B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
+    else if (B.lpr == 8) k_spmv_csr<MODE, FIN, false, 8><<<B.grid8, 256, 0, h->stream>>>(B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
+    else k_spmv_csr<MODE, FIN, false, 32><<<B.gridw, 256, 0, h->stream>>>(B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
     h->launch_count += 1;
     xreduce<FIN>(h, l, check);
 }
@@ -180,10 +199,9 @@ template <int MODE> void spmv_any(pgo_handle *h, int l, const double *x, const d
 void coarse_solve(pgo_handle *h, int l, const double *rhs, double *out);
 
 void dense_apply(pgo_handle *h, int l, const double *rhs, double *out) {
-    LevelBuf &B = h->lv[l];
-    xbarrier(h);                                     // every rank's rhs segment is complete
-    k_dense_apply<<<grid_for(B.d.n * 3, 8), 256, sizeof(double) * h->dense_m, h->stream>>>(B.d.n, h->dmap, h->rank, h->world, h->dense_m,
-                                                                                          h->Ainv, xref(h, rhs), out, h->S);
+    LevelBuf &B = h->lv[l];      // always a local (single-GPU or replicated) level
+    k_dense_apply<<<grid_for(B.d.n * 3, 8), 256, sizeof(double) * h->dense_m, h->stream>>>(B.d.n, h->dmap, 0, 1, h->dense_m,
+                                                                                          h->Ainv, xref(h, rhs, true), out, h->S);
     h->launch_count += 1;
 }
 
@@ -197,27 +215,31 @@ template <int FINK> void cycle(pgo_handle *h, int l, const double *rhs, double *
             // no direct solve possible: a few damped block-Jacobi sweeps
             k_dinv_apply<3, FIN_NONE><<<B.grid128, 128, 0, h->stream>>>(B.d, rhs, B.xa, B.omega, nullptr, h->S, h->partials, 1);
             h->launch_count += 1;
-            xbarrier(h);
+            lbarrier(h, l);
             spmv_any<2>(h, l, B.xa, rhs, B.res, B.omega, 1);
-            xbarrier(h);
+            lbarrier(h, l);
             spmv_any<2>(h, l, B.res, rhs, out, B.omega, 1);
-            xbarrier(h);
+            lbarrier(h, l);
         }
         return;
     }
     LevelBuf &C = h->lv[l + 1];
     k_dinv_apply<3, FIN_NONE><<<B.grid128, 128, 0, h->stream>>>(B.d, rhs, B.xa, B.omega, nullptr, h->S, h->partials, 1);
     h->launch_count += 1;
-    xbarrier(h);
+    lbarrier(h, l);
     spmv_any<1>(h, l, B.xa, rhs, B.res, 0.0, 1);
     k_restrict3<<<C.gridw, 256, 0, h->stream>>>(B.d, C.d, B.res, C.rhs, h->S);
     h->launch_count += 1;
+    if (C.first_repl) {                              // every rank restricted onto its own aggregates: all-gather the coarse rhs
+        lbarrier(h, l);
+        gather_rows(h, C.rhs, C.src_rows, 4, 1, 0, 1);
+    }
     coarse_solve(h, l + 1, C.rhs, C.sol);
     k_prolong3<<<B.grid128, 128, 0, h->stream>>>(B.d, C.sol, B.xa, h->S);
     h->launch_count += 1;
-    xbarrier(h);
+    lbarrier(h, l);
     spmv<2, FINK>(h, l, B.xa, rhs, out, B.omega, FINK == FIN_RZ ? h->q : nullptr, nullptr, 1);
-    if (FINK == FIN_NONE) xbarrier(h);               // FINK != NONE: the all-reduce is the barrier
+    if (FINK == FIN_NONE) lbarrier(h, l);            // FINK != NONE: the all-reduce is the barrier
 }
 
 // K-cycle: the coarse system of level l is solved by two flexible-CG steps preconditioned by the cycle of level l
@@ -277,7 +299,8 @@ int build_pcg_graph(pgo_handle *h) {
 int assemble(pgo_handle *h, double lambda, int add_lambda) {
     LevelBuf &B = h->lv[0];
     xbarrier(h, 0);                                  // every rank's poses are final
-    k_assemble_se2<<<B.grid128, 128, 0, h->stream>>>(B.d, xref(h, h->poses), h->poses, h->hz, h->r, h->anchor_row, h->opt.anchor_weight,
+    halo_pull(h, 0, h->poses, 4, 0);
+    k_assemble_se2<<<B.grid128, 128, 0, h->stream>>>(B.d, xref(h, h->poses, true), h->poses, h->hz, h->r, h->anchor_row, h->opt.anchor_weight,
                                                       add_lambda ? lambda : 0.0);
     h->launch_count += 1;
     CK(cudaGetLastError());
@@ -301,9 +324,9 @@ int estimate_omega(pgo_handle *h, int l) {
     double rho = 1.0;
     for (int it = 0; it < 10; it++) {
         // b = H a ; a' = Dinv b ; rho ~ |a'| / |a|
-        xbarrier(h, 0);
+        lbarrier(h, l, 0);
         spmv_any<0>(h, l, a, nullptr, b, 0.0, 0);
-        xbarrier(h, 0);
+        lbarrier(h, l, 0);
         k_dinv_apply<3, FIN_NONE><<<B.grid128, 128, 0, h->stream>>>(B.d, b, a, 1.0, nullptr, h->S, h->partials, 0);
         CK(cudaMemcpyAsync(v.data(), a, nd * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
@@ -330,33 +353,27 @@ int amg_setup(pgo_handle *h) {
         k_lever<<<F.grid128, 128, 0, h->stream>>>(F.d, C.d);
         CK(cudaMemsetAsync(C.d.val, 0, sizeof(double) * 9 * std::max<int64_t>(C.d.n_slots, 1), h->stream));
         CK(cudaMemsetAsync(C.d.diag, 0, sizeof(double) * 9 * C.d.n_pad, h->stream));
-        xbarrier(h, 0);                              // lever arms of neighbour rows on other ranks
-        if (F.jds) k_galerkin3_jds<<<F.grid128, 128, 0, h->stream>>>(F.d, C.d, xref(h, F.d.lev));
-        else k_galerkin3_csr<<<F.gridw, 256, 0, h->stream>>>(F.d, C.d, xref(h, F.d.lev));
+        lbarrier(h, l, 0);                           // lever arms of neighbour rows on other ranks
+        halo_pull(h, l, F.d.lev, 2, 0);
+        if (F.jds) k_galerkin3_jds<<<F.grid128, 128, 0, h->stream>>>(F.d, C.d, xref(h, F.d.lev, true));
+        else k_galerkin3_csr<<<F.gridw, 256, 0, h->stream>>>(F.d, C.d, xref(h, F.d.lev, true));
+        h->launch_count += 3;
+        if (C.first_repl) {                          // every rank built the coarse rows of its own aggregates: all-gather them
+            lbarrier(h, l, 0);
+            gather_rows(h, C.d.val, C.src_slots, 9, 1, 0, 0);
+            gather_rows(h, C.d.diag, C.src_rows, 1, 9, C.d.n_pad, 0);
+            gather_rows(h, C.d.pos, C.src_rows, 1, 2, C.d.n_pad, 0);
+        }
         k_invert_diag3<<<C.grid128, 128, 0, h->stream>>>(C.d);
-        h->launch_count += 4;
+        h->launch_count += 1;
     }
     if (h->sym.dense_coarsest) {
         LevelBuf &C = h->lv[last];
         const int m = h->dense_m;
         CK(cudaMemsetAsync(h->Ainv, 0, sizeof(double) * (size_t)m * m, h->stream));
-        if (C.jds) k_dense_assemble<true><<<C.grid128, 128, 0, h->stream>>>(C.d, h->dmap, h->rank, m, h->Ainv);
-        else k_dense_assemble<false><<<C.grid128, 128, 0, h->stream>>>(C.d, h->dmap, h->rank, m, h->Ainv);
+        if (C.jds) k_dense_assemble<true><<<C.grid128, 128, 0, h->stream>>>(C.d, h->dmap, 0, m, h->Ainv);
+        else k_dense_assemble<false><<<C.grid128, 128, 0, h->stream>>>(C.d, h->dmap, 0, m, h->Ainv);
         h->launch_count += 1;
-        if (h->world > 1) {
-            // publish this rank's rows, then collect everybody else's
-            const size_t row_bytes = sizeof(double) * (size_t)m;
-            const int r0 = h->dmap.off[h->rank] * 3, nr = (h->dmap.off[h->rank + 1] - h->dmap.off[h->rank]) * 3;
-            if (nr > 0) CK(cudaMemcpyAsync(h->Arows, h->Ainv + (size_t)r0 * m, row_bytes * nr, cudaMemcpyDeviceToDevice, h->stream));
-            xbarrier(h, 0);
-            XRef ar = xref(h, h->Arows);
-            for (int k = 0; k < h->world; k++) {
-                if (k == h->rank) continue;
-                const int k0 = h->dmap.off[k] * 3, kn = (h->dmap.off[k + 1] - h->dmap.off[k]) * 3;
-                if (kn > 0) CK(cudaMemcpyAsync(h->Ainv + (size_t)k0 * m, ar.p[k], row_bytes * kn, cudaMemcpyDeviceToDevice, h->stream));
-            }
-            xbarrier(h, 0);
-        }
         void *args[] = {(void *)&h->dense_m, (void *)&h->Ainv, (void *)&h->panelR, (void *)&h->panelC};
         CK(cudaLaunchCooperativeKernel((void *)k_dense_invert, dim3(h->invert_grid), dim3(256), args, 0, h->stream));
         h->launch_count += 1;
@@ -444,7 +461,8 @@ int retract(pgo_handle *h, double sign) {
 
 int chi2_launch(pgo_handle *h) {
     xbarrier(h, 0);
-    k_chi2_se2<<<grid_for(h->n_edges_loc, 256), 256, 0, h->stream>>>(h->n_edges_loc, h->ends, h->ed, h->poses, xref(h, h->poses), h->S, h->partials);
+    halo_pull(h, 0, h->poses, 4, 0);
+    k_chi2_se2<<<grid_for(h->n_edges_loc, 256), 256, 0, h->stream>>>(h->n_edges_loc, h->ends, h->ed, h->poses, xref(h, h->poses, true), h->S, h->partials);
     h->launch_count += 1;
     xreduce<FIN_CHI2>(h, 0, 0);
     CK(cudaGetLastError());
@@ -557,12 +575,27 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
         HostLevel &H = S.levels[l];
         LevelBuf &B = h->lv[l];
         LevelDev &d = B.d;
-        const int64_t r0 = H.part_off[rank], r1 = H.part_off[rank + 1];
-        const int64_t s0 = H.part_slot[rank], s1 = H.part_slot[rank + 1];
+        // a replicated level (sharded handles only) has ONE partition that every rank holds completely
+        B.repl = world > 1 && H.repl;
+        B.first_repl = B.repl && !S.levels[l - 1].repl;
+        if (B.repl && H.jds) return fail_create(h, PGO_ERR_UNSUPPORTED, "replicated levels must be block CSR");
+        const int pk = B.repl ? 0 : rank;              // partition of this level held by this rank
+        const int lworld = (int)H.part_real.size();
+        const int64_t r0 = H.part_off[pk], r1 = H.part_off[pk + 1];
+        const int64_t s0 = H.part_slot[pk], s1 = H.part_slot[pk + 1];
         B.jds = H.jds;
-        d.n = H.part_real[rank]; d.n_pad = r1 - r0; d.n_slots = s1 - s0; d.n_slices = H.jds ? d.n_pad / 32 : 0;
-        int64_t max_pad = 32;
-        for (int k = 0; k < world; k++) max_pad = std::max(max_pad, H.part_off[k + 1] - H.part_off[k]);
+        d.n = H.part_real[pk]; d.n_pad = r1 - r0; d.n_slots = s1 - s0; d.n_slices = H.jds ? d.n_pad / 32 : 0;
+        int64_t max_pad = 32, max_slots = 1;
+        for (int k = 0; k < lworld; k++) {
+            max_pad = std::max(max_pad, H.part_off[k + 1] - H.part_off[k]);
+            max_slots = std::max(max_slots, H.part_slot[k + 1] - H.part_slot[k]);
+        }
+        if (B.first_repl) {
+            for (int k = 0; k <= MAX_RANKS; k++) {
+                const int64_t row = H.src_off[std::min(k, world)];
+                B.src_rows.off[k] = row; B.src_slots.off[k] = H.adj_ptr[row];
+            }
+        }
         B.grid128 = grid_for(d.n_pad, 128);
         B.gridw = grid_for(d.n_pad, 8);
         B.grid8 = grid_for(d.n_pad, 32);
@@ -573,27 +606,65 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
         std::vector<int64_t> rp;
         if (H.jds) { rp.resize(d.n_slices + 1); for (int64_t i = 0; i <= d.n_slices; i++) rp[i] = H.slice_ptr[r0 / 32 + i] - s0; }
         else { rp.resize(d.n_pad + 1); for (int64_t i = 0; i <= d.n_pad; i++) rp[i] = H.adj_ptr[r0 + i] - s0; }
+        // halo of every partition of a sharded level: sorted unique rows of other partitions referenced by its blocks
+        int64_t max_halo = 0;
+        std::vector<int64_t> halo;                     // this rank's, as global padded rows
+        if (lworld > 1) {
+            std::vector<int64_t> tmp;
+            for (int k = 0; k < lworld; k++) {
+                tmp.clear();
+                for (int64_t q = H.adj_ptr[H.part_off[k]]; q < H.adj_ptr[H.part_off[k + 1]]; q++) {
+                    const int64_t nb = H.adj_nbr[q];
+                    if (nb < H.part_off[k] || nb >= H.part_off[k + 1]) tmp.push_back(nb);
+                }
+                std::sort(tmp.begin(), tmp.end());
+                tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+                max_halo = std::max<int64_t>(max_halo, (int64_t)tmp.size());
+                if (k == pk) halo = tmp;
+            }
+            B.n_halo = (int64_t)halo.size();
+            std::vector<uint32_t> hs(std::max<size_t>(halo.size(), 1), 0);
+            for (size_t i = 0; i < halo.size(); i++) { const int ow = H.part_of(halo[i]); hs[i] = ((uint32_t)ow << COL_OWNER_SHIFT) | (uint32_t)(halo[i] - H.part_off[ow]); }
+            CKC(upload(h, &B.halo_src, hs));
+            if (d.n_pad + max_halo > (int64_t)COL_LOCAL_MASK) return fail_create(h, PGO_ERR_ARG, "level too large for the column word");
+        }
+        max_pad += max_halo;                           // every vector of the level has room for the halo records behind its own rows
+        auto local_index = [&](int64_t nb) -> uint32_t {   // index of a neighbour row in this rank's (halo-extended) vectors
+            if (nb >= r0 && nb < r1) return (uint32_t)(nb - r0);
+            return (uint32_t)(d.n_pad + (std::lower_bound(halo.begin(), halo.end(), nb) - halo.begin()));
+        };
         std::vector<int32_t> dg(d.n_pad, 0);
         std::vector<uint32_t> cl(std::max<int64_t>(d.n_slots, 1), 0);
         for (int64_t r = r0; r < r1; r++) {
             dg[r - r0] = (int32_t)(H.adj_ptr[r + 1] - H.adj_ptr[r]);
-            for (int64_t q = H.adj_ptr[r]; q < H.adj_ptr[r + 1]; q++) {
-                const int64_t nb = H.adj_nbr[q];
-                const int ow = H.part_of(nb);
-                cl[H.adj_slot[q] - s0] = ((uint32_t)ow << COL_OWNER_SHIFT) | (uint32_t)(nb - H.part_off[ow]) | (H.adj_flags.empty() ? 0u : H.adj_flags[q]);
+            for (int64_t q = H.adj_ptr[r]; q < H.adj_ptr[r + 1]; q++)
+                cl[H.adj_slot[q] - s0] = local_index(H.adj_nbr[q]) | (H.adj_flags.empty() ? 0u : H.adj_flags[q]);
+        }
+        if (l == 0) {   // the chi2 edge list addresses the `to` pose the same way
+            h->to_index.resize(S.n_edges);
+            for (int64_t e = 0; e < S.n_edges; e++) {
+                const int64_t a = S.iperm[S.efrom[e]], b = S.iperm[S.eto[e]];
+                h->to_index[e] = (a >= r0 && a < r1) ? local_index(b) : 0u;
             }
         }
         int64_t *drp; int32_t *ddg; uint32_t *dcl;
         CKC(upload(h, &drp, rp)); CKC(upload(h, &ddg, dg)); CKC(upload(h, &dcl, cl));
         d.slice_ptr = drp; d.deg = ddg; d.col = dcl;
-        CKC(dalloc(h, &d.val, (size_t)9 * std::max<int64_t>(d.n_slots, 1)));
-        CKC(dalloc(h, &d.diag, (size_t)9 * d.n_pad));
+        if (B.first_repl) {   // gathered from the peers after the Galerkin product: peer-visible
+            arena_request(h, &d.val, (size_t)9 * max_slots);
+            arena_request(h, &d.diag, (size_t)9 * max_pad);
+            arena_request(h, &d.pos, (size_t)2 * max_pad);
+        } else {
+            CKC(dalloc(h, &d.val, (size_t)9 * std::max<int64_t>(d.n_slots, 1)));
+            CKC(dalloc(h, &d.diag, (size_t)9 * d.n_pad));
+            CKC(dalloc(h, &d.pos, (size_t)2 * d.n_pad));
+        }
         CKC(dalloc(h, &d.dinv, (size_t)9 * d.n_pad));
-        CKC(dalloc(h, &d.pos, (size_t)2 * d.n_pad));
         if (!H.agg.empty()) {
             HostLevel &Cn = S.levels[l + 1];
+            const int64_t c0 = Cn.part_off[(world > 1 && Cn.repl) ? 0 : rank];
             std::vector<int32_t> ag(d.n_pad, -1);
-            for (int64_t r = r0; r < r1; r++) if (H.agg[r] >= 0) ag[r - r0] = (int32_t)(H.agg[r] - Cn.part_off[rank]);
+            for (int64_t r = r0; r < r1; r++) if (H.agg[r] >= 0) ag[r - r0] = (int32_t)(H.agg[r] - c0);
             std::vector<int32_t> ct(H.ctgt.begin() + s0, H.ctgt.begin() + s1), cs(H.cstr.begin() + s0, H.cstr.begin() + s1);
             if (ct.empty()) { ct.push_back(0); cs.push_back(1); }
             int32_t *dag, *dct, *dcs;
@@ -602,11 +673,14 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
         }
         if (!H.mem_ptr.empty()) {
             HostLevel &Fn = S.levels[l - 1];
+            // first replicated level: only the rows built from this rank's finer rows have (local) members here; the
+            // other rows are gathered from the rank that owns their members
+            const int64_t o0 = B.first_repl ? H.src_off[rank] : r0, o1 = B.first_repl ? H.src_off[rank + 1] : r1;
             std::vector<int64_t> mp(d.n_pad + 1);
-            const int64_t m0 = H.mem_ptr[r0];
-            for (int64_t i = 0; i <= d.n_pad; i++) mp[i] = H.mem_ptr[r0 + i] - m0;
-            std::vector<int32_t> mi(H.mem_idx.begin() + m0, H.mem_idx.begin() + H.mem_ptr[r1]);
-            for (auto &v : mi) v -= (int32_t)Fn.part_off[rank];
+            const int64_t m0 = H.mem_ptr[o0];
+            for (int64_t i = 0; i <= d.n_pad; i++) mp[i] = H.mem_ptr[std::min(std::max(r0 + i, o0), o1)] - m0;
+            std::vector<int32_t> mi(H.mem_idx.begin() + m0, H.mem_idx.begin() + H.mem_ptr[o1]);
+            for (auto &v : mi) v -= (int32_t)Fn.part_off[(world > 1 && Fn.repl) ? 0 : rank];
             if (mi.empty()) mi.push_back(0);
             int64_t *dmp; int32_t *dmi;
             CKC(upload(h, &dmp, mp)); CKC(upload(h, &dmi, mi));
@@ -624,24 +698,19 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
             }
         }
         B.kcycle = l > 0 && l <= h->opt.amg_kcycle;
+        B.vec_rows = max_pad;
     }
     {
-        const HostLevel &H0 = S.levels[0];
-        int64_t max_pad = 32;
-        for (int k = 0; k < world; k++) max_pad = std::max(max_pad, H0.part_off[k + 1] - H0.part_off[k]);
-        const size_t vec = (size_t)4 * max_pad;
+        const size_t vec = (size_t)4 * h->lv[0].vec_rows;
         arena_request(h, &h->poses, vec);
         arena_request(h, &h->x, vec); arena_request(h, &h->r, vec); arena_request(h, &h->p, vec);
         arena_request(h, &h->q, vec); arena_request(h, &h->z, vec);
     }
     if (h->use_amg && S.dense_coarsest) {
-        const HostLevel &HL = S.levels[nl - 1];
+        const HostLevel &HL = S.levels[nl - 1];     // single GPU, or replicated: one partition
         h->dmap.off[0] = 0;
-        int64_t max_real = 1;
-        for (int k = 0; k < world; k++) { h->dmap.off[k + 1] = h->dmap.off[k] + (int32_t)HL.part_real[k]; max_real = std::max(max_real, HL.part_real[k]); }
-        for (int k = world; k < MAX_RANKS; k++) h->dmap.off[k + 1] = h->dmap.off[world];
+        for (int k = 0; k < MAX_RANKS; k++) h->dmap.off[k + 1] = (int32_t)HL.n;
         h->dense_m = (int)HL.n * 3;
-        if (world > 1) arena_request(h, &h->Arows, (size_t)3 * max_real * h->dense_m);
     }
     CKC(arena_commit(h));
     if (h->use_amg && S.dense_coarsest) {
@@ -714,14 +783,14 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
         double rec[10];
         for (int64_t i = 0; i < nm; i++) {
             const int64_t k = mine[i];
-            const int64_t a = S.iperm[S.efrom[k]], b = S.iperm[S.eto[k]];
-            const int ow = H0.part_of(b);
-            ends[i] = make_uint2((uint32_t)(a - r0), ((uint32_t)ow << COL_OWNER_SHIFT) | (uint32_t)(b - H0.part_off[ow]) | (ekind[k] == 1 ? COL_EDGE_XY : 0u));
+            const int64_t a = S.iperm[S.efrom[k]];
+            ends[i] = make_uint2((uint32_t)(a - r0), h->to_index[k] | (ekind[k] == 1 ? COL_EDGE_XY : 0u));
             edge_rec(k, rec);
             for (int c = 0; c < 10; c++) ed[(size_t)c * nm + i] = rec[c];
         }
         CKC(upload(h, &h->ends, ends));
         CKC(upload(h, &h->ed, ed));
+        h->to_index.clear(); h->to_index.shrink_to_fit();
         max_grid = std::max<int64_t>(max_grid, grid_for(nm, 256));
     }
     CKC(dalloc(h, &h->S, 1));
@@ -729,6 +798,8 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
     {
         Scalars s{};
         s.world = world;
+        s.repl_from = nl;
+        for (int l = nl - 1; l >= 1; l--) if (h->lv[l].repl) s.repl_from = l;
         CKU(cudaMemcpyAsync(h->S, &s, sizeof(Scalars), cudaMemcpyHostToDevice, h->stream));
     }
     CKU(cudaStreamSynchronize(h->stream));
@@ -1041,10 +1112,10 @@ int pgo_time_spmv(pgo_handle *h, int32_t repeats, double *avg_ms) {
     NEED_DEVICE(h);
     LevelBuf &B = h->lv[0];
     // p -> q with the PCG SpMV; done-flag test disabled so the launches always do the work, no cross-rank reduction
-    XRef xr = xref(h, h->p);
+    XRef xr = xref(h, h->p, true);
+    halo_pull(h, 0, h->p, 4, 0);
     auto launch = [&]() {
-        if (h->world > 1) k_spmv<3, 0, FIN_NONE, true><<<B.grid128, 128, 0, h->stream>>>(B.d, xr, h->p, nullptr, h->q, 0.0, nullptr, nullptr, h->S, h->partials, 0, 0);
-        else k_spmv<3, 0, FIN_NONE, false><<<B.grid128, 128, 0, h->stream>>>(B.d, xr, h->p, nullptr, h->q, 0.0, nullptr, nullptr, h->S, h->partials, 0, 0);
+        k_spmv<3, 0, FIN_NONE, false><<<B.grid128, 128, 0, h->stream>>>(B.d, xr, h->p, nullptr, h->q, 0.0, nullptr, nullptr, h->S, h->partials, 0, 0);
     };
     for (int i = 0; i < 3; i++) launch();
     CK(cudaEventRecord(h->ev[PGO_NUM_PHASES], h->stream));

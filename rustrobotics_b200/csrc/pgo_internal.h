@@ -36,6 +36,10 @@ struct HostLevel {
     std::vector<int64_t> part_real;   // [world]
     std::vector<int64_t> part_slot;   // [world + 1] slot range of each partition
     std::vector<uint8_t> real;        // [n_pad] 1 for real rows
+    // sharded handles: a small coarse level is REPLICATED (every rank holds all of it: part_off = {0, n_pad}); on the
+    // first replicated level src_off[k] .. src_off[k+1] are the rows whose members (finer rows) live on rank k
+    bool repl = false;
+    std::vector<int64_t> src_off;     // [world + 1], first replicated level only
     // JDS only
     int64_t n_slices = 0;
     std::vector<int64_t> slice_ptr;   // [n_slices + 1]
@@ -88,6 +92,7 @@ struct SymbolicOptions {
     int max_levels = 12;
     int agg_size = 16;
     int dense_max = 640;               // a level with at most this many rows is solved directly
+    int64_t repl_max_rows = 32768;     // world > 1: coarse levels up to this many rows are replicated on every rank
     int64_t jds_min_rows = INT64_MAX;     // coarse levels at least this large use the sliced storage (thread per row), smaller ones block CSR
     bool build_amg = true;
 };

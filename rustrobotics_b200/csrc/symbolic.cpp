@@ -191,13 +191,24 @@ static int32_t aggregate_partition(const HostLevel &F, int k, int max_size, std:
 }
 
 // Build the coarse level (block CSR, global padded numbering) from per-partition aggregate ids; fills F.agg, F.ctgt.
+// merge: F is sharded over pnc.size() partitions but C becomes one replicated partition (rows of rank k's aggregates at src_off[k])
 static void build_coarse_level(HostLevel &F, HostLevel &C, const std::vector<std::vector<int32_t>> &pagg,
-                               const std::vector<int64_t> &pnc, bool jds) {
+                               const std::vector<int64_t> &pnc, bool jds, bool merge) {
     const int world = (int)pnc.size();
-    layout_partitions(C, pnc);
+    std::vector<int64_t> cbase(world, 0);       // coarse row of partition k's aggregate 0
+    if (merge) {
+        int64_t tot = 0;
+        C.src_off.assign(world + 1, 0);
+        for (int k = 0; k < world; k++) { cbase[k] = tot; tot += pnc[k]; C.src_off[k + 1] = tot; }
+        layout_partitions(C, std::vector<int64_t>{tot});
+    } else {
+        layout_partitions(C, pnc);
+        for (int k = 0; k < world; k++) cbase[k] = C.part_off[k];
+    }
+    C.repl = merge || F.repl;
     F.agg.assign(F.n_pad, -1);
     for (int k = 0; k < world; k++)
-        for (int64_t i = 0; i < F.part_real[k]; i++) F.agg[F.part_off[k] + i] = (int32_t)(C.part_off[k] + pagg[k][i]);
+        for (int64_t i = 0; i < F.part_real[k]; i++) F.agg[F.part_off[k] + i] = (int32_t)(cbase[k] + pagg[k][i]);
     // members of every coarse row
     C.mem_ptr.assign(C.n_pad + 1, 0);
     for (int64_t r = 0; r < F.n_pad; r++) if (F.agg[r] >= 0) C.mem_ptr[F.agg[r] + 1]++;
@@ -233,10 +244,11 @@ static void build_coarse_level(HostLevel &F, HostLevel &C, const std::vector<std
             for (int64_t p = F.adj_ptr[r]; p < F.adj_ptr[r + 1]; p++) {
                 const int32_t J = F.agg[F.adj_nbr[p]];
                 const int64_t slot = F.adj_slot[p];
-                if (I == J) { F.ctgt[slot] = (int32_t)(-1 - (I - C.part_off[k])); continue; }
+                const int kc = merge ? 0 : k;
+                if (I == J) { F.ctgt[slot] = (int32_t)(-1 - (I - C.part_off[kc])); continue; }
                 auto b = C.adj_nbr.begin() + C.adj_ptr[I], e = C.adj_nbr.begin() + C.adj_ptr[I + 1];
                 const int64_t q = std::lower_bound(b, e, J) - C.adj_nbr.begin();
-                const int64_t cs = C.adj_slot[q] - C.part_slot[k];
+                const int64_t cs = C.adj_slot[q] - C.part_slot[kc];
                 if (jds) {
                     const int64_t lane = I & 31;
                     F.ctgt[slot] = (int32_t)((cs - lane) * 9 + lane);
@@ -250,7 +262,7 @@ static void build_coarse_level(HostLevel &F, HostLevel &C, const std::vector<std
 static void sort_aggregates_by_degree(const HostLevel &C, std::vector<std::vector<int32_t>> &pagg, const std::vector<int64_t> &pnc, int window) {
     const int world = (int)pnc.size();
     for (int k = 0; k < world; k++) {
-        const int64_t n = pnc[k], r0 = C.part_off[k];
+        const int64_t n = pnc[k], r0 = C.src_off.empty() ? C.part_off[k] : C.src_off[k];
         std::vector<int32_t> order(n), newid(n);
         std::iota(order.begin(), order.end(), 0);
         for (int64_t w = 0; w < n; w += window) {
@@ -378,22 +390,28 @@ bool build_symbolic(Symbolic &S, const SymbolicOptions &opt,
     if (!opt.build_amg) return true;
 
     // ---- aggregation hierarchy
+    const int64_t repl_max = std::max<int64_t>(opt.repl_max_rows, opt.dense_max);
     while (true) {
         const size_t lvl = S.levels.size() - 1;
-        if (S.levels[lvl].n <= opt.dense_max) { S.dense_coarsest = true; break; }
+        HostLevel &F = S.levels[lvl];
+        // a sharded level is never solved directly: in sharded handles the dense coarsest level is always a replicated one
+        if (F.n <= opt.dense_max && (world == 1 || F.repl)) { S.dense_coarsest = true; break; }
         if ((int)S.levels.size() >= opt.max_levels) break;
-        std::vector<std::vector<int32_t>> pagg(world);
-        std::vector<int64_t> pnc(world, 0);
+        const int fworld = (int)F.part_real.size();
+        std::vector<std::vector<int32_t>> pagg(fworld);
+        std::vector<int64_t> pnc(fworld, 0);
         int64_t nc = 0;
-        for (int k = 0; k < world; k++) { pnc[k] = aggregate_partition(S.levels[lvl], k, opt.agg_size, pagg[k]); nc += pnc[k]; }
-        if (nc > 0.8 * S.levels[lvl].n) break;                   // coarsening stalled
+        for (int k = 0; k < fworld; k++) { pnc[k] = aggregate_partition(F, k, opt.agg_size, pagg[k]); nc += pnc[k]; }
+        if (nc > 0.8 * F.n) break;                               // coarsening stalled
+        const bool merge = fworld > 1 && nc <= repl_max;
+        const bool jds = nc >= opt.jds_min_rows && !merge && !F.repl;
         S.levels.emplace_back();
-        build_coarse_level(S.levels[lvl], S.levels[lvl + 1], pagg, pnc, false);
-        if (nc >= opt.jds_min_rows) {
+        build_coarse_level(S.levels[lvl], S.levels[lvl + 1], pagg, pnc, false, merge);
+        if (jds) {
             // a large coarse level is streamed like level 0: one thread per row over the sliced storage
             sort_aggregates_by_degree(S.levels[lvl + 1], pagg, pnc, std::max(32, opt.sort_window / 32 * 32));
             S.levels[lvl + 1] = HostLevel();
-            build_coarse_level(S.levels[lvl], S.levels[lvl + 1], pagg, pnc, true);
+            build_coarse_level(S.levels[lvl], S.levels[lvl + 1], pagg, pnc, true, merge);
         }
         if (S.levels[lvl + 1].n_slots * 9 > 0x7fffffffll) { S.error = "coarse level exceeds 32-bit Galerkin targets"; return false; }
     }
