@@ -52,11 +52,19 @@ struct LevelDev {
     double *pos;                 // [2][n_pad] planes: position of each row (centroid on coarse levels)
     double *lev;                 // [n_pad][2]: lever arm of each row about its aggregate's centroid (peer-visible)
     const uint8_t *vkind;        // level 0 only (nullptr on coarse levels)
+    const double *quat;          // level 0 of an SE3 graph: the (halo-extended) pose records, 8 doubles per row, unit
+                                 // quaternion (w,x,y,z) at +4 (the rotation unknown is body-frame); nullptr otherwise
     const int32_t *agg; const int32_t *ctgt; const int32_t *cstr;   // towards the coarser level (local indices)
     const int64_t *mem_ptr; const int32_t *mem_idx;                 // members in the finer level (local rows)
 };
 
+// per block dimension (3: SE2 / XY graphs, 6: SE3 graphs): doubles per vector record, per pose record, geometry
+// dimension (positions / lever arms of the AMG transfer operators), doubles per lever-arm record, components of a
+// measurement record (z + upper triangle of Omega)
 template <int D> struct VecStride { static constexpr int value = (D == 3) ? 4 : D; };
+template <int D> struct Dim;
+template <> struct Dim<3> { static constexpr int VS = 4, PS = 4, NG = 2, LS = 2, NZ = 4, NW = 6, NM = 10; };
+template <> struct Dim<6> { static constexpr int VS = 6, PS = 8, NG = 3, LS = 4, NZ = 7, NW = 21, NM = 28; };
 
 __device__ __forceinline__ int ld_done(const Scalars *S) { return *(const volatile int *)&S->done; }
 
@@ -306,76 +314,84 @@ __global__ void __launch_bounds__(128) k_spmv(LevelDev L, const __grid_constant_
 // Coarse levels (L2-resident, latency-bound): block CSR, LPR lanes per block row (8 when rows are short, else a full
 // warp), 256 / LPR rows per CTA.  Same modes; K-cycle dots:
 //   FIN_K1: {x.y, x.u1}    FIN_K2: {x.u1, x.y, x.u2}      (x = c, y = H c)
-template <int MODE, int FIN, bool PEER, int LPR>
+template <int D, int MODE, int FIN, bool PEER, int LPR>
 __global__ void __launch_bounds__(256) k_spmv_csr(LevelDev L, const __grid_constant__ XRef xr, const double *__restrict__ x, const double *__restrict__ r,
                                                    double *__restrict__ y, double omega, const double *__restrict__ u1,
                                                    const double *__restrict__ u2, Scalars *S, double *partials, int lvl, int check_done) {
     if (check_done && ld_done(S)) return;
+    constexpr int DD = D * D, VS = VecStride<D>::value;
     const int sub = threadIdx.x & (LPR - 1);
     const int64_t row = (int64_t)blockIdx.x * (256 / LPR) + threadIdx.x / LPR;
     double dots[3] = {0.0, 0.0, 0.0};
     // whole warps take the branch together (LPR divides 32 and rows beyond n only occur at the tail)
     const bool live = row < L.n;
-    double a0 = 0, a1 = 0, a2 = 0;
+    double acc[D];
+#pragma unroll
+    for (int a = 0; a < D; a++) acc[a] = 0.0;
     if (live) {
         const int64_t b = L.slice_ptr[row], e = L.slice_ptr[row + 1];
         for (int64_t s = b + sub; s < e; s += LPR) {
             const uint32_t c = __ldg(L.col + s);
-            double xj[4];
-            ld_vec<4>(PEER ? xgather<4>(xr, c) : x + (int64_t)(c & COL_LOCAL_MASK) * 4, xj);
-            const double *v = L.val + s * 9;
-            a0 = fma(v[0], xj[0], fma(v[1], xj[1], fma(v[2], xj[2], a0)));
-            a1 = fma(v[3], xj[0], fma(v[4], xj[1], fma(v[5], xj[2], a1)));
-            a2 = fma(v[6], xj[0], fma(v[7], xj[1], fma(v[8], xj[2], a2)));
+            double xj[VS];
+            ld_vec<VS>(PEER ? xgather<VS>(xr, c) : x + (int64_t)(c & COL_LOCAL_MASK) * VS, xj);
+            const double *v = L.val + s * DD;
+#pragma unroll
+            for (int a = 0; a < D; a++)
+#pragma unroll
+                for (int q = 0; q < D; q++) acc[a] = fma(v[a * D + q], xj[q], acc[a]);
         }
     }
 #pragma unroll
     for (int o = LPR / 2; o > 0; o >>= 1) {
-        a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+#pragma unroll
+        for (int a = 0; a < D; a++) acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], o);
     }
     if (live && sub == 0) {
-        double xi[4], out[4] = {0, 0, 0, 0};
-        ld_vec<4>(x + row * 4, xi);
+        double xi[VS], out[VS];
+#pragma unroll
+        for (int a = 0; a < VS; a++) out[a] = 0.0;
+        ld_vec<VS>(x + row * VS, xi);
         const double *dg = L.diag + row;
-        double acc[3] = {a0, a1, a2};
 #pragma unroll
-        for (int a = 0; a < 3; a++)
+        for (int a = 0; a < D; a++)
 #pragma unroll
-            for (int q = 0; q < 3; q++) acc[a] = fma(dg[(int64_t)(a * 3 + q) * L.n_pad], xi[q], acc[a]);
+            for (int q = 0; q < D; q++) acc[a] = fma(dg[(int64_t)(a * D + q) * L.n_pad], xi[q], acc[a]);
         if (MODE == 0) {
 #pragma unroll
-            for (int a = 0; a < 3; a++) out[a] = acc[a];
+            for (int a = 0; a < D; a++) out[a] = acc[a];
             if (FIN == FIN_K1) {
-                double ui[4];
-                ld_vec<4>(u1 + row * 4, ui);
+                double ui[VS];
+                ld_vec<VS>(u1 + row * VS, ui);
 #pragma unroll
-                for (int a = 0; a < 3; a++) { dots[0] = fma(xi[a], acc[a], dots[0]); dots[1] = fma(xi[a], ui[a], dots[1]); }
+                for (int a = 0; a < D; a++) { dots[0] = fma(xi[a], acc[a], dots[0]); dots[1] = fma(xi[a], ui[a], dots[1]); }
             } else if (FIN == FIN_K2) {
-                double ui[4], wi[4];
-                ld_vec<4>(u1 + row * 4, ui);
-                ld_vec<4>(u2 + row * 4, wi);
+                double ui[VS], wi[VS];
+                ld_vec<VS>(u1 + row * VS, ui);
+                ld_vec<VS>(u2 + row * VS, wi);
 #pragma unroll
-                for (int a = 0; a < 3; a++) { dots[0] = fma(xi[a], ui[a], dots[0]); dots[1] = fma(xi[a], acc[a], dots[1]); dots[2] = fma(xi[a], wi[a], dots[2]); }
+                for (int a = 0; a < D; a++) { dots[0] = fma(xi[a], ui[a], dots[0]); dots[1] = fma(xi[a], acc[a], dots[1]); dots[2] = fma(xi[a], wi[a], dots[2]); }
             }
         } else {
-            double ri[4];
-            ld_vec<4>(r + row * 4, ri);
+            double ri[VS];
+            ld_vec<VS>(r + row * VS, ri);
             if (MODE == 1) {
 #pragma unroll
-                for (int a = 0; a < 3; a++) out[a] = ri[a] - acc[a];
+                for (int a = 0; a < D; a++) out[a] = ri[a] - acc[a];
             } else {
                 const double *di = L.dinv + row;
-                double t[3] = {ri[0] - acc[0], ri[1] - acc[1], ri[2] - acc[2]};
+                double t[D];
 #pragma unroll
-                for (int a = 0; a < 3; a++) {
+                for (int a = 0; a < D; a++) t[a] = ri[a] - acc[a];
+#pragma unroll
+                for (int a = 0; a < D; a++) {
                     double s = 0.0;
 #pragma unroll
-                    for (int q = 0; q < 3; q++) s = fma(di[(int64_t)(a * 3 + q) * L.n_pad], t[q], s);
+                    for (int q = 0; q < D; q++) s = fma(di[(int64_t)(a * D + q) * L.n_pad], t[q], s);
                     out[a] = fma(omega, s, xi[a]);
                 }
             }
         }
-        st_vec<4>(y + row * 4, out);
+        st_vec<VS>(y + row * VS, out);
     }
     reduce_and_finalize<256, FIN>(dots, S, partials, lvl);
 }
@@ -446,11 +462,11 @@ __global__ void __launch_bounds__(256) k_update_p(int64_t n_pad, double *__restr
 
 // K-cycle vector updates at level lvl:  WHICH 0: out = a - alpha_l b      WHICH 1: out = coef1_l a + coef2_l b
 template <int WHICH>
-__global__ void __launch_bounds__(256) k_kcombine(int64_t n_pad, const double *__restrict__ a, const double *__restrict__ b,
+__global__ void __launch_bounds__(256) k_kcombine(int64_t n_doubles, const double *__restrict__ a, const double *__restrict__ b,
                                                    double *__restrict__ out, const Scalars *S, int lvl) {
     if (ld_done(S)) return;
     const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 2;
-    if (i >= n_pad * 4) return;
+    if (i >= n_doubles) return;
     const double2 av = *reinterpret_cast<const double2 *>(a + i), bv = *reinterpret_cast<const double2 *>(b + i);
     double2 o;
     if (WHICH == 0) { const double al = S->k[lvl].alpha; o.x = fma(-al, bv.x, av.x); o.y = fma(-al, bv.y, av.y); }
@@ -459,106 +475,236 @@ __global__ void __launch_bounds__(256) k_kcombine(int64_t n_pad, const double *_
 }
 
 // ------------------------------------------------------------------------------------------------
-// Aggregation AMG transfer operators (D = 3).  The coarse unknown of an aggregate is a rigid motion
-// (tx, ty, theta) of its members about the aggregate centroid c:  P_i = [[1,0,-ly],[0,1,lx],[0,0,pz]],
-// l = pos_i - c (the row's lever arm) ; pz = 0 for landmark rows (their third, padding, unknown stays
-// decoupled).  Global rigid motions -- the near-null space of H that the 1e7 anchor barely pins -- are
-// represented exactly on every level.
+// Aggregation AMG transfer operators.  The coarse unknown of an aggregate is a rigid motion of its members about
+// the aggregate centroid c, expressed in the GLOBAL frame: (t, theta) for D = 3, (t, omega) for D = 6.  With the
+// lever arm l = pos_i - c of a fine row:
+//   D = 3:  P_i = [[1,0,-ly],[0,1,lx],[0,0,pz]]      pz = 0 for landmark rows (their third, padding, unknown stays decoupled)
+//   D = 6:  P_i = [[I, X],[0, Q]]   X w = w x l      Q = R_i^T on level 0 (the SE3 rotation unknown is body-frame,
+//                                                    R <- R Exp(dw): a global rotation w is dw_i = R_i^T w), Q = I on coarse levels
+// Global rigid motions -- the near-null space of H that the 1e7 anchor barely pins -- are represented exactly on
+// every level.
 __device__ __forceinline__ double row_pz(const LevelDev &L, int64_t row) { return (L.vkind && L.vkind[row] == 1) ? 0.0 : 1.0; }
 
-// rc_I = sum_{i in I} P_i^T res_i   (one warp per coarse row; fixed summation order => deterministic)
-__global__ void __launch_bounds__(256) k_restrict3(LevelDev F, LevelDev C, const double *__restrict__ res, double *__restrict__ rc,
-                                                    const Scalars *S) {
-    if (ld_done(S)) return;
-    const int lane = threadIdx.x & 31;
-    const int64_t I = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (I >= C.n_pad) return;
-    double s0 = 0, s1 = 0, s2 = 0;
-    if (I < C.n) {
-        for (int64_t m = C.mem_ptr[I] + lane; m < C.mem_ptr[I + 1]; m += 32) {
-            const int64_t i = C.mem_idx[m];
-            double r[4];
-            ld_vec<4>(res + i * 4, r);
-            const double2 l = *reinterpret_cast<const double2 *>(F.lev + i * 2);
-            s0 += r[0]; s1 += r[1];
-            s2 += fma(-l.y, r[0], fma(l.x, r[1], row_pz(F, i) * r[2]));
-        }
-        s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
-    }
-    if (lane == 0) {
-        double out[4] = {s0, s1, s2, 0.0};
-        st_vec<4>(rc + I * 4, out);
-    }
+__device__ __forceinline__ void quat_to_R(const double *q, double *R) {      // q = (w, x, y, z), row-major R
+    const double w = q[0], x = q[1], y = q[2], z = q[3];
+    R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - w * z);     R[2] = 2 * (x * z + w * y);
+    R[3] = 2 * (x * y + w * z);     R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - w * x);
+    R[6] = 2 * (x * z - w * y);     R[7] = 2 * (y * z + w * x);     R[8] = 1 - 2 * (x * x + y * y);
 }
 
-// x_i += P_i e_{agg(i)}
-__global__ void __launch_bounds__(128) k_prolong3(LevelDev F, const double *__restrict__ ec, double *__restrict__ x, const Scalars *S) {
-    if (ld_done(S)) return;
-    const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
-    if (i >= F.n) return;
-    const int64_t I = F.agg[i];
-    double e[4], xi[4];
-    ld_vec<4>(ec + I * 4, e);
-    ld_vec<4>(x + i * 4, xi);
+template <int D> struct Xfer;
+template <> struct Xfer<3> { double lx, ly, pz; };
+template <> struct Xfer<6> { double l[3]; double Q[9]; };
+
+__device__ __forceinline__ void xfer_rot(const double *quat_rec, double *Q) {    // Q = R^T, or I when there is no rotation record
+    if (quat_rec) {
+        double q[4], R[9];
+        ld_vec<4>(quat_rec, q);
+        quat_to_R(q, R);
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int b = 0; b < 3; b++) Q[3 * a + b] = R[3 * b + a];
+    } else {
+#pragma unroll
+        for (int a = 0; a < 9; a++) Q[a] = (a % 4 == 0) ? 1.0 : 0.0;
+    }
+}
+// P of one of this rank's rows
+template <int D> __device__ __forceinline__ Xfer<D> xfer_own(const LevelDev &F, int64_t i);
+template <> __device__ __forceinline__ Xfer<3> xfer_own<3>(const LevelDev &F, int64_t i) {
     const double2 l = *reinterpret_cast<const double2 *>(F.lev + i * 2);
-    xi[0] += fma(-l.y, e[2], e[0]);
-    xi[1] += fma(l.x, e[2], e[1]);
-    xi[2] += row_pz(F, i) * e[2];
-    st_vec<4>(x + i * 4, xi);
+    return Xfer<3>{l.x, l.y, row_pz(F, i)};
+}
+template <> __device__ __forceinline__ Xfer<6> xfer_own<6>(const LevelDev &F, int64_t i) {
+    Xfer<6> P;
+    double l[4];
+    ld_vec<4>(F.lev + i * 4, l);
+    P.l[0] = l[0]; P.l[1] = l[1]; P.l[2] = l[2];
+    xfer_rot(F.quat ? F.quat + i * 8 + 4 : nullptr, P.Q);
+    return P;
+}
+// P of the neighbour row a stored block points to (column word cw)
+template <int D> __device__ __forceinline__ Xfer<D> xfer_nbr(const LevelDev &F, const XRef &levr, uint32_t cw);
+template <> __device__ __forceinline__ Xfer<3> xfer_nbr<3>(const LevelDev &F, const XRef &levr, uint32_t cw) {
+    const double2 l = *reinterpret_cast<const double2 *>(xgather<2>(levr, cw));
+    // the neighbour is a landmark iff this is a pose-landmark edge seen from its pose (`from`) side (level 0 only)
+    const double pz = (F.vkind && (cw & COL_EDGE_XY) && !(cw & COL_ROLE_TO)) ? 0.0 : 1.0;
+    return Xfer<3>{l.x, l.y, pz};
+}
+template <> __device__ __forceinline__ Xfer<6> xfer_nbr<6>(const LevelDev &F, const XRef &levr, uint32_t cw) {
+    Xfer<6> P;
+    double l[4];
+    ld_vec<4>(xgather<4>(levr, cw), l);
+    P.l[0] = l[0]; P.l[1] = l[1]; P.l[2] = l[2];
+    xfer_rot(F.quat ? F.quat + (int64_t)(cw & COL_LOCAL_MASK) * 8 + 4 : nullptr, P.Q);     // halo rows sit behind the own rows
+    return P;
 }
 
-// centroid of the members (one warp per coarse row)
-__global__ void __launch_bounds__(256) k_coarse_pos(LevelDev F, LevelDev C) {
-    const int lane = threadIdx.x & 31;
-    const int64_t I = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (I >= C.n_pad) return;
-    double sx = 0, sy = 0;
-    if (I < C.n) {
-        const int64_t b = C.mem_ptr[I], e = C.mem_ptr[I + 1];
-        for (int64_t m = b + lane; m < e; m += 32) { const int64_t i = C.mem_idx[m]; sx += F.pos[i]; sy += F.pos[F.n_pad + i]; }
-        const double inv = e > b ? 1.0 / (double)(e - b) : 0.0;     // rows built by another rank have no members here
-        sx = warp_sum(sx) * inv; sy = warp_sum(sy) * inv;
-    }
-    if (lane == 0) { C.pos[I] = sx; C.pos[C.n_pad + I] = sy; }
+// s += P^T r
+__device__ __forceinline__ void xfer_restrict(const Xfer<3> &P, const double *r, double *s) {
+    s[0] += r[0]; s[1] += r[1];
+    s[2] += fma(-P.ly, r[0], fma(P.lx, r[1], P.pz * r[2]));
 }
-
-// lever arm of every fine row about its aggregate's centroid
-__global__ void __launch_bounds__(128) k_lever(LevelDev F, LevelDev C) {
-    const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
-    if (i >= F.n_pad) return;
-    double2 l = make_double2(0.0, 0.0);
-    if (i < F.n) { const int64_t I = F.agg[i]; l.x = F.pos[i] - C.pos[I]; l.y = F.pos[F.n_pad + i] - C.pos[C.n_pad + I]; }
-    *reinterpret_cast<double2 *>(F.lev + i * 2) = l;
+__device__ __forceinline__ void xfer_restrict(const Xfer<6> &P, const double *r, double *s) {
+    s[0] += r[0]; s[1] += r[1]; s[2] += r[2];
+    // X^T r_t = l x r_t ; Q^T r_w
+    s[3] += (P.l[1] * r[2] - P.l[2] * r[1]) + (P.Q[0] * r[3] + P.Q[3] * r[4] + P.Q[6] * r[5]);
+    s[4] += (P.l[2] * r[0] - P.l[0] * r[2]) + (P.Q[1] * r[3] + P.Q[4] * r[4] + P.Q[7] * r[5]);
+    s[5] += (P.l[0] * r[1] - P.l[1] * r[0]) + (P.Q[2] * r[3] + P.Q[5] * r[4] + P.Q[8] * r[5]);
 }
-
-// G = P_i^T H P_j for 3x3 blocks
-__device__ __forceinline__ void ptap3(const double *h, double dxi, double dyi, double pzi, double dxj, double dyj, double pzj, double *g) {
+// x += P e
+__device__ __forceinline__ void xfer_prolong(const Xfer<3> &P, const double *e, double *x) {
+    x[0] += fma(-P.ly, e[2], e[0]);
+    x[1] += fma(P.lx, e[2], e[1]);
+    x[2] += P.pz * e[2];
+}
+__device__ __forceinline__ void xfer_prolong(const Xfer<6> &P, const double *e, double *x) {
+    // X w = w x l
+    x[0] += e[0] + (e[4] * P.l[2] - e[5] * P.l[1]);
+    x[1] += e[1] + (e[5] * P.l[0] - e[3] * P.l[2]);
+    x[2] += e[2] + (e[3] * P.l[1] - e[4] * P.l[0]);
+    x[3] += P.Q[0] * e[3] + P.Q[1] * e[4] + P.Q[2] * e[5];
+    x[4] += P.Q[3] * e[3] + P.Q[4] * e[4] + P.Q[5] * e[5];
+    x[5] += P.Q[6] * e[3] + P.Q[7] * e[4] + P.Q[8] * e[5];
+}
+// g = P_i^T h P_j
+__device__ __forceinline__ void xfer_ptap(const double *h, const Xfer<3> &Pi, const Xfer<3> &Pj, double *g) {
     double m[9];
 #pragma unroll
     for (int a = 0; a < 3; a++) {
         m[3 * a + 0] = h[3 * a + 0];
         m[3 * a + 1] = h[3 * a + 1];
-        m[3 * a + 2] = fma(-dyj, h[3 * a + 0], fma(dxj, h[3 * a + 1], pzj * h[3 * a + 2]));
+        m[3 * a + 2] = fma(-Pj.ly, h[3 * a + 0], fma(Pj.lx, h[3 * a + 1], Pj.pz * h[3 * a + 2]));
     }
 #pragma unroll
     for (int b = 0; b < 3; b++) {
         g[b] = m[b];
         g[3 + b] = m[3 + b];
-        g[6 + b] = fma(-dyi, m[b], fma(dxi, m[3 + b], pzi * m[6 + b]));
+        g[6 + b] = fma(-Pi.ly, m[b], fma(Pi.lx, m[3 + b], Pi.pz * m[6 + b]));
+    }
+}
+__device__ __forceinline__ void xfer_ptap(const double *h, const Xfer<6> &Pi, const Xfer<6> &Pj, double *g) {
+    double m[36];
+    const double *l = Pj.l, *Q = Pj.Q;
+#pragma unroll
+    for (int a = 0; a < 6; a++) {
+        const double *ha = h + 6 * a;
+        m[6 * a + 0] = ha[0]; m[6 * a + 1] = ha[1]; m[6 * a + 2] = ha[2];
+        // row * X = l x row_t ; row_w * Q
+        m[6 * a + 3] = (l[1] * ha[2] - l[2] * ha[1]) + (ha[3] * Q[0] + ha[4] * Q[3] + ha[5] * Q[6]);
+        m[6 * a + 4] = (l[2] * ha[0] - l[0] * ha[2]) + (ha[3] * Q[1] + ha[4] * Q[4] + ha[5] * Q[7]);
+        m[6 * a + 5] = (l[0] * ha[1] - l[1] * ha[0]) + (ha[3] * Q[2] + ha[4] * Q[5] + ha[5] * Q[8]);
+    }
+    l = Pi.l; Q = Pi.Q;
+#pragma unroll
+    for (int b = 0; b < 6; b++) {
+        const double m0 = m[b], m1 = m[6 + b], m2 = m[12 + b], m3 = m[18 + b], m4 = m[24 + b], m5 = m[30 + b];
+        g[b] = m0; g[6 + b] = m1; g[12 + b] = m2;
+        // X^T col_t = l x col_t ; Q^T col_w
+        g[18 + b] = (l[1] * m2 - l[2] * m1) + (Q[0] * m3 + Q[3] * m4 + Q[6] * m5);
+        g[24 + b] = (l[2] * m0 - l[0] * m2) + (Q[1] * m3 + Q[4] * m4 + Q[7] * m5);
+        g[30 + b] = (l[0] * m1 - l[1] * m0) + (Q[2] * m3 + Q[5] * m4 + Q[8] * m5);
     }
 }
 
+// rc_I = sum_{i in I} P_i^T res_i   (one warp per coarse row; fixed summation order => deterministic)
+template <int D>
+__global__ void __launch_bounds__(256) k_restrict(LevelDev F, LevelDev C, const double *__restrict__ res, double *__restrict__ rc,
+                                                   const Scalars *S) {
+    if (ld_done(S)) return;
+    constexpr int VS = VecStride<D>::value;
+    const int lane = threadIdx.x & 31;
+    const int64_t I = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (I >= C.n_pad) return;
+    double s[VS];
+#pragma unroll
+    for (int a = 0; a < VS; a++) s[a] = 0.0;
+    if (I < C.n) {
+        for (int64_t m = C.mem_ptr[I] + lane; m < C.mem_ptr[I + 1]; m += 32) {
+            const int64_t i = C.mem_idx[m];
+            double r[VS];
+            ld_vec<VS>(res + i * VS, r);
+            xfer_restrict(xfer_own<D>(F, i), r, s);
+        }
+#pragma unroll
+        for (int a = 0; a < D; a++) s[a] = warp_sum(s[a]);
+    }
+    if (lane == 0) st_vec<VS>(rc + I * VS, s);
+}
+
+// x_i += P_i e_{agg(i)}
+template <int D>
+__global__ void __launch_bounds__(128) k_prolong(LevelDev F, const double *__restrict__ ec, double *__restrict__ x, const Scalars *S) {
+    if (ld_done(S)) return;
+    constexpr int VS = VecStride<D>::value;
+    const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (i >= F.n) return;
+    const int64_t I = F.agg[i];
+    double e[VS], xi[VS];
+    ld_vec<VS>(ec + I * VS, e);
+    ld_vec<VS>(x + i * VS, xi);
+    xfer_prolong(xfer_own<D>(F, i), e, xi);
+    st_vec<VS>(x + i * VS, xi);
+}
+
+// centroid of the members (one warp per coarse row); NG position planes
+template <int NG>
+__global__ void __launch_bounds__(256) k_coarse_pos(LevelDev F, LevelDev C) {
+    const int lane = threadIdx.x & 31;
+    const int64_t I = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (I >= C.n_pad) return;
+    double sp[NG];
+#pragma unroll
+    for (int g = 0; g < NG; g++) sp[g] = 0.0;
+    if (I < C.n) {
+        const int64_t b = C.mem_ptr[I], e = C.mem_ptr[I + 1];
+        for (int64_t m = b + lane; m < e; m += 32) {
+            const int64_t i = C.mem_idx[m];
+#pragma unroll
+            for (int g = 0; g < NG; g++) sp[g] += F.pos[(int64_t)g * F.n_pad + i];
+        }
+        const double inv = e > b ? 1.0 / (double)(e - b) : 0.0;     // rows built by another rank have no members here
+#pragma unroll
+        for (int g = 0; g < NG; g++) sp[g] = warp_sum(sp[g]) * inv;
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int g = 0; g < NG; g++) C.pos[(int64_t)g * C.n_pad + I] = sp[g];
+    }
+}
+
+// lever arm of every fine row about its aggregate's centroid: records of LS = 2 (NG = 2) or 4 (NG = 3) doubles
+template <int NG>
+__global__ void __launch_bounds__(128) k_lever(LevelDev F, LevelDev C) {
+    constexpr int LS = NG == 2 ? 2 : 4;
+    const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (i >= F.n_pad) return;
+    double l[LS];
+#pragma unroll
+    for (int g = 0; g < LS; g++) l[g] = 0.0;
+    if (i < F.n) {
+        const int64_t I = F.agg[i];
+#pragma unroll
+        for (int g = 0; g < NG; g++) l[g] = F.pos[(int64_t)g * F.n_pad + i] - C.pos[(int64_t)g * C.n_pad + I];
+    }
+    st_vec<LS>(F.lev + i * LS, l);
+}
+
+template <int DD>
 __device__ __forceinline__ void galerkin_scatter(const LevelDev &C, int32_t tgt, int32_t stride, const double *g) {
     double *dst = tgt < 0 ? C.diag + (int64_t)(-1 - tgt) : C.val + (int64_t)tgt;
     const int64_t st = tgt < 0 ? C.n_pad : (int64_t)stride;
 #pragma unroll
-    for (int q = 0; q < 9; q++) atomicAdd(dst + (int64_t)q * st, g[q]);
+    for (int q = 0; q < DD; q++) atomicAdd(dst + (int64_t)q * st, g[q]);
 }
 
 // Galerkin product Hc = P^T H P: every fine block adds P_i^T H_ij P_j into the coarse block of (agg i, agg j), which
 // lives in a row this rank owns.  Several fine blocks share a coarse block, hence atomics (coarse levels only; the
 // Gauss-Newton system itself is assembled without atomics).  Level-0 source (JDS): one thread per row.
-__global__ void __launch_bounds__(128) k_galerkin3_jds(LevelDev F, LevelDev C, const __grid_constant__ XRef levr) {
+template <int D>
+__global__ void __launch_bounds__(128) k_galerkin_jds(LevelDev F, LevelDev C, const __grid_constant__ XRef levr) {
+    constexpr int DD = D * D;
     const int64_t row = (int64_t)blockIdx.x * 128 + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int64_t slice = row >> 5;
@@ -566,16 +712,13 @@ __global__ void __launch_bounds__(128) k_galerkin3_jds(LevelDev F, LevelDev C, c
     const int mydeg = F.deg[row];
     const int maxdeg = __shfl_sync(0xffffffffu, mydeg, 0);
     const bool real = row < F.n;
-    double dxi = 0, dyi = 0, pzi = 1;
+    Xfer<D> Pi = xfer_own<D>(F, real ? row : 0);
     if (real) {
-        const double2 l = *reinterpret_cast<const double2 *>(F.lev + row * 2);
-        dxi = l.x; dyi = l.y;
-        pzi = row_pz(F, row);
-        double h[9], g[9];
+        double h[DD], g[DD];
 #pragma unroll
-        for (int q = 0; q < 9; q++) h[q] = F.diag[(int64_t)q * F.n_pad + row];
-        ptap3(h, dxi, dyi, pzi, dxi, dyi, pzi, g);
-        galerkin_scatter(C, -1 - F.agg[row], 0, g);
+        for (int q = 0; q < DD; q++) h[q] = F.diag[(int64_t)q * F.n_pad + row];
+        xfer_ptap(h, Pi, Pi, g);
+        galerkin_scatter<DD>(C, -1 - F.agg[row], 0, g);
     }
     const int64_t base = F.slice_ptr[slice];
     int64_t off = 0;
@@ -585,41 +728,41 @@ __global__ void __launch_bounds__(128) k_galerkin3_jds(LevelDev F, LevelDev C, c
         if (active) {
             const int64_t slot = base + off + lane;
             const uint32_t cw = F.col[slot];
-            const double2 lj = *reinterpret_cast<const double2 *>(xgather<2>(levr, cw));
-            const double *v = F.val + (base + off) * 9 + lane;
-            double h[9], g[9];
+            const Xfer<D> Pj = xfer_nbr<D>(F, levr, cw);
+            const double *v = F.val + (base + off) * DD + lane;
+            double h[DD], g[DD];
 #pragma unroll
-            for (int q = 0; q < 9; q++) h[q] = v[(int64_t)q * cnt];
-            // the neighbour is a landmark iff this is a pose-landmark edge seen from its pose (`from`) side
-            const double pzj = ((cw & COL_EDGE_XY) && !(cw & COL_ROLE_TO)) ? 0.0 : 1.0;
-            ptap3(h, dxi, dyi, pzi, lj.x, lj.y, pzj, g);
-            galerkin_scatter(C, F.ctgt[slot], F.cstr[slot], g);
+            for (int q = 0; q < DD; q++) h[q] = v[(int64_t)q * cnt];
+            xfer_ptap(h, Pi, Pj, g);
+            galerkin_scatter<DD>(C, F.ctgt[slot], F.cstr[slot], g);
         }
         off += cnt;
     }
 }
 
 // coarse source (block CSR): one warp per row
-__global__ void __launch_bounds__(256) k_galerkin3_csr(LevelDev F, LevelDev C, const __grid_constant__ XRef levr) {
+template <int D>
+__global__ void __launch_bounds__(256) k_galerkin_csr(LevelDev F, LevelDev C, const __grid_constant__ XRef levr) {
+    constexpr int DD = D * D;
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= F.n) return;
-    const double2 l = *reinterpret_cast<const double2 *>(F.lev + row * 2);
+    const Xfer<D> Pi = xfer_own<D>(F, row);
     if (lane == 0) {
-        double h[9], g[9];
+        double h[DD], g[DD];
 #pragma unroll
-        for (int q = 0; q < 9; q++) h[q] = F.diag[(int64_t)q * F.n_pad + row];
-        ptap3(h, l.x, l.y, 1.0, l.x, l.y, 1.0, g);
-        galerkin_scatter(C, -1 - F.agg[row], 0, g);
+        for (int q = 0; q < DD; q++) h[q] = F.diag[(int64_t)q * F.n_pad + row];
+        xfer_ptap(h, Pi, Pi, g);
+        galerkin_scatter<DD>(C, -1 - F.agg[row], 0, g);
     }
     for (int64_t s = F.slice_ptr[row] + lane; s < F.slice_ptr[row + 1]; s += 32) {
-        const double2 lj = *reinterpret_cast<const double2 *>(xgather<2>(levr, F.col[s]));
-        const double *v = F.val + s * 9;
-        double h[9], g[9];
+        const Xfer<D> Pj = xfer_nbr<D>(F, levr, F.col[s]);
+        const double *v = F.val + s * DD;
+        double h[DD], g[DD];
 #pragma unroll
-        for (int q = 0; q < 9; q++) h[q] = v[q];
-        ptap3(h, l.x, l.y, 1.0, lj.x, lj.y, 1.0, g);
-        galerkin_scatter(C, F.ctgt[s], F.cstr[s], g);
+        for (int q = 0; q < DD; q++) h[q] = v[q];
+        xfer_ptap(h, Pi, Pj, g);
+        galerkin_scatter<DD>(C, F.ctgt[s], F.cstr[s], g);
     }
 }
 
@@ -632,49 +775,74 @@ __device__ __forceinline__ void inv3(const double *a, double *o) {
     o[3] = c01 * id; o[4] = (a[0] * a[8] - a[2] * a[6]) * id; o[5] = (a[2] * a[3] - a[0] * a[5]) * id;
     o[6] = c02 * id; o[7] = (a[1] * a[6] - a[0] * a[7]) * id; o[8] = (a[0] * a[4] - a[1] * a[3]) * id;
 }
+// inverse of a small SPD block: cofactors for 3x3, in-register Gauss-Jordan without pivoting for 6x6
+template <int D> __device__ __forceinline__ void inv_block(const double *a, double *o) {
+    if constexpr (D == 3) { inv3(a, o); } else {
+#pragma unroll
+    for (int q = 0; q < D * D; q++) o[q] = a[q];
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+        const double piv = 1.0 / o[k * D + k];
+#pragma unroll
+        for (int j = 0; j < D; j++) if (j != k) o[k * D + j] *= piv;
+#pragma unroll
+        for (int i = 0; i < D; i++) {
+            if (i == k) continue;
+            const double f = o[i * D + k];
+#pragma unroll
+            for (int j = 0; j < D; j++) if (j != k) o[i * D + j] = fma(-f, o[k * D + j], o[i * D + j]);
+            o[i * D + k] = -f * piv;
+        }
+        o[k * D + k] = piv;
+    }
+    }
+}
 
-__global__ void __launch_bounds__(128) k_invert_diag3(LevelDev L) {
+template <int D>
+__global__ void __launch_bounds__(128) k_invert_diag(LevelDev L) {
+    constexpr int DD = D * D;
     const int64_t row = (int64_t)blockIdx.x * 128 + threadIdx.x;
     if (row >= L.n_pad) return;
-    double a[9], o[9];
+    double a[DD], o[DD];
 #pragma unroll
-    for (int q = 0; q < 9; q++) a[q] = L.diag[(int64_t)q * L.n_pad + row];
+    for (int q = 0; q < DD; q++) a[q] = L.diag[(int64_t)q * L.n_pad + row];
     if (row < L.n) {
-        // an aggregate made of landmarks that all sit on its centroid (e.g. a single landmark) has no
+        // D = 3: an aggregate made of landmarks that all sit on its centroid (e.g. a single landmark) has no
         // rotational unknown: P^T H P is exactly singular in theta.  Decouple that unknown (its restricted
         // residual is always 0) so that the level stays SPD.
-        if (!(a[8] > 1e-14 * (a[0] + a[4]))) {
+        if (D == 3 && !(a[8] > 1e-14 * (a[0] + a[4]))) {
             a[2] = a[5] = a[6] = a[7] = 0.0; a[8] = 1.0;
             L.diag[(int64_t)2 * L.n_pad + row] = 0.0; L.diag[(int64_t)5 * L.n_pad + row] = 0.0;
             L.diag[(int64_t)6 * L.n_pad + row] = 0.0; L.diag[(int64_t)7 * L.n_pad + row] = 0.0;
             L.diag[(int64_t)8 * L.n_pad + row] = 1.0;
         }
-        inv3(a, o);
+        inv_block<D>(a, o);
     } else {
 #pragma unroll
-        for (int q = 0; q < 9; q++) o[q] = 0.0;
+        for (int q = 0; q < DD; q++) o[q] = 0.0;
     }
 #pragma unroll
-    for (int q = 0; q < 9; q++) L.dinv[(int64_t)q * L.n_pad + row] = o[q];
+    for (int q = 0; q < DD; q++) L.dinv[(int64_t)q * L.n_pad + row] = o[q];
 }
 
 // ------------------------------------------------------------------------------------------------
 // Coarsest level: explicit dense inverse.  The level's rows are numbered densely across ranks:
-// dense index of (rank k, local row i) = dense_off[k] + i ; m = 3 * sum of real rows.
+// dense index of (rank k, local row i) = dense_off[k] + i ; m = D * sum of real rows.
 struct DenseMap { int32_t off[MAX_RANKS + 1]; };
 
 __device__ __forceinline__ int dense_col(const DenseMap &dm, uint32_t colword) {
     return dm.off[(colword >> COL_OWNER_SHIFT) & (MAX_RANKS - 1)] + (int)(colword & COL_LOCAL_MASK);
 }
 
-// scatter this rank's block rows into rows [3*dense_off[rank], ...) of the (pre-zeroed) dense matrix A (m x m, row-major)
-template <bool JDS>
+// scatter this rank's block rows into rows [D*dense_off[rank], ...) of the (pre-zeroed) dense matrix A (m x m, row-major)
+template <int D, bool JDS>
 __global__ void __launch_bounds__(128) k_dense_assemble(LevelDev L, DenseMap dm, int rank, int m, double *__restrict__ A) {
+    constexpr int DD = D * D;
     const int64_t row = (int64_t)blockIdx.x * 128 + threadIdx.x;
     if (row >= L.n) return;
     const int gi = dm.off[rank] + (int)row;
-    for (int a = 0; a < 3; a++)
-        for (int b = 0; b < 3; b++) A[(int64_t)(gi * 3 + a) * m + gi * 3 + b] = L.diag[(int64_t)(a * 3 + b) * L.n_pad + row];
+    for (int a = 0; a < D; a++)
+        for (int b = 0; b < D; b++) A[(int64_t)(gi * D + a) * m + gi * D + b] = L.diag[(int64_t)(a * D + b) * L.n_pad + row];
     if (JDS) {
         const int64_t slice = row >> 5; const int lane = (int)(row & 31);
         const int64_t base = L.slice_ptr[slice];
@@ -684,17 +852,17 @@ __global__ void __launch_bounds__(128) k_dense_assemble(LevelDev L, DenseMap dm,
             int cnt = 0;
             while (cnt < 32 && L.deg[slice * 32 + cnt] > k) cnt++;
             const int gj = dense_col(dm, L.col[base + off + lane]);
-            const double *v = L.val + (base + off) * 9 + lane;
-            for (int a = 0; a < 3; a++)
-                for (int b = 0; b < 3; b++) A[(int64_t)(gi * 3 + a) * m + gj * 3 + b] += v[(int64_t)(a * 3 + b) * cnt];   // duplicate edges sum
+            const double *v = L.val + (base + off) * DD + lane;
+            for (int a = 0; a < D; a++)
+                for (int b = 0; b < D; b++) A[(int64_t)(gi * D + a) * m + gj * D + b] += v[(int64_t)(a * D + b) * cnt];   // duplicate edges sum
             off += cnt;
         }
     } else {
         for (int64_t s = L.slice_ptr[row]; s < L.slice_ptr[row + 1]; s++) {
             const int gj = dense_col(dm, L.col[s]);
-            const double *v = L.val + s * 9;
-            for (int a = 0; a < 3; a++)
-                for (int b = 0; b < 3; b++) A[(int64_t)(gi * 3 + a) * m + gj * 3 + b] = v[a * 3 + b];
+            const double *v = L.val + s * DD;
+            for (int a = 0; a < D; a++)
+                for (int b = 0; b < D; b++) A[(int64_t)(gi * D + a) * m + gj * D + b] = v[a * D + b];
         }
     }
 }
@@ -783,39 +951,41 @@ __global__ void __launch_bounds__(256) k_dense_invert(int m, double *__restrict_
 }
 
 // x_own = Ainv[own rows, :] r  on the coarsest level; r is gathered from all ranks.  One warp per scalar row.
+template <int D>
 __global__ void __launch_bounds__(256) k_dense_apply(int64_t n_local, DenseMap dm, int rank, int world, int m, const double *__restrict__ Ainv,
                                                       const __grid_constant__ XRef rr, double *__restrict__ x, const Scalars *S) {
     if (ld_done(S)) return;
+    constexpr int VS = VecStride<D>::value;
     extern __shared__ double sr[];
     for (int t = threadIdx.x; t < m; t += 256) {
-        const int g = t / 3, c = t - 3 * g;
+        const int g = t / D, c = t - D * g;
         int k = 0;
         while (k + 1 < world && g >= dm.off[k + 1]) k++;
-        sr[t] = rr.p[k][(int64_t)(g - dm.off[k]) * 4 + c];
+        sr[t] = rr.p[k][(int64_t)(g - dm.off[k]) * VS + c];
     }
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int64_t srow = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);      // local scalar row
-    if (srow >= n_local * 3) return;
-    const double *a = Ainv + ((int64_t)dm.off[rank] * 3 + srow) * m;
+    if (srow >= n_local * D) return;
+    const double *a = Ainv + ((int64_t)dm.off[rank] * D + srow) * m;
     double s = 0.0;
     for (int j = lane; j < m; j += 32) s = fma(__ldg(a + j), sr[j], s);
     s = warp_sum(s);
-    if (lane == 0) x[(srow / 3) * 4 + (srow % 3)] = s;
+    if (lane == 0) x[(srow / D) * VS + (srow % D)] = s;
 }
 
-// Halo exchange: v[(n_pad + i) * STRIDE ...] <- the record of row halo_src[i] in its owner's copy of v (peer HBM, NVLink).
+// Halo exchange: v[(n_pad + i) * stride ...] <- the record of row halo_src[i] in its owner's copy of v (peer HBM, NVLink).
 // One thread per halo row: independent remote reads, so the NVLink latency is paid once per exchange, not per gather.
-template <int STRIDE>
+// stride (doubles per record) is even.
 __global__ void __launch_bounds__(128) k_halo_pull(double *__restrict__ v, const __grid_constant__ XRef peers, const uint32_t *__restrict__ halo_src,
-                                                    int64_t n_halo, int64_t n_pad, const Scalars *S, int check_done) {
+                                                    int64_t n_halo, int64_t n_pad, int stride, const Scalars *S, int check_done) {
     if (check_done && ld_done(S)) return;
     const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
     if (i >= n_halo) return;
-    const double *src = xgather<STRIDE>(peers, halo_src[i]);
-    double *dst = v + (n_pad + i) * STRIDE;
-#pragma unroll
-    for (int c = 0; c < STRIDE; c += 2) *reinterpret_cast<double2 *>(dst + c) = *reinterpret_cast<const double2 *>(src + c);
+    const uint32_t cw = halo_src[i];
+    const double *src = peers.p[(cw >> COL_OWNER_SHIFT) & (MAX_RANKS - 1)] + (int64_t)(cw & COL_LOCAL_MASK) * stride;
+    double *dst = v + (n_pad + i) * stride;
+    for (int c = 0; c < stride; c += 2) *reinterpret_cast<double2 *>(dst + c) = *reinterpret_cast<const double2 *>(src + c);
 }
 
 // First replicated level of a sharded handle: copy the element ranges the OTHER ranks produced from their (identically
@@ -1051,6 +1221,275 @@ __global__ void __launch_bounds__(256) k_export_poses(int64_t n, const int64_t *
     double *v = values + row_valofs[row];
     v[0] = p[0]; v[1] = p[1];
     if (vkind[row] == 0) v[2] = atan2(p[3], p[2]);
+}
+
+// ================================================================================================
+// SE(3) -- repo-defined semantics, parity unpinned: the reference parses SE3 graphs but optimize is todo!() for them
+// (pose_graph_optimization.rs:241, 357, 570); SURVEY 8(c) fixes the natural extension of the SE2 convention, restated
+// on the CPU in oracle/pgo_oracle.c (se3_error_jac):
+//   E = Z^-1 X1^-1 X2 ;  e = [ Rz^T (R1^T (t2 - t1) - tz) ; Log(qz^-1 q1^-1 q2) ]  in R^6
+//   retraction  t += dt (global frame),  q <- q Exp(dw) (body frame), renormalised
+//   A = [[-Rz^T R1^T, Rz^T [R1^T d]x], [0, -Jr^-1(e_w) R2^T R1]]    B = [[Rz^T R1^T, 0], [0, Jr^-1(e_w)]]
+// Pose record: 8 doubles (x, y, z, 0, qw, qx, qy, qz) = two 32-byte sectors; measurement: t(3), q(w,x,y,z), upper
+// triangle of Omega (21), streamed component-major like the SE2 one.
+__device__ __forceinline__ void quat_mul(const double *a, const double *b, double *o) {
+    o[0] = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+    o[1] = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+    o[2] = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+    o[3] = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+}
+__device__ __forceinline__ void mat3_mul(const double *a, const double *b, double *o) {
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) o[3 * i + j] = a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j];
+}
+__device__ __forceinline__ void mat3_tmul(const double *a, const double *b, double *o) {    // a^T b
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) o[3 * i + j] = a[i] * b[j] + a[3 + i] * b[3 + j] + a[6 + i] * b[6 + j];
+}
+
+// x1, x2: pose records (8 doubles) ; z: t(3), q(4).  e[6]; with JAC also the 3x3 pieces of A and B:
+//   M = Rz^T R1^T, T = Rz^T [u]x, JR = Jri R2^T R1, Jri = Jr^-1(e_w)
+template <bool JAC>
+__device__ __forceinline__ void se3_edge(const double *x1, const double *x2, const double *z, double *e, double *M, double *T, double *JR, double *Jri) {
+    double R1[9], Rz[9];
+    quat_to_R(x1 + 4, R1); quat_to_R(z + 3, Rz);
+    const double d0 = x2[0] - x1[0], d1 = x2[1] - x1[1], d2 = x2[2] - x1[2];
+    double u[3], w[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) { u[i] = R1[i] * d0 + R1[3 + i] * d1 + R1[6 + i] * d2; w[i] = u[i] - z[i]; }
+#pragma unroll
+    for (int i = 0; i < 3; i++) e[i] = Rz[i] * w[0] + Rz[3 + i] * w[1] + Rz[6 + i] * w[2];
+    const double qzi[4] = {z[3], -z[4], -z[5], -z[6]}, q1i[4] = {x1[4], -x1[5], -x1[6], -x1[7]};
+    double t[4], qe[4];
+    quat_mul(qzi, q1i, t); quat_mul(t, x2 + 4, qe);
+    {   // Log
+        double qw = qe[0], qx = qe[1], qy = qe[2], qz = qe[3];
+        if (qw < 0) { qw = -qw; qx = -qx; qy = -qy; qz = -qz; }
+        const double n = sqrt(qx * qx + qy * qy + qz * qz);
+        const double k = (n < 1e-12) ? 2.0 / qw : 2.0 * atan2(n, qw) / n;
+        e[3] = k * qx; e[4] = k * qy; e[5] = k * qz;
+    }
+    if (!JAC) return;
+    double R2[9], R1Rz[9];
+    quat_to_R(x2 + 4, R2);
+    mat3_mul(R1, Rz, R1Rz);                  // (R1 Rz)^T = Rz^T R1^T
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) M[3 * i + j] = R1Rz[3 * j + i];
+    const double Su[9] = {0.0, -u[2], u[1], u[2], 0.0, -u[0], -u[1], u[0], 0.0};
+    mat3_tmul(Rz, Su, T);
+    {   // inverse right Jacobian of SO(3): I + 1/2 [p]x + k [p]x^2
+        const double p0 = e[3], p1 = e[4], p2 = e[5];
+        const double th2 = p0 * p0 + p1 * p1 + p2 * p2, th = sqrt(th2);
+        const double k = (th < 1e-5) ? (1.0 / 12.0 + th2 / 720.0) : (1.0 / th2 - (1.0 + cos(th)) / (2.0 * th * sin(th)));
+        const double Sp[9] = {0.0, -p2, p1, p2, 0.0, -p0, -p1, p0, 0.0};
+        double S2[9];
+        mat3_mul(Sp, Sp, S2);
+#pragma unroll
+        for (int i = 0; i < 9; i++) Jri[i] = 0.5 * Sp[i] + k * S2[i];
+        Jri[0] += 1.0; Jri[4] += 1.0; Jri[8] += 1.0;
+    }
+    double R2tR1[9];
+    mat3_tmul(R2, R1, R2tR1);
+    mat3_mul(Jri, R2tR1, JR);
+}
+
+__device__ __forceinline__ void sym6_expand(const double *w, double *W) {     // upper triangle (21, row-major) -> full 6x6
+    int p = 0;
+#pragma unroll
+    for (int r = 0; r < 6; r++)
+#pragma unroll
+        for (int c = r; c < 6; c++) { W[6 * r + c] = w[p]; W[6 * c + r] = w[p]; p++; }
+}
+
+// Fused linearise + assemble + block-Jacobi setup for SE3 graphs (6x6 blocks); same structure as k_assemble_se2: one
+// thread per block row walks its half edges, single writer per block, no atomics.
+__global__ void __launch_bounds__(128) k_assemble_se3(LevelDev L, const double *__restrict__ poses, const double *__restrict__ hz,
+                                                       double *__restrict__ rvec, int64_t anchor_row, double anchor_w, double lambda) {
+    const int64_t row = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int64_t slice = row >> 5;
+    if (slice >= L.n_slices) return;
+    const int mydeg = L.deg[row];
+    const int maxdeg = __shfl_sync(0xffffffffu, mydeg, 0);
+    double xi[8];
+    ld_vec<8>(poses + row * 8, xi);
+    double Hd[36], g[6];
+#pragma unroll
+    for (int q = 0; q < 36; q++) Hd[q] = 0.0;
+#pragma unroll
+    for (int q = 0; q < 6; q++) g[q] = 0.0;
+    const int64_t base = L.slice_ptr[slice];
+    int64_t off = 0;
+    for (int k = 0; k < maxdeg; k++) {
+        const bool active = k < mydeg;
+        const int cnt = __popc(__ballot_sync(0xffffffffu, active));
+        if (active) {
+            const uint32_t cw = __ldg(L.col + base + off + lane);
+            const bool to_side = (cw & COL_ROLE_TO) != 0;
+            double xj[8], z[7], wu[21];
+            ld_vec<8>(poses + (int64_t)(cw & COL_LOCAL_MASK) * 8, xj);
+            const double *m = hz + (base + off) * 28 + lane;
+#pragma unroll
+            for (int q = 0; q < 7; q++) z[q] = __ldg(m + (int64_t)q * cnt);
+#pragma unroll
+            for (int q = 0; q < 21; q++) wu[q] = __ldg(m + (int64_t)(7 + q) * cnt);
+            double e[6], M[9], T[9], JR[9], Jri[9];
+            se3_edge<true>(to_side ? xj : xi, to_side ? xi : xj, z, e, M, T, JR, Jri);
+            // J = Jacobian w.r.t. this row's pose, K = w.r.t. the neighbour's (A / B of the edge, or B / A)
+            double J[36], K[36];
+#pragma unroll
+            for (int q = 0; q < 36; q++) { J[q] = 0.0; K[q] = 0.0; }
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    const double a_tt = -M[3 * i + j], a_tw = T[3 * i + j], a_ww = -JR[3 * i + j];
+                    const double b_tt = M[3 * i + j], b_ww = Jri[3 * i + j];
+                    J[6 * i + j] = to_side ? b_tt : a_tt;
+                    J[6 * i + 3 + j] = to_side ? 0.0 : a_tw;
+                    J[6 * (3 + i) + 3 + j] = to_side ? b_ww : a_ww;
+                    K[6 * i + j] = to_side ? a_tt : b_tt;
+                    K[6 * i + 3 + j] = to_side ? a_tw : 0.0;
+                    K[6 * (3 + i) + 3 + j] = to_side ? a_ww : b_ww;
+                }
+            double W[36], WJ[36];
+            sym6_expand(wu, W);
+#pragma unroll
+            for (int r = 0; r < 6; r++)
+#pragma unroll
+                for (int c = 0; c < 6; c++) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int q = 0; q < 6; q++) s = fma(W[6 * r + q], J[6 * q + c], s);
+                    WJ[6 * r + c] = s;
+                }
+            // own diagonal contribution J^T W J, gradient J^T W e, off-diagonal block J^T W K = (W J)^T K
+#pragma unroll
+            for (int r = 0; r < 6; r++) {
+                double s = 0.0;
+#pragma unroll
+                for (int q = 0; q < 6; q++) s = fma(WJ[6 * q + r], e[q], s);
+                g[r] += s;
+#pragma unroll
+                for (int c = 0; c < 6; c++) {
+                    double h = 0.0;
+#pragma unroll
+                    for (int q = 0; q < 6; q++) h = fma(J[6 * q + r], WJ[6 * q + c], h);
+                    Hd[6 * r + c] += h;
+                }
+            }
+            double *v = L.val + (base + off) * 36 + lane;
+#pragma unroll
+            for (int r = 0; r < 6; r++)
+#pragma unroll
+                for (int c = 0; c < 6; c++) {
+                    double h = 0.0;
+#pragma unroll
+                    for (int q = 0; q < 6; q++) h = fma(WJ[6 * q + r], K[6 * q + c], h);
+                    v[(int64_t)(6 * r + c) * cnt] = h;
+                }
+        }
+        off += cnt;
+    }
+    const bool real = row < L.n;
+    if (real) {
+#pragma unroll
+        for (int a = 0; a < 6; a++) Hd[7 * a] += lambda + (row == anchor_row ? anchor_w : 0.0);
+    }
+    double Di[36];
+    if (real) inv_block<6>(Hd, Di);
+    else {
+#pragma unroll
+        for (int q = 0; q < 36; q++) Di[q] = 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < 36; q++) {
+        L.diag[(int64_t)q * L.n_pad + row] = Hd[q];
+        L.dinv[(int64_t)q * L.n_pad + row] = Di[q];
+    }
+    double out[6] = {-g[0], -g[1], -g[2], -g[3], -g[4], -g[5]};
+    st_vec<6>(rvec + row * 6, out);
+    L.pos[row] = xi[0]; L.pos[L.n_pad + row] = xi[1]; L.pos[2 * L.n_pad + row] = xi[2];
+}
+
+// chi2 of an SE3 graph: ed = [28][n_edges] planes, ends as in k_chi2_se2
+__global__ void __launch_bounds__(256) k_chi2_se3(int64_t n_edges, const uint2 *__restrict__ ends, const double *__restrict__ ed,
+                                                   const double *__restrict__ poses, Scalars *S, double *partials) {
+    const int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    double c = 0.0;
+    if (k < n_edges) {
+        const uint2 en = ends[k];
+        double x1[8], x2[8], z[7], wu[21], W[36], e[6];
+        ld_vec<8>(poses + (int64_t)en.x * 8, x1);
+        ld_vec<8>(poses + (int64_t)(en.y & COL_LOCAL_MASK) * 8, x2);
+#pragma unroll
+        for (int q = 0; q < 7; q++) z[q] = __ldg(ed + (int64_t)q * n_edges + k);
+#pragma unroll
+        for (int q = 0; q < 21; q++) wu[q] = __ldg(ed + (int64_t)(7 + q) * n_edges + k);
+        se3_edge<false>(x1, x2, z, e, nullptr, nullptr, nullptr, nullptr);
+        sym6_expand(wu, W);
+#pragma unroll
+        for (int cc = 0; cc < 6; cc++) {
+            double t = 0.0;
+#pragma unroll
+            for (int r = 0; r < 6; r++) t = fma(e[r], W[6 * r + cc], t);
+            c = fma(t, e[cc], c);
+        }
+    }
+    reduce_and_finalize<256, FIN_CHI2>(&c, S, partials, 0);
+}
+
+// t += dt ; q <- normalise(q Exp(dw)) ; ||dx||^2
+__global__ void __launch_bounds__(256) k_retract_se3(LevelDev L, double *__restrict__ poses, const double *__restrict__ dx, double sign,
+                                                      Scalars *S, double *partials) {
+    const int64_t row = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    double n2 = 0.0;
+    if (row < L.n) {
+        double p[8], d[6];
+        ld_vec<8>(poses + row * 8, p);
+        ld_vec<6>(dx + row * 6, d);
+#pragma unroll
+        for (int a = 0; a < 6; a++) n2 = fma(d[a], d[a], n2);
+        p[0] = fma(sign, d[0], p[0]); p[1] = fma(sign, d[1], p[1]); p[2] = fma(sign, d[2], p[2]);
+        const double w0 = sign * d[3], w1 = sign * d[4], w2 = sign * d[5];
+        const double th = sqrt(w0 * w0 + w1 * w1 + w2 * w2);
+        double sh, ch;
+        sincos(0.5 * th, &sh, &ch);
+        const double k = (th < 1e-12) ? 0.5 - th * th / 48.0 : sh / th;
+        const double dq[4] = {ch, k * w0, k * w1, k * w2};
+        double q[4];
+        quat_mul(p + 4, dq, q);
+        const double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+        p[4] = q[0] / n; p[5] = q[1] / n; p[6] = q[2] / n; p[7] = q[3] / n;
+        st_vec<8>(poses + row * 8, p);
+    }
+    reduce_and_finalize<256, FIN_NORM>(&n2, S, partials, 0);
+}
+
+// g2o-layout SE3 vertex values (x y z qx qy qz qw) <-> pose records (x, y, z, 0, qw, qx, qy, qz), quaternion normalised on the way in
+__global__ void __launch_bounds__(256) k_import_poses_se3(int64_t n, const int64_t *__restrict__ row_valofs, const double *__restrict__ values,
+                                                           double *__restrict__ poses) {
+    const int64_t row = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (row >= n) return;
+    const double *v = values + row_valofs[row];
+    const double nq = sqrt(v[3] * v[3] + v[4] * v[4] + v[5] * v[5] + v[6] * v[6]);
+    const double p[8] = {v[0], v[1], v[2], 0.0, v[6] / nq, v[3] / nq, v[4] / nq, v[5] / nq};
+    st_vec<8>(poses + row * 8, p);
+}
+__global__ void __launch_bounds__(256) k_export_poses_se3(int64_t n, const int64_t *__restrict__ row_valofs, const double *__restrict__ poses,
+                                                           double *__restrict__ values) {
+    const int64_t row = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (row >= n) return;
+    double p[8];
+    ld_vec<8>(poses + row * 8, p);
+    double *v = values + row_valofs[row];
+    v[0] = p[0]; v[1] = p[1]; v[2] = p[2]; v[3] = p[5]; v[4] = p[6]; v[5] = p[7]; v[6] = p[4];
 }
 
 } // namespace pgo

@@ -59,21 +59,24 @@ __global__ void __launch_bounds__(32) k_xreduce(Comm *mine, CommRef peers, int r
 }
 
 // {a.b (, b.c)} over the local rows -> FIN (used when the preconditioner itself has no kernel to fuse the dots into)
-template <int FIN>
+template <int D, int FIN>
 __global__ void __launch_bounds__(128) k_dots(int64_t n_pad, const double *__restrict__ a, const double *__restrict__ b,
                                                const double *__restrict__ c, Scalars *S, double *partials) {
     if (ld_done(S)) return;
+    constexpr int VS = VecStride<D>::value;
     const int64_t row = (int64_t)blockIdx.x * 128 + threadIdx.x;
     double dots[2] = {0.0, 0.0};
     if (row < n_pad) {
-        double av[4], bv[4];
-        ld_vec<4>(a + row * 4, av);
-        ld_vec<4>(b + row * 4, bv);
-        dots[0] = av[0] * bv[0] + av[1] * bv[1] + av[2] * bv[2];
+        double av[VS], bv[VS];
+        ld_vec<VS>(a + row * VS, av);
+        ld_vec<VS>(b + row * VS, bv);
+#pragma unroll
+        for (int q = 0; q < D; q++) dots[0] = fma(av[q], bv[q], dots[0]);
         if (FIN == FIN_RZ) {
-            double cv[4];
-            ld_vec<4>(c + row * 4, cv);
-            dots[1] = cv[0] * bv[0] + cv[1] * bv[1] + cv[2] * bv[2];
+            double cv[VS];
+            ld_vec<VS>(c + row * VS, cv);
+#pragma unroll
+            for (int q = 0; q < D; q++) dots[1] = fma(cv[q], bv[q], dots[1]);
         }
     }
     reduce_and_finalize<128, FIN>(dots, S, partials, 0);

@@ -26,6 +26,7 @@ using namespace pgo;
 namespace {
 
 thread_local std::string g_create_error;
+const int KDIM[3] = {3, 2, 6};     // scalar dimension of a vertex kind (g2o.rs:61,68,77)
 
 #define NEED_DEVICE(h)                                                                             \
     do {                                                                                           \
@@ -167,8 +168,7 @@ void halo_pull(pgo_handle *h, int l, const double *v, int stride, int check_done
     LevelBuf &B = h->lv[l];
     if (h->world == 1 || B.repl || B.n_halo == 0) return;
     double *w = const_cast<double *>(v);
-    if (stride == 4) k_halo_pull<4><<<grid_for(B.n_halo, 128), 128, 0, h->stream>>>(w, xref(h, v), B.halo_src, B.n_halo, B.d.n_pad, h->S, check_done);
-    else k_halo_pull<2><<<grid_for(B.n_halo, 128), 128, 0, h->stream>>>(w, xref(h, v), B.halo_src, B.n_halo, B.d.n_pad, h->S, check_done);
+    k_halo_pull<<<grid_for(B.n_halo, 128), 128, 0, h->stream>>>(w, xref(h, v), B.halo_src, B.n_halo, B.d.n_pad, stride, h->S, check_done);
     h->launch_count += 1;
 }
 
@@ -181,112 +181,112 @@ void gather_rows(pgo_handle *h, double *v, const SegMap &seg, int comps, int n_p
 }
 
 // ---- SpMV launcher: sliced storage (level 0 and large coarse levels) or block CSR
-template <int MODE, int FIN> void spmv(pgo_handle *h, int l, const double *x, const double *r, double *y, double omega,
-                                       const double *u1, const double *u2, int check) {
+template <int D, int MODE, int FIN> void spmv(pgo_handle *h, int l, const double *x, const double *r, double *y, double omega,
+                                              const double *u1, const double *u2, int check) {
     LevelBuf &B = h->lv[l];
-    halo_pull(h, l, x, 4, check);                    // the caller's barrier made the peers' x final
+    halo_pull(h, l, x, VecStride<D>::value, check);  // the caller's barrier made the peers' x final
     const XRef xr = xref(h, x, true);
-    if (B.jds) k_spmv<3, MODE, FIN, false><<<B.grid128, 128, 0, h->stream>>>(B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
-    else if (B.lpr == 8) k_spmv_csr<MODE, FIN, false, 8><<<B.grid8, 256, 0, h->stream>>>(B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
-    else k_spmv_csr<MODE, FIN, false, 32><<<B.gridw, 256, 0, h->stream>>>(B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
+    if (B.jds) k_spmv<D, MODE, FIN, false><<<B.grid128, 128, 0, h->stream>>>(B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
+    else if (B.lpr == 8) k_spmv_csr<D, MODE, FIN, false, 8><<<B.grid8, 256, 0, h->stream>>>(B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
+    else k_spmv_csr<D, MODE, FIN, false, 32><<<B.gridw, 256, 0, h->stream>>>(B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
     h->launch_count += 1;
     xreduce<FIN>(h, l, check);
 }
-template <int MODE> void spmv_any(pgo_handle *h, int l, const double *x, const double *r, double *y, double omega, int check) {
-    spmv<MODE, FIN_NONE>(h, l, x, r, y, omega, nullptr, nullptr, check);
+template <int D, int MODE> void spmv_any(pgo_handle *h, int l, const double *x, const double *r, double *y, double omega, int check) {
+    spmv<D, MODE, FIN_NONE>(h, l, x, r, y, omega, nullptr, nullptr, check);
 }
 
-void coarse_solve(pgo_handle *h, int l, const double *rhs, double *out);
+template <int D> void coarse_solve(pgo_handle *h, int l, const double *rhs, double *out);
 
-void dense_apply(pgo_handle *h, int l, const double *rhs, double *out) {
+template <int D> void dense_apply(pgo_handle *h, int l, const double *rhs, double *out) {
     LevelBuf &B = h->lv[l];      // always a local (single-GPU or replicated) level
-    k_dense_apply<<<grid_for(B.d.n * 3, 8), 256, sizeof(double) * h->dense_m, h->stream>>>(B.d.n, h->dmap, 0, 1, h->dense_m,
-                                                                                          h->Ainv, xref(h, rhs, true), out, h->S);
+    k_dense_apply<D><<<grid_for(B.d.n * D, 8), 256, sizeof(double) * h->dense_m, h->stream>>>(B.d.n, h->dmap, 0, 1, h->dense_m,
+                                                                                             h->Ainv, xref(h, rhs, true), out, h->S);
     h->launch_count += 1;
 }
 
 // ---- one multigrid cycle at level l: out = M_l(rhs).  FINK: dots fused into the last kernel (level 0 only).
-template <int FINK> void cycle(pgo_handle *h, int l, const double *rhs, double *out) {
+template <int D, int FINK> void cycle(pgo_handle *h, int l, const double *rhs, double *out) {
     LevelBuf &B = h->lv[l];
     const int last = (int)h->lv.size() - 1;
     if (l == last) {
-        if (h->sym.dense_coarsest) dense_apply(h, l, rhs, out);
+        if (h->sym.dense_coarsest) dense_apply<D>(h, l, rhs, out);
         else {
             // no direct solve possible: a few damped block-Jacobi sweeps
-            k_dinv_apply<3, FIN_NONE><<<B.grid128, 128, 0, h->stream>>>(B.d, rhs, B.xa, B.omega, nullptr, h->S, h->partials, 1);
+            k_dinv_apply<D, FIN_NONE><<<B.grid128, 128, 0, h->stream>>>(B.d, rhs, B.xa, B.omega, nullptr, h->S, h->partials, 1);
             h->launch_count += 1;
             lbarrier(h, l);
-            spmv_any<2>(h, l, B.xa, rhs, B.res, B.omega, 1);
+            spmv_any<D, 2>(h, l, B.xa, rhs, B.res, B.omega, 1);
             lbarrier(h, l);
-            spmv_any<2>(h, l, B.res, rhs, out, B.omega, 1);
+            spmv_any<D, 2>(h, l, B.res, rhs, out, B.omega, 1);
             lbarrier(h, l);
         }
         return;
     }
     LevelBuf &C = h->lv[l + 1];
-    k_dinv_apply<3, FIN_NONE><<<B.grid128, 128, 0, h->stream>>>(B.d, rhs, B.xa, B.omega, nullptr, h->S, h->partials, 1);
+    k_dinv_apply<D, FIN_NONE><<<B.grid128, 128, 0, h->stream>>>(B.d, rhs, B.xa, B.omega, nullptr, h->S, h->partials, 1);
     h->launch_count += 1;
     lbarrier(h, l);
-    spmv_any<1>(h, l, B.xa, rhs, B.res, 0.0, 1);
-    k_restrict3<<<C.gridw, 256, 0, h->stream>>>(B.d, C.d, B.res, C.rhs, h->S);
+    spmv_any<D, 1>(h, l, B.xa, rhs, B.res, 0.0, 1);
+    k_restrict<D><<<C.gridw, 256, 0, h->stream>>>(B.d, C.d, B.res, C.rhs, h->S);
     h->launch_count += 1;
     if (C.first_repl) {                              // every rank restricted onto its own aggregates: all-gather the coarse rhs
         lbarrier(h, l);
-        gather_rows(h, C.rhs, C.src_rows, 4, 1, 0, 1);
+        gather_rows(h, C.rhs, C.src_rows, VecStride<D>::value, 1, 0, 1);
     }
-    coarse_solve(h, l + 1, C.rhs, C.sol);
-    k_prolong3<<<B.grid128, 128, 0, h->stream>>>(B.d, C.sol, B.xa, h->S);
+    coarse_solve<D>(h, l + 1, C.rhs, C.sol);
+    k_prolong<D><<<B.grid128, 128, 0, h->stream>>>(B.d, C.sol, B.xa, h->S);
     h->launch_count += 1;
     lbarrier(h, l);
-    spmv<2, FINK>(h, l, B.xa, rhs, out, B.omega, FINK == FIN_RZ ? h->q : nullptr, nullptr, 1);
+    spmv<D, 2, FINK>(h, l, B.xa, rhs, out, B.omega, FINK == FIN_RZ ? h->q : nullptr, nullptr, 1);
     if (FINK == FIN_NONE) lbarrier(h, l);            // FINK != NONE: the all-reduce is the barrier
 }
 
 // K-cycle: the coarse system of level l is solved by two flexible-CG steps preconditioned by the cycle of level l
-void coarse_solve(pgo_handle *h, int l, const double *rhs, double *out) {
+template <int D> void coarse_solve(pgo_handle *h, int l, const double *rhs, double *out) {
     LevelBuf &B = h->lv[l];
     const int last = (int)h->lv.size() - 1;
-    if (l == last || !B.kcycle) { cycle<FIN_NONE>(h, l, rhs, out); return; }
-    cycle<FIN_NONE>(h, l, rhs, B.c1);
-    spmv<0, FIN_K1>(h, l, B.c1, nullptr, B.v1, 0.0, rhs, nullptr, 1);
-    k_kcombine<0><<<B.gridv, 256, 0, h->stream>>>(B.d.n_pad, rhs, B.v1, B.r1, h->S, l);
-    cycle<FIN_NONE>(h, l, B.r1, B.c2);
-    spmv<0, FIN_K2>(h, l, B.c2, nullptr, B.v2, 0.0, B.v1, B.r1, 1);
-    k_kcombine<1><<<B.gridv, 256, 0, h->stream>>>(B.d.n_pad, B.c1, B.c2, out, h->S, l);
+    if (l == last || !B.kcycle) { cycle<D, FIN_NONE>(h, l, rhs, out); return; }
+    cycle<D, FIN_NONE>(h, l, rhs, B.c1);
+    spmv<D, 0, FIN_K1>(h, l, B.c1, nullptr, B.v1, 0.0, rhs, nullptr, 1);
+    k_kcombine<0><<<B.gridv, 256, 0, h->stream>>>(B.d.n_pad * VecStride<D>::value, rhs, B.v1, B.r1, h->S, l);
+    cycle<D, FIN_NONE>(h, l, B.r1, B.c2);
+    spmv<D, 0, FIN_K2>(h, l, B.c2, nullptr, B.v2, 0.0, B.v1, B.r1, 1);
+    k_kcombine<1><<<B.gridv, 256, 0, h->stream>>>(B.d.n_pad * VecStride<D>::value, B.c1, B.c2, out, h->S, l);
     h->launch_count += 2;
 }
 
-template <int FINK> void precondition(pgo_handle *h) {   // z = M^-1 r (+ r.z, z.q)
+template <int D, int FINK> void precondition(pgo_handle *h) {   // z = M^-1 r (+ r.z, z.q)
     LevelBuf &B = h->lv[0];
-    if (h->use_amg && h->lv.size() > 1) cycle<FINK>(h, 0, h->r, h->z);
+    if (h->use_amg && h->lv.size() > 1) cycle<D, FINK>(h, 0, h->r, h->z);
     else if (h->use_amg && h->sym.dense_coarsest) {      // the whole system fits the direct solve
-        dense_apply(h, 0, h->r, h->z);
-        k_dots<FINK><<<B.grid128, 128, 0, h->stream>>>(B.d.n_pad, h->r, h->z, h->q, h->S, h->partials);
+        dense_apply<D>(h, 0, h->r, h->z);
+        k_dots<D, FINK><<<B.grid128, 128, 0, h->stream>>>(B.d.n_pad, h->r, h->z, h->q, h->S, h->partials);
         h->launch_count += 1;
         xreduce<FINK>(h, 0, 1);
     } else {
-        k_dinv_apply<3, FINK><<<B.grid128, 128, 0, h->stream>>>(B.d, h->r, h->z, 1.0, h->q, h->S, h->partials, 1);
+        k_dinv_apply<D, FINK><<<B.grid128, 128, 0, h->stream>>>(B.d, h->r, h->z, 1.0, h->q, h->S, h->partials, 1);
         h->launch_count += 1;
         xreduce<FINK>(h, 0, 1);
     }
 }
 
-void pcg_iteration(pgo_handle *h) {
+template <int D> void pcg_iteration(pgo_handle *h) {
     LevelBuf &B = h->lv[0];
-    spmv<0, FIN_PQ>(h, 0, h->p, nullptr, h->q, 0.0, nullptr, nullptr, 1);
-    k_update_xr<3><<<B.gridv, 256, 0, h->stream>>>(B.d.n_pad, h->x, h->r, h->p, h->q, h->S);
-    precondition<FIN_RZ>(h);
-    k_update_p<3><<<B.gridv, 256, 0, h->stream>>>(B.d.n_pad, h->p, h->z, h->S);
+    spmv<D, 0, FIN_PQ>(h, 0, h->p, nullptr, h->q, 0.0, nullptr, nullptr, 1);
+    k_update_xr<D><<<B.gridv, 256, 0, h->stream>>>(B.d.n_pad, h->x, h->r, h->p, h->q, h->S);
+    precondition<D, FIN_RZ>(h);
+    k_update_p<D><<<B.gridv, 256, 0, h->stream>>>(B.d.n_pad, h->p, h->z, h->S);
     h->launch_count += 2;
     xbarrier(h);                                     // p complete on every rank before the next SpMV reads it
 }
 
-int build_pcg_graph(pgo_handle *h) {
+template <int D> int build_pcg_graph(pgo_handle *h) {
     if (h->pcg_graph) return PGO_OK;
     cudaGraph_t g = nullptr;
     int64_t before = h->launch_count;
     CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-    for (int i = 0; i < h->chunk; i++) pcg_iteration(h);
+    for (int i = 0; i < h->chunk; i++) pcg_iteration<D>(h);
     CK(cudaStreamEndCapture(h->stream, &g));
     h->launches_per_iter = (h->launch_count - before) / h->chunk;
     h->launch_count = before;
@@ -296,12 +296,13 @@ int build_pcg_graph(pgo_handle *h) {
 }
 
 // ---- assemble the Gauss-Newton system at the current poses (H in lv[0], b in h->r)
-int assemble(pgo_handle *h, double lambda, int add_lambda) {
+template <int D> int assemble(pgo_handle *h, double lambda, int add_lambda) {
     LevelBuf &B = h->lv[0];
     xbarrier(h, 0);                                  // every rank's poses are final
-    halo_pull(h, 0, h->poses, 4, 0);
-    k_assemble_se2<<<B.grid128, 128, 0, h->stream>>>(B.d, xref(h, h->poses, true), h->poses, h->hz, h->r, h->anchor_row, h->opt.anchor_weight,
-                                                      add_lambda ? lambda : 0.0);
+    halo_pull(h, 0, h->poses, Dim<D>::PS, 0);
+    if (D == 3) k_assemble_se2<<<B.grid128, 128, 0, h->stream>>>(B.d, xref(h, h->poses, true), h->poses, h->hz, h->r, h->anchor_row, h->opt.anchor_weight,
+                                                                  add_lambda ? lambda : 0.0);
+    else k_assemble_se3<<<B.grid128, 128, 0, h->stream>>>(B.d, h->poses, h->hz, h->r, h->anchor_row, h->opt.anchor_weight, add_lambda ? lambda : 0.0);
     h->launch_count += 1;
     CK(cudaGetLastError());
     return PGO_OK;
@@ -309,14 +310,15 @@ int assemble(pgo_handle *h, double lambda, int add_lambda) {
 
 // power iteration for rho(Dinv H) on one level -> damping of the block-Jacobi smoother (the norm is taken over the
 // local rows only: an estimate is all that is needed)
-int estimate_omega(pgo_handle *h, int l) {
+template <int D> int estimate_omega(pgo_handle *h, int l) {
+    constexpr int VS = VecStride<D>::value;
     LevelBuf &B = h->lv[l];
-    const int64_t nd = B.d.n_pad * 4;
+    const int64_t nd = B.d.n_pad * VS;
     std::vector<double> v(nd, 0.0);
     uint64_t s = 0x9E3779B97F4A7C15ull;
     for (int64_t i = 0; i < B.d.n; i++)
-        for (int c = 0; c < 3; c++) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; v[i * 4 + c] = (double)(s >> 11) / 9007199254740992.0 - 0.5; }
-    if (l == 0) {   // keep the landmark padding unknown out of it
+        for (int c = 0; c < D; c++) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; v[i * VS + c] = (double)(s >> 11) / 9007199254740992.0 - 0.5; }
+    if (l == 0 && D == 3) {   // keep the landmark padding unknown out of it
         for (int64_t i = 0; i < B.d.n; i++) if (h->sym.vkind[h->sym.perm[h->row0 + i]] == 1) v[i * 4 + 2] = 0.0;
     }
     double *a = B.xa, *b = B.res;
@@ -325,9 +327,9 @@ int estimate_omega(pgo_handle *h, int l) {
     for (int it = 0; it < 10; it++) {
         // b = H a ; a' = Dinv b ; rho ~ |a'| / |a|
         lbarrier(h, l, 0);
-        spmv_any<0>(h, l, a, nullptr, b, 0.0, 0);
+        spmv_any<D, 0>(h, l, a, nullptr, b, 0.0, 0);
         lbarrier(h, l, 0);
-        k_dinv_apply<3, FIN_NONE><<<B.grid128, 128, 0, h->stream>>>(B.d, b, a, 1.0, nullptr, h->S, h->partials, 0);
+        k_dinv_apply<D, FIN_NONE><<<B.grid128, 128, 0, h->stream>>>(B.d, b, a, 1.0, nullptr, h->S, h->partials, 0);
         CK(cudaMemcpyAsync(v.data(), a, nd * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
         double nrm = 0.0;
@@ -344,35 +346,36 @@ int estimate_omega(pgo_handle *h, int l) {
 }
 
 // numeric setup of the hierarchy for the current H: coarse positions, Galerkin products, inverses
-int amg_setup(pgo_handle *h) {
+template <int D> int amg_setup(pgo_handle *h) {
+    constexpr int DD = D * D, NG = Dim<D>::NG, LS = Dim<D>::LS;
     if (!h->use_amg) return PGO_OK;
     const int last = (int)h->lv.size() - 1;
     for (int l = 0; l < last; l++) {
         LevelBuf &F = h->lv[l], &C = h->lv[l + 1];
-        k_coarse_pos<<<C.gridw, 256, 0, h->stream>>>(F.d, C.d);
-        k_lever<<<F.grid128, 128, 0, h->stream>>>(F.d, C.d);
-        CK(cudaMemsetAsync(C.d.val, 0, sizeof(double) * 9 * std::max<int64_t>(C.d.n_slots, 1), h->stream));
-        CK(cudaMemsetAsync(C.d.diag, 0, sizeof(double) * 9 * C.d.n_pad, h->stream));
+        k_coarse_pos<NG><<<C.gridw, 256, 0, h->stream>>>(F.d, C.d);
+        k_lever<NG><<<F.grid128, 128, 0, h->stream>>>(F.d, C.d);
+        CK(cudaMemsetAsync(C.d.val, 0, sizeof(double) * DD * std::max<int64_t>(C.d.n_slots, 1), h->stream));
+        CK(cudaMemsetAsync(C.d.diag, 0, sizeof(double) * DD * C.d.n_pad, h->stream));
         lbarrier(h, l, 0);                           // lever arms of neighbour rows on other ranks
-        halo_pull(h, l, F.d.lev, 2, 0);
-        if (F.jds) k_galerkin3_jds<<<F.grid128, 128, 0, h->stream>>>(F.d, C.d, xref(h, F.d.lev, true));
-        else k_galerkin3_csr<<<F.gridw, 256, 0, h->stream>>>(F.d, C.d, xref(h, F.d.lev, true));
+        halo_pull(h, l, F.d.lev, LS, 0);
+        if (F.jds) k_galerkin_jds<D><<<F.grid128, 128, 0, h->stream>>>(F.d, C.d, xref(h, F.d.lev, true));
+        else k_galerkin_csr<D><<<F.gridw, 256, 0, h->stream>>>(F.d, C.d, xref(h, F.d.lev, true));
         h->launch_count += 3;
         if (C.first_repl) {                          // every rank built the coarse rows of its own aggregates: all-gather them
             lbarrier(h, l, 0);
-            gather_rows(h, C.d.val, C.src_slots, 9, 1, 0, 0);
-            gather_rows(h, C.d.diag, C.src_rows, 1, 9, C.d.n_pad, 0);
-            gather_rows(h, C.d.pos, C.src_rows, 1, 2, C.d.n_pad, 0);
+            gather_rows(h, C.d.val, C.src_slots, DD, 1, 0, 0);
+            gather_rows(h, C.d.diag, C.src_rows, 1, DD, C.d.n_pad, 0);
+            gather_rows(h, C.d.pos, C.src_rows, 1, NG, C.d.n_pad, 0);
         }
-        k_invert_diag3<<<C.grid128, 128, 0, h->stream>>>(C.d);
+        k_invert_diag<D><<<C.grid128, 128, 0, h->stream>>>(C.d);
         h->launch_count += 1;
     }
     if (h->sym.dense_coarsest) {
         LevelBuf &C = h->lv[last];
         const int m = h->dense_m;
         CK(cudaMemsetAsync(h->Ainv, 0, sizeof(double) * (size_t)m * m, h->stream));
-        if (C.jds) k_dense_assemble<true><<<C.grid128, 128, 0, h->stream>>>(C.d, h->dmap, 0, m, h->Ainv);
-        else k_dense_assemble<false><<<C.grid128, 128, 0, h->stream>>>(C.d, h->dmap, 0, m, h->Ainv);
+        if (C.jds) k_dense_assemble<D, true><<<C.grid128, 128, 0, h->stream>>>(C.d, h->dmap, 0, m, h->Ainv);
+        else k_dense_assemble<D, false><<<C.grid128, 128, 0, h->stream>>>(C.d, h->dmap, 0, m, h->Ainv);
         h->launch_count += 1;
         void *args[] = {(void *)&h->dense_m, (void *)&h->Ainv, (void *)&h->panelR, (void *)&h->panelC};
         CK(cudaLaunchCooperativeKernel((void *)k_dense_invert, dim3(h->invert_grid), dim3(256), args, 0, h->stream));
@@ -382,7 +385,7 @@ int amg_setup(pgo_handle *h) {
     if (!h->omega_ready) {
         for (int l = 0; l < (int)h->lv.size(); l++) {
             if (l == last && h->sym.dense_coarsest) continue;
-            int rc = estimate_omega(h, l);
+            int rc = estimate_omega<D>(h, l);
             if (rc) return rc;
         }
         h->omega_ready = true;
@@ -406,15 +409,15 @@ int comm_status(pgo_handle *h, const Scalars &s) {
 }
 
 // solve H x = b (b in h->r, destroyed) ; x in h->x
-int solve(pgo_handle *h, int32_t *iters_out) {
+template <int D> int solve(pgo_handle *h, int32_t *iters_out) {
     LevelBuf &B = h->lv[0];
-    const int64_t nd = B.d.n_pad * 4;
+    const int64_t nd = B.d.n_pad * VecStride<D>::value;
     int rc = reset_scalars(h);
     if (rc) return rc;
-    rc = build_pcg_graph(h);
+    rc = build_pcg_graph<D>(h);
     if (rc) return rc;
     CK(cudaMemsetAsync(h->x, 0, nd * sizeof(double), h->stream));
-    precondition<FIN_RZ_INIT>(h);
+    precondition<D, FIN_RZ_INIT>(h);
     CK(cudaMemcpyAsync(h->p, h->z, nd * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     xbarrier(h);
     // keep two graph launches in flight; poll the pinned scalars of the older one
@@ -450,24 +453,29 @@ int solve(pgo_handle *h, int32_t *iters_out) {
     return PGO_OK;
 }
 
-int retract(pgo_handle *h, double sign) {
+template <int D> int retract(pgo_handle *h, double sign) {
     LevelBuf &B = h->lv[0];
-    k_retract_se2<<<grid_for(B.d.n, 256), 256, 0, h->stream>>>(B.d, h->poses, h->x, sign, h->S, h->partials);
+    if (D == 3) k_retract_se2<<<grid_for(B.d.n, 256), 256, 0, h->stream>>>(B.d, h->poses, h->x, sign, h->S, h->partials);
+    else k_retract_se3<<<grid_for(B.d.n, 256), 256, 0, h->stream>>>(B.d, h->poses, h->x, sign, h->S, h->partials);
     h->launch_count += 1;
     xreduce<FIN_NORM>(h, 0, 0);                      // also: every rank's poses are updated before anyone reads them
     CK(cudaGetLastError());
     return PGO_OK;
 }
 
-int chi2_launch(pgo_handle *h) {
+template <int D> int chi2_launch(pgo_handle *h) {
     xbarrier(h, 0);
-    halo_pull(h, 0, h->poses, 4, 0);
-    k_chi2_se2<<<grid_for(h->n_edges_loc, 256), 256, 0, h->stream>>>(h->n_edges_loc, h->ends, h->ed, h->poses, xref(h, h->poses, true), h->S, h->partials);
+    halo_pull(h, 0, h->poses, Dim<D>::PS, 0);
+    if (D == 3) k_chi2_se2<<<grid_for(h->n_edges_loc, 256), 256, 0, h->stream>>>(h->n_edges_loc, h->ends, h->ed, h->poses, xref(h, h->poses, true), h->S, h->partials);
+    else k_chi2_se3<<<grid_for(h->n_edges_loc, 256), 256, 0, h->stream>>>(h->n_edges_loc, h->ends, h->ed, h->poses, h->S, h->partials);
     h->launch_count += 1;
     xreduce<FIN_CHI2>(h, 0, 0);
     CK(cudaGetLastError());
     return PGO_OK;
 }
+
+// block dimension dispatch: 3 (SE2 / XY graphs) or 6 (SE3 graphs)
+#define BY_D(h, fn, ...) ((h)->sym.D == 6 ? fn<6>(__VA_ARGS__) : fn<3>(__VA_ARGS__))
 
 int fail_create(pgo_handle *h, int rc, const std::string &msg) {
     g_create_error = msg.empty() ? h->err : msg;
@@ -551,7 +559,8 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
     so.build_amg = h->use_amg;
     if (!build_symbolic(h->sym, so, nv, vid, vkind, ne, ekind, efrom, eto)) return fail_create(h, PGO_ERR_ARG, h->sym.error);
     Symbolic &S = h->sym;
-    if (S.D != 3) return fail_create(h, PGO_ERR_UNSUPPORTED, "SE3 graphs are not supported by this build yet");
+    // per-dimension record sizes (kernels.cuh: Dim<D>)
+    const int D = S.D, DD = D * D, VS = D == 6 ? 6 : 4, PS = D == 6 ? 8 : 4, NG = D == 6 ? 3 : 2, LS = D == 6 ? 4 : 2, NM = D == 6 ? 28 : 10;
 
     if (h->opt.device == -2) { *out = h; return PGO_OK; }   // structure-only handle (no device): symbolic-pass queries only
     int ndev = 0;
@@ -600,7 +609,7 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
         B.gridw = grid_for(d.n_pad, 8);
         B.grid8 = grid_for(d.n_pad, 32);
         B.lpr = (!H.jds && d.n > 0 && d.n_slots <= 12 * d.n) ? 8 : 32;     // short rows: 8 lanes per row
-        B.gridv = grid_for(d.n_pad * 2, 256);
+        B.gridv = grid_for(d.n_pad * (VS / 2), 256);
         max_grid = std::max<int64_t>(max_grid, std::max(B.grid128, B.gridw));
         // row pointers
         std::vector<int64_t> rp;
@@ -651,15 +660,15 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
         CKC(upload(h, &drp, rp)); CKC(upload(h, &ddg, dg)); CKC(upload(h, &dcl, cl));
         d.slice_ptr = drp; d.deg = ddg; d.col = dcl;
         if (B.first_repl) {   // gathered from the peers after the Galerkin product: peer-visible
-            arena_request(h, &d.val, (size_t)9 * max_slots);
-            arena_request(h, &d.diag, (size_t)9 * max_pad);
-            arena_request(h, &d.pos, (size_t)2 * max_pad);
+            arena_request(h, &d.val, (size_t)DD * max_slots);
+            arena_request(h, &d.diag, (size_t)DD * max_pad);
+            arena_request(h, &d.pos, (size_t)NG * max_pad);
         } else {
-            CKC(dalloc(h, &d.val, (size_t)9 * std::max<int64_t>(d.n_slots, 1)));
-            CKC(dalloc(h, &d.diag, (size_t)9 * d.n_pad));
-            CKC(dalloc(h, &d.pos, (size_t)2 * d.n_pad));
+            CKC(dalloc(h, &d.val, (size_t)DD * std::max<int64_t>(d.n_slots, 1)));
+            CKC(dalloc(h, &d.diag, (size_t)DD * d.n_pad));
+            CKC(dalloc(h, &d.pos, (size_t)NG * d.n_pad));
         }
-        CKC(dalloc(h, &d.dinv, (size_t)9 * d.n_pad));
+        CKC(dalloc(h, &d.dinv, (size_t)DD * d.n_pad));
         if (!H.agg.empty()) {
             HostLevel &Cn = S.levels[l + 1];
             const int64_t c0 = Cn.part_off[(world > 1 && Cn.repl) ? 0 : rank];
@@ -687,8 +696,8 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
             d.mem_ptr = dmp; d.mem_idx = dmi;
         }
         // peer-visible vectors of this level
-        const size_t vec = (size_t)4 * max_pad;
-        arena_request(h, &d.lev, (size_t)2 * max_pad);
+        const size_t vec = (size_t)VS * max_pad;
+        arena_request(h, &d.lev, (size_t)LS * max_pad);
         if (h->use_amg) {
             arena_request(h, &B.xa, vec); arena_request(h, &B.res, vec);
             if (l > 0) {
@@ -701,8 +710,8 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
         B.vec_rows = max_pad;
     }
     {
-        const size_t vec = (size_t)4 * h->lv[0].vec_rows;
-        arena_request(h, &h->poses, vec);
+        const size_t vec = (size_t)VS * h->lv[0].vec_rows;
+        arena_request(h, &h->poses, (size_t)PS * h->lv[0].vec_rows);
         arena_request(h, &h->x, vec); arena_request(h, &h->r, vec); arena_request(h, &h->p, vec);
         arena_request(h, &h->q, vec); arena_request(h, &h->z, vec);
     }
@@ -710,7 +719,7 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
         const HostLevel &HL = S.levels[nl - 1];     // single GPU, or replicated: one partition
         h->dmap.off[0] = 0;
         for (int k = 0; k < MAX_RANKS; k++) h->dmap.off[k + 1] = (int32_t)HL.n;
-        h->dense_m = (int)HL.n * 3;
+        h->dense_m = (int)HL.n * D;
     }
     CKC(arena_commit(h));
     if (h->use_amg && S.dense_coarsest) {
@@ -723,7 +732,8 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
         CKU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
         h->invert_grid = std::max(1, std::min(per_sm, 2) * sms);
         h->invert_grid = std::min(h->invert_grid, std::max(sms, ((m + 7) / 8) * ((m + 255) / 256)));
-        CKU(cudaFuncSetAttribute(k_dense_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 3 * 1024)));
+        CKU(cudaFuncSetAttribute(k_dense_apply<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 6 * 1024)));
+        CKU(cudaFuncSetAttribute(k_dense_apply<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 6 * 1024)));
     }
     h->chunk = h->use_amg ? 4 : 16;
 
@@ -741,8 +751,10 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
         CKC(upload(h, &h->row_valofs, rvo));
         CKC(dalloc(h, &h->vstage, (size_t)S.n_values));
         CKU(cudaMemcpyAsync(h->vstage, vval, S.n_values * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        k_import_poses<<<grid_for(h->n_loc, 256), 256, 0, h->stream>>>(h->n_loc, h->row_valofs, dvk, h->vstage, h->poses);
+        if (D == 6) k_import_poses_se3<<<grid_for(h->n_loc, 256), 256, 0, h->stream>>>(h->n_loc, h->row_valofs, h->vstage, h->poses);
+        else k_import_poses<<<grid_for(h->n_loc, 256), 256, 0, h->stream>>>(h->n_loc, h->row_valofs, dvk, h->vstage, h->poses);
         CKU(cudaGetLastError());
+        if (D == 6) h->lv[0].d.quat = h->poses;
     }
     {
         const int64_t ag = S.anchor >= 0 ? S.iperm[S.anchor] : -1;
@@ -750,25 +762,32 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
     }
     // ---- measurements: per-edge packed offsets
     std::vector<int64_t> mofs(ne + 1, 0), iofs(ne + 1, 0);
-    for (int64_t k = 0; k < ne; k++) { mofs[k + 1] = mofs[k] + (ekind[k] == 0 ? 3 : 2); iofs[k + 1] = iofs[k] + (ekind[k] == 0 ? 6 : 3); }
-    auto edge_rec = [&](int64_t k, double *o) {   // z: x y cos sin ; Omega upper (6)
+    static const int NMEAS[3] = {3, 2, 7}, NINFO[3] = {6, 3, 21};
+    for (int64_t k = 0; k < ne; k++) { mofs[k + 1] = mofs[k] + NMEAS[ekind[k]]; iofs[k + 1] = iofs[k] + NINFO[ekind[k]]; }
+    auto edge_rec = [&](int64_t k, double *o) {   // SE2: z = x y cos sin ; Omega upper (6).  SE3: z = t(3) q(w,x,y,z) normalised ; Omega upper (21)
         const double *m = emeas + mofs[k], *w = einfo + iofs[k];
-        for (int c = 0; c < 10; c++) o[c] = 0.0;
+        for (int c = 0; c < NM; c++) o[c] = 0.0;
+        if (ekind[k] == 2) {
+            const double nq = std::sqrt(m[3] * m[3] + m[4] * m[4] + m[5] * m[5] + m[6] * m[6]);
+            o[0] = m[0]; o[1] = m[1]; o[2] = m[2]; o[3] = m[6] / nq; o[4] = m[3] / nq; o[5] = m[4] / nq; o[6] = m[5] / nq;
+            for (int c = 0; c < 21; c++) o[7 + c] = w[c];
+            return;
+        }
         o[0] = m[0]; o[1] = m[1];
         if (ekind[k] == 0) { o[2] = std::cos(m[2]); o[3] = std::sin(m[2]); for (int c = 0; c < 6; c++) o[4 + c] = w[c]; }
         else { for (int c = 0; c < 3; c++) o[4 + c] = w[c]; }
     };
     {   // half-edge stream, laid out like val with 10 components
-        std::vector<double> hz((size_t)10 * std::max<int64_t>(s1 - s0, 1), 0.0);
-        double rec[10];
+        std::vector<double> hz((size_t)NM * std::max<int64_t>(s1 - s0, 1), 0.0);
+        double rec[28];
         for (int64_t r = r0; r < r0 + h->n_loc; r++) {
             const int lane = (int)(r & 31);
             for (int64_t qi = H0.adj_ptr[r]; qi < H0.adj_ptr[r + 1]; qi++) {
                 const int64_t slot = H0.adj_slot[qi] - s0;
                 const int64_t cnt = H0.adj_cnt[qi];
                 edge_rec(S.slot_edge[H0.adj_slot[qi]], rec);
-                double *dst = hz.data() + (slot - lane) * 10 + lane;
-                for (int c = 0; c < 10; c++) dst[c * cnt] = rec[c];
+                double *dst = hz.data() + (slot - lane) * NM + lane;
+                for (int c = 0; c < NM; c++) dst[c * cnt] = rec[c];
             }
         }
         CKC(upload(h, &h->hz, hz));
@@ -779,14 +798,14 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
         const int64_t nm = (int64_t)mine.size();
         h->n_edges_loc = nm;
         std::vector<uint2> ends(std::max<int64_t>(nm, 1));
-        std::vector<double> ed((size_t)10 * std::max<int64_t>(nm, 1), 0.0);
-        double rec[10];
+        std::vector<double> ed((size_t)NM * std::max<int64_t>(nm, 1), 0.0);
+        double rec[28];
         for (int64_t i = 0; i < nm; i++) {
             const int64_t k = mine[i];
             const int64_t a = S.iperm[S.efrom[k]];
             ends[i] = make_uint2((uint32_t)(a - r0), h->to_index[k] | (ekind[k] == 1 ? COL_EDGE_XY : 0u));
             edge_rec(k, rec);
-            for (int c = 0; c < 10; c++) ed[(size_t)c * nm + i] = rec[c];
+            for (int c = 0; c < NM; c++) ed[(size_t)c * nm + i] = rec[c];
         }
         CKC(upload(h, &h->ends, ends));
         CKC(upload(h, &h->ed, ed));
@@ -869,7 +888,7 @@ int pgo_get_sizes(const pgo_handle *h, int64_t *nv, int64_t *ne, int64_t *len, i
 int pgo_chi2(pgo_handle *h, double *chi2) {
     if (!h || !chi2) return PGO_ERR_ARG;
     NEED_DEVICE(h);
-    int rc = chi2_launch(h);
+    int rc = BY_D(h, chi2_launch, h);
     if (rc) return rc;
     CK(cudaMemcpyAsync(&h->hS[0], h->S, sizeof(Scalars), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -884,20 +903,20 @@ int pgo_gn_step(pgo_handle *h, double lambda, int add_lambda, double *norm_dx, d
     auto mark = [&](int i) { cudaEventRecord(h->ev[i], h->stream); };
     int64_t lc[6];
     mark(0); lc[0] = h->launch_count;
-    int rc = assemble(h, lambda, add_lambda);
+    int rc = BY_D(h, assemble, h, lambda, add_lambda);
     if (rc) return rc;
     mark(1); lc[1] = h->launch_count;
-    rc = amg_setup(h);
+    rc = BY_D(h, amg_setup, h);
     if (rc) return rc;
     mark(2); lc[2] = h->launch_count;
     int32_t iters = 0;
-    int src = solve(h, &iters);
+    int src = BY_D(h, solve, h, &iters);
     if (src != PGO_OK && src != PGO_ERR_NOT_CONVERGED) return src;
     mark(3); lc[3] = h->launch_count;
-    rc = retract(h, 1.0);
+    rc = BY_D(h, retract, h, 1.0);
     if (rc) return rc;
     mark(4); lc[4] = h->launch_count;
-    rc = chi2_launch(h);
+    rc = BY_D(h, chi2_launch, h);
     if (rc) return rc;
     mark(5); lc[5] = h->launch_count;
     CK(cudaMemcpyAsync(&h->hS[0], h->S, sizeof(Scalars), cudaMemcpyDeviceToHost, h->stream));
@@ -919,7 +938,7 @@ int pgo_undo_last_step(pgo_handle *h) {
     if (!h) return PGO_ERR_ARG;
     NEED_DEVICE(h);
     if (!h->have_step) { h->err = "pgo_undo_last_step: no step to undo"; return PGO_ERR_ARG; }
-    int rc = retract(h, -1.0);
+    int rc = BY_D(h, retract, h, -1.0);
     if (rc) return rc;
     CK(cudaStreamSynchronize(h->stream));
     return PGO_OK;
@@ -928,11 +947,11 @@ int pgo_undo_last_step(pgo_handle *h) {
 int pgo_linearize_and_solve(pgo_handle *h, int32_t *pcg_iterations) {
     if (!h) return PGO_ERR_ARG;
     NEED_DEVICE(h);
-    int rc = assemble(h, 0.0, 0);
+    int rc = BY_D(h, assemble, h, 0.0, 0);
     if (rc) return rc;
-    rc = amg_setup(h);
+    rc = BY_D(h, amg_setup, h);
     if (rc) return rc;
-    return solve(h, pcg_iterations);
+    return BY_D(h, solve, h, pcg_iterations);
 }
 
 // vertex values of the rows this rank owns are a contiguous span of the packed array (contiguous vertex ranges)
@@ -949,7 +968,8 @@ int pgo_get_poses(pgo_handle *h, double *out, int64_t n_values) {
     if (n_values != S.n_values) { h->err = "pgo_get_poses: wrong buffer length"; return PGO_ERR_ARG; }
     int64_t o0, o1;
     owned_span(h, &o0, &o1);
-    k_export_poses<<<grid_for(h->n_loc, 256), 256, 0, h->stream>>>(h->n_loc, h->row_valofs, h->lv[0].d.vkind, h->poses, h->vstage);
+    if (S.D == 6) k_export_poses_se3<<<grid_for(h->n_loc, 256), 256, 0, h->stream>>>(h->n_loc, h->row_valofs, h->poses, h->vstage);
+    else k_export_poses<<<grid_for(h->n_loc, 256), 256, 0, h->stream>>>(h->n_loc, h->row_valofs, h->lv[0].d.vkind, h->poses, h->vstage);
     h->launch_count += 1;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out + o0, h->vstage + o0, (o1 - o0) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -965,7 +985,8 @@ int pgo_set_poses(pgo_handle *h, const double *in, int64_t n_values) {
     int64_t o0, o1;
     owned_span(h, &o0, &o1);
     CK(cudaMemcpyAsync(h->vstage + o0, in + o0, (o1 - o0) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    k_import_poses<<<grid_for(h->n_loc, 256), 256, 0, h->stream>>>(h->n_loc, h->row_valofs, h->lv[0].d.vkind, h->vstage, h->poses);
+    if (S.D == 6) k_import_poses_se3<<<grid_for(h->n_loc, 256), 256, 0, h->stream>>>(h->n_loc, h->row_valofs, h->vstage, h->poses);
+    else k_import_poses<<<grid_for(h->n_loc, 256), 256, 0, h->stream>>>(h->n_loc, h->row_valofs, h->lv[0].d.vkind, h->vstage, h->poses);
     h->launch_count += 1;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));   // `in` is borrowed for the duration of the call only
@@ -976,7 +997,7 @@ int pgo_set_poses(pgo_handle *h, const double *in, int64_t n_values) {
 int pgo_snapshot_poses(pgo_handle *h) {
     if (!h) return PGO_ERR_ARG;
     NEED_DEVICE(h);
-    const size_t cnt = (size_t)4 * h->n_pad_loc;
+    const size_t cnt = (size_t)(h->sym.D == 6 ? 8 : 4) * h->n_pad_loc;
     if (!h->poses_saved) { int rc = dalloc(h, &h->poses_saved, cnt, false); if (rc) return rc; }
     CK(cudaMemcpyAsync(h->poses_saved, h->poses, cnt * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -987,7 +1008,7 @@ int pgo_restore_poses(pgo_handle *h) {
     if (!h) return PGO_ERR_ARG;
     NEED_DEVICE(h);
     if (!h->poses_saved) { h->err = "pgo_restore_poses: no snapshot"; return PGO_ERR_ARG; }
-    CK(cudaMemcpyAsync(h->poses, h->poses_saved, (size_t)4 * h->n_pad_loc * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->poses, h->poses_saved, (size_t)(h->sym.D == 6 ? 8 : 4) * h->n_pad_loc * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->have_step = false;
     return PGO_OK;
@@ -998,13 +1019,14 @@ int pgo_get_dx(pgo_handle *h, double *out, int64_t len) {
     NEED_DEVICE(h);
     const Symbolic &S = h->sym;
     if (len != S.len) { h->err = "pgo_get_dx: wrong buffer length"; return PGO_ERR_ARG; }
-    std::vector<double> xs((size_t)4 * h->n_pad_loc);
+    const int VS = S.D == 6 ? 6 : 4;
+    std::vector<double> xs((size_t)VS * h->n_pad_loc);
     CK(cudaMemcpyAsync(xs.data(), h->x, xs.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     for (int64_t r = 0; r < h->n_loc; r++) {
         const int64_t v = S.perm[h->row0 + r];
-        const int d = S.vkind[v] == 0 ? 3 : 2;
-        for (int c = 0; c < d; c++) out[S.voffset[v] + c] = xs[4 * r + c];
+        const int d = KDIM[S.vkind[v]];
+        for (int c = 0; c < d; c++) out[S.voffset[v] + c] = xs[VS * r + c];
     }
     return PGO_OK;
 }
@@ -1044,17 +1066,18 @@ int pgo_get_system(pgo_handle *h, double lambda, int add_lambda, double *csc_val
     NEED_DEVICE(h);
     Symbolic &S = h->sym;
     if (!build_csc_pattern(S)) { h->err = S.error; return PGO_ERR_UNSUPPORTED; }
-    int rc = assemble(h, lambda, add_lambda);
+    int rc = BY_D(h, assemble, h, lambda, add_lambda);
     if (rc) return rc;
     HostLevel &H = S.levels[0];
+    const int D = S.D, DD = D * D, VS = D == 6 ? 6 : 4;
     const int64_t r0 = h->row0, s0 = H.part_slot[h->rank], s1 = H.part_slot[h->rank + 1], npl = h->n_pad_loc;
-    std::vector<double> val((size_t)9 * std::max<int64_t>(s1 - s0, 1)), diag((size_t)9 * npl), rv((size_t)4 * npl);
+    std::vector<double> val((size_t)DD * std::max<int64_t>(s1 - s0, 1)), diag((size_t)DD * npl), rv((size_t)VS * npl);
     CK(cudaMemcpyAsync(val.data(), h->lv[0].d.val, val.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(diag.data(), h->lv[0].d.diag, diag.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(rv.data(), h->r, rv.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     // canonical block values of the owned block rows (duplicate edges between a vertex pair sum into one block)
-    std::vector<double> blk((size_t)9 * S.bcol.size(), 0.0);
+    std::vector<double> blk((size_t)DD * S.bcol.size(), 0.0);
     auto find = [&](int32_t rr, int32_t cc) -> int64_t {
         auto bb = S.bcol.begin() + S.brow_ptr[rr], ee = S.bcol.begin() + S.brow_ptr[rr + 1];
         return std::lower_bound(bb, ee, cc) - S.bcol.begin();
@@ -1062,27 +1085,27 @@ int pgo_get_system(pgo_handle *h, double lambda, int add_lambda, double *csc_val
     for (int64_t r = 0; r < h->n_loc; r++) {
         const int32_t u = S.perm[r0 + r];
         const int lane = (int)(r & 31);
-        double *d = &blk[9 * find(u, u)];
-        for (int c = 0; c < 9; c++) d[c] += diag[(size_t)c * npl + r];
+        double *d = &blk[DD * find(u, u)];
+        for (int c = 0; c < DD; c++) d[c] += diag[(size_t)c * npl + r];
         for (int64_t qi = H.adj_ptr[r0 + r]; qi < H.adj_ptr[r0 + r + 1]; qi++) {
             const int64_t slot = H.adj_slot[qi] - s0, cnt = H.adj_cnt[qi];
             const int32_t v = S.perm[H.adj_nbr[qi]];
-            double *o = &blk[9 * find(u, v)];
-            const double *src = val.data() + (slot - lane) * 9 + lane;
-            for (int c = 0; c < 9; c++) o[c] += src[c * cnt];
+            double *o = &blk[DD * find(u, v)];
+            const double *src = val.data() + (slot - lane) * DD + lane;
+            for (int c = 0; c < DD; c++) o[c] += src[c * cnt];
         }
     }
     if (csc_values) {
         int64_t o = 0;
         for (int64_t v = 0; v < S.n; v++) {
-            const int dv = S.vkind[v] == 0 ? 3 : 2;
+            const int dv = KDIM[S.vkind[v]];
             for (int c = 0; c < dv; c++)
                 for (int64_t pp = S.brow_ptr[v]; pp < S.brow_ptr[v + 1]; pp++) {
                     const int32_t u = S.bcol[pp];
-                    const int du = S.vkind[u] == 0 ? 3 : 2;
+                    const int du = KDIM[S.vkind[u]];
                     if (u >= S.vrange[h->rank] && u < S.vrange[h->rank + 1]) {
                         const int64_t bi = find(u, (int32_t)v);                    // block (row u, col v)
-                        for (int rr = 0; rr < du; rr++) csc_values[o + rr] = blk[9 * bi + 3 * rr + c];
+                        for (int rr = 0; rr < du; rr++) csc_values[o + rr] = blk[DD * bi + D * rr + c];
                     }
                     o += du;
                 }
@@ -1091,8 +1114,8 @@ int pgo_get_system(pgo_handle *h, double lambda, int add_lambda, double *csc_val
     if (b) {
         for (int64_t r = 0; r < h->n_loc; r++) {
             const int64_t v = S.perm[r0 + r];
-            const int d = S.vkind[v] == 0 ? 3 : 2;
-            for (int c = 0; c < d; c++) b[S.voffset[v] + c] = rv[4 * r + c];
+            const int d = KDIM[S.vkind[v]];
+            for (int c = 0; c < d; c++) b[S.voffset[v] + c] = rv[VS * r + c];
         }
     }
     return PGO_OK;
@@ -1113,9 +1136,10 @@ int pgo_time_spmv(pgo_handle *h, int32_t repeats, double *avg_ms) {
     LevelBuf &B = h->lv[0];
     // p -> q with the PCG SpMV; done-flag test disabled so the launches always do the work, no cross-rank reduction
     XRef xr = xref(h, h->p, true);
-    halo_pull(h, 0, h->p, 4, 0);
+    halo_pull(h, 0, h->p, h->sym.D == 6 ? 6 : 4, 0);
     auto launch = [&]() {
-        k_spmv<3, 0, FIN_NONE, false><<<B.grid128, 128, 0, h->stream>>>(B.d, xr, h->p, nullptr, h->q, 0.0, nullptr, nullptr, h->S, h->partials, 0, 0);
+        if (h->sym.D == 6) k_spmv<6, 0, FIN_NONE, false><<<B.grid128, 128, 0, h->stream>>>(B.d, xr, h->p, nullptr, h->q, 0.0, nullptr, nullptr, h->S, h->partials, 0, 0);
+        else k_spmv<3, 0, FIN_NONE, false><<<B.grid128, 128, 0, h->stream>>>(B.d, xr, h->p, nullptr, h->q, 0.0, nullptr, nullptr, h->S, h->partials, 0, 0);
     };
     for (int i = 0; i < 3; i++) launch();
     CK(cudaEventRecord(h->ev[PGO_NUM_PHASES], h->stream));

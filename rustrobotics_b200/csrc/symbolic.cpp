@@ -193,7 +193,7 @@ static int32_t aggregate_partition(const HostLevel &F, int k, int max_size, std:
 // Build the coarse level (block CSR, global padded numbering) from per-partition aggregate ids; fills F.agg, F.ctgt.
 // merge: F is sharded over pnc.size() partitions but C becomes one replicated partition (rows of rank k's aggregates at src_off[k])
 static void build_coarse_level(HostLevel &F, HostLevel &C, const std::vector<std::vector<int32_t>> &pagg,
-                               const std::vector<int64_t> &pnc, bool jds, bool merge) {
+                               const std::vector<int64_t> &pnc, bool jds, bool merge, int DD) {
     const int world = (int)pnc.size();
     std::vector<int64_t> cbase(world, 0);       // coarse row of partition k's aggregate 0
     if (merge) {
@@ -251,9 +251,9 @@ static void build_coarse_level(HostLevel &F, HostLevel &C, const std::vector<std
                 const int64_t cs = C.adj_slot[q] - C.part_slot[kc];
                 if (jds) {
                     const int64_t lane = I & 31;
-                    F.ctgt[slot] = (int32_t)((cs - lane) * 9 + lane);
+                    F.ctgt[slot] = (int32_t)((cs - lane) * DD + lane);
                     F.cstr[slot] = C.adj_cnt[q];
-                } else F.ctgt[slot] = (int32_t)(cs * 9);
+                } else F.ctgt[slot] = (int32_t)(cs * DD);
             }
         }
 }
@@ -406,14 +406,14 @@ bool build_symbolic(Symbolic &S, const SymbolicOptions &opt,
         const bool merge = fworld > 1 && nc <= repl_max;
         const bool jds = nc >= opt.jds_min_rows && !merge && !F.repl;
         S.levels.emplace_back();
-        build_coarse_level(S.levels[lvl], S.levels[lvl + 1], pagg, pnc, false, merge);
+        build_coarse_level(S.levels[lvl], S.levels[lvl + 1], pagg, pnc, false, merge, S.D * S.D);
         if (jds) {
             // a large coarse level is streamed like level 0: one thread per row over the sliced storage
             sort_aggregates_by_degree(S.levels[lvl + 1], pagg, pnc, std::max(32, opt.sort_window / 32 * 32));
             S.levels[lvl + 1] = HostLevel();
-            build_coarse_level(S.levels[lvl], S.levels[lvl + 1], pagg, pnc, true, merge);
+            build_coarse_level(S.levels[lvl], S.levels[lvl + 1], pagg, pnc, true, merge, S.D * S.D);
         }
-        if (S.levels[lvl + 1].n_slots * 9 > 0x7fffffffll) { S.error = "coarse level exceeds 32-bit Galerkin targets"; return false; }
+        if (S.levels[lvl + 1].n_slots * S.D * S.D > 0x7fffffffll) { S.error = "coarse level exceeds 32-bit Galerkin targets"; return false; }
     }
     return true;
 }

@@ -20,6 +20,9 @@ from oracle.oracle import OraclePoseGraph  # noqa: E402
 
 DATASETS = Path("/root/reference/dataset/g2o")
 SE2_FILES = ["simulation-pose-pose", "simulation-pose-landmark", "intel", "dlr", "input_M3500_g2o"]
+# SE(3): the reference only PARSES these (optimize is todo!() for SE3, pose_graph_optimization.rs:241,357,570); the results stored
+# for them are the oracle's own (repo-defined semantics) -- parity unpinned.
+SE3_FILES = ["sphere2500", "parking-garage"]
 
 
 def pattern_hash(col_ptr, row_idx):
@@ -28,12 +31,12 @@ def pattern_hash(col_ptr, row_idx):
 
 def main():
     out = Path(__file__).resolve().parent
-    for name in SE2_FILES:
+    for name in SE2_FILES + SE3_FILES:
         g = OraclePoseGraph.from_g2o(DATASETS / f"{name}.g2o")
         arrays = g.arrays()
         sls = g.build_linear_system()
         dx0 = sls.solve()
-        errs, norms = g.optimize(100, return_norms=True)
+        errs, norms = g.optimize(100 if name in SE2_FILES else 12, return_norms=True)
         _, _, _, final = g.vertices()
         np.savez_compressed(out / f"{name}.npz", **arrays, len=np.int64(g.len), chi2_history=np.array(errs),
                             norm_history=np.array(norms), final_values=final, dx0=dx0, puts=np.int64(sls.puts),

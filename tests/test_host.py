@@ -78,7 +78,7 @@ def _structure_handle(graph):
     return PoseGraph(graph=graph, options=Options(device=-2))
 
 
-@pytest.mark.parametrize("name", SE2_GRAPHS)
+@pytest.mark.parametrize("name", SE2_GRAPHS + ["sphere2500", "parking-garage"])
 def test_pattern_bit_exact(built, name):
     """the symbolic pass's scalar CSC pattern == the pattern the reference's COO puts turn into (oracle)"""
     gold = load_golden(name)
@@ -91,7 +91,7 @@ def test_pattern_bit_exact(built, name):
     assert h == str(gold["pattern_sha256"])
 
 
-@pytest.mark.parametrize("name", SE2_GRAPHS)
+@pytest.mark.parametrize("name", SE2_GRAPHS + ["sphere2500", "parking-garage"])
 def test_block_structure_and_slot_map(built, name):
     """block CSR + edge->slot map against a direct restatement of update_linear_system's four set_matrix calls"""
     gold = load_golden(name)

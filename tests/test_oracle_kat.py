@@ -79,3 +79,40 @@ def test_lm_bookkeeping(graphs):                   # :275-286: LM runs, error hi
     errs = g.optimize(20)
     assert errs[0] == pytest.approx(3030.313, abs=1e-2)
     assert min(errs) < 480.0
+
+
+# ---- SE(3): repo-defined semantics (the reference's optimize is todo!() for SE3) -- parity unpinned -----------
+@pytest.mark.parametrize("name", ["sphere2500", "parking-garage"])
+def test_se3_jacobians_match_finite_differences(name):
+    """A, B of se3_error_jac (oracle/pgo_oracle.c) are the derivatives of e w.r.t. the retraction of update_nodes
+    (t += dt, q <- q Exp(dw)): central differences through the oracle's own update_nodes / error."""
+    from conftest import graph_of, load_golden
+    from oracle.oracle import OraclePoseGraph
+    g = graph_of(load_golden(name))
+    o = OraclePoseGraph.from_arrays(**g)
+    _, _, off, _ = o.vertices()
+    ek, fi, ti = o.edge_endpoints()
+    s0 = o.state().copy()
+    h = 1e-6
+    for k in (0, 7, len(ek) // 2, len(ek) - 1):
+        e0, A, B = o.edge_linearize(k)
+        for J, v in ((A, fi[k]), (B, ti[k])):
+            num = np.zeros((6, 6))
+            for c in range(6):
+                cols = []
+                for sgn in (+1.0, -1.0):
+                    dx = np.zeros(o.len)
+                    dx[off[v] + c] = sgn * h
+                    o.set_state(s0)
+                    o.update_nodes(dx)
+                    cols.append(o.edge_linearize(k)[0])
+                num[:, c] = (cols[0] - cols[1]) / (2 * h)
+            o.set_state(s0)
+            np.testing.assert_allclose(J, num, atol=2e-6 * max(1.0, np.abs(num).max()))
+
+
+def test_se3_oracle_converges_on_the_bundled_graphs():
+    from conftest import load_golden
+    for name, final in (("sphere2500", 1351.3623), ("parking-garage", 1.26838)):
+        hist = load_golden(name)["chi2_history"]
+        assert abs(hist[-1] - final) <= 1e-3 * final and hist[-1] < 1e-3 * hist[0]
