@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -557,6 +558,7 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
     so.agg_size = h->opt.amg_aggregate_size;
     so.dense_max = h->opt.amg_dense_max;
     so.build_amg = h->use_amg;
+    if (const char *e = std::getenv("PGO_REPL_MAX_ROWS")) so.repl_max_rows = std::atoll(e);      // tuning knob (sharded handles)
     if (!build_symbolic(h->sym, so, nv, vid, vkind, ne, ekind, efrom, eto)) return fail_create(h, PGO_ERR_ARG, h->sym.error);
     Symbolic &S = h->sym;
     // per-dimension record sizes (kernels.cuh: Dim<D>)
