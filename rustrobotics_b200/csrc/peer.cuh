@@ -61,8 +61,8 @@ __global__ void __launch_bounds__(32) k_xreduce(Comm *mine, CommRef peers, int r
 // {a.b (, b.c)} over the local rows -> FIN (used when the preconditioner itself has no kernel to fuse the dots into)
 template <int D, int FIN>
 __global__ void __launch_bounds__(128) k_dots(int64_t n_pad, const double *__restrict__ a, const double *__restrict__ b,
-                                               const double *__restrict__ c, Scalars *S, double *partials) {
-    if (ld_done(S)) return;
+                                               const double *__restrict__ c, Scalars *S, double *partials, int lvl, int check_done) {
+    if (check_done && ld_done(S)) return;
     constexpr int VS = VecStride<D>::value;
     const int64_t row = (int64_t)blockIdx.x * 128 + threadIdx.x;
     double dots[2] = {0.0, 0.0};
@@ -79,7 +79,16 @@ __global__ void __launch_bounds__(128) k_dots(int64_t n_pad, const double *__res
             for (int q = 0; q < D; q++) dots[1] = fma(cv[q], bv[q], dots[1]);
         }
     }
-    reduce_and_finalize<128, FIN>(dots, S, partials, 0);
+    reduce_and_finalize<128, FIN>(dots, S, partials, lvl);
+}
+
+// v *= s
+__global__ void __launch_bounds__(256) k_scale(int64_t n_doubles, double *__restrict__ v, double s) {
+    const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 2;
+    if (i >= n_doubles) return;
+    double2 t = *reinterpret_cast<double2 *>(v + i);
+    t.x *= s; t.y *= s;
+    *reinterpret_cast<double2 *>(v + i) = t;
 }
 
 } // namespace pgo

@@ -262,7 +262,7 @@ template <int D, int FINK> void precondition(pgo_handle *h) {   // z = M^-1 r (+
     if (h->use_amg && h->lv.size() > 1) cycle<D, FINK>(h, 0, h->r, h->z);
     else if (h->use_amg && h->sym.dense_coarsest) {      // the whole system fits the direct solve
         dense_apply<D>(h, 0, h->r, h->z);
-        k_dots<D, FINK><<<B.grid128, 128, 0, h->stream>>>(B.d.n_pad, h->r, h->z, h->q, h->S, h->partials);
+        k_dots<D, FINK><<<B.grid128, 128, 0, h->stream>>>(B.d.n_pad, h->r, h->z, h->q, h->S, h->partials, 0, 1);
         h->launch_count += 1;
         xreduce<FINK>(h, 0, 1);
     } else {
@@ -309,37 +309,47 @@ template <int D> int assemble(pgo_handle *h, double lambda, int add_lambda) {
     return PGO_OK;
 }
 
-// power iteration for rho(Dinv H) on one level -> damping of the block-Jacobi smoother (the norm is taken over the
-// local rows only: an estimate is all that is needed)
+int comm_status(pgo_handle *h, const Scalars &s) {
+    if (s.status == ST_COMM) { h->err = "peer synchronisation timed out (a rank is missing or out of step)"; return PGO_ERR_NCCL; }
+    return PGO_OK;
+}
+
+// power iteration for rho(Dinv H) on one level -> damping of the block-Jacobi smoother.  The norm is reduced over ALL
+// ranks on the device (same value, hence the same omega, everywhere); the host only reads one scalar per iteration.
 template <int D> int estimate_omega(pgo_handle *h, int l) {
     constexpr int VS = VecStride<D>::value;
     LevelBuf &B = h->lv[l];
     const int64_t nd = B.d.n_pad * VS;
     std::vector<double> v(nd, 0.0);
-    uint64_t s = 0x9E3779B97F4A7C15ull;
+    // the start vector is a function of the GLOBAL row, so that it does not depend on the partition
+    const int64_t g0 = B.repl ? 0 : h->sym.levels[l].part_off[h->rank];
     for (int64_t i = 0; i < B.d.n; i++)
-        for (int c = 0; c < D; c++) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; v[i * VS + c] = (double)(s >> 11) / 9007199254740992.0 - 0.5; }
+        for (int c = 0; c < D; c++) {
+            uint64_t s = 0x9E3779B97F4A7C15ull * (uint64_t)((g0 + i) * 8 + c + 1);
+            s ^= s >> 29; s *= 0xBF58476D1CE4E5B9ull; s ^= s >> 32;
+            v[i * VS + c] = (double)(s >> 11) / 9007199254740992.0 - 0.5;
+        }
     if (l == 0 && D == 3) {   // keep the landmark padding unknown out of it
         for (int64_t i = 0; i < B.d.n; i++) if (h->sym.vkind[h->sym.perm[h->row0 + i]] == 1) v[i * 4 + 2] = 0.0;
     }
     double *a = B.xa, *b = B.res;
     CK(cudaMemcpyAsync(a, v.data(), nd * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     double rho = 1.0;
-    for (int it = 0; it < 10; it++) {
+    for (int it = 0; it < 12; it++) {
         // b = H a ; a' = Dinv b ; rho ~ |a'| / |a|
         lbarrier(h, l, 0);
         spmv_any<D, 0>(h, l, a, nullptr, b, 0.0, 0);
-        lbarrier(h, l, 0);
         k_dinv_apply<D, FIN_NONE><<<B.grid128, 128, 0, h->stream>>>(B.d, b, a, 1.0, nullptr, h->S, h->partials, 0);
-        CK(cudaMemcpyAsync(v.data(), a, nd * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        k_dots<D, FIN_NORM><<<B.grid128, 128, 0, h->stream>>>(B.d.n_pad, a, a, nullptr, h->S, h->partials, l, 0);
+        xreduce<FIN_NORM>(h, l, 0);
+        CK(cudaMemcpyAsync(&h->hS[0], h->S, sizeof(Scalars), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
-        double nrm = 0.0;
-        for (double t : v) nrm += t * t;
-        nrm = std::sqrt(nrm);
-        if (!(nrm > 0.0) || !std::isfinite(nrm)) { rho = 2.0; nrm = 1.0; }
-        else rho = nrm;                  // |a| was normalised to 1
-        for (double &t : v) t /= nrm;
-        CK(cudaMemcpyAsync(a, v.data(), nd * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        int rc = comm_status(h, h->hS[0]);
+        if (rc) return rc;
+        const double nrm = std::sqrt(h->hS[0].norm2_dx);
+        if (!(nrm > 0.0) || !std::isfinite(nrm)) { rho = 2.0; break; }
+        if (it > 0) rho = nrm;                                   // |a| was normalised to 1 by the previous pass
+        k_scale<<<grid_for(nd / 2, 256), 256, 0, h->stream>>>(nd, a, 1.0 / nrm);
     }
     B.omega = 4.0 / (3.0 * 1.1 * std::max(rho, 1.0));
     if (B.omega > 1.0) B.omega = 1.0;
@@ -401,11 +411,6 @@ int reset_scalars(pgo_handle *h) {
     s.max_iters = h->opt.pcg_max_iterations;
     // counters / epoch / world must survive (they are always consistent between kernels); everything before them is re-initialised
     CK(cudaMemcpyAsync(h->S, &s, offsetof(Scalars, counter), cudaMemcpyHostToDevice, h->stream));
-    return PGO_OK;
-}
-
-int comm_status(pgo_handle *h, const Scalars &s) {
-    if (s.status == ST_COMM) { h->err = "peer synchronisation timed out (a rank is missing or out of step)"; return PGO_ERR_NCCL; }
     return PGO_OK;
 }
 
