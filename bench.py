@@ -34,7 +34,18 @@ sys.path.insert(0, str(ROOT))
 
 METRIC = "gn_edges_per_sec"
 UNIT = "edges/s"
-CPU_SAMPLE_POSES = 100_000
+CPU_SAMPLE_POSES = 100_000          # Manhattan SE2 sample of the CPU arm
+CPU_SAMPLE_POSES_SE3 = 25_000       # sphere SE3 sample (50 levels x 500)
+
+
+def make_graph(workload: str, n_poses: int):
+    """(graph arrays, block dimension, description) of a BASELINE.json workload"""
+    from rustrobotics_b200.synthetic import manhattan_se2, sphere_se3
+    if workload == "sphere":
+        g = sphere_se3(max(2, n_poses // 500), 500)
+        return g, 6, "synthetic sphere SE3 pose graph (6x6 blocks; repo-defined SE3 semantics, parity unpinned), {} poses / {} edges, seed 42 (BASELINE configs[4])"
+    g = manhattan_se2(n_poses)
+    return g, 3, "synthetic Manhattan-world SE2 pose graph, {} poses / {} edges, seed 42 (BASELINE configs[3])"
 
 
 def log(*a):
@@ -109,13 +120,12 @@ def ncu_traffic():
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(n_poses: int, steps: int, warmup: int):
-    """The reference's CPU path (oracle restatement) on a bounded sample: a Manhattan graph of `n_poses` poses.
+def cpu_reference_run(n_poses: int, steps: int, warmup: int, workload: str = "manhattan"):
+    """The reference's CPU path (oracle restatement) on a bounded sample: a graph of `n_poses` poses of the workload.
     Every step is one GN iteration from the same initial guess.  -> (edges/s, seconds per step, description, cores)"""
     import numpy as np
     from oracle.oracle import OraclePoseGraph
-    from rustrobotics_b200.synthetic import manhattan_se2
-    g = manhattan_se2(n_poses)
+    g, _, _ = make_graph(workload, n_poses)
     ne = len(g["edge_from"])
     o = OraclePoseGraph.from_arrays(**g)
     s0 = o.state().copy()
@@ -137,7 +147,7 @@ def cpu_reference_run(n_poses: int, steps: int, warmup: int):
             ts.append(dt)
         log(f"[cpu] GN iteration {i}: {dt:.2f} s")
     sec = sum(ts) / len(ts)
-    sample = (f"Manhattan SE2 {n_poses} poses / {ne} edges (seed 42), {steps} GN iteration(s) from the initial guess; "
+    sample = (f"{'sphere SE3' if workload == 'sphere' else 'Manhattan SE2'} {len(g['vertex_id'])} poses / {ne} edges (seed 42), {steps} GN iteration(s) from the initial guess; "
               f"oracle/ restatement: sequential COO assembly + COO->CSC + SciPy SuperLU (stand-in for UMFPACK) + retract + chi2; "
               f"assembly single-threaded like the reference, BLAS threads available to SuperLU: {blas_threads}")
     return ne / sec, sec, sample, 1
@@ -147,14 +157,15 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    n = min(args.poses, CPU_SAMPLE_POSES)
-    val, sec, sample, cores = cpu_reference_run(n, args.steps, args.warmup)
+    n = min(args.poses, CPU_SAMPLE_POSES_SE3 if args.workload == "sphere" else CPU_SAMPLE_POSES)
+    val, sec, sample, cores = cpu_reference_run(n, args.steps, args.warmup, args.workload)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "gn_iterations_per_sec": 1.0 / sec,
-        "config": {"workload": f"synthetic Manhattan SE2, {args.poses} poses / {4 * args.poses} edges (BASELINE configs[3]); "
-                               f"CPU arm runs the bounded sample below", "sample_poses": n},
+        "config": {"workload": (f"synthetic sphere SE3, {args.poses} poses (BASELINE configs[4]); " if args.workload == "sphere" else
+                                f"synthetic Manhattan SE2, {args.poses} poses / {4 * args.poses} edges (BASELINE configs[3]); ") +
+                               "CPU arm runs the bounded sample below", "sample_poses": n},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "host_cpus": os.cpu_count(),
@@ -180,7 +191,6 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from rustrobotics_b200 import Options, PoseGraph, _build
-    from rustrobotics_b200.synthetic import manhattan_se2
     _build.build()
 
     def barrier():
@@ -189,7 +199,7 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     t0 = time.perf_counter()
-    g = manhattan_se2(args.poses)
+    g, D, wl_desc = make_graph(args.workload, args.poses)
     n_poses, n_edges = len(g["vertex_id"]), len(g["edge_from"])
     t_gen = time.perf_counter() - t0
     t0 = time.perf_counter()
@@ -235,7 +245,8 @@ def run_b200(args):
     barrier()
     st = pg.stats()
     nb = st["block_rows"] + st["offdiag_blocks"]          # blocks of H incl. diagonal
-    spmv_bytes = 76 * nb + 52 * st["block_rows"]          # 72B + 4B (col) + 4N (row ptr) + 24N (x) + 24N (y)
+    # 8 D^2 B (values) + 4B (col) + 4N (row ptr) + 8 D N (x) + 8 D N (y)  [D = 3: 76B + 52N]
+    spmv_bytes = (8 * D * D + 4) * nb + (4 + 16 * D) * st["block_rows"]
     peak, peak_src = measured_peak_hbm()
     achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9
     tr = ncu_traffic()
@@ -275,28 +286,27 @@ def run_b200(args):
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            v, sec, sample, cores = cpu_reference_run(CPU_SAMPLE_POSES, 2, 0)
+            v, sec, sample, cores = cpu_reference_run(CPU_SAMPLE_POSES_SE3 if D == 6 else CPU_SAMPLE_POSES, 2, 0, args.workload)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "s_per_gn_iteration": sec}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"synthetic Manhattan-world SE2 pose graph, {n_poses} poses / {n_edges} edges, seed 42 "
-                                   f"(BASELINE configs[3]); 1 step = 1 Gauss-Newton iteration from the initial guess",
+            "config": {"workload": wl_desc.format(n_poses, n_edges) + "; 1 step = 1 Gauss-Newton iteration from the initial guess",
                        "poses": n_poses, "edges": n_edges, "pcg_rtol": args.pcg_rtol,
                        "preconditioner": "aggregation-AMG K-cycle (flexible PCG)" if args.preconditioner == 1 else "block-Jacobi",
                        "parallelism": "single GPU" if world == 1 else
                        f"1 graph sharded over {world} GPUs by contiguous vertex ranges; halo rows read from peer HBM (NVLink), "
                        f"device-side peer-memory all-reduce for the dot products",
-                       "l2": "working set 2.4 GB >> 126 MB L2, no flush needed"},
+                       "l2": f"working set {st['device_bytes'] * world / 1e9:.1f} GB >> 126 MB L2, no flush needed"},
             "gn_iterations_per_sec": 1e3 / step_ms, "pcg_iterations_per_step": sum(pcg_its) / len(pcg_its),
             "wall_ms_per_step": wall_ms, "phase_ms": phases, "create_s": t_create,
             "partition": pg.partition() if world > 1 else None,
             "chi2": {"initial": chi2_0, "after_step": last[1], "norm_dx": last[0]},
-            "roofline": {"bound": "hbm", "kernel": "k_spmv<3,0> (fine-level BSR SpMV)" + ("" if world == 1 else ", rank 0's shard"), "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": f"k_spmv<{D},0> (fine-level BSR SpMV)" + ("" if world == 1 else ", rank 0's shard"), "achieved": achieved, "peak": peak,
                          "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "ms_per_launch": spmv_ms,
                          "algorithmic_bytes_per_launch": spmv_bytes,
-                         "traffic": (tr or {}).get("dram_bytes_per_launch")},
+                         "traffic": (tr or {}).get("dram_bytes_per_launch") if (D == 3 and world == 1 and n_poses == 1_000_000) else None},
             "cpu_baseline": cpu,
             "e2e": {"value": total_edges / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(init_np.nbytes), "d2h_bytes_per_step": int(out_np.nbytes) + 20 * world},
@@ -315,12 +325,16 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--poses", type=int, default=1_000_000)
+    ap.add_argument("--workload", default="manhattan", choices=["manhattan", "sphere"],
+                    help="manhattan = BASELINE configs[3] (the headline, default); sphere = configs[4] (SE3, 6x6 blocks)")
+    ap.add_argument("--poses", type=int, default=None, help="default: 1M (manhattan) / 250k (sphere)")
     ap.add_argument("--pcg-rtol", type=float, default=1e-8)
     ap.add_argument("--preconditioner", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    if args.poses is None:
+        args.poses = 250_000 if args.workload == "sphere" else 1_000_000
     if args.impl == "reference":
         return run_reference(args)
     return run_b200(args)

@@ -267,3 +267,26 @@ def test_config4_full_size_properties(built):
     assert pg.global_error() == c0
     m1, d1, jt1 = pg.gn_step(allow_not_converged=False)
     assert abs(m1 - n1) <= 1e-6 * n1 and abs(d1 - c1) <= CHI2_RTOL * c1 and abs(jt1 - it1) <= 0.05 * it1
+
+
+def test_cpp_example_and_bench_drivers(built, g2o_files, tmp_path):
+    """examples/pose_graph_optimization.cpp (reference examples/mapping/pose_graph_optimization.rs:49-50) and
+    benches/graph_slam.cpp (reference benches/graph_slam.rs:6-13) through the C++ host mirror"""
+    import json
+    import subprocess
+    from conftest import ROOT
+    subprocess.check_call(["make", "-C", str(ROOT / "examples")], stdout=subprocess.DEVNULL)
+    r = subprocess.run([str(ROOT / "examples" / "pose_graph_optimization"), str(g2o_files["intel"]), "GaussNewton", "plot"],
+                       capture_output=True, text=True, cwd=tmp_path, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "Loaded graph with 1728 nodes and 4830 edges" in r.stdout
+    final = float(r.stdout.strip().splitlines()[-1].split()[2])
+    want, eps = KAT.FINAL_ERROR["intel"]
+    assert abs(final - want) <= eps
+    assert list((tmp_path / "img").glob("*.svg"))                       # plot=true writes img/*.svg (:375-431)
+    r = subprocess.run([str(ROOT / "examples" / "graph_slam"), str(g2o_files["intel"]), "3"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["bench"] == "graph_slam_intel" and abs(out["final_chi2"] - want) <= eps and out["mean_ms"] > 0
+    r = subprocess.run([str(ROOT / "examples" / "pose_graph_optimization"), str(tmp_path / "missing.g2o")], capture_output=True, text=True)
+    assert r.returncode == 1 and "error:" in r.stderr
