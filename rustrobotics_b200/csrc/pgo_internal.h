@@ -92,7 +92,7 @@ struct SymbolicOptions {
     int max_levels = 12;
     int agg_size = 16;
     int dense_max = 640;               // a level with at most this many rows is solved directly
-    int64_t repl_max_rows = 32768;     // world > 1: coarse levels up to this many rows are replicated on every rank
+    int64_t repl_max_rows = 131072;    // world > 1: coarse levels up to this many rows are replicated on every rank (no cross-rank sync inside them)
     int64_t jds_min_rows = INT64_MAX;     // coarse levels at least this large use the sliced storage (thread per row), smaller ones block CSR
     bool build_amg = true;
 };
