@@ -85,7 +85,9 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // Block-level sum of NV values; the block writes its partials, the LAST block to arrive sums all partials in a
 // fixed order (deterministic) and returns true in thread 0 with `total` set.  counter wraps to 0.
-template <int NT, int NV> __device__ bool block_sum_last(const double *v, double *partials, unsigned *counter, double *total) {
+// (vb, nvb) = this block's index and the block count of the launch: blockIdx.x / gridDim.x for a plain kernel, the virtual
+// block of a stage when the stage runs inside the persistent coarse-tail kernel (k_tail).
+template <int NT, int NV> __device__ bool block_sum_last(const double *v, double *partials, unsigned *counter, double *total, unsigned vb, unsigned nvb) {
     __shared__ double sm[NV][NT / 32];
     __shared__ bool is_last;
 #pragma unroll
@@ -100,11 +102,11 @@ template <int NT, int NV> __device__ bool block_sum_last(const double *v, double
             double s = 0;
 #pragma unroll
             for (int w = 0; w < NT / 32; w++) s += sm[k][w];
-            partials[(size_t)blockIdx.x * NV + k] = s;
+            partials[(size_t)vb * NV + k] = s;
         }
         __threadfence();
-        unsigned t = atomicInc(counter, gridDim.x - 1);
-        is_last = (t == gridDim.x - 1);
+        unsigned t = atomicInc(counter, nvb - 1);
+        is_last = (t == nvb - 1);
     }
     __syncthreads();
     if (!is_last) return false;
@@ -112,7 +114,7 @@ template <int NT, int NV> __device__ bool block_sum_last(const double *v, double
     double s[NV];
 #pragma unroll
     for (int k = 0; k < NV; k++) s[k] = 0;
-    for (unsigned i = threadIdx.x; i < gridDim.x; i += NT)
+    for (unsigned i = threadIdx.x; i < nvb; i += NT)
 #pragma unroll
         for (int k = 0; k < NV; k++) s[k] += __ldcg(partials + (size_t)i * NV + k);
     __syncthreads();
@@ -178,11 +180,12 @@ __device__ __forceinline__ void finalize(int FIN, Scalars *S, const double *t, i
     __threadfence();
 }
 
-template <int NT, int FIN> __device__ __forceinline__ void reduce_and_finalize(const double *dots, Scalars *S, double *partials, int lvl) {
+template <int NT, int FIN> __device__ __forceinline__ void reduce_and_finalize(const double *dots, Scalars *S, double *partials, int lvl,
+                                                                              unsigned vb, unsigned nvb) {
     if (FIN == FIN_NONE) return;
     constexpr int NV = fin_ndot(FIN) > 0 ? fin_ndot(FIN) : 1;
     double total[NV];
-    if (block_sum_last<NT, NV>(dots, partials, &S->counter[FIN], total)) {
+    if (block_sum_last<NT, NV>(dots, partials, &S->counter[FIN], total, vb, nvb)) {
         if (S->world > 1 && lvl < S->repl_from) {
 #pragma unroll
             for (int k = 0; k < NV; k++) S->loc[k] = total[k];
@@ -308,20 +311,19 @@ __global__ void __launch_bounds__(128) k_spmv(LevelDev L, const __grid_constant_
         }
         st_vec<VS>(y + row * VS, out);
     }
-    reduce_and_finalize<128, FIN>(dots, S, partials, lvl);
+    reduce_and_finalize<128, FIN>(dots, S, partials, lvl, blockIdx.x, gridDim.x);
 }
 
 // Coarse levels (L2-resident, latency-bound): block CSR, LPR lanes per block row (8 when rows are short, else a full
 // warp), 256 / LPR rows per CTA.  Same modes; K-cycle dots:
 //   FIN_K1: {x.y, x.u1}    FIN_K2: {x.u1, x.y, x.u2}      (x = c, y = H c)
 template <int D, int MODE, int FIN, bool PEER, int LPR>
-__global__ void __launch_bounds__(256) k_spmv_csr(LevelDev L, const __grid_constant__ XRef xr, const double *__restrict__ x, const double *__restrict__ r,
-                                                   double *__restrict__ y, double omega, const double *__restrict__ u1,
-                                                   const double *__restrict__ u2, Scalars *S, double *partials, int lvl, int check_done) {
-    if (check_done && ld_done(S)) return;
+__device__ __forceinline__ void spmv_csr_body(const LevelDev &L, const XRef &xr, const double *__restrict__ x, const double *__restrict__ r,
+                                              double *__restrict__ y, double omega, const double *__restrict__ u1,
+                                              const double *__restrict__ u2, Scalars *S, double *partials, int lvl, unsigned vb, unsigned nvb) {
     constexpr int DD = D * D, VS = VecStride<D>::value;
     const int sub = threadIdx.x & (LPR - 1);
-    const int64_t row = (int64_t)blockIdx.x * (256 / LPR) + threadIdx.x / LPR;
+    const int64_t row = (int64_t)vb * (256 / LPR) + threadIdx.x / LPR;
     double dots[3] = {0.0, 0.0, 0.0};
     // whole warps take the branch together (LPR divides 32 and rows beyond n only occur at the tail)
     const bool live = row < L.n;
@@ -393,16 +395,22 @@ __global__ void __launch_bounds__(256) k_spmv_csr(LevelDev L, const __grid_const
         }
         st_vec<VS>(y + row * VS, out);
     }
-    reduce_and_finalize<256, FIN>(dots, S, partials, lvl);
+    reduce_and_finalize<256, FIN>(dots, S, partials, lvl, vb, nvb);
+}
+template <int D, int MODE, int FIN, bool PEER, int LPR>
+__global__ void __launch_bounds__(256) k_spmv_csr(LevelDev L, const __grid_constant__ XRef xr, const double *__restrict__ x, const double *__restrict__ r,
+                                                   double *__restrict__ y, double omega, const double *__restrict__ u1,
+                                                   const double *__restrict__ u2, Scalars *S, double *partials, int lvl, int check_done) {
+    if (check_done && ld_done(S)) return;
+    spmv_csr_body<D, MODE, FIN, PEER, LPR>(L, xr, x, r, y, omega, u1, u2, S, partials, lvl, blockIdx.x, gridDim.x);
 }
 
 // x = omega Dinv r  (pre-smoothing from a zero guess; with FIN: block-Jacobi z = Dinv r and r.z (, z.u1))
-template <int D, int FIN>
-__global__ void __launch_bounds__(128) k_dinv_apply(LevelDev L, const double *__restrict__ r, double *__restrict__ x, double omega,
-                                                     const double *__restrict__ u1, Scalars *S, double *partials, int check_done) {
-    if (check_done && ld_done(S)) return;
+template <int D, int FIN, int NT>
+__device__ __forceinline__ void dinv_apply_body(const LevelDev &L, const double *__restrict__ r, double *__restrict__ x, double omega,
+                                                const double *__restrict__ u1, Scalars *S, double *partials, unsigned vb, unsigned nvb) {
     constexpr int VS = VecStride<D>::value;
-    const int64_t row = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    const int64_t row = (int64_t)vb * NT + threadIdx.x;
     double dots[2] = {0.0, 0.0};
     if (row < L.n_pad) {
         double ri[VS], out[VS];
@@ -426,7 +434,13 @@ __global__ void __launch_bounds__(128) k_dinv_apply(LevelDev L, const double *__
         }
         st_vec<VS>(x + row * VS, out);
     }
-    reduce_and_finalize<128, FIN>(dots, S, partials, 0);
+    reduce_and_finalize<NT, FIN>(dots, S, partials, 0, vb, nvb);
+}
+template <int D, int FIN>
+__global__ void __launch_bounds__(128) k_dinv_apply(LevelDev L, const double *__restrict__ r, double *__restrict__ x, double omega,
+                                                     const double *__restrict__ u1, Scalars *S, double *partials, int check_done) {
+    if (check_done && ld_done(S)) return;
+    dinv_apply_body<D, FIN, 128>(L, r, x, omega, u1, S, partials, blockIdx.x, gridDim.x);
 }
 
 // x += alpha p ; r -= alpha q
@@ -462,16 +476,21 @@ __global__ void __launch_bounds__(256) k_update_p(int64_t n_pad, double *__restr
 
 // K-cycle vector updates at level lvl:  WHICH 0: out = a - alpha_l b      WHICH 1: out = coef1_l a + coef2_l b
 template <int WHICH>
-__global__ void __launch_bounds__(256) k_kcombine(int64_t n_doubles, const double *__restrict__ a, const double *__restrict__ b,
-                                                   double *__restrict__ out, const Scalars *S, int lvl) {
-    if (ld_done(S)) return;
-    const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 2;
+__device__ __forceinline__ void kcombine_body(int64_t n_doubles, const double *__restrict__ a, const double *__restrict__ b,
+                                              double *__restrict__ out, const Scalars *S, int lvl, unsigned vb) {
+    const int64_t i = ((int64_t)vb * 256 + threadIdx.x) * 2;
     if (i >= n_doubles) return;
     const double2 av = *reinterpret_cast<const double2 *>(a + i), bv = *reinterpret_cast<const double2 *>(b + i);
     double2 o;
     if (WHICH == 0) { const double al = S->k[lvl].alpha; o.x = fma(-al, bv.x, av.x); o.y = fma(-al, bv.y, av.y); }
     else { const double c1 = S->k[lvl].coef1, c2 = S->k[lvl].coef2; o.x = fma(c1, av.x, c2 * bv.x); o.y = fma(c1, av.y, c2 * bv.y); }
     *reinterpret_cast<double2 *>(out + i) = o;
+}
+template <int WHICH>
+__global__ void __launch_bounds__(256) k_kcombine(int64_t n_doubles, const double *__restrict__ a, const double *__restrict__ b,
+                                                   double *__restrict__ out, const Scalars *S, int lvl) {
+    if (ld_done(S)) return;
+    kcombine_body<WHICH>(n_doubles, a, b, out, S, lvl, blockIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -610,12 +629,10 @@ __device__ __forceinline__ void xfer_ptap(const double *h, const Xfer<6> &Pi, co
 
 // rc_I = sum_{i in I} P_i^T res_i   (one warp per coarse row; fixed summation order => deterministic)
 template <int D>
-__global__ void __launch_bounds__(256) k_restrict(LevelDev F, LevelDev C, const double *__restrict__ res, double *__restrict__ rc,
-                                                   const Scalars *S) {
-    if (ld_done(S)) return;
+__device__ __forceinline__ void restrict_body(const LevelDev &F, const LevelDev &C, const double *__restrict__ res, double *__restrict__ rc, unsigned vb) {
     constexpr int VS = VecStride<D>::value;
     const int lane = threadIdx.x & 31;
-    const int64_t I = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int64_t I = (int64_t)vb * 8 + (threadIdx.x >> 5);
     if (I >= C.n_pad) return;
     double s[VS];
 #pragma unroll
@@ -632,13 +649,18 @@ __global__ void __launch_bounds__(256) k_restrict(LevelDev F, LevelDev C, const 
     }
     if (lane == 0) st_vec<VS>(rc + I * VS, s);
 }
+template <int D>
+__global__ void __launch_bounds__(256) k_restrict(LevelDev F, LevelDev C, const double *__restrict__ res, double *__restrict__ rc,
+                                                   const Scalars *S) {
+    if (ld_done(S)) return;
+    restrict_body<D>(F, C, res, rc, blockIdx.x);
+}
 
 // x_i += P_i e_{agg(i)}
-template <int D>
-__global__ void __launch_bounds__(128) k_prolong(LevelDev F, const double *__restrict__ ec, double *__restrict__ x, const Scalars *S) {
-    if (ld_done(S)) return;
+template <int D, int NT>
+__device__ __forceinline__ void prolong_body(const LevelDev &F, const double *__restrict__ ec, double *__restrict__ x, unsigned vb) {
     constexpr int VS = VecStride<D>::value;
-    const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    const int64_t i = (int64_t)vb * NT + threadIdx.x;
     if (i >= F.n) return;
     const int64_t I = F.agg[i];
     double e[VS], xi[VS];
@@ -646,6 +668,11 @@ __global__ void __launch_bounds__(128) k_prolong(LevelDev F, const double *__res
     ld_vec<VS>(x + i * VS, xi);
     xfer_prolong(xfer_own<D>(F, i), e, xi);
     st_vec<VS>(x + i * VS, xi);
+}
+template <int D>
+__global__ void __launch_bounds__(128) k_prolong(LevelDev F, const double *__restrict__ ec, double *__restrict__ x, const Scalars *S) {
+    if (ld_done(S)) return;
+    prolong_body<D, 128>(F, ec, x, blockIdx.x);
 }
 
 // centroid of the members (one warp per coarse row); NG position planes
@@ -952,9 +979,8 @@ __global__ void __launch_bounds__(256) k_dense_invert(int m, double *__restrict_
 
 // x_own = Ainv[own rows, :] r  on the coarsest level; r is gathered from all ranks.  One warp per scalar row.
 template <int D>
-__global__ void __launch_bounds__(256) k_dense_apply(int64_t n_local, DenseMap dm, int rank, int world, int m, const double *__restrict__ Ainv,
-                                                      const __grid_constant__ XRef rr, double *__restrict__ x, const Scalars *S) {
-    if (ld_done(S)) return;
+__device__ __forceinline__ void dense_apply_body(int64_t n_local, const DenseMap &dm, int rank, int world, int m, const double *__restrict__ Ainv,
+                                                 const XRef &rr, double *__restrict__ x, unsigned vb) {
     constexpr int VS = VecStride<D>::value;
     extern __shared__ double sr[];
     for (int t = threadIdx.x; t < m; t += 256) {
@@ -965,13 +991,19 @@ __global__ void __launch_bounds__(256) k_dense_apply(int64_t n_local, DenseMap d
     }
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const int64_t srow = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);      // local scalar row
+    const int64_t srow = (int64_t)vb * 8 + (threadIdx.x >> 5);      // local scalar row
     if (srow >= n_local * D) return;
     const double *a = Ainv + ((int64_t)dm.off[rank] * D + srow) * m;
     double s = 0.0;
     for (int j = lane; j < m; j += 32) s = fma(__ldg(a + j), sr[j], s);
     s = warp_sum(s);
     if (lane == 0) x[(srow / D) * VS + (srow % D)] = s;
+}
+template <int D>
+__global__ void __launch_bounds__(256) k_dense_apply(int64_t n_local, DenseMap dm, int rank, int world, int m, const double *__restrict__ Ainv,
+                                                      const __grid_constant__ XRef rr, double *__restrict__ x, const Scalars *S) {
+    if (ld_done(S)) return;
+    dense_apply_body<D>(n_local, dm, rank, world, m, Ainv, rr, x, blockIdx.x);
 }
 
 // Halo exchange: v[(n_pad + i) * stride ...] <- the record of row halo_src[i] in its owner's copy of v (peer HBM, NVLink).
@@ -1173,7 +1205,7 @@ __global__ void __launch_bounds__(256) k_chi2_se2(int64_t n_edges, const uint2 *
             c = e0 * (w[0] * e0 + w[1] * e1) + e1 * (w[1] * e0 + w[2] * e1);
         }
     }
-    reduce_and_finalize<256, FIN_CHI2>(&c, S, partials, 0);
+    reduce_and_finalize<256, FIN_CHI2>(&c, S, partials, 0, blockIdx.x, gridDim.x);
 }
 
 // update_nodes (:229-245): t += dx.xy (global frame), r <- r * (cos dth, sin dth) without
@@ -1197,7 +1229,7 @@ __global__ void __launch_bounds__(256) k_retract_se2(LevelDev L, double *__restr
         }
         st_vec<4>(poses + row * 4, p);
     }
-    reduce_and_finalize<256, FIN_NORM>(&n2, S, partials, 0);
+    reduce_and_finalize<256, FIN_NORM>(&n2, S, partials, 0, blockIdx.x, gridDim.x);
 }
 
 // pgo_set_poses / pgo_get_poses: g2o-layout vertex values (x y theta | x y, lut order, packed) <-> the
@@ -1442,7 +1474,7 @@ __global__ void __launch_bounds__(256) k_chi2_se3(int64_t n_edges, const uint2 *
             c = fma(t, e[cc], c);
         }
     }
-    reduce_and_finalize<256, FIN_CHI2>(&c, S, partials, 0);
+    reduce_and_finalize<256, FIN_CHI2>(&c, S, partials, 0, blockIdx.x, gridDim.x);
 }
 
 // t += dt ; q <- normalise(q Exp(dw)) ; ||dx||^2
@@ -1469,7 +1501,7 @@ __global__ void __launch_bounds__(256) k_retract_se3(LevelDev L, double *__restr
         p[4] = q[0] / n; p[5] = q[1] / n; p[6] = q[2] / n; p[7] = q[3] / n;
         st_vec<8>(poses + row * 8, p);
     }
-    reduce_and_finalize<256, FIN_NORM>(&n2, S, partials, 0);
+    reduce_and_finalize<256, FIN_NORM>(&n2, S, partials, 0, blockIdx.x, gridDim.x);
 }
 
 // g2o-layout SE3 vertex values (x y z qx qy qz qw) <-> pose records (x, y, z, 0, qw, qx, qy, qz), quaternion normalised on the way in

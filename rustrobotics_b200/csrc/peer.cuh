@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(128) k_dots(int64_t n_pad, const double *__res
             for (int q = 0; q < D; q++) dots[1] = fma(cv[q], bv[q], dots[1]);
         }
     }
-    reduce_and_finalize<128, FIN>(dots, S, partials, lvl);
+    reduce_and_finalize<128, FIN>(dots, S, partials, lvl, blockIdx.x, gridDim.x);
 }
 
 // v *= s

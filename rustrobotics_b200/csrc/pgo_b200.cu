@@ -21,6 +21,7 @@
 #include "../../include/pgo_b200.h"
 #include "kernels.cuh"
 #include "peer.cuh"
+#include "tail.cuh"
 
 using namespace pgo;
 
@@ -95,9 +96,22 @@ struct pgo_handle {
     DenseMap dmap{};
     int dense_m = 0, invert_grid = 0;
     bool use_amg = false, omega_ready = false;
+    bool tail_fail = false;
+    bool opt_tail = false;             // PGO_TAIL=1 enables the persistent coarse-tail kernel.  OFF by default: measured on B200
+                                       // (profiles/r01j_tail_experiment.log) it is 8 % SLOWER than one graph-launched kernel per
+                                       // stage: a stage is a ~3 us chain of dependent L2 loads either way, a grid-wide barrier
+                                       // costs about what a kernel boundary inside a CUDA graph costs, and the 80-register
+                                       // persistent CTAs hold fewer warps in flight for the 62k-row level than stand-alone launches
+    int tail_ctas_per_sm = 4;          // PGO_TAIL_CTAS_PER_SM
+    int64_t tail_max_rows = 262144;    // a level larger than this is bandwidth-bound on its own: not worth serialising in the tail
     int64_t anchor_row = -1;
     cudaGraphExec_t pcg_graph = nullptr;
     int chunk = 8;
+    // persistent coarse-tail kernel (tail.cuh): levels >= tail_level run as ONE cooperative launch per coarse solve
+    int tail_level = -1, tail_grid = 0, tail_ops = 0;
+    size_t tail_smem = 0;
+    TailOp *tail_prog = nullptr;
+    LevelDev *tail_lv = nullptr;
     int64_t launches_per_iter = 0;
     cudaEvent_t ev[PGO_NUM_PHASES + 2]{}, poll_ev[2]{};
     double ms[PGO_NUM_PHASES]{};
@@ -206,6 +220,100 @@ template <int D> void dense_apply(pgo_handle *h, int l, const double *rhs, doubl
     h->launch_count += 1;
 }
 
+// ---- persistent coarse tail: record the stage program of coarse_solve(T, lv[T].rhs -> lv[T].sol), launch it
+template <int D> void rec_coarse_solve(pgo_handle *h, int l, const double *rhs, double *out, std::vector<TailOp> &P);
+
+inline TailOp tail_op(int type, int lvl, int nvb) { TailOp o{}; o.type = type; o.lvl = lvl; o.nvb = nvb; o.fin = FIN_NONE; return o; }
+
+template <int D> void rec_spmv(pgo_handle *h, int l, int mode, int fin, const double *x, const double *r, double *y, double omega,
+                               const double *u1, const double *u2, std::vector<TailOp> &P) {
+    LevelBuf &B = h->lv[l];
+    TailOp o = tail_op(TOP_SPMV, l, B.lpr == 8 ? B.grid8 : B.gridw);       // the grids of the stand-alone launches
+    o.mode = mode; o.fin = fin; o.lpr = B.lpr == 8 ? 8 : 32;
+    o.a = x; o.b = r; o.c = u1; o.d = u2; o.out = y; o.omega = omega;
+    P.push_back(o);
+}
+
+template <int D> void rec_cycle(pgo_handle *h, int l, const double *rhs, double *out, std::vector<TailOp> &P) {
+    LevelBuf &B = h->lv[l];
+    const int last = (int)h->lv.size() - 1;
+    const int nvb_rows = grid_for(B.d.n_pad, 256);
+    if (l == last) {
+        if (h->sym.dense_coarsest) {
+            TailOp o = tail_op(TOP_DENSE, l, grid_for(B.d.n * D, 8)); o.a = rhs; o.out = out; P.push_back(o);
+        } else {
+            TailOp o = tail_op(TOP_DINV, l, nvb_rows); o.a = rhs; o.out = B.xa; o.omega = B.omega; P.push_back(o);
+            rec_spmv<D>(h, l, 2, FIN_NONE, B.xa, rhs, B.res, B.omega, nullptr, nullptr, P);
+            rec_spmv<D>(h, l, 2, FIN_NONE, B.res, rhs, out, B.omega, nullptr, nullptr, P);
+        }
+        return;
+    }
+    LevelBuf &C = h->lv[l + 1];
+    { TailOp o = tail_op(TOP_DINV, l, nvb_rows); o.a = rhs; o.out = B.xa; o.omega = B.omega; P.push_back(o); }
+    rec_spmv<D>(h, l, 1, FIN_NONE, B.xa, rhs, B.res, 0.0, nullptr, nullptr, P);
+    { TailOp o = tail_op(TOP_RESTRICT, l, C.gridw); o.a = B.res; o.out = C.rhs; P.push_back(o); }
+    rec_coarse_solve<D>(h, l + 1, C.rhs, C.sol, P);
+    { TailOp o = tail_op(TOP_PROLONG, l, nvb_rows); o.a = C.sol; o.out = B.xa; P.push_back(o); }
+    rec_spmv<D>(h, l, 2, FIN_NONE, B.xa, rhs, out, B.omega, nullptr, nullptr, P);
+}
+
+template <int D> void rec_coarse_solve(pgo_handle *h, int l, const double *rhs, double *out, std::vector<TailOp> &P) {
+    LevelBuf &B = h->lv[l];
+    const int last = (int)h->lv.size() - 1;
+    if (l == last || !B.kcycle) { rec_cycle<D>(h, l, rhs, out, P); return; }
+    rec_cycle<D>(h, l, rhs, B.c1, P);
+    rec_spmv<D>(h, l, 0, FIN_K1, B.c1, nullptr, B.v1, 0.0, rhs, nullptr, P);
+    { TailOp o = tail_op(TOP_KCOMBINE, l, B.gridv); o.mode = 0; o.a = rhs; o.b = B.v1; o.out = B.r1; P.push_back(o); }
+    rec_cycle<D>(h, l, B.r1, B.c2, P);
+    rec_spmv<D>(h, l, 0, FIN_K2, B.c2, nullptr, B.v2, 0.0, B.v1, B.r1, P);
+    { TailOp o = tail_op(TOP_KCOMBINE, l, B.gridv); o.mode = 1; o.a = B.c1; o.b = B.c2; o.out = out; P.push_back(o); }
+}
+
+// (re)build the stage program; called whenever the PCG graph is (re)captured (the smoother dampings are baked in)
+template <int D> int build_tail(pgo_handle *h) {
+    h->tail_level = -1;
+    if (!h->use_amg || !h->opt_tail) return PGO_OK;
+    const int nl = (int)h->lv.size(), last = nl - 1;
+    int T = -1;
+    for (int l = 1; l < last; l++) {
+        bool ok = (h->world == 1 || h->lv[l].repl) && h->lv[l].d.n <= h->tail_max_rows;
+        for (int k = l; k < nl && ok; k++) ok = !h->lv[k].jds;
+        if (ok) { T = l; break; }
+    }
+    if (T < 0) return PGO_OK;
+    std::vector<TailOp> P;
+    rec_coarse_solve<D>(h, T, h->lv[T].rhs, h->lv[T].sol, P);
+    std::vector<LevelDev> lv(nl);
+    for (int l = 0; l < nl; l++) lv[l] = h->lv[l].d;
+    if (!h->tail_lv) { int rc = dalloc(h, &h->tail_lv, (size_t)nl, false); if (rc) return rc; }
+    CK(cudaMemcpyAsync(h->tail_lv, lv.data(), nl * sizeof(LevelDev), cudaMemcpyHostToDevice, h->stream));
+    if (!h->tail_prog || (int)P.size() > h->tail_ops) { int rc = dalloc(h, &h->tail_prog, P.size(), false); if (rc) return rc; }
+    CK(cudaMemcpyAsync(h->tail_prog, P.data(), P.size() * sizeof(TailOp), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));          // P / lv are stack-owned
+    h->tail_ops = (int)P.size();
+    h->tail_smem = h->sym.dense_coarsest ? sizeof(double) * (size_t)h->dense_m : 0;
+    int per_sm = 0, sms = 0, coop = 0;
+    CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+    CK(cudaFuncSetAttribute(k_tail<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(h->tail_smem, 1024)));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tail<D>, 256, h->tail_smem));
+    if (!coop || per_sm < 1) return PGO_OK;        // no cooperative launch: keep the stage-per-kernel path
+    h->tail_grid = std::min(per_sm, h->tail_ctas_per_sm) * sms;
+    h->tail_level = T;
+    return PGO_OK;
+}
+
+template <int D> void launch_tail(pgo_handle *h) {
+    TailCtx T{};
+    T.prog = h->tail_prog; T.n_ops = h->tail_ops; T.lv = h->tail_lv;
+    T.dmap = h->dmap; T.dense_m = h->dense_m; T.Ainv = h->Ainv;
+    T.S = h->S; T.partials = h->partials;
+    void *args[] = {(void *)&T};
+    cudaError_t e = cudaLaunchCooperativeKernel((void *)k_tail<D>, dim3(h->tail_grid), dim3(256), args, h->tail_smem, h->stream);
+    if (e != cudaSuccess) { h->tail_fail = true; h->err = std::string("cooperative launch of the coarse-tail kernel failed: ") + cudaGetErrorString(e); }
+    h->launch_count += 1;
+}
+
 // ---- one multigrid cycle at level l: out = M_l(rhs).  FINK: dots fused into the last kernel (level 0 only).
 template <int D, int FINK> void cycle(pgo_handle *h, int l, const double *rhs, double *out) {
     LevelBuf &B = h->lv[l];
@@ -235,7 +343,8 @@ template <int D, int FINK> void cycle(pgo_handle *h, int l, const double *rhs, d
         lbarrier(h, l);
         gather_rows(h, C.rhs, C.src_rows, VecStride<D>::value, 1, 0, 1);
     }
-    coarse_solve<D>(h, l + 1, C.rhs, C.sol);
+    if (h->tail_level == l + 1) launch_tail<D>(h);   // the whole coarse solve C.rhs -> C.sol in one cooperative launch
+    else coarse_solve<D>(h, l + 1, C.rhs, C.sol);
     k_prolong<D><<<B.grid128, 128, 0, h->stream>>>(B.d, C.sol, B.xa, h->S);
     h->launch_count += 1;
     lbarrier(h, l);
@@ -284,11 +393,21 @@ template <int D> void pcg_iteration(pgo_handle *h) {
 
 template <int D> int build_pcg_graph(pgo_handle *h) {
     if (h->pcg_graph) return PGO_OK;
+    { int rc = build_tail<D>(h); if (rc) return rc; }
     cudaGraph_t g = nullptr;
     int64_t before = h->launch_count;
     CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
     for (int i = 0; i < h->chunk; i++) pcg_iteration<D>(h);
-    CK(cudaStreamEndCapture(h->stream, &g));
+    cudaError_t ce = cudaStreamEndCapture(h->stream, &g);
+    if (h->tail_fail || (ce != cudaSuccess && h->tail_level >= 0)) {
+        // the cooperative launch cannot be captured on this driver: fall back to one kernel per stage
+        if (g) cudaGraphDestroy(g);
+        (void)cudaGetLastError();
+        h->tail_fail = false; h->opt_tail = false; h->tail_level = -1; h->err.clear();
+        h->launch_count = before;
+        return build_pcg_graph<D>(h);
+    }
+    CK(ce);
     h->launches_per_iter = (h->launch_count - before) / h->chunk;
     h->launch_count = before;
     CK(cudaGraphInstantiate(&h->pcg_graph, g, 0));
@@ -424,6 +543,7 @@ template <int D> int solve(pgo_handle *h, int32_t *iters_out) {
     if (rc) return rc;
     CK(cudaMemsetAsync(h->x, 0, nd * sizeof(double), h->stream));
     precondition<D, FIN_RZ_INIT>(h);
+    if (h->tail_fail) { h->tail_fail = false; return PGO_ERR_CUDA; }
     CK(cudaMemcpyAsync(h->p, h->z, nd * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     xbarrier(h);
     // keep two graph launches in flight; poll the pinned scalars of the older one
@@ -563,7 +683,10 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
     so.agg_size = h->opt.amg_aggregate_size;
     so.dense_max = h->opt.amg_dense_max;
     so.build_amg = h->use_amg;
-    if (const char *e = std::getenv("PGO_REPL_MAX_ROWS")) so.repl_max_rows = std::atoll(e);      // tuning knob (sharded handles)
+    if (const char *e = std::getenv("PGO_REPL_MAX_ROWS")) so.repl_max_rows = std::atoll(e);      // tuning knobs
+    if (const char *e = std::getenv("PGO_TAIL")) h->opt_tail = std::atoi(e) != 0;
+    if (const char *e = std::getenv("PGO_TAIL_CTAS_PER_SM")) h->tail_ctas_per_sm = std::max(1, std::atoi(e));
+    if (const char *e = std::getenv("PGO_TAIL_MAX_ROWS")) h->tail_max_rows = std::atoll(e);
     if (!build_symbolic(h->sym, so, nv, vid, vkind, ne, ekind, efrom, eto)) return fail_create(h, PGO_ERR_ARG, h->sym.error);
     Symbolic &S = h->sym;
     // per-dimension record sizes (kernels.cuh: Dim<D>)
