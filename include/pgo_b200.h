@@ -61,6 +61,11 @@ typedef struct {
     int32_t amg_aggregate_size;/* upper bound on the members of an aggregate; 0 = default */
     int32_t amg_kcycle;        /* coarse levels 1..amg_kcycle are solved by a K-cycle (two Krylov-accelerated cycles per
                                 * visit, Notay), deeper ones by a V-cycle; 0 = plain V-cycle; default: all levels */
+    int32_t amg_fp64_storage;  /* 0 (default): the SpMVs INSIDE the multigrid cycle (smoother, residual, K-cycle products) read
+                                * fp32 copies of the stored blocks of every level and accumulate in fp64 -- the preconditioner
+                                * is an approximate operator anyway, and half the bytes is half the time of an HBM-bound
+                                * kernel; the PCG operator H p, the residual recurrence, all dot products and the result stay
+                                * fp64, so the solve converges to the same pcg_rtol.  1: everything reads the fp64 blocks */
 } pgo_options;
 
 /* fills *opt with the defaults (anchor 1e7, rtol 1e-10, max 200000 iterations, AMG K-cycle, single GPU) */
@@ -156,6 +161,9 @@ int pgo_get_timings(pgo_handle *h, double *ms_per_phase, int64_t *launches_per_p
 /* time `repeats` back-to-back launches of the fine-level BSR SpMV (the dominant kernel) on the
  * handle's stream with CUDA events; returns the average ms per launch */
 int pgo_time_spmv(pgo_handle *h, int32_t repeats, double *avg_ms);
+/* diagnostic: average time (ms) of ONE coarse solve of AMG level `level` >= 1 (the whole K-cycle subtree below it), launched as
+ * a CUDA graph like inside the PCG loop; needs a previous pgo_gn_step / pgo_linearize_and_solve */
+int pgo_time_coarse(pgo_handle *h, int32_t level, int32_t repeats, double *avg_ms);
 /* structure statistics for the roofline accounting: block rows, off-diagonal blocks, stored slots */
 int pgo_get_stats(const pgo_handle *h, int64_t *n_block_rows, int64_t *n_offdiag_blocks,
                   int64_t *n_levels, int64_t *device_bytes);

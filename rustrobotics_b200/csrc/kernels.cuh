@@ -49,6 +49,8 @@ struct LevelDev {
     const int64_t *slice_ptr;                 // JDS: [n_slices + 1] ; CSR: row_ptr [n_pad + 1]
     const int32_t *deg; const uint32_t *col;
     double *val, *diag, *dinv;
+    float *valf;                 // fp32 copy of val (same layout) read by the SpMVs INSIDE the multigrid cycle when the
+                                 // preconditioner is stored in reduced precision (the PCG operator itself stays fp64)
     double *pos;                 // [2][n_pad] planes: position of each row (centroid on coarse levels)
     double *lev;                 // [n_pad][2]: lever arm of each row about its aggregate's centroid (peer-visible)
     const uint8_t *vkind;        // level 0 only (nullptr on coarse levels)
@@ -65,6 +67,21 @@ template <int D> struct VecStride { static constexpr int value = (D == 3) ? 4 : 
 template <int D> struct Dim;
 template <> struct Dim<3> { static constexpr int VS = 4, PS = 4, NG = 2, LS = 2, NZ = 4, NW = 6, NM = 10; };
 template <> struct Dim<6> { static constexpr int VS = 6, PS = 8, NG = 3, LS = 4, NZ = 7, NW = 21, NM = 28; };
+
+// Programmatic dependent launch: the FIRST statement of every kernel.  A grid launched with the programmatic-serialisation
+// attribute (launch_k in pgo_b200.cu) is scheduled while its predecessor drains; griddepcontrol.wait blocks until the
+// predecessor grid has completed and its writes are visible, so nothing may be read before it -- not even the `done`
+// flag.  Every kernel executes the wait (transitively every earlier kernel of the stream has completed by then) and
+// only then lets its own successor start launching.  A no-op for grids launched without the attribute.
+#define PDL_ENTER()                                                 \
+    do {                                                            \
+        asm volatile("griddepcontrol.wait;" ::: "memory");          \
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); \
+    } while (0)
+
+template <typename VT> __device__ __forceinline__ const VT *level_val(const LevelDev &L);
+template <> __device__ __forceinline__ const double *level_val<double>(const LevelDev &L) { return L.val; }
+template <> __device__ __forceinline__ const float *level_val<float>(const LevelDev &L) { return L.valf; }
 
 __device__ __forceinline__ int ld_done(const Scalars *S) { return *(const volatile int *)&S->done; }
 
@@ -200,10 +217,11 @@ template <int NT, int FIN> __device__ __forceinline__ void reduce_and_finalize(c
 //   MODE 1: y = r - H x                  (residual)
 //   MODE 2: y = x + omega Dinv (r - H x) (damped block-Jacobi sweep; + r.y -> FIN_RZ_INIT, + {r.y, y.u1} -> FIN_RZ)
 // Large coarse levels use the same kernel (K-cycle dots FIN_K1 / FIN_K2 as in k_spmv_csr).
-template <int D, int MODE, int FIN, bool PEER>
+template <int D, int MODE, int FIN, bool PEER, typename VT = double, int U = 1>
 __global__ void __launch_bounds__(128) k_spmv(LevelDev L, const __grid_constant__ XRef xr, const double *__restrict__ x, const double *__restrict__ r,
                                                double *__restrict__ y, double omega, const double *__restrict__ u1, const double *__restrict__ u2,
                                                Scalars *S, double *partials, int lvl, int check_done) {
+    PDL_ENTER();
     if (check_done && ld_done(S)) return;
     constexpr int DD = D * D, VS = VecStride<D>::value;
     const int64_t row = (int64_t)blockIdx.x * 128 + threadIdx.x;
@@ -218,45 +236,77 @@ __global__ void __launch_bounds__(128) k_spmv(LevelDev L, const __grid_constant_
     if (live) {
         const int mydeg = L.deg[row];
         const int maxdeg = __shfl_sync(0xffffffffu, mydeg, 0);
-        ld_vec<VS>(x + row * VS, xi);
-        const double *dg = L.diag + row;
-#pragma unroll
-        for (int a = 0; a < D; a++)
-#pragma unroll
-            for (int b = 0; b < D; b++) acc[a] = fma(__ldg(dg + (int64_t)(a * D + b) * L.n_pad), xi[b], acc[a]);
         const int64_t base = L.slice_ptr[slice];
-        // software pipeline: the column word and the gathered x record of entry k+1 are requested while the block of
-        // entry k is multiplied, so the dependent chain col -> gather never sits on the critical path of an iteration
-        int64_t off = 0;
-        uint32_t c_nxt = 0;
-        double xn[VS];
+        const VT *__restrict__ vals = level_val<VT>(L) + base * DD + lane;
+        const uint32_t *__restrict__ cols = L.col + base + lane;
+        // The kernel is bound by the bytes it keeps in flight (one warp streams one slice; every load is a dependence-free
+        // coalesced 8- or 4-byte-per-lane access), so an iteration requests ALL the loads of its U entries ("columns" of the
+        // slice) before the first multiply -- U x D^2 block values + U gathered x records -- plus the column words of the
+        // NEXT iteration, so the chain col -> gather never sits inside an iteration.  Measured on B200 (1M-pose SE2 graph,
+        // profiles/r01l_spmv_sweep.log): U = 1 at 52 registers / 9 CTAs per SM is the optimum, 130 us (fp64 blocks, 86 % of
+        // the measured HBM peak; the previous gather-ahead loop: 147 us) and 100 us (fp32 blocks); U = 2 (78 registers) 137 /
+        // 104 us, U = 4 (128 registers) 142 / 136 us; capping registers for 12 / 14 CTAs per SM: 139 / 170 us (spills).
+        uint32_t cw[U];
+        {
+            int64_t o = 0;
 #pragma unroll
-        for (int a = 0; a < VS; a++) xn[a] = 0.0;
-        if (mydeg > 0) {
-            c_nxt = __ldg(L.col + base + lane);
-            ld_vec<VS>(PEER ? xgather<VS>(xr, c_nxt) : x + (int64_t)(c_nxt & COL_LOCAL_MASK) * VS, xn);
+            for (int j = 0; j < U; j++) {
+                cw[j] = 0;
+                if (j < mydeg) cw[j] = __ldg(cols + o);
+                o += __popc(__ballot_sync(0xffffffffu, j < mydeg));
+            }
         }
-        int cnt = __popc(__ballot_sync(0xffffffffu, 0 < mydeg));
-        for (int k = 0; k < maxdeg; k++) {
-            const bool active = k < mydeg;
-            const int cnt_nxt = __popc(__ballot_sync(0xffffffffu, k + 1 < mydeg));
-            double xj[VS];
+        ld_vec<VS>(x + row * VS, xi);
+        int64_t off = 0;
+        for (int k = 0; k < maxdeg; k += U) {
+            int cn[U];
+            int64_t of[U];
 #pragma unroll
-            for (int a = 0; a < VS; a++) xj[a] = xn[a];
-            if (k + 1 < mydeg) c_nxt = __ldg(L.col + base + off + cnt + lane);
-            if (active) {
-                const double *v = L.val + (base + off) * DD + lane;
-                double h[DD];
+            for (int j = 0; j < U; j++) {
+                cn[j] = __popc(__ballot_sync(0xffffffffu, k + j < mydeg));
+                of[j] = off;
+                off += cn[j];
+            }
+            double xj[U][VS];
+            VT hv[U][DD];
 #pragma unroll
-                for (int q = 0; q < DD; q++) h[q] = __ldg(v + (int64_t)q * cnt);
-                if (k + 1 < mydeg) ld_vec<VS>(PEER ? xgather<VS>(xr, c_nxt) : x + (int64_t)(c_nxt & COL_LOCAL_MASK) * VS, xn);
+            for (int j = 0; j < U; j++) {
+#pragma unroll
+                for (int a = 0; a < VS; a++) xj[j][a] = 0.0;
+#pragma unroll
+                for (int q = 0; q < DD; q++) hv[j][q] = (VT)0;
+                if (k + j < mydeg) {
+                    ld_vec<VS>(PEER ? xgather<VS>(xr, cw[j]) : x + (int64_t)(cw[j] & COL_LOCAL_MASK) * VS, xj[j]);
+                    const VT *v = vals + of[j] * DD;
+#pragma unroll
+                    for (int q = 0; q < DD; q++) hv[j][q] = __ldg(v + (int64_t)q * cn[j]);
+                }
+            }
+            {
+                int64_t o = off;
+#pragma unroll
+                for (int j = 0; j < U; j++) {
+                    const bool on = k + U + j < mydeg;
+                    cw[j] = on ? __ldg(cols + o) : 0u;
+                    o += __popc(__ballot_sync(0xffffffffu, on));
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < U; j++)
 #pragma unroll
                 for (int a = 0; a < D; a++)
 #pragma unroll
-                    for (int b = 0; b < D; b++) acc[a] = fma(h[a * D + b], xj[b], acc[a]);
-            }
-            off += cnt;
-            cnt = cnt_nxt;
+                    for (int b = 0; b < D; b++) acc[a] = fma((double)hv[j][a * D + b], xj[j][b], acc[a]);
+        }
+        {   // diagonal block last: its D^2 loads are not held in registers across the loop
+            const double *dg = L.diag + row;
+            double dgv[DD];
+#pragma unroll
+            for (int q = 0; q < DD; q++) dgv[q] = __ldg(dg + (int64_t)q * L.n_pad);
+#pragma unroll
+            for (int a = 0; a < D; a++)
+#pragma unroll
+                for (int b = 0; b < D; b++) acc[a] = fma(dgv[a * D + b], xi[b], acc[a]);
         }
     }
     double dots[3] = {0.0, 0.0, 0.0};
@@ -317,7 +367,7 @@ __global__ void __launch_bounds__(128) k_spmv(LevelDev L, const __grid_constant_
 // Coarse levels (L2-resident, latency-bound): block CSR, LPR lanes per block row (8 when rows are short, else a full
 // warp), 256 / LPR rows per CTA.  Same modes; K-cycle dots:
 //   FIN_K1: {x.y, x.u1}    FIN_K2: {x.u1, x.y, x.u2}      (x = c, y = H c)
-template <int D, int MODE, int FIN, bool PEER, int LPR>
+template <int D, int MODE, int FIN, bool PEER, int LPR, typename VT = double>
 __device__ __forceinline__ void spmv_csr_body(const LevelDev &L, const XRef &xr, const double *__restrict__ x, const double *__restrict__ r,
                                               double *__restrict__ y, double omega, const double *__restrict__ u1,
                                               const double *__restrict__ u2, Scalars *S, double *partials, int lvl, unsigned vb, unsigned nvb) {
@@ -336,11 +386,11 @@ __device__ __forceinline__ void spmv_csr_body(const LevelDev &L, const XRef &xr,
             const uint32_t c = __ldg(L.col + s);
             double xj[VS];
             ld_vec<VS>(PEER ? xgather<VS>(xr, c) : x + (int64_t)(c & COL_LOCAL_MASK) * VS, xj);
-            const double *v = L.val + s * DD;
+            const VT *v = level_val<VT>(L) + s * DD;
 #pragma unroll
             for (int a = 0; a < D; a++)
 #pragma unroll
-                for (int q = 0; q < D; q++) acc[a] = fma(v[a * D + q], xj[q], acc[a]);
+                for (int q = 0; q < D; q++) acc[a] = fma((double)v[a * D + q], xj[q], acc[a]);
         }
     }
 #pragma unroll
@@ -397,12 +447,13 @@ __device__ __forceinline__ void spmv_csr_body(const LevelDev &L, const XRef &xr,
     }
     reduce_and_finalize<256, FIN>(dots, S, partials, lvl, vb, nvb);
 }
-template <int D, int MODE, int FIN, bool PEER, int LPR>
+template <int D, int MODE, int FIN, bool PEER, int LPR, typename VT = double>
 __global__ void __launch_bounds__(256) k_spmv_csr(LevelDev L, const __grid_constant__ XRef xr, const double *__restrict__ x, const double *__restrict__ r,
                                                    double *__restrict__ y, double omega, const double *__restrict__ u1,
                                                    const double *__restrict__ u2, Scalars *S, double *partials, int lvl, int check_done) {
+    PDL_ENTER();
     if (check_done && ld_done(S)) return;
-    spmv_csr_body<D, MODE, FIN, PEER, LPR>(L, xr, x, r, y, omega, u1, u2, S, partials, lvl, blockIdx.x, gridDim.x);
+    spmv_csr_body<D, MODE, FIN, PEER, LPR, VT>(L, xr, x, r, y, omega, u1, u2, S, partials, lvl, blockIdx.x, gridDim.x);
 }
 
 // x = omega Dinv r  (pre-smoothing from a zero guess; with FIN: block-Jacobi z = Dinv r and r.z (, z.u1))
@@ -439,14 +490,26 @@ __device__ __forceinline__ void dinv_apply_body(const LevelDev &L, const double 
 template <int D, int FIN>
 __global__ void __launch_bounds__(128) k_dinv_apply(LevelDev L, const double *__restrict__ r, double *__restrict__ x, double omega,
                                                      const double *__restrict__ u1, Scalars *S, double *partials, int check_done) {
+    PDL_ENTER();
     if (check_done && ld_done(S)) return;
     dinv_apply_body<D, FIN, 128>(L, r, x, omega, u1, S, partials, blockIdx.x, gridDim.x);
+}
+
+// fp32 copy of a level's stored blocks (same layout), for the SpMVs inside the multigrid cycle
+__global__ void __launch_bounds__(256) k_to_float(int64_t n, const double *__restrict__ src, float *__restrict__ dst) {
+    PDL_ENTER();
+    const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 2;
+    if (i + 1 < n) {
+        const double2 v = *reinterpret_cast<const double2 *>(src + i);
+        *reinterpret_cast<float2 *>(dst + i) = make_float2((float)v.x, (float)v.y);
+    } else if (i < n) dst[i] = (float)src[i];
 }
 
 // x += alpha p ; r -= alpha q
 template <int D>
 __global__ void __launch_bounds__(256) k_update_xr(int64_t n_pad, double *__restrict__ x, double *__restrict__ r,
                                                     const double *__restrict__ p, const double *__restrict__ q, const Scalars *S) {
+    PDL_ENTER();
     if (ld_done(S)) return;
     constexpr int VS = VecStride<D>::value;
     const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 2;       // in doubles
@@ -463,6 +526,7 @@ __global__ void __launch_bounds__(256) k_update_xr(int64_t n_pad, double *__rest
 // p = z + beta p
 template <int D>
 __global__ void __launch_bounds__(256) k_update_p(int64_t n_pad, double *__restrict__ p, const double *__restrict__ z, const Scalars *S) {
+    PDL_ENTER();
     if (ld_done(S)) return;
     constexpr int VS = VecStride<D>::value;
     const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 2;
@@ -489,6 +553,7 @@ __device__ __forceinline__ void kcombine_body(int64_t n_doubles, const double *_
 template <int WHICH>
 __global__ void __launch_bounds__(256) k_kcombine(int64_t n_doubles, const double *__restrict__ a, const double *__restrict__ b,
                                                    double *__restrict__ out, const Scalars *S, int lvl) {
+    PDL_ENTER();
     if (ld_done(S)) return;
     kcombine_body<WHICH>(n_doubles, a, b, out, S, lvl, blockIdx.x);
 }
@@ -652,6 +717,7 @@ __device__ __forceinline__ void restrict_body(const LevelDev &F, const LevelDev 
 template <int D>
 __global__ void __launch_bounds__(256) k_restrict(LevelDev F, LevelDev C, const double *__restrict__ res, double *__restrict__ rc,
                                                    const Scalars *S) {
+    PDL_ENTER();
     if (ld_done(S)) return;
     restrict_body<D>(F, C, res, rc, blockIdx.x);
 }
@@ -671,6 +737,7 @@ __device__ __forceinline__ void prolong_body(const LevelDev &F, const double *__
 }
 template <int D>
 __global__ void __launch_bounds__(128) k_prolong(LevelDev F, const double *__restrict__ ec, double *__restrict__ x, const Scalars *S) {
+    PDL_ENTER();
     if (ld_done(S)) return;
     prolong_body<D, 128>(F, ec, x, blockIdx.x);
 }
@@ -678,6 +745,7 @@ __global__ void __launch_bounds__(128) k_prolong(LevelDev F, const double *__res
 // centroid of the members (one warp per coarse row); NG position planes
 template <int NG>
 __global__ void __launch_bounds__(256) k_coarse_pos(LevelDev F, LevelDev C) {
+    PDL_ENTER();
     const int lane = threadIdx.x & 31;
     const int64_t I = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (I >= C.n_pad) return;
@@ -704,6 +772,7 @@ __global__ void __launch_bounds__(256) k_coarse_pos(LevelDev F, LevelDev C) {
 // lever arm of every fine row about its aggregate's centroid: records of LS = 2 (NG = 2) or 4 (NG = 3) doubles
 template <int NG>
 __global__ void __launch_bounds__(128) k_lever(LevelDev F, LevelDev C) {
+    PDL_ENTER();
     constexpr int LS = NG == 2 ? 2 : 4;
     const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
     if (i >= F.n_pad) return;
@@ -731,6 +800,7 @@ __device__ __forceinline__ void galerkin_scatter(const LevelDev &C, int32_t tgt,
 // Gauss-Newton system itself is assembled without atomics).  Level-0 source (JDS): one thread per row.
 template <int D>
 __global__ void __launch_bounds__(128) k_galerkin_jds(LevelDev F, LevelDev C, const __grid_constant__ XRef levr) {
+    PDL_ENTER();
     constexpr int DD = D * D;
     const int64_t row = (int64_t)blockIdx.x * 128 + threadIdx.x;
     const int lane = threadIdx.x & 31;
@@ -770,6 +840,7 @@ __global__ void __launch_bounds__(128) k_galerkin_jds(LevelDev F, LevelDev C, co
 // coarse source (block CSR): one warp per row
 template <int D>
 __global__ void __launch_bounds__(256) k_galerkin_csr(LevelDev F, LevelDev C, const __grid_constant__ XRef levr) {
+    PDL_ENTER();
     constexpr int DD = D * D;
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -827,6 +898,7 @@ template <int D> __device__ __forceinline__ void inv_block(const double *a, doub
 
 template <int D>
 __global__ void __launch_bounds__(128) k_invert_diag(LevelDev L) {
+    PDL_ENTER();
     constexpr int DD = D * D;
     const int64_t row = (int64_t)blockIdx.x * 128 + threadIdx.x;
     if (row >= L.n_pad) return;
@@ -864,6 +936,7 @@ __device__ __forceinline__ int dense_col(const DenseMap &dm, uint32_t colword) {
 // scatter this rank's block rows into rows [D*dense_off[rank], ...) of the (pre-zeroed) dense matrix A (m x m, row-major)
 template <int D, bool JDS>
 __global__ void __launch_bounds__(128) k_dense_assemble(LevelDev L, DenseMap dm, int rank, int m, double *__restrict__ A) {
+    PDL_ENTER();
     constexpr int DD = D * D;
     const int64_t row = (int64_t)blockIdx.x * 128 + threadIdx.x;
     if (row >= L.n) return;
@@ -901,6 +974,7 @@ __global__ void __launch_bounds__(128) k_dense_assemble(LevelDev L, DenseMap dm,
 //   phase 2  A_pp <- A_pp^-1 ; A_pj <- R_j ; A_ip <- -Cp_i A_pp^-1 ; A_ij <- A_ij - Cp_i R_j   (tiles of 8 rows x 256 columns)
 constexpr int GJ_W = 24;
 __global__ void __launch_bounds__(256) k_dense_invert(int m, double *__restrict__ A, double *__restrict__ R, double *__restrict__ Cp) {
+    PDL_ENTER();
     cg::grid_group grid = cg::this_grid();
     __shared__ double P[GJ_W][GJ_W + 1];
     __shared__ double Cs[8][GJ_W];
@@ -1002,6 +1076,7 @@ __device__ __forceinline__ void dense_apply_body(int64_t n_local, const DenseMap
 template <int D>
 __global__ void __launch_bounds__(256) k_dense_apply(int64_t n_local, DenseMap dm, int rank, int world, int m, const double *__restrict__ Ainv,
                                                       const __grid_constant__ XRef rr, double *__restrict__ x, const Scalars *S) {
+    PDL_ENTER();
     if (ld_done(S)) return;
     dense_apply_body<D>(n_local, dm, rank, world, m, Ainv, rr, x, blockIdx.x);
 }
@@ -1011,6 +1086,7 @@ __global__ void __launch_bounds__(256) k_dense_apply(int64_t n_local, DenseMap d
 // stride (doubles per record) is even.
 __global__ void __launch_bounds__(128) k_halo_pull(double *__restrict__ v, const __grid_constant__ XRef peers, const uint32_t *__restrict__ halo_src,
                                                     int64_t n_halo, int64_t n_pad, int stride, const Scalars *S, int check_done) {
+    PDL_ENTER();
     if (check_done && ld_done(S)) return;
     const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
     if (i >= n_halo) return;
@@ -1026,6 +1102,7 @@ __global__ void __launch_bounds__(128) k_halo_pull(double *__restrict__ v, const
 __global__ void __launch_bounds__(256) k_gather_peer(double *__restrict__ v, const __grid_constant__ XRef src, const __grid_constant__ SegMap seg,
                                                       int rank, int world, int comps, int n_planes, int64_t plane_stride,
                                                       const Scalars *S, int check_done) {
+    PDL_ENTER();
     if (check_done && ld_done(S)) return;
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= seg.off[world] * comps) return;
@@ -1082,6 +1159,7 @@ __device__ __forceinline__ void xtwy3(const double *X, const double *w, const do
 // hz: measurement stream laid out like val with 10 components (z: x y cos sin ; Omega upper 6).
 __global__ void __launch_bounds__(128) k_assemble_se2(LevelDev L, const __grid_constant__ XRef posr, const double *__restrict__ poses, const double *__restrict__ hz,
                                                        double *__restrict__ rvec, int64_t anchor_row, double anchor_w, double lambda) {
+    PDL_ENTER();
     const int64_t row = (int64_t)blockIdx.x * 128 + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int64_t slice = row >> 5;
@@ -1182,6 +1260,7 @@ __global__ void __launch_bounds__(128) k_assemble_se2(LevelDev L, const __grid_c
 // ends: .x = local row of `from`, .y = column word of `to` (COL_EDGE_XY marks a pose-landmark edge)
 __global__ void __launch_bounds__(256) k_chi2_se2(int64_t n_edges, const uint2 *__restrict__ ends, const double *__restrict__ ed,
                                                    const double *__restrict__ poses, const __grid_constant__ XRef posr, Scalars *S, double *partials) {
+    PDL_ENTER();
     const int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x;
     double c = 0.0;
     if (k < n_edges) {
@@ -1212,6 +1291,7 @@ __global__ void __launch_bounds__(256) k_chi2_se2(int64_t n_edges, const uint2 *
 // renormalisation; landmarks l += dx.  Also ||dx||^2 (:273).  sign = -1 undoes a step (:277).
 __global__ void __launch_bounds__(256) k_retract_se2(LevelDev L, double *__restrict__ poses, const double *__restrict__ dx, double sign,
                                                       Scalars *S, double *partials) {
+    PDL_ENTER();
     const int64_t row = (int64_t)blockIdx.x * 256 + threadIdx.x;
     double n2 = 0.0;
     if (row < L.n) {
@@ -1237,6 +1317,7 @@ __global__ void __launch_bounds__(256) k_retract_se2(LevelDev L, double *__restr
 // atan2(im, re) on the way out.  row_valofs is relative to the first value this rank owns.
 __global__ void __launch_bounds__(256) k_import_poses(int64_t n, const int64_t *__restrict__ row_valofs, const uint8_t *__restrict__ vkind,
                                                        const double *__restrict__ values, double *__restrict__ poses) {
+    PDL_ENTER();
     const int64_t row = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (row >= n) return;
     const double *v = values + row_valofs[row];
@@ -1246,6 +1327,7 @@ __global__ void __launch_bounds__(256) k_import_poses(int64_t n, const int64_t *
 }
 __global__ void __launch_bounds__(256) k_export_poses(int64_t n, const int64_t *__restrict__ row_valofs, const uint8_t *__restrict__ vkind,
                                                        const double *__restrict__ poses, double *__restrict__ values) {
+    PDL_ENTER();
     const int64_t row = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (row >= n) return;
     double p[4];
@@ -1343,6 +1425,7 @@ __device__ __forceinline__ void sym6_expand(const double *w, double *W) {     //
 // thread per block row walks its half edges, single writer per block, no atomics.
 __global__ void __launch_bounds__(128) k_assemble_se3(LevelDev L, const double *__restrict__ poses, const double *__restrict__ hz,
                                                        double *__restrict__ rvec, int64_t anchor_row, double anchor_w, double lambda) {
+    PDL_ENTER();
     const int64_t row = (int64_t)blockIdx.x * 128 + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int64_t slice = row >> 5;
@@ -1453,6 +1536,7 @@ __global__ void __launch_bounds__(128) k_assemble_se3(LevelDev L, const double *
 // chi2 of an SE3 graph: ed = [28][n_edges] planes, ends as in k_chi2_se2
 __global__ void __launch_bounds__(256) k_chi2_se3(int64_t n_edges, const uint2 *__restrict__ ends, const double *__restrict__ ed,
                                                    const double *__restrict__ poses, Scalars *S, double *partials) {
+    PDL_ENTER();
     const int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x;
     double c = 0.0;
     if (k < n_edges) {
@@ -1480,6 +1564,7 @@ __global__ void __launch_bounds__(256) k_chi2_se3(int64_t n_edges, const uint2 *
 // t += dt ; q <- normalise(q Exp(dw)) ; ||dx||^2
 __global__ void __launch_bounds__(256) k_retract_se3(LevelDev L, double *__restrict__ poses, const double *__restrict__ dx, double sign,
                                                       Scalars *S, double *partials) {
+    PDL_ENTER();
     const int64_t row = (int64_t)blockIdx.x * 256 + threadIdx.x;
     double n2 = 0.0;
     if (row < L.n) {
@@ -1507,6 +1592,7 @@ __global__ void __launch_bounds__(256) k_retract_se3(LevelDev L, double *__restr
 // g2o-layout SE3 vertex values (x y z qx qy qz qw) <-> pose records (x, y, z, 0, qw, qx, qy, qz), quaternion normalised on the way in
 __global__ void __launch_bounds__(256) k_import_poses_se3(int64_t n, const int64_t *__restrict__ row_valofs, const double *__restrict__ values,
                                                            double *__restrict__ poses) {
+    PDL_ENTER();
     const int64_t row = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (row >= n) return;
     const double *v = values + row_valofs[row];
@@ -1516,6 +1602,7 @@ __global__ void __launch_bounds__(256) k_import_poses_se3(int64_t n, const int64
 }
 __global__ void __launch_bounds__(256) k_export_poses_se3(int64_t n, const int64_t *__restrict__ row_valofs, const double *__restrict__ poses,
                                                            double *__restrict__ values) {
+    PDL_ENTER();
     const int64_t row = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (row >= n) return;
     double p[8];

@@ -20,6 +20,7 @@ struct CommRef { Comm *p[MAX_RANKS]; };
 
 template <int FIN>
 __global__ void __launch_bounds__(32) k_xreduce(Comm *mine, CommRef peers, int rank, int world, Scalars *S, int lvl, int check_done) {
+    PDL_ENTER();
     if (check_done && ld_done(S)) return;
     constexpr int NV = fin_ndot(FIN);
     __shared__ unsigned long long ep;
@@ -62,6 +63,7 @@ __global__ void __launch_bounds__(32) k_xreduce(Comm *mine, CommRef peers, int r
 template <int D, int FIN>
 __global__ void __launch_bounds__(128) k_dots(int64_t n_pad, const double *__restrict__ a, const double *__restrict__ b,
                                                const double *__restrict__ c, Scalars *S, double *partials, int lvl, int check_done) {
+    PDL_ENTER();
     if (check_done && ld_done(S)) return;
     constexpr int VS = VecStride<D>::value;
     const int64_t row = (int64_t)blockIdx.x * 128 + threadIdx.x;
@@ -84,6 +86,7 @@ __global__ void __launch_bounds__(128) k_dots(int64_t n_pad, const double *__res
 
 // v *= s
 __global__ void __launch_bounds__(256) k_scale(int64_t n_doubles, double *__restrict__ v, double s) {
+    PDL_ENTER();
     const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 2;
     if (i >= n_doubles) return;
     double2 t = *reinterpret_cast<double2 *>(v + i);

@@ -16,6 +16,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "../../include/pgo_b200.h"
@@ -96,6 +98,9 @@ struct pgo_handle {
     DenseMap dmap{};
     int dense_m = 0, invert_grid = 0;
     bool use_amg = false, omega_ready = false;
+    bool pdl = true;                   // programmatic dependent launch of every kernel (PGO_PDL=0 disables)
+    cudaError_t launch_err = cudaSuccess;
+    bool lowp = false;                 // the cycle's SpMVs read fp32 copies of the stored blocks (opt.amg_fp64_storage == 0)
     bool tail_fail = false;
     bool opt_tail = false;             // PGO_TAIL=1 enables the persistent coarse-tail kernel.  OFF by default: measured on B200
                                        // (profiles/r01j_tail_experiment.log) it is 8 % SLOWER than one graph-launched kernel per
@@ -138,6 +143,22 @@ template <typename T> int upload(pgo_handle *h, T **p, const std::vector<T> &v) 
     return PGO_OK;
 }
 
+// Every kernel is launched through here.  With programmatic dependent launch (PGO_PDL, default on) the launch carries
+// cudaLaunchAttributeProgrammaticStreamSerialization: the grid is scheduled while its predecessor drains and blocks in
+// griddepcontrol.wait (PDL_ENTER, the first statement of every kernel) until the predecessor has completed and flushed,
+// so the ~2-3 us launch ramp of the ~70 small dependent kernels of one PCG iteration overlaps the previous kernel.
+template <typename... KArgs, typename... Args>
+inline void launch_k(pgo_handle *h, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args &&...args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = h->pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+    if (e != cudaSuccess && h->launch_err == cudaSuccess) h->launch_err = e;
+}
+
 inline int grid_for(int64_t n, int bs) { return (int)std::max<int64_t>(1, (n + bs - 1) / bs); }
 
 // peer-visible vectors are carved from one arena whose layout is identical on every rank (sizes use the
@@ -171,7 +192,7 @@ XRef xref(const pgo_handle *h, const double *local, bool repl = false) {
 // ---- cross-rank stage barrier / all-reduce of the partial sums a kernel left in S->loc (world > 1 only)
 template <int FIN> void xreduce(pgo_handle *h, int lvl, int check_done) {
     if (h->world == 1 || h->lv[lvl].repl) return;
-    k_xreduce<FIN><<<1, 32, 0, h->stream>>>(h->comm, h->comm_ref, h->rank, h->world, h->S, lvl, check_done);
+    launch_k(h, k_xreduce<FIN>, 1, 32, 0, h->comm, h->comm_ref, h->rank, h->world, h->S, lvl, check_done);
     h->launch_count += 1;
 }
 inline void xbarrier(pgo_handle *h, int check_done = 1) { xreduce<FIN_NONE>(h, 0, check_done); }
@@ -183,7 +204,7 @@ void halo_pull(pgo_handle *h, int l, const double *v, int stride, int check_done
     LevelBuf &B = h->lv[l];
     if (h->world == 1 || B.repl || B.n_halo == 0) return;
     double *w = const_cast<double *>(v);
-    k_halo_pull<<<grid_for(B.n_halo, 128), 128, 0, h->stream>>>(w, xref(h, v), B.halo_src, B.n_halo, B.d.n_pad, stride, h->S, check_done);
+    launch_k(h, k_halo_pull, grid_for(B.n_halo, 128), 128, 0, w, xref(h, v), B.halo_src, B.n_halo, B.d.n_pad, stride, h->S, check_done);
     h->launch_count += 1;
 }
 
@@ -191,31 +212,38 @@ void halo_pull(pgo_handle *h, int l, const double *v, int stride, int check_done
 void gather_rows(pgo_handle *h, double *v, const SegMap &seg, int comps, int n_planes, int64_t plane_stride, int check_done) {
     const int64_t total = (int64_t)seg.off[h->world] * comps;
     if (total == 0) return;
-    k_gather_peer<<<grid_for(total, 256), 256, 0, h->stream>>>(v, xref(h, v), seg, h->rank, h->world, comps, n_planes, plane_stride, h->S, check_done);
+    launch_k(h, k_gather_peer, grid_for(total, 256), 256, 0, v, xref(h, v), seg, h->rank, h->world, comps, n_planes, plane_stride, h->S, check_done);
     h->launch_count += 1;
 }
 
 // ---- SpMV launcher: sliced storage (level 0 and large coarse levels) or block CSR
-template <int D, int MODE, int FIN> void spmv(pgo_handle *h, int l, const double *x, const double *r, double *y, double omega,
-                                              const double *u1, const double *u2, int check) {
+template <int D, int MODE, int FIN, typename VT> void spmv_launch(pgo_handle *h, int l, const double *x, const double *r, double *y, double omega,
+                                                                  const double *u1, const double *u2, int check) {
     LevelBuf &B = h->lv[l];
-    halo_pull(h, l, x, VecStride<D>::value, check);  // the caller's barrier made the peers' x final
     const XRef xr = xref(h, x, true);
-    if (B.jds) k_spmv<D, MODE, FIN, false><<<B.grid128, 128, 0, h->stream>>>(B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
-    else if (B.lpr == 8) k_spmv_csr<D, MODE, FIN, false, 8><<<B.grid8, 256, 0, h->stream>>>(B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
-    else k_spmv_csr<D, MODE, FIN, false, 32><<<B.gridw, 256, 0, h->stream>>>(B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
+    if (B.jds) launch_k(h, k_spmv<D, MODE, FIN, false, VT>, B.grid128, 128, 0, B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
+    else if (B.lpr == 8) launch_k(h, k_spmv_csr<D, MODE, FIN, false, 8, VT>, B.grid8, 256, 0, B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
+    else launch_k(h, k_spmv_csr<D, MODE, FIN, false, 32, VT>, B.gridw, 256, 0, B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
+}
+// CYC: the product belongs to the multigrid cycle (the preconditioner), which may read the fp32 copy of the blocks;
+// the PCG operator product, the setup and the diagnostics always read the fp64 blocks
+template <int D, int MODE, int FIN, bool CYC = false> void spmv(pgo_handle *h, int l, const double *x, const double *r, double *y, double omega,
+                                                                const double *u1, const double *u2, int check) {
+    halo_pull(h, l, x, VecStride<D>::value, check);  // the caller's barrier made the peers' x final
+    if (CYC && h->lowp) spmv_launch<D, MODE, FIN, float>(h, l, x, r, y, omega, u1, u2, check);
+    else spmv_launch<D, MODE, FIN, double>(h, l, x, r, y, omega, u1, u2, check);
     h->launch_count += 1;
     xreduce<FIN>(h, l, check);
 }
-template <int D, int MODE> void spmv_any(pgo_handle *h, int l, const double *x, const double *r, double *y, double omega, int check) {
-    spmv<D, MODE, FIN_NONE>(h, l, x, r, y, omega, nullptr, nullptr, check);
+template <int D, int MODE, bool CYC = false> void spmv_any(pgo_handle *h, int l, const double *x, const double *r, double *y, double omega, int check) {
+    spmv<D, MODE, FIN_NONE, CYC>(h, l, x, r, y, omega, nullptr, nullptr, check);
 }
 
 template <int D> void coarse_solve(pgo_handle *h, int l, const double *rhs, double *out);
 
 template <int D> void dense_apply(pgo_handle *h, int l, const double *rhs, double *out) {
     LevelBuf &B = h->lv[l];      // always a local (single-GPU or replicated) level
-    k_dense_apply<D><<<grid_for(B.d.n * D, 8), 256, sizeof(double) * h->dense_m, h->stream>>>(B.d.n, h->dmap, 0, 1, h->dense_m,
+    launch_k(h, k_dense_apply<D>, grid_for(B.d.n * D, 8), 256, sizeof(double) * h->dense_m, B.d.n, h->dmap, 0, 1, h->dense_m,
                                                                                              h->Ainv, xref(h, rhs, true), out, h->S);
     h->launch_count += 1;
 }
@@ -322,22 +350,22 @@ template <int D, int FINK> void cycle(pgo_handle *h, int l, const double *rhs, d
         if (h->sym.dense_coarsest) dense_apply<D>(h, l, rhs, out);
         else {
             // no direct solve possible: a few damped block-Jacobi sweeps
-            k_dinv_apply<D, FIN_NONE><<<B.grid128, 128, 0, h->stream>>>(B.d, rhs, B.xa, B.omega, nullptr, h->S, h->partials, 1);
+            launch_k(h, k_dinv_apply<D, FIN_NONE>, B.grid128, 128, 0, B.d, rhs, B.xa, B.omega, nullptr, h->S, h->partials, 1);
             h->launch_count += 1;
             lbarrier(h, l);
-            spmv_any<D, 2>(h, l, B.xa, rhs, B.res, B.omega, 1);
+            spmv_any<D, 2, true>(h, l, B.xa, rhs, B.res, B.omega, 1);
             lbarrier(h, l);
-            spmv_any<D, 2>(h, l, B.res, rhs, out, B.omega, 1);
+            spmv_any<D, 2, true>(h, l, B.res, rhs, out, B.omega, 1);
             lbarrier(h, l);
         }
         return;
     }
     LevelBuf &C = h->lv[l + 1];
-    k_dinv_apply<D, FIN_NONE><<<B.grid128, 128, 0, h->stream>>>(B.d, rhs, B.xa, B.omega, nullptr, h->S, h->partials, 1);
+    launch_k(h, k_dinv_apply<D, FIN_NONE>, B.grid128, 128, 0, B.d, rhs, B.xa, B.omega, nullptr, h->S, h->partials, 1);
     h->launch_count += 1;
     lbarrier(h, l);
-    spmv_any<D, 1>(h, l, B.xa, rhs, B.res, 0.0, 1);
-    k_restrict<D><<<C.gridw, 256, 0, h->stream>>>(B.d, C.d, B.res, C.rhs, h->S);
+    spmv_any<D, 1, true>(h, l, B.xa, rhs, B.res, 0.0, 1);
+    launch_k(h, k_restrict<D>, C.gridw, 256, 0, B.d, C.d, B.res, C.rhs, h->S);
     h->launch_count += 1;
     if (C.first_repl) {                              // every rank restricted onto its own aggregates: all-gather the coarse rhs
         lbarrier(h, l);
@@ -345,10 +373,10 @@ template <int D, int FINK> void cycle(pgo_handle *h, int l, const double *rhs, d
     }
     if (h->tail_level == l + 1) launch_tail<D>(h);   // the whole coarse solve C.rhs -> C.sol in one cooperative launch
     else coarse_solve<D>(h, l + 1, C.rhs, C.sol);
-    k_prolong<D><<<B.grid128, 128, 0, h->stream>>>(B.d, C.sol, B.xa, h->S);
+    launch_k(h, k_prolong<D>, B.grid128, 128, 0, B.d, C.sol, B.xa, h->S);
     h->launch_count += 1;
     lbarrier(h, l);
-    spmv<D, 2, FINK>(h, l, B.xa, rhs, out, B.omega, FINK == FIN_RZ ? h->q : nullptr, nullptr, 1);
+    spmv<D, 2, FINK, true>(h, l, B.xa, rhs, out, B.omega, FINK == FIN_RZ ? h->q : nullptr, nullptr, 1);
     if (FINK == FIN_NONE) lbarrier(h, l);            // FINK != NONE: the all-reduce is the barrier
 }
 
@@ -358,11 +386,11 @@ template <int D> void coarse_solve(pgo_handle *h, int l, const double *rhs, doub
     const int last = (int)h->lv.size() - 1;
     if (l == last || !B.kcycle) { cycle<D, FIN_NONE>(h, l, rhs, out); return; }
     cycle<D, FIN_NONE>(h, l, rhs, B.c1);
-    spmv<D, 0, FIN_K1>(h, l, B.c1, nullptr, B.v1, 0.0, rhs, nullptr, 1);
-    k_kcombine<0><<<B.gridv, 256, 0, h->stream>>>(B.d.n_pad * VecStride<D>::value, rhs, B.v1, B.r1, h->S, l);
+    spmv<D, 0, FIN_K1, true>(h, l, B.c1, nullptr, B.v1, 0.0, rhs, nullptr, 1);
+    launch_k(h, k_kcombine<0>, B.gridv, 256, 0, B.d.n_pad * VecStride<D>::value, rhs, B.v1, B.r1, h->S, l);
     cycle<D, FIN_NONE>(h, l, B.r1, B.c2);
-    spmv<D, 0, FIN_K2>(h, l, B.c2, nullptr, B.v2, 0.0, B.v1, B.r1, 1);
-    k_kcombine<1><<<B.gridv, 256, 0, h->stream>>>(B.d.n_pad * VecStride<D>::value, B.c1, B.c2, out, h->S, l);
+    spmv<D, 0, FIN_K2, true>(h, l, B.c2, nullptr, B.v2, 0.0, B.v1, B.r1, 1);
+    launch_k(h, k_kcombine<1>, B.gridv, 256, 0, B.d.n_pad * VecStride<D>::value, B.c1, B.c2, out, h->S, l);
     h->launch_count += 2;
 }
 
@@ -371,11 +399,11 @@ template <int D, int FINK> void precondition(pgo_handle *h) {   // z = M^-1 r (+
     if (h->use_amg && h->lv.size() > 1) cycle<D, FINK>(h, 0, h->r, h->z);
     else if (h->use_amg && h->sym.dense_coarsest) {      // the whole system fits the direct solve
         dense_apply<D>(h, 0, h->r, h->z);
-        k_dots<D, FINK><<<B.grid128, 128, 0, h->stream>>>(B.d.n_pad, h->r, h->z, h->q, h->S, h->partials, 0, 1);
+        launch_k(h, k_dots<D, FINK>, B.grid128, 128, 0, B.d.n_pad, h->r, h->z, h->q, h->S, h->partials, 0, 1);
         h->launch_count += 1;
         xreduce<FINK>(h, 0, 1);
     } else {
-        k_dinv_apply<D, FINK><<<B.grid128, 128, 0, h->stream>>>(B.d, h->r, h->z, 1.0, h->q, h->S, h->partials, 1);
+        launch_k(h, k_dinv_apply<D, FINK>, B.grid128, 128, 0, B.d, h->r, h->z, 1.0, h->q, h->S, h->partials, 1);
         h->launch_count += 1;
         xreduce<FINK>(h, 0, 1);
     }
@@ -384,9 +412,9 @@ template <int D, int FINK> void precondition(pgo_handle *h) {   // z = M^-1 r (+
 template <int D> void pcg_iteration(pgo_handle *h) {
     LevelBuf &B = h->lv[0];
     spmv<D, 0, FIN_PQ>(h, 0, h->p, nullptr, h->q, 0.0, nullptr, nullptr, 1);
-    k_update_xr<D><<<B.gridv, 256, 0, h->stream>>>(B.d.n_pad, h->x, h->r, h->p, h->q, h->S);
+    launch_k(h, k_update_xr<D>, B.gridv, 256, 0, B.d.n_pad, h->x, h->r, h->p, h->q, h->S);
     precondition<D, FIN_RZ>(h);
-    k_update_p<D><<<B.gridv, 256, 0, h->stream>>>(B.d.n_pad, h->p, h->z, h->S);
+    launch_k(h, k_update_p<D>, B.gridv, 256, 0, B.d.n_pad, h->p, h->z, h->S);
     h->launch_count += 2;
     xbarrier(h);                                     // p complete on every rank before the next SpMV reads it
 }
@@ -407,11 +435,20 @@ template <int D> int build_pcg_graph(pgo_handle *h) {
         h->launch_count = before;
         return build_pcg_graph<D>(h);
     }
-    CK(ce);
+    cudaError_t ie = ce;
+    if (ie == cudaSuccess && h->launch_err != cudaSuccess) ie = h->launch_err;
+    if (ie == cudaSuccess) ie = cudaGraphInstantiate(&h->pcg_graph, g, 0);
+    if (g) cudaGraphDestroy(g);
+    if (ie != cudaSuccess && h->pdl) {
+        // programmatic dependent launch edges not accepted by this driver inside a captured graph: plain launches
+        (void)cudaGetLastError();
+        h->pdl = false; h->launch_err = cudaSuccess; h->pcg_graph = nullptr;
+        h->launch_count = before;
+        return build_pcg_graph<D>(h);
+    }
+    CK(ie);
     h->launches_per_iter = (h->launch_count - before) / h->chunk;
     h->launch_count = before;
-    CK(cudaGraphInstantiate(&h->pcg_graph, g, 0));
-    cudaGraphDestroy(g);
     return PGO_OK;
 }
 
@@ -420,11 +457,11 @@ template <int D> int assemble(pgo_handle *h, double lambda, int add_lambda) {
     LevelBuf &B = h->lv[0];
     xbarrier(h, 0);                                  // every rank's poses are final
     halo_pull(h, 0, h->poses, Dim<D>::PS, 0);
-    if (D == 3) k_assemble_se2<<<B.grid128, 128, 0, h->stream>>>(B.d, xref(h, h->poses, true), h->poses, h->hz, h->r, h->anchor_row, h->opt.anchor_weight,
+    if (D == 3) launch_k(h, k_assemble_se2, B.grid128, 128, 0, B.d, xref(h, h->poses, true), h->poses, h->hz, h->r, h->anchor_row, h->opt.anchor_weight,
                                                                   add_lambda ? lambda : 0.0);
-    else k_assemble_se3<<<B.grid128, 128, 0, h->stream>>>(B.d, h->poses, h->hz, h->r, h->anchor_row, h->opt.anchor_weight, add_lambda ? lambda : 0.0);
+    else launch_k(h, k_assemble_se3, B.grid128, 128, 0, B.d, h->poses, h->hz, h->r, h->anchor_row, h->opt.anchor_weight, add_lambda ? lambda : 0.0);
     h->launch_count += 1;
-    CK(cudaGetLastError());
+    CK(cudaGetLastError()); CK(h->launch_err);
     return PGO_OK;
 }
 
@@ -458,8 +495,8 @@ template <int D> int estimate_omega(pgo_handle *h, int l) {
         // b = H a ; a' = Dinv b ; rho ~ |a'| / |a|
         lbarrier(h, l, 0);
         spmv_any<D, 0>(h, l, a, nullptr, b, 0.0, 0);
-        k_dinv_apply<D, FIN_NONE><<<B.grid128, 128, 0, h->stream>>>(B.d, b, a, 1.0, nullptr, h->S, h->partials, 0);
-        k_dots<D, FIN_NORM><<<B.grid128, 128, 0, h->stream>>>(B.d.n_pad, a, a, nullptr, h->S, h->partials, l, 0);
+        launch_k(h, k_dinv_apply<D, FIN_NONE>, B.grid128, 128, 0, B.d, b, a, 1.0, nullptr, h->S, h->partials, 0);
+        launch_k(h, k_dots<D, FIN_NORM>, B.grid128, 128, 0, B.d.n_pad, a, a, nullptr, h->S, h->partials, l, 0);
         xreduce<FIN_NORM>(h, l, 0);
         CK(cudaMemcpyAsync(&h->hS[0], h->S, sizeof(Scalars), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
@@ -468,7 +505,7 @@ template <int D> int estimate_omega(pgo_handle *h, int l) {
         const double nrm = std::sqrt(h->hS[0].norm2_dx);
         if (!(nrm > 0.0) || !std::isfinite(nrm)) { rho = 2.0; break; }
         if (it > 0) rho = nrm;                                   // |a| was normalised to 1 by the previous pass
-        k_scale<<<grid_for(nd / 2, 256), 256, 0, h->stream>>>(nd, a, 1.0 / nrm);
+        launch_k(h, k_scale, grid_for(nd / 2, 256), 256, 0, nd, a, 1.0 / nrm);
     }
     B.omega = 4.0 / (3.0 * 1.1 * std::max(rho, 1.0));
     if (B.omega > 1.0) B.omega = 1.0;
@@ -480,16 +517,24 @@ template <int D> int amg_setup(pgo_handle *h) {
     constexpr int DD = D * D, NG = Dim<D>::NG, LS = Dim<D>::LS;
     if (!h->use_amg) return PGO_OK;
     const int last = (int)h->lv.size() - 1;
+    auto to_float = [&](LevelBuf &B) {               // fp32 copy of the stored blocks for the cycle's SpMVs
+        if (!h->lowp || !B.d.valf) return;
+        const int64_t nv = (int64_t)DD * B.d.n_slots;
+        if (nv == 0) return;
+        launch_k(h, k_to_float, grid_for((nv + 1) / 2, 256), 256, 0, nv, B.d.val, B.d.valf);
+        h->launch_count += 1;
+    };
+    to_float(h->lv[0]);
     for (int l = 0; l < last; l++) {
         LevelBuf &F = h->lv[l], &C = h->lv[l + 1];
-        k_coarse_pos<NG><<<C.gridw, 256, 0, h->stream>>>(F.d, C.d);
-        k_lever<NG><<<F.grid128, 128, 0, h->stream>>>(F.d, C.d);
+        launch_k(h, k_coarse_pos<NG>, C.gridw, 256, 0, F.d, C.d);
+        launch_k(h, k_lever<NG>, F.grid128, 128, 0, F.d, C.d);
         CK(cudaMemsetAsync(C.d.val, 0, sizeof(double) * DD * std::max<int64_t>(C.d.n_slots, 1), h->stream));
         CK(cudaMemsetAsync(C.d.diag, 0, sizeof(double) * DD * C.d.n_pad, h->stream));
         lbarrier(h, l, 0);                           // lever arms of neighbour rows on other ranks
         halo_pull(h, l, F.d.lev, LS, 0);
-        if (F.jds) k_galerkin_jds<D><<<F.grid128, 128, 0, h->stream>>>(F.d, C.d, xref(h, F.d.lev, true));
-        else k_galerkin_csr<D><<<F.gridw, 256, 0, h->stream>>>(F.d, C.d, xref(h, F.d.lev, true));
+        if (F.jds) launch_k(h, k_galerkin_jds<D>, F.grid128, 128, 0, F.d, C.d, xref(h, F.d.lev, true));
+        else launch_k(h, k_galerkin_csr<D>, F.gridw, 256, 0, F.d, C.d, xref(h, F.d.lev, true));
         h->launch_count += 3;
         if (C.first_repl) {                          // every rank built the coarse rows of its own aggregates: all-gather them
             lbarrier(h, l, 0);
@@ -497,21 +542,22 @@ template <int D> int amg_setup(pgo_handle *h) {
             gather_rows(h, C.d.diag, C.src_rows, 1, DD, C.d.n_pad, 0);
             gather_rows(h, C.d.pos, C.src_rows, 1, NG, C.d.n_pad, 0);
         }
-        k_invert_diag<D><<<C.grid128, 128, 0, h->stream>>>(C.d);
+        launch_k(h, k_invert_diag<D>, C.grid128, 128, 0, C.d);
         h->launch_count += 1;
+        if (!(l + 1 == last && h->sym.dense_coarsest)) to_float(C);
     }
     if (h->sym.dense_coarsest) {
         LevelBuf &C = h->lv[last];
         const int m = h->dense_m;
         CK(cudaMemsetAsync(h->Ainv, 0, sizeof(double) * (size_t)m * m, h->stream));
-        if (C.jds) k_dense_assemble<D, true><<<C.grid128, 128, 0, h->stream>>>(C.d, h->dmap, 0, m, h->Ainv);
-        else k_dense_assemble<D, false><<<C.grid128, 128, 0, h->stream>>>(C.d, h->dmap, 0, m, h->Ainv);
+        if (C.jds) launch_k(h, k_dense_assemble<D, true>, C.grid128, 128, 0, C.d, h->dmap, 0, m, h->Ainv);
+        else launch_k(h, k_dense_assemble<D, false>, C.grid128, 128, 0, C.d, h->dmap, 0, m, h->Ainv);
         h->launch_count += 1;
         void *args[] = {(void *)&h->dense_m, (void *)&h->Ainv, (void *)&h->panelR, (void *)&h->panelC};
         CK(cudaLaunchCooperativeKernel((void *)k_dense_invert, dim3(h->invert_grid), dim3(256), args, 0, h->stream));
         h->launch_count += 1;
     }
-    CK(cudaGetLastError());
+    CK(cudaGetLastError()); CK(h->launch_err);
     if (!h->omega_ready) {
         for (int l = 0; l < (int)h->lv.size(); l++) {
             if (l == last && h->sym.dense_coarsest) continue;
@@ -581,22 +627,51 @@ template <int D> int solve(pgo_handle *h, int32_t *iters_out) {
 
 template <int D> int retract(pgo_handle *h, double sign) {
     LevelBuf &B = h->lv[0];
-    if (D == 3) k_retract_se2<<<grid_for(B.d.n, 256), 256, 0, h->stream>>>(B.d, h->poses, h->x, sign, h->S, h->partials);
-    else k_retract_se3<<<grid_for(B.d.n, 256), 256, 0, h->stream>>>(B.d, h->poses, h->x, sign, h->S, h->partials);
+    if (D == 3) launch_k(h, k_retract_se2, grid_for(B.d.n, 256), 256, 0, B.d, h->poses, h->x, sign, h->S, h->partials);
+    else launch_k(h, k_retract_se3, grid_for(B.d.n, 256), 256, 0, B.d, h->poses, h->x, sign, h->S, h->partials);
     h->launch_count += 1;
     xreduce<FIN_NORM>(h, 0, 0);                      // also: every rank's poses are updated before anyone reads them
-    CK(cudaGetLastError());
+    CK(cudaGetLastError()); CK(h->launch_err);
     return PGO_OK;
 }
 
 template <int D> int chi2_launch(pgo_handle *h) {
     xbarrier(h, 0);
     halo_pull(h, 0, h->poses, Dim<D>::PS, 0);
-    if (D == 3) k_chi2_se2<<<grid_for(h->n_edges_loc, 256), 256, 0, h->stream>>>(h->n_edges_loc, h->ends, h->ed, h->poses, xref(h, h->poses, true), h->S, h->partials);
-    else k_chi2_se3<<<grid_for(h->n_edges_loc, 256), 256, 0, h->stream>>>(h->n_edges_loc, h->ends, h->ed, h->poses, h->S, h->partials);
+    if (D == 3) launch_k(h, k_chi2_se2, grid_for(h->n_edges_loc, 256), 256, 0, h->n_edges_loc, h->ends, h->ed, h->poses, xref(h, h->poses, true), h->S, h->partials);
+    else launch_k(h, k_chi2_se3, grid_for(h->n_edges_loc, 256), 256, 0, h->n_edges_loc, h->ends, h->ed, h->poses, h->S, h->partials);
     h->launch_count += 1;
     xreduce<FIN_CHI2>(h, 0, 0);
-    CK(cudaGetLastError());
+    CK(cudaGetLastError()); CK(h->launch_err);
+    return PGO_OK;
+}
+
+// diagnostic: average time of ONE coarse solve at `level` (the K-cycle subtree below it), graph-launched like inside the PCG loop
+template <int D> int time_coarse(pgo_handle *h, int level, int repeats, double *avg_ms) {
+    if (!h->use_amg || level < 1 || level >= (int)h->lv.size()) { h->err = "pgo_time_coarse: no such coarse level"; return PGO_ERR_ARG; }
+    if (h->world > 1 && !h->lv[level].repl) { h->err = "pgo_time_coarse: sharded level"; return PGO_ERR_UNSUPPORTED; }
+    int rc = reset_scalars(h);
+    if (rc) return rc;
+    LevelBuf &B = h->lv[level];
+    cudaGraph_t g = nullptr;
+    cudaGraphExec_t ge = nullptr;
+    const int64_t before = h->launch_count;
+    CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    coarse_solve<D>(h, level, B.rhs, B.sol);
+    CK(cudaStreamEndCapture(h->stream, &g));
+    const int64_t per = h->launch_count - before;
+    CK(cudaGraphInstantiate(&ge, g, 0));
+    cudaGraphDestroy(g);
+    for (int i = 0; i < 3; i++) CK(cudaGraphLaunch(ge, h->stream));
+    CK(cudaEventRecord(h->ev[PGO_NUM_PHASES], h->stream));
+    for (int i = 0; i < repeats; i++) CK(cudaGraphLaunch(ge, h->stream));
+    CK(cudaEventRecord(h->ev[PGO_NUM_PHASES + 1], h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, h->ev[PGO_NUM_PHASES], h->ev[PGO_NUM_PHASES + 1]));
+    cudaGraphExecDestroy(ge);
+    *avg_ms = ms / repeats;
+    h->launch_count = before + per * (repeats + 3);
     return PGO_OK;
 }
 
@@ -684,9 +759,11 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
     so.dense_max = h->opt.amg_dense_max;
     so.build_amg = h->use_amg;
     if (const char *e = std::getenv("PGO_REPL_MAX_ROWS")) so.repl_max_rows = std::atoll(e);      // tuning knobs
+    if (const char *e = std::getenv("PGO_PDL")) h->pdl = std::atoi(e) != 0;
     if (const char *e = std::getenv("PGO_TAIL")) h->opt_tail = std::atoi(e) != 0;
     if (const char *e = std::getenv("PGO_TAIL_CTAS_PER_SM")) h->tail_ctas_per_sm = std::max(1, std::atoi(e));
     if (const char *e = std::getenv("PGO_TAIL_MAX_ROWS")) h->tail_max_rows = std::atoll(e);
+    h->lowp = h->use_amg && h->opt.amg_fp64_storage == 0 && !h->opt_tail;   // the coarse-tail experiment only knows fp64 blocks
     if (!build_symbolic(h->sym, so, nv, vid, vkind, ne, ekind, efrom, eto)) return fail_create(h, PGO_ERR_ARG, h->sym.error);
     Symbolic &S = h->sym;
     // per-dimension record sizes (kernels.cuh: Dim<D>)
@@ -799,6 +876,7 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
             CKC(dalloc(h, &d.pos, (size_t)NG * d.n_pad));
         }
         CKC(dalloc(h, &d.dinv, (size_t)DD * d.n_pad));
+        if (h->lowp && !(l == nl - 1 && S.dense_coarsest)) CKC(dalloc(h, &d.valf, (size_t)DD * std::max<int64_t>(d.n_slots, 1)));
         if (!H.agg.empty()) {
             HostLevel &Cn = S.levels[l + 1];
             const int64_t c0 = Cn.part_off[(world > 1 && Cn.repl) ? 0 : rank];
@@ -881,8 +959,8 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
         CKC(upload(h, &h->row_valofs, rvo));
         CKC(dalloc(h, &h->vstage, (size_t)S.n_values));
         CKU(cudaMemcpyAsync(h->vstage, vval, S.n_values * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        if (D == 6) k_import_poses_se3<<<grid_for(h->n_loc, 256), 256, 0, h->stream>>>(h->n_loc, h->row_valofs, h->vstage, h->poses);
-        else k_import_poses<<<grid_for(h->n_loc, 256), 256, 0, h->stream>>>(h->n_loc, h->row_valofs, dvk, h->vstage, h->poses);
+        if (D == 6) launch_k(h, k_import_poses_se3, grid_for(h->n_loc, 256), 256, 0, h->n_loc, h->row_valofs, h->vstage, h->poses);
+        else launch_k(h, k_import_poses, grid_for(h->n_loc, 256), 256, 0, h->n_loc, h->row_valofs, dvk, h->vstage, h->poses);
         CKU(cudaGetLastError());
         if (D == 6) h->lv[0].d.quat = h->poses;
     }
@@ -1098,10 +1176,10 @@ int pgo_get_poses(pgo_handle *h, double *out, int64_t n_values) {
     if (n_values != S.n_values) { h->err = "pgo_get_poses: wrong buffer length"; return PGO_ERR_ARG; }
     int64_t o0, o1;
     owned_span(h, &o0, &o1);
-    if (S.D == 6) k_export_poses_se3<<<grid_for(h->n_loc, 256), 256, 0, h->stream>>>(h->n_loc, h->row_valofs, h->poses, h->vstage);
-    else k_export_poses<<<grid_for(h->n_loc, 256), 256, 0, h->stream>>>(h->n_loc, h->row_valofs, h->lv[0].d.vkind, h->poses, h->vstage);
+    if (S.D == 6) launch_k(h, k_export_poses_se3, grid_for(h->n_loc, 256), 256, 0, h->n_loc, h->row_valofs, h->poses, h->vstage);
+    else launch_k(h, k_export_poses, grid_for(h->n_loc, 256), 256, 0, h->n_loc, h->row_valofs, h->lv[0].d.vkind, h->poses, h->vstage);
     h->launch_count += 1;
-    CK(cudaGetLastError());
+    CK(cudaGetLastError()); CK(h->launch_err);
     CK(cudaMemcpyAsync(out + o0, h->vstage + o0, (o1 - o0) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return PGO_OK;
@@ -1115,10 +1193,10 @@ int pgo_set_poses(pgo_handle *h, const double *in, int64_t n_values) {
     int64_t o0, o1;
     owned_span(h, &o0, &o1);
     CK(cudaMemcpyAsync(h->vstage + o0, in + o0, (o1 - o0) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    if (S.D == 6) k_import_poses_se3<<<grid_for(h->n_loc, 256), 256, 0, h->stream>>>(h->n_loc, h->row_valofs, h->vstage, h->poses);
-    else k_import_poses<<<grid_for(h->n_loc, 256), 256, 0, h->stream>>>(h->n_loc, h->row_valofs, h->lv[0].d.vkind, h->vstage, h->poses);
+    if (S.D == 6) launch_k(h, k_import_poses_se3, grid_for(h->n_loc, 256), 256, 0, h->n_loc, h->row_valofs, h->vstage, h->poses);
+    else launch_k(h, k_import_poses, grid_for(h->n_loc, 256), 256, 0, h->n_loc, h->row_valofs, h->lv[0].d.vkind, h->vstage, h->poses);
     h->launch_count += 1;
-    CK(cudaGetLastError());
+    CK(cudaGetLastError()); CK(h->launch_err);
     CK(cudaStreamSynchronize(h->stream));   // `in` is borrowed for the duration of the call only
     h->have_step = false;
     return PGO_OK;
@@ -1265,11 +1343,11 @@ int pgo_time_spmv(pgo_handle *h, int32_t repeats, double *avg_ms) {
     NEED_DEVICE(h);
     LevelBuf &B = h->lv[0];
     // p -> q with the PCG SpMV; done-flag test disabled so the launches always do the work, no cross-rank reduction
-    XRef xr = xref(h, h->p, true);
     halo_pull(h, 0, h->p, h->sym.D == 6 ? 6 : 4, 0);
+    const bool f32 = h->lowp && std::getenv("PGO_TIME_SPMV_F32") != nullptr;     // diagnostic: time the fp32-storage residual product instead
     auto launch = [&]() {
-        if (h->sym.D == 6) k_spmv<6, 0, FIN_NONE, false><<<B.grid128, 128, 0, h->stream>>>(B.d, xr, h->p, nullptr, h->q, 0.0, nullptr, nullptr, h->S, h->partials, 0, 0);
-        else k_spmv<3, 0, FIN_NONE, false><<<B.grid128, 128, 0, h->stream>>>(B.d, xr, h->p, nullptr, h->q, 0.0, nullptr, nullptr, h->S, h->partials, 0, 0);
+        if (h->sym.D == 6) { if (f32) spmv_launch<6, 1, FIN_NONE, float>(h, 0, h->p, h->r, h->q, 0.0, nullptr, nullptr, 0); else spmv_launch<6, 0, FIN_NONE, double>(h, 0, h->p, nullptr, h->q, 0.0, nullptr, nullptr, 0); }
+        else { if (f32) spmv_launch<3, 1, FIN_NONE, float>(h, 0, h->p, h->r, h->q, 0.0, nullptr, nullptr, 0); else spmv_launch<3, 0, FIN_NONE, double>(h, 0, h->p, nullptr, h->q, 0.0, nullptr, nullptr, 0); }
     };
     for (int i = 0; i < 3; i++) launch();
     CK(cudaEventRecord(h->ev[PGO_NUM_PHASES], h->stream));
@@ -1282,6 +1360,13 @@ int pgo_time_spmv(pgo_handle *h, int32_t repeats, double *avg_ms) {
     h->ms[PGO_PHASE_SPMV_FINE] = *avg_ms;
     h->launch_count += repeats + 3;
     return PGO_OK;
+}
+
+int pgo_time_coarse(pgo_handle *h, int32_t level, int32_t repeats, double *avg_ms) {
+    if (!h || !avg_ms || repeats <= 0) return PGO_ERR_ARG;
+    NEED_DEVICE(h);
+    if (!h->have_step) { h->err = "pgo_time_coarse: run a Gauss-Newton step first (the hierarchy must be set up)"; return PGO_ERR_ARG; }
+    return BY_D(h, time_coarse, h, level, repeats, avg_ms);
 }
 
 int pgo_get_stats(const pgo_handle *h, int64_t *rows, int64_t *offdiag, int64_t *levels, int64_t *bytes) {

@@ -45,6 +45,7 @@ __device__ __forceinline__ void tail_spmv(const TailOp &op, const LevelDev &L, c
 
 template <int D>
 __global__ void __launch_bounds__(256, 3) k_tail(const __grid_constant__ TailCtx T) {
+    PDL_ENTER();
     if (ld_done(T.S)) return;                       // set only by fine-level kernels, so every CTA sees the same value
     cg::grid_group grid = cg::this_grid();
     XRef none{};

@@ -12,7 +12,7 @@ P = C.c_void_p
 ABI_SYMBOLS = [
     "pgo_default_options", "pgo_create", "pgo_destroy", "pgo_last_error", "pgo_get_sizes", "pgo_chi2", "pgo_gn_step",
     "pgo_undo_last_step", "pgo_get_poses", "pgo_set_poses", "pgo_get_dx", "pgo_linearize_and_solve", "pgo_get_pattern",
-    "pgo_get_block_structure", "pgo_get_anchor", "pgo_get_system", "pgo_get_timings", "pgo_time_spmv", "pgo_get_stats",
+    "pgo_get_block_structure", "pgo_get_anchor", "pgo_get_system", "pgo_get_timings", "pgo_time_spmv", "pgo_time_coarse", "pgo_get_stats",
     "pgo_version", "pgo_snapshot_poses", "pgo_restore_poses", "pgo_shard_handle_bytes", "pgo_shard_export",
     "pgo_shard_connect", "pgo_get_partition", "pgo_get_level_sizes",
 ]
@@ -22,7 +22,7 @@ class pgo_options(C.Structure):
     _fields_ = [("anchor_weight", C.c_double), ("pcg_rtol", C.c_double), ("pcg_max_iterations", C.c_int32),
                 ("preconditioner", C.c_int32), ("sort_window", C.c_int32), ("amg_max_levels", C.c_int32),
                 ("device", C.c_int32), ("world", C.c_int32), ("rank", C.c_int32), ("amg_dense_max", C.c_int32),
-                ("amg_aggregate_size", C.c_int32), ("amg_kcycle", C.c_int32)]
+                ("amg_aggregate_size", C.c_int32), ("amg_kcycle", C.c_int32), ("amg_fp64_storage", C.c_int32)]
 
 
 def lib_path() -> Path:
@@ -66,6 +66,7 @@ def lib():
     L.pgo_get_system.argtypes = [P, dbl, C.c_int, P, P]
     L.pgo_get_timings.argtypes = [P, P, P, i32]
     L.pgo_time_spmv.argtypes = [P, i32, C.POINTER(dbl)]
+    L.pgo_time_coarse.argtypes = [P, i32, i32, C.POINTER(dbl)]
     L.pgo_get_stats.argtypes = [P, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
     # C++ host mirror
     L.pg_last_error.restype = C.c_char_p
