@@ -211,6 +211,74 @@ template <int NT, int FIN> __device__ __forceinline__ void reduce_and_finalize(c
     }
 }
 
+// Tail of the sliced SpMV of one block row (shared by k_spmv and k_spmv_tma): adds the diagonal block, applies the MODE,
+// stores y and returns this row's contributions to the fused dot products.
+template <int D, int MODE, int FIN>
+__device__ __forceinline__ void spmv_row_finish(const LevelDev &L, int64_t row, double *acc, const double *xi, const double *__restrict__ r,
+                                                double *__restrict__ y, double omega, const double *__restrict__ u1,
+                                                const double *__restrict__ u2, double *dots) {
+    constexpr int DD = D * D, VS = VecStride<D>::value;
+    {   // diagonal block last: its D^2 loads are not held in registers across the loop
+        const double *dg = L.diag + row;
+        double dgv[DD];
+#pragma unroll
+        for (int q = 0; q < DD; q++) dgv[q] = __ldg(dg + (int64_t)q * L.n_pad);
+#pragma unroll
+        for (int a = 0; a < D; a++)
+#pragma unroll
+            for (int b = 0; b < D; b++) acc[a] = fma(dgv[a * D + b], xi[b], acc[a]);
+    }
+    double out[VS];
+#pragma unroll
+    for (int a = 0; a < VS; a++) out[a] = 0.0;
+    if (MODE == 0) {
+#pragma unroll
+        for (int a = 0; a < D; a++) out[a] = acc[a];
+        if (FIN == FIN_K1) {
+            double ui[VS];
+            ld_vec<VS>(u1 + row * VS, ui);
+#pragma unroll
+            for (int a = 0; a < D; a++) { dots[0] = fma(xi[a], acc[a], dots[0]); dots[1] = fma(xi[a], ui[a], dots[1]); }
+        } else if (FIN == FIN_K2) {
+            double ui[VS], wi[VS];
+            ld_vec<VS>(u1 + row * VS, ui);
+            ld_vec<VS>(u2 + row * VS, wi);
+#pragma unroll
+            for (int a = 0; a < D; a++) { dots[0] = fma(xi[a], ui[a], dots[0]); dots[1] = fma(xi[a], acc[a], dots[1]); dots[2] = fma(xi[a], wi[a], dots[2]); }
+        } else {
+#pragma unroll
+            for (int a = 0; a < D; a++) dots[0] = fma(xi[a], acc[a], dots[0]);
+        }
+    } else {
+        double ri[VS];
+        ld_vec<VS>(r + row * VS, ri);
+        if (MODE == 1) {
+#pragma unroll
+            for (int a = 0; a < D; a++) out[a] = ri[a] - acc[a];
+        } else {
+            double t[D];
+#pragma unroll
+            for (int a = 0; a < D; a++) t[a] = ri[a] - acc[a];
+            const double *di = L.dinv + row;
+#pragma unroll
+            for (int a = 0; a < D; a++) {
+                double s = 0.0;
+#pragma unroll
+                for (int b = 0; b < D; b++) s = fma(__ldg(di + (int64_t)(a * D + b) * L.n_pad), t[b], s);
+                out[a] = fma(omega, s, xi[a]);
+                dots[0] = fma(ri[a], out[a], dots[0]);
+            }
+            if (FIN == FIN_RZ) {
+                double ui[VS];
+                ld_vec<VS>(u1 + row * VS, ui);
+#pragma unroll
+                for (int a = 0; a < D; a++) dots[1] = fma(ui[a], out[a], dots[1]);
+            }
+        }
+    }
+    st_vec<VS>(y + row * VS, out);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Level 0: BSR SpMV over the sliced jagged storage, one thread per block row.
 //   MODE 0: y = H x                      (+ x.y  -> FIN_PQ)
@@ -232,6 +300,7 @@ __global__ void __launch_bounds__(128) k_spmv(LevelDev L, const __grid_constant_
     for (int a = 0; a < D; a++) acc[a] = 0.0;
 #pragma unroll
     for (int a = 0; a < VS; a++) xi[a] = 0.0;
+    double dots[3] = {0.0, 0.0, 0.0};
     const bool live = slice < L.n_slices;
     if (live) {
         const int mydeg = L.deg[row];
@@ -298,68 +367,148 @@ __global__ void __launch_bounds__(128) k_spmv(LevelDev L, const __grid_constant_
 #pragma unroll
                     for (int b = 0; b < D; b++) acc[a] = fma((double)hv[j][a * D + b], xj[j][b], acc[a]);
         }
-        {   // diagonal block last: its D^2 loads are not held in registers across the loop
-            const double *dg = L.diag + row;
-            double dgv[DD];
-#pragma unroll
-            for (int q = 0; q < DD; q++) dgv[q] = __ldg(dg + (int64_t)q * L.n_pad);
-#pragma unroll
-            for (int a = 0; a < D; a++)
-#pragma unroll
-                for (int b = 0; b < D; b++) acc[a] = fma(dgv[a * D + b], xi[b], acc[a]);
-        }
+        spmv_row_finish<D, MODE, FIN>(L, row, acc, xi, r, y, omega, u1, u2, dots);
     }
+    reduce_and_finalize<128, FIN>(dots, S, partials, lvl, blockIdx.x, gridDim.x);
+}
+
+// ---- TMA-staged variant of the sliced SpMV -----------------------------------------------------------------------
+// Same mapping (one thread per block row, one warp per 32-row slice), but the block values -- >= 90 % of the bytes -- do
+// not pass through registers while in flight: lane 0 of every warp streams the slice's columns with 1-D bulk copies
+// (cp.async.bulk global -> shared, completion on an mbarrier) into a private ring of NS slots, NS columns ahead of the
+// multiply, so the bytes in flight per SM are bounded by shared memory (NS x 2.3 KB per warp at D = 3 / fp64) instead
+// of by registers x occupancy.  A column starts on an 8-byte (fp64) or 4-byte (fp32) boundary, so the copy is widened to
+// the enclosing 16-byte-aligned window (the few extra bytes belong to the neighbouring columns / the allocation's pad).
+// The gathered x records stay in registers, requested PD = 2 columns ahead, the column words PD + 1 ahead.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+template <int D, typename VT> struct TmaSlot { static constexpr int BYTES = (32 * D * D * (int)sizeof(VT) + 16 + 15) / 16 * 16; };
+template <int D, typename VT> inline size_t spmv_tma_smem(int ns) { return (size_t)4 * ns * TmaSlot<D, VT>::BYTES + (size_t)4 * ns * 8; }
+
+template <int D, int MODE, int FIN, typename VT>
+__global__ void __launch_bounds__(128) k_spmv_tma(LevelDev L, const double *__restrict__ x, const double *__restrict__ r, double *__restrict__ y,
+                                                   double omega, const double *__restrict__ u1, const double *__restrict__ u2, Scalars *S,
+                                                   double *partials, int lvl, int check_done, int NS) {
+    PDL_ENTER();
+    if (check_done && ld_done(S)) return;
+    constexpr int DD = D * D, VS = VecStride<D>::value, PD = 2, SLOT = TmaSlot<D, VT>::BYTES;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(128) unsigned char tma_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    const int64_t slice = row >> 5;
+    double acc[D], xi[VS];
+#pragma unroll
+    for (int a = 0; a < D; a++) acc[a] = 0.0;
+#pragma unroll
+    for (int a = 0; a < VS; a++) xi[a] = 0.0;
     double dots[3] = {0.0, 0.0, 0.0};
+    const bool live = slice < L.n_slices;
     if (live) {
-        double out[VS];
-#pragma unroll
-        for (int a = 0; a < VS; a++) out[a] = 0.0;
-        if (MODE == 0) {
-#pragma unroll
-            for (int a = 0; a < D; a++) out[a] = acc[a];
-            if (FIN == FIN_K1) {
-                double ui[VS];
-                ld_vec<VS>(u1 + row * VS, ui);
-#pragma unroll
-                for (int a = 0; a < D; a++) { dots[0] = fma(xi[a], acc[a], dots[0]); dots[1] = fma(xi[a], ui[a], dots[1]); }
-            } else if (FIN == FIN_K2) {
-                double ui[VS], wi[VS];
-                ld_vec<VS>(u1 + row * VS, ui);
-                ld_vec<VS>(u2 + row * VS, wi);
-#pragma unroll
-                for (int a = 0; a < D; a++) { dots[0] = fma(xi[a], ui[a], dots[0]); dots[1] = fma(xi[a], acc[a], dots[1]); dots[2] = fma(xi[a], wi[a], dots[2]); }
-            } else {
-#pragma unroll
-                for (int a = 0; a < D; a++) dots[0] = fma(xi[a], acc[a], dots[0]);
-            }
-        } else {
-            double ri[VS];
-            ld_vec<VS>(r + row * VS, ri);
-            if (MODE == 1) {
-#pragma unroll
-                for (int a = 0; a < D; a++) out[a] = ri[a] - acc[a];
-            } else {
-                double t[D];
-#pragma unroll
-                for (int a = 0; a < D; a++) t[a] = ri[a] - acc[a];
-                const double *di = L.dinv + row;
-#pragma unroll
-                for (int a = 0; a < D; a++) {
-                    double s = 0.0;
-#pragma unroll
-                    for (int b = 0; b < D; b++) s = fma(__ldg(di + (int64_t)(a * D + b) * L.n_pad), t[b], s);
-                    out[a] = fma(omega, s, xi[a]);
-                    dots[0] = fma(ri[a], out[a], dots[0]);
-                }
-                if (FIN == FIN_RZ) {
-                    double ui[VS];
-                    ld_vec<VS>(u1 + row * VS, ui);
-#pragma unroll
-                    for (int a = 0; a < D; a++) dots[1] = fma(ui[a], out[a], dots[1]);
-                }
-            }
+        unsigned char *ring = tma_smem + (size_t)warp * NS * SLOT;
+        const uint32_t ring_s = smem_u32(ring);
+        const uint32_t bar_s = smem_u32(tma_smem + (size_t)4 * NS * SLOT) + (uint32_t)warp * NS * 8;
+        if (lane == 0) {
+            for (int q = 0; q < NS; q++) mbar_init(bar_s + 8 * q, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-        st_vec<VS>(y + row * VS, out);
+        __syncwarp();
+        const int mydeg = L.deg[row];
+        const int maxdeg = __shfl_sync(FULL, mydeg, 0);
+        const int64_t base = L.slice_ptr[slice];
+        const unsigned char *vbytes = reinterpret_cast<const unsigned char *>(level_val<VT>(L) + base * DD);
+        const uint32_t *__restrict__ cols = L.col + base + lane;
+        // producer cursor: next column to copy, its offset (in stored blocks) inside the slice, its ring slot
+        int ki = 0, si = 0;
+        int64_t off_i = 0;
+        auto issue = [&]() {
+            const int c = __popc(__ballot_sync(FULL, ki < mydeg));
+            if (ki < maxdeg) {
+                const unsigned char *src = vbytes + off_i * (int64_t)(DD * sizeof(VT));
+                const uintptr_t a = reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)15;
+                const uint32_t bytes = ((uint32_t)(reinterpret_cast<uintptr_t>(src) - a) + (uint32_t)c * DD * (uint32_t)sizeof(VT) + 15u) & ~15u;
+                if (lane == 0) {
+                    mbar_expect_tx(bar_s + 8 * si, bytes);
+                    bulk_g2s(ring_s + (uint32_t)si * SLOT, reinterpret_cast<const void *>(a), bytes, bar_s + 8 * si);
+                }
+                off_i += c;
+            }
+            ki++;
+            si = (si + 1 == NS) ? 0 : si + 1;
+        };
+        for (int q = 0; q < NS; q++) issue();
+        // column-word cursor
+        int kc = 0;
+        int64_t off_c = 0;
+        auto next_cw = [&]() -> uint32_t {
+            const bool on = kc < mydeg;
+            const uint32_t w = on ? __ldg(cols + off_c) : 0u;
+            off_c += __popc(__ballot_sync(FULL, on));
+            kc++;
+            return w;
+        };
+        double xq[PD][VS];
+#pragma unroll
+        for (int j = 0; j < PD; j++) {
+            const uint32_t w = next_cw();
+#pragma unroll
+            for (int a = 0; a < VS; a++) xq[j][a] = 0.0;
+            if (j < mydeg) ld_vec<VS>(x + (int64_t)(w & COL_LOCAL_MASK) * VS, xq[j]);
+        }
+        uint32_t cwn = next_cw();            // column word of entry PD
+        ld_vec<VS>(x + row * VS, xi);
+        int64_t off = 0;
+        int sc = 0;
+        uint32_t parity = 0;
+        for (int k = 0; k < maxdeg; k++) {
+            const int cnt = __popc(__ballot_sync(FULL, k < mydeg));
+            double xj[VS];
+#pragma unroll
+            for (int a = 0; a < VS; a++) xj[a] = xq[0][a];
+#pragma unroll
+            for (int j = 0; j + 1 < PD; j++)
+#pragma unroll
+                for (int a = 0; a < VS; a++) xq[j][a] = xq[j + 1][a];
+#pragma unroll
+            for (int a = 0; a < VS; a++) xq[PD - 1][a] = 0.0;
+            if (k + PD < mydeg) ld_vec<VS>(x + (int64_t)(cwn & COL_LOCAL_MASK) * VS, xq[PD - 1]);
+            cwn = next_cw();
+            mbar_wait(bar_s + 8 * sc, parity);
+            if (k < mydeg) {
+                const unsigned char *src = vbytes + off * (int64_t)(DD * sizeof(VT));
+                const uint32_t delta = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15);
+                const VT *v = reinterpret_cast<const VT *>(ring + (size_t)sc * SLOT + delta) + lane;
+                VT hv[DD];
+#pragma unroll
+                for (int q = 0; q < DD; q++) hv[q] = v[q * cnt];
+#pragma unroll
+                for (int a = 0; a < D; a++)
+#pragma unroll
+                    for (int b = 0; b < D; b++) acc[a] = fma((double)hv[a * D + b], xj[b], acc[a]);
+            }
+            off += cnt;
+            sc++;
+            if (sc == NS) { sc = 0; parity ^= 1u; }
+            __syncwarp();                    // every lane has read its values: the slot may be overwritten
+            issue();
+        }
+        spmv_row_finish<D, MODE, FIN>(L, row, acc, xi, r, y, omega, u1, u2, dots);
     }
     reduce_and_finalize<128, FIN>(dots, S, partials, lvl, blockIdx.x, gridDim.x);
 }
@@ -523,6 +672,35 @@ __global__ void __launch_bounds__(256) k_update_xr(int64_t n_pad, double *__rest
     *reinterpret_cast<double2 *>(r + i) = rv;
 }
 
+// x += alpha p ; r -= alpha q ; xa = omega Dinv r   (the PCG update fused with the pre-smoothing step of the cycle that follows:
+// the new residual is used while it is still in registers)
+template <int D>
+__global__ void __launch_bounds__(128) k_update_xr_dinv(LevelDev L, double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p,
+                                                         const double *__restrict__ q, double *__restrict__ xa, double omega, const Scalars *S) {
+    PDL_ENTER();
+    if (ld_done(S)) return;
+    constexpr int VS = VecStride<D>::value;
+    const int64_t row = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (row >= L.n_pad) return;
+    const double a = S->alpha;
+    double xv[VS], rv[VS], pv[VS], qv[VS], out[VS];
+    ld_vec<VS>(x + row * VS, xv); ld_vec<VS>(p + row * VS, pv);
+    ld_vec<VS>(r + row * VS, rv); ld_vec<VS>(q + row * VS, qv);
+#pragma unroll
+    for (int c = 0; c < VS; c++) { xv[c] = fma(a, pv[c], xv[c]); rv[c] = fma(-a, qv[c], rv[c]); out[c] = 0.0; }
+    st_vec<VS>(x + row * VS, xv);
+    st_vec<VS>(r + row * VS, rv);
+    const double *di = L.dinv + row;
+#pragma unroll
+    for (int c = 0; c < D; c++) {
+        double s = 0.0;
+#pragma unroll
+        for (int b = 0; b < D; b++) s = fma(__ldg(di + (int64_t)(c * D + b) * L.n_pad), rv[b], s);
+        out[c] = omega * s;
+    }
+    st_vec<VS>(xa + row * VS, out);
+}
+
 // p = z + beta p
 template <int D>
 __global__ void __launch_bounds__(256) k_update_p(int64_t n_pad, double *__restrict__ p, const double *__restrict__ z, const Scalars *S) {
@@ -556,6 +734,33 @@ __global__ void __launch_bounds__(256) k_kcombine(int64_t n_doubles, const doubl
     PDL_ENTER();
     if (ld_done(S)) return;
     kcombine_body<WHICH>(n_doubles, a, b, out, S, lvl, blockIdx.x);
+}
+
+// K-cycle, fused: r1 = rhs - alpha_l v1 (the residual after the first inner step) and the pre-smoothing step of the cycle
+// that follows, xa = omega Dinv r1, while r1 is still in registers
+template <int D>
+__global__ void __launch_bounds__(128) k_kresid_dinv(LevelDev L, const double *__restrict__ rhs, const double *__restrict__ v1, double *__restrict__ r1,
+                                                      double *__restrict__ xa, double omega, const Scalars *S, int lvl) {
+    PDL_ENTER();
+    if (ld_done(S)) return;
+    constexpr int VS = VecStride<D>::value;
+    const int64_t row = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (row >= L.n_pad) return;
+    const double al = S->k[lvl].alpha;
+    double a[VS], b[VS], out[VS];
+    ld_vec<VS>(rhs + row * VS, a); ld_vec<VS>(v1 + row * VS, b);
+#pragma unroll
+    for (int c = 0; c < VS; c++) { a[c] = fma(-al, b[c], a[c]); out[c] = 0.0; }
+    st_vec<VS>(r1 + row * VS, a);
+    const double *di = L.dinv + row;
+#pragma unroll
+    for (int c = 0; c < D; c++) {
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < D; q++) s = fma(__ldg(di + (int64_t)(c * D + q) * L.n_pad), a[q], s);
+        out[c] = omega * s;
+    }
+    st_vec<VS>(xa + row * VS, out);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -732,6 +937,26 @@ __device__ __forceinline__ void prolong_body(const LevelDev &F, const double *__
     double e[VS], xi[VS];
     ld_vec<VS>(ec + I * VS, e);
     ld_vec<VS>(x + i * VS, xi);
+    xfer_prolong(xfer_own<D>(F, i), e, xi);
+    st_vec<VS>(x + i * VS, xi);
+}
+// x_i += P_i (coef1 c1 + coef2 c2)_{agg(i)}: prolongation fused with the final combination of the coarse level's K-cycle
+template <int D>
+__global__ void __launch_bounds__(128) k_prolong_k(LevelDev F, const double *__restrict__ c1, const double *__restrict__ c2, double *__restrict__ x,
+                                                    const Scalars *S, int clvl) {
+    PDL_ENTER();
+    if (ld_done(S)) return;
+    constexpr int VS = VecStride<D>::value;
+    const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (i >= F.n) return;
+    const double k1 = S->k[clvl].coef1, k2 = S->k[clvl].coef2;
+    const int64_t I = F.agg[i];
+    double e[VS], e2[VS], xi[VS];
+    ld_vec<VS>(c1 + I * VS, e);
+    ld_vec<VS>(c2 + I * VS, e2);
+    ld_vec<VS>(x + i * VS, xi);
+#pragma unroll
+    for (int c = 0; c < VS; c++) e[c] = fma(k1, e[c], k2 * e2[c]);
     xfer_prolong(xfer_own<D>(F, i), e, xi);
     st_vec<VS>(x + i * VS, xi);
 }
@@ -972,82 +1197,124 @@ __global__ void __launch_bounds__(128) k_dense_assemble(LevelDev L, DenseMap dm,
 //   phase 0  every CTA inverts the pivot block A_pp in shared memory (redundantly: cheaper than a third sync)
 //   phase 1  R = A_pp^-1 A_p: (w x m) and Cp = A_:p (m x w) go to scratch
 //   phase 2  A_pp <- A_pp^-1 ; A_pj <- R_j ; A_ip <- -Cp_i A_pp^-1 ; A_ij <- A_ij - Cp_i R_j   (tiles of 8 rows x 256 columns)
-constexpr int GJ_W = 24;
-__global__ void __launch_bounds__(256) k_dense_invert(int m, double *__restrict__ A, double *__restrict__ R, double *__restrict__ Cp) {
+// In-place-style inverse of the dense coarsest matrix (symmetric positive definite, m <= 3 * 1024 + ...): right-looking
+// BLOCKED Gauss-Jordan without pivoting, panel width 32, as a persistent cooperative kernel with ONE grid barrier per
+// panel.  With pivot block P = A[pp] the panel step is
+//     A[pp] <- P^-1        A[p,r] <- P^-1 A[p,r] (= R)        A[r,p] <- -A[r,p] P^-1        A[r,r] <- A[r,r] - A[r,p] R
+// Every CTA inverts the 32x32 pivot block itself (shared memory, 32 unblocked steps) and recomputes the slice of R its
+// 64x64 tiles need, so nothing has to be exchanged inside a panel step; the step reads `src` and writes the whole
+// matrix to `dst` (ping-pong, both L2-resident), which removes every read-after-write hazard between tiles.  The matrix
+// is treated as padded with an identity block up to a multiple of 32.  The host passes the buffers such that the
+// result of the last panel lands in the caller's Ainv.
+constexpr int GJ_W = 32, GJ_T = 64;
+constexpr size_t GJ_SMEM = sizeof(double) * (2 * GJ_W * (GJ_W + 1) + 2 * GJ_W * GJ_T + GJ_T * (GJ_W + 1));
+__global__ void __launch_bounds__(256) k_dense_invert(int m, double *__restrict__ bufA, double *__restrict__ bufB) {
     PDL_ENTER();
     cg::grid_group grid = cg::this_grid();
-    __shared__ double P[GJ_W][GJ_W + 1];
-    __shared__ double Cs[8][GJ_W];
+    extern __shared__ double gj_smem[];
+    double (*Pb)[GJ_W][GJ_W + 1] = reinterpret_cast<double (*)[GJ_W][GJ_W + 1]>(gj_smem);                      // [2][32][33]
+    double (*Xr)[GJ_T] = reinterpret_cast<double (*)[GJ_T]>(gj_smem + 2 * GJ_W * (GJ_W + 1));                 // [32][64] raw panel rows
+    double (*Xb)[GJ_T] = reinterpret_cast<double (*)[GJ_T]>(gj_smem + 2 * GJ_W * (GJ_W + 1) + GJ_W * GJ_T);   // [32][64] R (or P^-1 columns)
+    double (*Cb)[GJ_W + 1] = reinterpret_cast<double (*)[GJ_W + 1]>(gj_smem + 2 * GJ_W * (GJ_W + 1) + 2 * GJ_W * GJ_T);   // [64][33]
     const int tid = threadIdx.x;
-    const int gtid = blockIdx.x * 256 + tid, gsize = gridDim.x * 256;
-    const int n_rg = (m + 7) / 8, n_cc = (m + 255) / 256;
+    const int nt = (m + GJ_T - 1) / GJ_T;
+    const double *src = bufA;
+    double *dst = bufB;
     for (int p0 = 0; p0 < m; p0 += GJ_W) {
-        const int w = min(GJ_W, m - p0);
-        // ---- phase 0
-        for (int t = tid; t < w * w; t += 256) P[t / w][t % w] = __ldcg(A + (int64_t)(p0 + t / w) * m + p0 + t % w);
+        // ---- pivot block -> Pb[0], inverted by 32 unblocked Gauss-Jordan steps ping-ponging Pb[0] <-> Pb[1]
+        for (int t = tid; t < GJ_W * GJ_W; t += 256) {
+            const int i = t / GJ_W, j = t % GJ_W;
+            const int gi = p0 + i, gj = p0 + j;
+            Pb[0][i][j] = (gi < m && gj < m) ? __ldcg(src + (int64_t)gi * m + gj) : (i == j ? 1.0 : 0.0);
+        }
         __syncthreads();
-        for (int k = 0; k < w; k++) {
-            double nv[3]; int ne = 0;
-            const double ikk = 1.0 / P[k][k];
-            for (int t = tid; t < w * w; t += 256, ne++) {
-                const int i = t / w, j = t % w;
-                double v;
-                if (i == k && j == k) v = ikk;
-                else if (i == k) v = P[k][j] * ikk;
-                else if (j == k) v = -P[i][k] * ikk;
-                else v = P[i][j] - P[i][k] * P[k][j] * ikk;
-                nv[ne] = v;
-            }
-            __syncthreads();
-            ne = 0;
-            for (int t = tid; t < w * w; t += 256, ne++) P[t / w][t % w] = nv[ne];
-            __syncthreads();
-        }
-        // ---- phase 1
-        for (int j = gtid; j < m; j += gsize) {
-            double a[GJ_W];
+        {
+            const int i = tid >> 3, j0 = (tid & 7) * 4;
+            for (int k = 0; k < GJ_W; k++) {
+                const double (*Pi)[GJ_W + 1] = Pb[k & 1];
+                double (*Po)[GJ_W + 1] = Pb[(k & 1) ^ 1];
+                const double ikk = 1.0 / Pi[k][k];
+                const double pik = Pi[i][k];
 #pragma unroll
-            for (int l = 0; l < GJ_W; l++) a[l] = l < w ? __ldcg(A + (int64_t)(p0 + l) * m + j) : 0.0;
-            for (int k = 0; k < w; k++) {
-                double s = 0.0;
-#pragma unroll
-                for (int l = 0; l < GJ_W; l++) s = fma(P[k][l < w ? l : 0], a[l], s);   // a[l] = 0 beyond w
-                R[(int64_t)k * m + j] = s;
-            }
-            for (int k = 0; k < w; k++) Cp[(int64_t)j * GJ_W + k] = __ldcg(A + (int64_t)j * m + p0 + k);
-        }
-        grid.sync();
-        // ---- phase 2
-        for (int tile = blockIdx.x; tile < n_rg * n_cc; tile += gridDim.x) {
-            const int i0 = (tile / n_cc) * 8, j = (tile % n_cc) * 256 + tid;
-            __syncthreads();
-            if (tid < 8 * GJ_W) { const int i = i0 + tid / GJ_W; Cs[tid / GJ_W][tid % GJ_W] = (i < m && tid % GJ_W < w) ? __ldcg(Cp + (int64_t)i * GJ_W + tid % GJ_W) : 0.0; }
-            __syncthreads();
-            if (j >= m) continue;
-            const bool jin = j >= p0 && j < p0 + w;
-            double r[GJ_W];
-#pragma unroll
-            for (int k = 0; k < GJ_W; k++) r[k] = (k < w && !jin) ? __ldcg(R + (int64_t)k * m + j) : 0.0;
-#pragma unroll
-            for (int ii = 0; ii < 8; ii++) {
-                const int i = i0 + ii;
-                if (i >= m) break;
-                const bool iin = i >= p0 && i < p0 + w;
-                double v;
-                if (iin && jin) v = P[i - p0][j - p0];
-                else if (iin) v = __ldcg(R + (int64_t)(i - p0) * m + j);
-                else if (jin) {
-                    v = 0.0;
-                    for (int l = 0; l < w; l++) v = fma(-Cs[ii][l], P[l][j - p0], v);
-                } else {
-                    v = __ldcg(A + (int64_t)i * m + j);
-#pragma unroll
-                    for (int k = 0; k < GJ_W; k++) v = fma(-Cs[ii][k], r[k], v);
+                for (int jj = 0; jj < 4; jj++) {
+                    const int j = j0 + jj;
+                    double v;
+                    if (i == k) v = (j == k) ? ikk : Pi[k][j] * ikk;
+                    else if (j == k) v = -pik * ikk;
+                    else v = Pi[i][j] - pik * Pi[k][j] * ikk;
+                    Po[i][j] = v;
                 }
-                A[(int64_t)i * m + j] = v;
+                __syncthreads();
+            }
+        }
+        const double (*Pinv)[GJ_W + 1] = Pb[0];          // 32 steps: the result is back in Pb[0]
+        // ---- tiles
+        for (int tile = blockIdx.x; tile < nt * nt; tile += gridDim.x) {
+            const int i0 = (tile / nt) * GJ_T, j0 = (tile % nt) * GJ_T;
+            __syncthreads();                              // the previous tile's shared arrays are free
+            for (int t = tid; t < GJ_W * GJ_T; t += 256) {       // panel rows of this column block
+                const int l = t / GJ_T, jj = t % GJ_T;
+                const int gi = p0 + l, gj = j0 + jj;
+                Xr[l][jj] = (gi < m && gj < m) ? __ldcg(src + (int64_t)gi * m + gj) : 0.0;
+            }
+            for (int t = tid; t < GJ_T * GJ_W; t += 256) {       // panel columns of this row block
+                const int ii = t / GJ_W, l = t % GJ_W;
+                const int gi = i0 + ii, gj = p0 + l;
+                Cb[ii][l] = (gi < m && gj < m) ? __ldcg(src + (int64_t)gi * m + gj) : 0.0;
+            }
+            __syncthreads();
+            // X[l][j] = (P^-1 A[p, j])[l] outside the panel columns, P^-1[l][j - p0] inside them
+            for (int t = tid; t < GJ_W * GJ_T; t += 256) {
+                const int l = t / GJ_T, jj = t % GJ_T;
+                const int gj = j0 + jj;
+                double v;
+                if (gj >= p0 && gj < p0 + GJ_W) v = Pinv[l][gj - p0];
+                else {
+                    v = 0.0;
+#pragma unroll 8
+                    for (int q = 0; q < GJ_W; q++) v = fma(Pinv[l][q], Xr[q][jj], v);
+                }
+                Xb[l][jj] = v;
+            }
+            __syncthreads();
+            const int ty = tid >> 4, tx = tid & 15;
+            double acc[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) acc[a][c] = 0.0;
+#pragma unroll 4
+            for (int l = 0; l < GJ_W; l++) {
+                double cv[4], xv[4];
+#pragma unroll
+                for (int a = 0; a < 4; a++) cv[a] = Cb[ty * 4 + a][l];
+#pragma unroll
+                for (int c = 0; c < 4; c++) xv[c] = Xb[l][tx + 16 * c];
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) acc[a][c] = fma(cv[a], xv[c], acc[a][c]);
+            }
+#pragma unroll
+            for (int a = 0; a < 4; a++) {
+                const int gi = i0 + ty * 4 + a;
+                if (gi >= m) continue;
+                const bool iin = gi >= p0 && gi < p0 + GJ_W;
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const int gj = j0 + tx + 16 * c;
+                    if (gj >= m) continue;
+                    const bool jin = gj >= p0 && gj < p0 + GJ_W;
+                    double v;
+                    if (iin) v = Xb[gi - p0][tx + 16 * c];            // P^-1 (jin) or R
+                    else if (jin) v = -acc[a][c];
+                    else v = __ldcg(src + (int64_t)gi * m + gj) - acc[a][c];
+                    dst[(int64_t)gi * m + gj] = v;
+                }
             }
         }
         grid.sync();
+        const double *t = src; src = dst; dst = const_cast<double *>(t);
     }
 }
 

@@ -94,10 +94,11 @@ struct pgo_handle {
     double *x = nullptr, *r = nullptr, *p = nullptr, *q = nullptr, *z = nullptr;
     Scalars *S = nullptr, *hS = nullptr;   // device / pinned host (2 slots)
     double *partials = nullptr;
-    double *Ainv = nullptr, *panelR = nullptr, *panelC = nullptr;
+    double *Ainv = nullptr, *Awork = nullptr;   // explicit inverse of the coarsest matrix; second buffer of the ping-pong inversion
     DenseMap dmap{};
     int dense_m = 0, invert_grid = 0;
     bool use_amg = false, omega_ready = false;
+    int spmv_tma64 = 0, spmv_tma32 = 0; // PGO_SPMV_TMA64 / PGO_SPMV_TMA32: ring depth of the TMA-staged sliced SpMV (0: register-staged kernel)
     bool pdl = true;                   // programmatic dependent launch of every kernel (PGO_PDL=0 disables)
     cudaError_t launch_err = cudaSuccess;
     bool lowp = false;                 // the cycle's SpMVs read fp32 copies of the stored blocks (opt.amg_fp64_storage == 0)
@@ -221,7 +222,14 @@ template <int D, int MODE, int FIN, typename VT> void spmv_launch(pgo_handle *h,
                                                                   const double *u1, const double *u2, int check) {
     LevelBuf &B = h->lv[l];
     const XRef xr = xref(h, x, true);
-    if (B.jds) launch_k(h, k_spmv<D, MODE, FIN, false, VT>, B.grid128, 128, 0, B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
+    if (B.jds) {
+        const int ns = std::is_same<VT, float>::value ? h->spmv_tma32 : h->spmv_tma64;
+        if (ns > 0) {                                // TMA-staged variant: ring of ns columns per warp in shared memory
+            const size_t smem = spmv_tma_smem<D, VT>(ns);
+            if (smem > 48 * 1024) cudaFuncSetAttribute(k_spmv_tma<D, MODE, FIN, VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            launch_k(h, k_spmv_tma<D, MODE, FIN, VT>, B.grid128, 128, smem, B.d, x, r, y, omega, u1, u2, h->S, h->partials, l, check, ns);
+        } else launch_k(h, k_spmv<D, MODE, FIN, false, VT>, B.grid128, 128, 0, B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
+    }
     else if (B.lpr == 8) launch_k(h, k_spmv_csr<D, MODE, FIN, false, 8, VT>, B.grid8, 256, 0, B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
     else launch_k(h, k_spmv_csr<D, MODE, FIN, false, 32, VT>, B.gridw, 256, 0, B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
 }
@@ -239,7 +247,7 @@ template <int D, int MODE, bool CYC = false> void spmv_any(pgo_handle *h, int l,
     spmv<D, MODE, FIN_NONE, CYC>(h, l, x, r, y, omega, nullptr, nullptr, check);
 }
 
-template <int D> void coarse_solve(pgo_handle *h, int l, const double *rhs, double *out);
+template <int D> void coarse_solve(pgo_handle *h, int l, const double *rhs, double *out, bool defer_combine = false);
 
 template <int D> void dense_apply(pgo_handle *h, int l, const double *rhs, double *out) {
     LevelBuf &B = h->lv[l];      // always a local (single-GPU or replicated) level
@@ -343,7 +351,8 @@ template <int D> void launch_tail(pgo_handle *h) {
 }
 
 // ---- one multigrid cycle at level l: out = M_l(rhs).  FINK: dots fused into the last kernel (level 0 only).
-template <int D, int FINK> void cycle(pgo_handle *h, int l, const double *rhs, double *out) {
+// PRE: the pre-smoothing step xa = omega Dinv rhs was already done by the caller (fused into the PCG update kernel)
+template <int D, int FINK, bool PRE = false> void cycle(pgo_handle *h, int l, const double *rhs, double *out) {
     LevelBuf &B = h->lv[l];
     const int last = (int)h->lv.size() - 1;
     if (l == last) {
@@ -361,8 +370,10 @@ template <int D, int FINK> void cycle(pgo_handle *h, int l, const double *rhs, d
         return;
     }
     LevelBuf &C = h->lv[l + 1];
-    launch_k(h, k_dinv_apply<D, FIN_NONE>, B.grid128, 128, 0, B.d, rhs, B.xa, B.omega, nullptr, h->S, h->partials, 1);
-    h->launch_count += 1;
+    if (!PRE) {
+        launch_k(h, k_dinv_apply<D, FIN_NONE>, B.grid128, 128, 0, B.d, rhs, B.xa, B.omega, nullptr, h->S, h->partials, 1);
+        h->launch_count += 1;
+    }
     lbarrier(h, l);
     spmv_any<D, 1, true>(h, l, B.xa, rhs, B.res, 0.0, 1);
     launch_k(h, k_restrict<D>, C.gridw, 256, 0, B.d, C.d, B.res, C.rhs, h->S);
@@ -371,9 +382,12 @@ template <int D, int FINK> void cycle(pgo_handle *h, int l, const double *rhs, d
         lbarrier(h, l);
         gather_rows(h, C.rhs, C.src_rows, VecStride<D>::value, 1, 0, 1);
     }
+    // a K-cycle level leaves its two search directions in C.c1 / C.c2; their final combination is folded into the prolongation
+    const bool kfold = h->tail_level != l + 1 && l + 1 != last && C.kcycle;
     if (h->tail_level == l + 1) launch_tail<D>(h);   // the whole coarse solve C.rhs -> C.sol in one cooperative launch
-    else coarse_solve<D>(h, l + 1, C.rhs, C.sol);
-    launch_k(h, k_prolong<D>, B.grid128, 128, 0, B.d, C.sol, B.xa, h->S);
+    else coarse_solve<D>(h, l + 1, C.rhs, C.sol, kfold);
+    if (kfold) launch_k(h, k_prolong_k<D>, B.grid128, 128, 0, B.d, C.c1, C.c2, B.xa, h->S, l + 1);
+    else launch_k(h, k_prolong<D>, B.grid128, 128, 0, B.d, C.sol, B.xa, h->S);
     h->launch_count += 1;
     lbarrier(h, l);
     spmv<D, 2, FINK, true>(h, l, B.xa, rhs, out, B.omega, FINK == FIN_RZ ? h->q : nullptr, nullptr, 1);
@@ -381,22 +395,26 @@ template <int D, int FINK> void cycle(pgo_handle *h, int l, const double *rhs, d
 }
 
 // K-cycle: the coarse system of level l is solved by two flexible-CG steps preconditioned by the cycle of level l
-template <int D> void coarse_solve(pgo_handle *h, int l, const double *rhs, double *out) {
+template <int D> void coarse_solve(pgo_handle *h, int l, const double *rhs, double *out, bool defer_combine) {
     LevelBuf &B = h->lv[l];
     const int last = (int)h->lv.size() - 1;
     if (l == last || !B.kcycle) { cycle<D, FIN_NONE>(h, l, rhs, out); return; }
     cycle<D, FIN_NONE>(h, l, rhs, B.c1);
     spmv<D, 0, FIN_K1, true>(h, l, B.c1, nullptr, B.v1, 0.0, rhs, nullptr, 1);
-    launch_k(h, k_kcombine<0>, B.gridv, 256, 0, B.d.n_pad * VecStride<D>::value, rhs, B.v1, B.r1, h->S, l);
-    cycle<D, FIN_NONE>(h, l, B.r1, B.c2);
+    // r1 = rhs - alpha v1, fused with the pre-smoothing step of the second cycle
+    launch_k(h, k_kresid_dinv<D>, B.grid128, 128, 0, B.d, rhs, B.v1, B.r1, B.xa, B.omega, h->S, l);
+    h->launch_count += 1;
+    cycle<D, FIN_NONE, true>(h, l, B.r1, B.c2);
     spmv<D, 0, FIN_K2, true>(h, l, B.c2, nullptr, B.v2, 0.0, B.v1, B.r1, 1);
-    launch_k(h, k_kcombine<1>, B.gridv, 256, 0, B.d.n_pad * VecStride<D>::value, B.c1, B.c2, out, h->S, l);
-    h->launch_count += 2;
+    if (!defer_combine) {                            // else: the caller's prolongation applies coef1 c1 + coef2 c2
+        launch_k(h, k_kcombine<1>, B.gridv, 256, 0, B.d.n_pad * VecStride<D>::value, B.c1, B.c2, out, h->S, l);
+        h->launch_count += 1;
+    }
 }
 
-template <int D, int FINK> void precondition(pgo_handle *h) {   // z = M^-1 r (+ r.z, z.q)
+template <int D, int FINK, bool PRE = false> void precondition(pgo_handle *h) {   // z = M^-1 r (+ r.z, z.q)
     LevelBuf &B = h->lv[0];
-    if (h->use_amg && h->lv.size() > 1) cycle<D, FINK>(h, 0, h->r, h->z);
+    if (h->use_amg && h->lv.size() > 1) cycle<D, FINK, PRE>(h, 0, h->r, h->z);
     else if (h->use_amg && h->sym.dense_coarsest) {      // the whole system fits the direct solve
         dense_apply<D>(h, 0, h->r, h->z);
         launch_k(h, k_dots<D, FINK>, B.grid128, 128, 0, B.d.n_pad, h->r, h->z, h->q, h->S, h->partials, 0, 1);
@@ -412,8 +430,13 @@ template <int D, int FINK> void precondition(pgo_handle *h) {   // z = M^-1 r (+
 template <int D> void pcg_iteration(pgo_handle *h) {
     LevelBuf &B = h->lv[0];
     spmv<D, 0, FIN_PQ>(h, 0, h->p, nullptr, h->q, 0.0, nullptr, nullptr, 1);
-    launch_k(h, k_update_xr<D>, B.gridv, 256, 0, B.d.n_pad, h->x, h->r, h->p, h->q, h->S);
-    precondition<D, FIN_RZ>(h);
+    if (h->use_amg && h->lv.size() > 1) {
+        launch_k(h, k_update_xr_dinv<D>, B.grid128, 128, 0, B.d, h->x, h->r, h->p, h->q, B.xa, B.omega, h->S);
+        precondition<D, FIN_RZ, true>(h);
+    } else {
+        launch_k(h, k_update_xr<D>, B.gridv, 256, 0, B.d.n_pad, h->x, h->r, h->p, h->q, h->S);
+        precondition<D, FIN_RZ>(h);
+    }
     launch_k(h, k_update_p<D>, B.gridv, 256, 0, B.d.n_pad, h->p, h->z, h->S);
     h->launch_count += 2;
     xbarrier(h);                                     // p complete on every rank before the next SpMV reads it
@@ -549,12 +572,15 @@ template <int D> int amg_setup(pgo_handle *h) {
     if (h->sym.dense_coarsest) {
         LevelBuf &C = h->lv[last];
         const int m = h->dense_m;
-        CK(cudaMemsetAsync(h->Ainv, 0, sizeof(double) * (size_t)m * m, h->stream));
-        if (C.jds) launch_k(h, k_dense_assemble<D, true>, C.grid128, 128, 0, C.d, h->dmap, 0, m, h->Ainv);
-        else launch_k(h, k_dense_assemble<D, false>, C.grid128, 128, 0, C.d, h->dmap, 0, m, h->Ainv);
+        // ping-pong blocked Gauss-Jordan: the matrix is assembled into the buffer from which the last panel step writes Ainv
+        const int n_panels = (m + GJ_W - 1) / GJ_W;
+        double *first = (n_panels % 2 == 0) ? h->Ainv : h->Awork, *second = (n_panels % 2 == 0) ? h->Awork : h->Ainv;
+        CK(cudaMemsetAsync(first, 0, sizeof(double) * (size_t)m * m, h->stream));
+        if (C.jds) launch_k(h, k_dense_assemble<D, true>, C.grid128, 128, 0, C.d, h->dmap, 0, m, first);
+        else launch_k(h, k_dense_assemble<D, false>, C.grid128, 128, 0, C.d, h->dmap, 0, m, first);
         h->launch_count += 1;
-        void *args[] = {(void *)&h->dense_m, (void *)&h->Ainv, (void *)&h->panelR, (void *)&h->panelC};
-        CK(cudaLaunchCooperativeKernel((void *)k_dense_invert, dim3(h->invert_grid), dim3(256), args, 0, h->stream));
+        void *args[] = {(void *)&h->dense_m, (void *)&first, (void *)&second};
+        CK(cudaLaunchCooperativeKernel((void *)k_dense_invert, dim3(h->invert_grid), dim3(256), args, GJ_SMEM, h->stream));
         h->launch_count += 1;
     }
     CK(cudaGetLastError()); CK(h->launch_err);
@@ -759,6 +785,8 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
     so.dense_max = h->opt.amg_dense_max;
     so.build_amg = h->use_amg;
     if (const char *e = std::getenv("PGO_REPL_MAX_ROWS")) so.repl_max_rows = std::atoll(e);      // tuning knobs
+    if (const char *e = std::getenv("PGO_SPMV_TMA64")) h->spmv_tma64 = std::max(0, std::min(16, std::atoi(e)));
+    if (const char *e = std::getenv("PGO_SPMV_TMA32")) h->spmv_tma32 = std::max(0, std::min(16, std::atoi(e)));
     if (const char *e = std::getenv("PGO_PDL")) h->pdl = std::atoi(e) != 0;
     if (const char *e = std::getenv("PGO_TAIL")) h->opt_tail = std::atoi(e) != 0;
     if (const char *e = std::getenv("PGO_TAIL_CTAS_PER_SM")) h->tail_ctas_per_sm = std::max(1, std::atoi(e));
@@ -871,12 +899,12 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
             arena_request(h, &d.diag, (size_t)DD * max_pad);
             arena_request(h, &d.pos, (size_t)NG * max_pad);
         } else {
-            CKC(dalloc(h, &d.val, (size_t)DD * std::max<int64_t>(d.n_slots, 1)));
+            CKC(dalloc(h, &d.val, (size_t)DD * std::max<int64_t>(d.n_slots, 1) + 2));      // + 16 bytes: the TMA-staged SpMV copies 16-byte-aligned windows
             CKC(dalloc(h, &d.diag, (size_t)DD * d.n_pad));
             CKC(dalloc(h, &d.pos, (size_t)NG * d.n_pad));
         }
         CKC(dalloc(h, &d.dinv, (size_t)DD * d.n_pad));
-        if (h->lowp && !(l == nl - 1 && S.dense_coarsest)) CKC(dalloc(h, &d.valf, (size_t)DD * std::max<int64_t>(d.n_slots, 1)));
+        if (h->lowp && !(l == nl - 1 && S.dense_coarsest)) CKC(dalloc(h, &d.valf, (size_t)DD * std::max<int64_t>(d.n_slots, 1) + 4));
         if (!H.agg.empty()) {
             HostLevel &Cn = S.levels[l + 1];
             const int64_t c0 = Cn.part_off[(world > 1 && Cn.repl) ? 0 : rank];
@@ -933,13 +961,13 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
     if (h->use_amg && S.dense_coarsest) {
         const int m = h->dense_m;
         CKC(dalloc(h, &h->Ainv, (size_t)m * m));
-        CKC(dalloc(h, &h->panelR, (size_t)GJ_W * m));
-        CKC(dalloc(h, &h->panelC, (size_t)GJ_W * m));
+        CKC(dalloc(h, &h->Awork, (size_t)m * m));
         int per_sm = 0, sms = 0;
-        CKU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dense_invert, 256, 0));
+        CKU(cudaFuncSetAttribute(k_dense_invert, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GJ_SMEM));
+        CKU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dense_invert, 256, GJ_SMEM));
         CKU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
-        h->invert_grid = std::max(1, std::min(per_sm, 2) * sms);
-        h->invert_grid = std::min(h->invert_grid, std::max(sms, ((m + 7) / 8) * ((m + 255) / 256)));
+        const int nt = (m + GJ_T - 1) / GJ_T;
+        h->invert_grid = std::max(1, std::min(std::max(per_sm, 1) * sms, nt * nt));
         CKU(cudaFuncSetAttribute(k_dense_apply<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 6 * 1024)));
         CKU(cudaFuncSetAttribute(k_dense_apply<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 6 * 1024)));
     }
