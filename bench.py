@@ -294,7 +294,7 @@ def run_b200(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl_desc.format(n_poses, n_edges) + "; 1 step = 1 Gauss-Newton iteration from the initial guess",
                        "poses": n_poses, "edges": n_edges, "pcg_rtol": args.pcg_rtol,
-                       "preconditioner": "aggregation-AMG K-cycle (flexible PCG)" if args.preconditioner == 1 else "block-Jacobi",
+                       "preconditioner": "aggregation-AMG K-cycle (flexible PCG); the cycle's SpMVs read fp32 copies of the stored blocks and accumulate in fp64, the PCG operator / residual / dot products are fp64" if args.preconditioner == 1 else "block-Jacobi",
                        "parallelism": "single GPU" if world == 1 else
                        f"1 graph sharded over {world} GPUs by contiguous vertex ranges; halo rows read from peer HBM (NVLink), "
                        f"device-side peer-memory all-reduce for the dot products",

@@ -49,6 +49,7 @@ struct LevelDev {
     const int64_t *slice_ptr;                 // JDS: [n_slices + 1] ; CSR: row_ptr [n_pad + 1]
     const int32_t *deg; const uint32_t *col;
     double *val, *diag, *dinv;
+    float *diagf, *dinvf;        // fp32 copies of diag / dinv (sliced levels only), same use as valf
     float *valf;                 // fp32 copy of val (same layout) read by the SpMVs INSIDE the multigrid cycle when the
                                  // preconditioner is stored in reduced precision (the PCG operator itself stays fp64)
     double *pos;                 // [2][n_pad] planes: position of each row (centroid on coarse levels)
@@ -82,6 +83,12 @@ template <> struct Dim<6> { static constexpr int VS = 6, PS = 8, NG = 3, LS = 4,
 template <typename VT> __device__ __forceinline__ const VT *level_val(const LevelDev &L);
 template <> __device__ __forceinline__ const double *level_val<double>(const LevelDev &L) { return L.val; }
 template <> __device__ __forceinline__ const float *level_val<float>(const LevelDev &L) { return L.valf; }
+template <typename VT> __device__ __forceinline__ const VT *level_diag(const LevelDev &L);
+template <> __device__ __forceinline__ const double *level_diag<double>(const LevelDev &L) { return L.diag; }
+template <> __device__ __forceinline__ const float *level_diag<float>(const LevelDev &L) { return L.diagf; }
+template <typename VT> __device__ __forceinline__ const VT *level_dinv(const LevelDev &L);
+template <> __device__ __forceinline__ const double *level_dinv<double>(const LevelDev &L) { return L.dinv; }
+template <> __device__ __forceinline__ const float *level_dinv<float>(const LevelDev &L) { return L.dinvf; }
 
 __device__ __forceinline__ int ld_done(const Scalars *S) { return *(const volatile int *)&S->done; }
 
@@ -213,20 +220,20 @@ template <int NT, int FIN> __device__ __forceinline__ void reduce_and_finalize(c
 
 // Tail of the sliced SpMV of one block row (shared by k_spmv and k_spmv_tma): adds the diagonal block, applies the MODE,
 // stores y and returns this row's contributions to the fused dot products.
-template <int D, int MODE, int FIN>
+template <int D, int MODE, int FIN, typename VT>
 __device__ __forceinline__ void spmv_row_finish(const LevelDev &L, int64_t row, double *acc, const double *xi, const double *__restrict__ r,
                                                 double *__restrict__ y, double omega, const double *__restrict__ u1,
                                                 const double *__restrict__ u2, double *dots) {
     constexpr int DD = D * D, VS = VecStride<D>::value;
     {   // diagonal block last: its D^2 loads are not held in registers across the loop
-        const double *dg = L.diag + row;
-        double dgv[DD];
+        const VT *dg = level_diag<VT>(L) + row;
+        VT dgv[DD];
 #pragma unroll
         for (int q = 0; q < DD; q++) dgv[q] = __ldg(dg + (int64_t)q * L.n_pad);
 #pragma unroll
         for (int a = 0; a < D; a++)
 #pragma unroll
-            for (int b = 0; b < D; b++) acc[a] = fma(dgv[a * D + b], xi[b], acc[a]);
+            for (int b = 0; b < D; b++) acc[a] = fma((double)dgv[a * D + b], xi[b], acc[a]);
     }
     double out[VS];
 #pragma unroll
@@ -259,12 +266,12 @@ __device__ __forceinline__ void spmv_row_finish(const LevelDev &L, int64_t row, 
             double t[D];
 #pragma unroll
             for (int a = 0; a < D; a++) t[a] = ri[a] - acc[a];
-            const double *di = L.dinv + row;
+            const VT *di = level_dinv<VT>(L) + row;
 #pragma unroll
             for (int a = 0; a < D; a++) {
                 double s = 0.0;
 #pragma unroll
-                for (int b = 0; b < D; b++) s = fma(__ldg(di + (int64_t)(a * D + b) * L.n_pad), t[b], s);
+                for (int b = 0; b < D; b++) s = fma((double)__ldg(di + (int64_t)(a * D + b) * L.n_pad), t[b], s);
                 out[a] = fma(omega, s, xi[a]);
                 dots[0] = fma(ri[a], out[a], dots[0]);
             }
@@ -367,7 +374,7 @@ __global__ void __launch_bounds__(128) k_spmv(LevelDev L, const __grid_constant_
 #pragma unroll
                     for (int b = 0; b < D; b++) acc[a] = fma((double)hv[j][a * D + b], xj[j][b], acc[a]);
         }
-        spmv_row_finish<D, MODE, FIN>(L, row, acc, xi, r, y, omega, u1, u2, dots);
+        spmv_row_finish<D, MODE, FIN, VT>(L, row, acc, xi, r, y, omega, u1, u2, dots);
     }
     reduce_and_finalize<128, FIN>(dots, S, partials, lvl, blockIdx.x, gridDim.x);
 }
@@ -508,7 +515,7 @@ __global__ void __launch_bounds__(128) k_spmv_tma(LevelDev L, const double *__re
             __syncwarp();                    // every lane has read its values: the slot may be overwritten
             issue();
         }
-        spmv_row_finish<D, MODE, FIN>(L, row, acc, xi, r, y, omega, u1, u2, dots);
+        spmv_row_finish<D, MODE, FIN, VT>(L, row, acc, xi, r, y, omega, u1, u2, dots);
     }
     reduce_and_finalize<128, FIN>(dots, S, partials, lvl, blockIdx.x, gridDim.x);
 }

@@ -61,7 +61,7 @@ struct LevelBuf {
     double *rhs = nullptr, *sol = nullptr, *xa = nullptr, *res = nullptr;      // cycle work vectors
     double *c1 = nullptr, *c2 = nullptr, *v1 = nullptr, *v2 = nullptr, *r1 = nullptr;   // K-cycle work vectors
     double omega = 0.6;
-    int grid128 = 0, gridw = 0, gridv = 0, grid8 = 0, lpr = 32;
+    int grid128 = 0, gridw = 0, gridv = 0, grid8 = 0, grid4 = 0, lpr = 32;
 };
 
 struct ArenaReq { double **p; size_t count; };
@@ -99,6 +99,7 @@ struct pgo_handle {
     int dense_m = 0, invert_grid = 0;
     bool use_amg = false, omega_ready = false;
     int spmv_tma64 = 0, spmv_tma32 = 0; // PGO_SPMV_TMA64 / PGO_SPMV_TMA32: ring depth of the TMA-staged sliced SpMV (0: register-staged kernel)
+    int64_t lpr4_min_rows = 16384;     // PGO_LPR4_MIN_ROWS
     bool pdl = true;                   // programmatic dependent launch of every kernel (PGO_PDL=0 disables)
     cudaError_t launch_err = cudaSuccess;
     bool lowp = false;                 // the cycle's SpMVs read fp32 copies of the stored blocks (opt.amg_fp64_storage == 0)
@@ -230,6 +231,7 @@ template <int D, int MODE, int FIN, typename VT> void spmv_launch(pgo_handle *h,
             launch_k(h, k_spmv_tma<D, MODE, FIN, VT>, B.grid128, 128, smem, B.d, x, r, y, omega, u1, u2, h->S, h->partials, l, check, ns);
         } else launch_k(h, k_spmv<D, MODE, FIN, false, VT>, B.grid128, 128, 0, B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
     }
+    else if (B.lpr == 4) launch_k(h, k_spmv_csr<D, MODE, FIN, false, 4, VT>, B.grid4, 256, 0, B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
     else if (B.lpr == 8) launch_k(h, k_spmv_csr<D, MODE, FIN, false, 8, VT>, B.grid8, 256, 0, B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
     else launch_k(h, k_spmv_csr<D, MODE, FIN, false, 32, VT>, B.gridw, 256, 0, B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
 }
@@ -546,6 +548,12 @@ template <int D> int amg_setup(pgo_handle *h) {
         if (nv == 0) return;
         launch_k(h, k_to_float, grid_for((nv + 1) / 2, 256), 256, 0, nv, B.d.val, B.d.valf);
         h->launch_count += 1;
+        if (B.d.diagf) {                             // sliced levels: the diagonal blocks and their inverses too
+            const int64_t nd = (int64_t)DD * B.d.n_pad;
+            launch_k(h, k_to_float, grid_for((nd + 1) / 2, 256), 256, 0, nd, B.d.diag, B.d.diagf);
+            launch_k(h, k_to_float, grid_for((nd + 1) / 2, 256), 256, 0, nd, B.d.dinv, B.d.dinvf);
+            h->launch_count += 2;
+        }
     };
     to_float(h->lv[0]);
     for (int l = 0; l < last; l++) {
@@ -787,6 +795,7 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
     if (const char *e = std::getenv("PGO_REPL_MAX_ROWS")) so.repl_max_rows = std::atoll(e);      // tuning knobs
     if (const char *e = std::getenv("PGO_SPMV_TMA64")) h->spmv_tma64 = std::max(0, std::min(16, std::atoi(e)));
     if (const char *e = std::getenv("PGO_SPMV_TMA32")) h->spmv_tma32 = std::max(0, std::min(16, std::atoi(e)));
+    if (const char *e = std::getenv("PGO_LPR4_MIN_ROWS")) h->lpr4_min_rows = std::atoll(e);
     if (const char *e = std::getenv("PGO_PDL")) h->pdl = std::atoi(e) != 0;
     if (const char *e = std::getenv("PGO_TAIL")) h->opt_tail = std::atoi(e) != 0;
     if (const char *e = std::getenv("PGO_TAIL_CTAS_PER_SM")) h->tail_ctas_per_sm = std::max(1, std::atoi(e));
@@ -843,7 +852,10 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
         B.grid128 = grid_for(d.n_pad, 128);
         B.gridw = grid_for(d.n_pad, 8);
         B.grid8 = grid_for(d.n_pad, 32);
+        B.grid4 = grid_for(d.n_pad, 64);
         B.lpr = (!H.jds && d.n > 0 && d.n_slots <= 12 * d.n) ? 8 : 32;     // short rows: 8 lanes per row
+        // a big level with short rows: 4 lanes per row, so that the whole level is (about) one wave of CTAs
+        if (B.lpr == 8 && d.n >= h->lpr4_min_rows && !h->opt_tail) B.lpr = 4;
         B.gridv = grid_for(d.n_pad * (VS / 2), 256);
         max_grid = std::max<int64_t>(max_grid, std::max(B.grid128, B.gridw));
         // row pointers
@@ -904,6 +916,10 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
             CKC(dalloc(h, &d.pos, (size_t)NG * d.n_pad));
         }
         CKC(dalloc(h, &d.dinv, (size_t)DD * d.n_pad));
+        if (h->lowp && H.jds) {
+            CKC(dalloc(h, &d.diagf, (size_t)DD * d.n_pad));
+            CKC(dalloc(h, &d.dinvf, (size_t)DD * d.n_pad));
+        }
         if (h->lowp && !(l == nl - 1 && S.dense_coarsest)) CKC(dalloc(h, &d.valf, (size_t)DD * std::max<int64_t>(d.n_slots, 1) + 4));
         if (!H.agg.empty()) {
             HostLevel &Cn = S.levels[l + 1];
