@@ -61,6 +61,9 @@ typedef struct {
     int32_t amg_aggregate_size;/* upper bound on the members of an aggregate; 0 = default */
     int32_t amg_kcycle;        /* coarse levels 1..amg_kcycle are solved by a K-cycle (two Krylov-accelerated cycles per
                                 * visit, Notay), deeper ones by a V-cycle; 0 = plain V-cycle; default: all levels */
+    int32_t amg_kcycle3;       /* coarse levels 1..amg_kcycle3 run THREE inner flexible-CG steps per K-cycle visit instead of two
+                                * (a more accurate coarse solve: fewer PCG iterations, 1.5x the coarse work); 0 = none;
+                                * -1 (default) = level 1 for SE2 / XY graphs, none for SE3 graphs */
     int32_t amg_fp64_storage;  /* 0 (default): the SpMVs INSIDE the multigrid cycle (smoother, residual, K-cycle products) read
                                 * fp32 copies of the stored blocks of every level and accumulate in fp64 -- the preconditioner
                                 * is an approximate operator anyway, and half the bytes is half the time of an HBM-bound
@@ -68,7 +71,7 @@ typedef struct {
                                 * fp64, so the solve converges to the same pcg_rtol.  1: everything reads the fp64 blocks */
 } pgo_options;
 
-/* fills *opt with the defaults (anchor 1e7, rtol 1e-10, max 200000 iterations, AMG K-cycle, single GPU) */
+/* fills *opt with the defaults (anchor 1e7, rtol 1e-10, max 200000 iterations, AMG K-cycle, fp32 preconditioner storage, single GPU) */
 void pgo_default_options(pgo_options *opt);
 
 /*

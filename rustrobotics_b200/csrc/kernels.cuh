@@ -20,20 +20,20 @@ namespace cg = cooperative_groups;
 
 // ------------------------------------------------------------------------------------------------
 constexpr int MAX_LEVELS = 12;
-struct KScal { double alpha, coef1, coef2, rho1, a1; };
+struct KScal { double alpha, coef1, coef2, coef3, rho1, a1, rho2, gam21, alpha2, e1, e2; int steps, pad_; };
 struct Scalars {
     double rz, rz0, pq, alpha, beta, tol2;
     double norm2_dx, chi2;
     int iters, max_iters, done, status;
-    unsigned counter[8];            // everything from here on survives the per-solve reset
+    unsigned counter[12];           // everything from here on survives the per-solve reset
     int world, repl_from;           // sharded handles: levels >= repl_from are replicated (their sums are already global)
     unsigned long long epoch;       // cross-rank barrier epoch (peer.cuh)
     KScal k[MAX_LEVELS];
     double loc[4];                  // sharded mode: this rank's partial sums, reduced across ranks by k_xreduce
 };
 enum { ST_OK = 0, ST_BREAKDOWN = 1, ST_MAXIT = 2, ST_COMM = 3 };
-enum { FIN_NONE = 0, FIN_PQ = 1, FIN_RZ = 2, FIN_RZ_INIT = 3, FIN_NORM = 4, FIN_CHI2 = 5, FIN_K1 = 6, FIN_K2 = 7 };
-__host__ __device__ constexpr int fin_ndot(int FIN) { return FIN == FIN_K2 ? 3 : (FIN == FIN_RZ || FIN == FIN_K1) ? 2 : FIN == FIN_NONE ? 0 : 1; }
+enum { FIN_NONE = 0, FIN_PQ = 1, FIN_RZ = 2, FIN_RZ_INIT = 3, FIN_NORM = 4, FIN_CHI2 = 5, FIN_K1 = 6, FIN_K2 = 7, FIN_K3 = 8 };
+__host__ __device__ constexpr int fin_ndot(int FIN) { return FIN == FIN_K3 ? 4 : FIN == FIN_K2 ? 3 : (FIN == FIN_RZ || FIN == FIN_K1) ? 2 : FIN == FIN_NONE ? 0 : 1; }
 
 // one vector (or pose / lever-arm array) as seen from this rank: p[k] = base of rank k's segment
 struct XRef { const double *p[MAX_RANKS]; };
@@ -190,15 +190,36 @@ __device__ __forceinline__ void finalize(int FIN, Scalars *S, const double *t, i
         K.rho1 = t[0]; K.a1 = t[1];
         K.alpha = (t[0] > 0.0) ? t[1] / t[0] : 0.0;
     } else if (FIN == FIN_K2) {
-        // second step: t = {c2.v1, c2.v2, c2.r1}; x = coef1 c1 + coef2 c2 (Notay's K-cycle, two FCG steps)
+        // second step: t = {c2.v1, c2.v2, c2.r1}.  Two-step K-cycle (Notay): x = coef1 c1 + coef2 c2.  Three-step K-cycle
+        // (flexible CG with full orthogonalisation of the search directions d1 = c1, d2 = c2 - (gam21/rho1) c1, ...):
+        // the residual after the second step is r2 = r1 - alpha2 (v2 - (gam21/rho1) v1) = r1 - e2 v2 + e1 v1.
         KScal &K = S->k[lvl];
         const double rho1 = K.rho1, a1 = K.a1, gam = t[0], beta = t[1], a2 = t[2];
         const double rho2 = beta - gam * gam / rho1;
-        if (rho1 > 0.0 && rho2 > 1e-12 * beta && rho2 == rho2) {
+        const bool ok = rho1 > 0.0 && rho2 > 1e-12 * beta && rho2 == rho2;
+        if (ok) {
             K.coef1 = a1 / rho1 - gam * a2 / (rho1 * rho2);
             K.coef2 = a2 / rho2;
         } else {
             K.coef1 = K.alpha; K.coef2 = 0.0;
+        }
+        K.coef3 = 0.0;
+        K.rho2 = ok ? rho2 : 0.0; K.gam21 = ok ? gam : 0.0;
+        K.alpha2 = ok ? a2 / rho2 : 0.0;
+        K.e2 = K.alpha2; K.e1 = ok ? K.alpha2 * gam / rho1 : 0.0;
+    } else if (FIN == FIN_K3) {
+        // third step: t = {c3.v1, c3.v2, c3.v3, c3.r2};  d3 = c3 - (g31/rho1) c1 - (g32/rho2) d2 with g32 = c3.(A d2)
+        KScal &K = S->k[lvl];
+        const double rho1 = K.rho1, rho2 = K.rho2, g21 = K.gam21;
+        if (rho1 > 0.0 && rho2 > 0.0) {
+            const double g31 = t[0], g32 = t[1] - (g21 / rho1) * t[0];
+            const double rho3 = t[2] - g31 * g31 / rho1 - g32 * g32 / rho2;
+            if (rho3 > 1e-12 * t[2] && rho3 == rho3) {
+                const double a3 = t[3] / rho3, b32 = g32 / rho2, b31 = g31 / rho1, b21 = g21 / rho1;
+                K.coef1 += a3 * (b32 * b21 - b31);
+                K.coef2 -= a3 * b32;
+                K.coef3 = a3;
+            }
         }
     }
     __threadfence();
@@ -252,6 +273,16 @@ __device__ __forceinline__ void spmv_row_finish(const LevelDev &L, int64_t row, 
             ld_vec<VS>(u2 + row * VS, wi);
 #pragma unroll
             for (int a = 0; a < D; a++) { dots[0] = fma(xi[a], ui[a], dots[0]); dots[1] = fma(xi[a], acc[a], dots[1]); dots[2] = fma(xi[a], wi[a], dots[2]); }
+        } else if (FIN == FIN_K3) {      // {x.u1, x.u2, x.y, x.r}: r carries the third vector (MODE 0 does not use it otherwise)
+            double ui[VS], wi[VS], zi[VS];
+            ld_vec<VS>(u1 + row * VS, ui);
+            ld_vec<VS>(u2 + row * VS, wi);
+            ld_vec<VS>(r + row * VS, zi);
+#pragma unroll
+            for (int a = 0; a < D; a++) {
+                dots[0] = fma(xi[a], ui[a], dots[0]); dots[1] = fma(xi[a], wi[a], dots[1]);
+                dots[2] = fma(xi[a], acc[a], dots[2]); dots[3] = fma(xi[a], zi[a], dots[3]);
+            }
         } else {
 #pragma unroll
             for (int a = 0; a < D; a++) dots[0] = fma(xi[a], acc[a], dots[0]);
@@ -307,7 +338,7 @@ __global__ void __launch_bounds__(128) k_spmv(LevelDev L, const __grid_constant_
     for (int a = 0; a < D; a++) acc[a] = 0.0;
 #pragma unroll
     for (int a = 0; a < VS; a++) xi[a] = 0.0;
-    double dots[3] = {0.0, 0.0, 0.0};
+    double dots[4] = {0.0, 0.0, 0.0, 0.0};
     const bool live = slice < L.n_slices;
     if (live) {
         const int mydeg = L.deg[row];
@@ -425,7 +456,7 @@ __global__ void __launch_bounds__(128) k_spmv_tma(LevelDev L, const double *__re
     for (int a = 0; a < D; a++) acc[a] = 0.0;
 #pragma unroll
     for (int a = 0; a < VS; a++) xi[a] = 0.0;
-    double dots[3] = {0.0, 0.0, 0.0};
+    double dots[4] = {0.0, 0.0, 0.0, 0.0};
     const bool live = slice < L.n_slices;
     if (live) {
         unsigned char *ring = tma_smem + (size_t)warp * NS * SLOT;
@@ -530,7 +561,7 @@ __device__ __forceinline__ void spmv_csr_body(const LevelDev &L, const XRef &xr,
     constexpr int DD = D * D, VS = VecStride<D>::value;
     const int sub = threadIdx.x & (LPR - 1);
     const int64_t row = (int64_t)vb * (256 / LPR) + threadIdx.x / LPR;
-    double dots[3] = {0.0, 0.0, 0.0};
+    double dots[4] = {0.0, 0.0, 0.0, 0.0};
     // whole warps take the branch together (LPR divides 32 and rows beyond n only occur at the tail)
     const bool live = row < L.n;
     double acc[D];
@@ -578,6 +609,16 @@ __device__ __forceinline__ void spmv_csr_body(const LevelDev &L, const XRef &xr,
                 ld_vec<VS>(u2 + row * VS, wi);
 #pragma unroll
                 for (int a = 0; a < D; a++) { dots[0] = fma(xi[a], ui[a], dots[0]); dots[1] = fma(xi[a], acc[a], dots[1]); dots[2] = fma(xi[a], wi[a], dots[2]); }
+            } else if (FIN == FIN_K3) {
+                double ui[VS], wi[VS], zi[VS];
+                ld_vec<VS>(u1 + row * VS, ui);
+                ld_vec<VS>(u2 + row * VS, wi);
+                ld_vec<VS>(r + row * VS, zi);
+#pragma unroll
+                for (int a = 0; a < D; a++) {
+                    dots[0] = fma(xi[a], ui[a], dots[0]); dots[1] = fma(xi[a], wi[a], dots[1]);
+                    dots[2] = fma(xi[a], acc[a], dots[2]); dots[3] = fma(xi[a], zi[a], dots[3]);
+                }
             }
         } else {
             double ri[VS];
@@ -726,38 +767,54 @@ __global__ void __launch_bounds__(256) k_update_p(int64_t n_pad, double *__restr
 // K-cycle vector updates at level lvl:  WHICH 0: out = a - alpha_l b      WHICH 1: out = coef1_l a + coef2_l b
 template <int WHICH>
 __device__ __forceinline__ void kcombine_body(int64_t n_doubles, const double *__restrict__ a, const double *__restrict__ b,
-                                              double *__restrict__ out, const Scalars *S, int lvl, unsigned vb) {
+                                              double *__restrict__ out, const Scalars *S, int lvl, unsigned vb, const double *__restrict__ third = nullptr) {
     const int64_t i = ((int64_t)vb * 256 + threadIdx.x) * 2;
     if (i >= n_doubles) return;
     const double2 av = *reinterpret_cast<const double2 *>(a + i), bv = *reinterpret_cast<const double2 *>(b + i);
     double2 o;
     if (WHICH == 0) { const double al = S->k[lvl].alpha; o.x = fma(-al, bv.x, av.x); o.y = fma(-al, bv.y, av.y); }
     else { const double c1 = S->k[lvl].coef1, c2 = S->k[lvl].coef2; o.x = fma(c1, av.x, c2 * bv.x); o.y = fma(c1, av.y, c2 * bv.y); }
+    if (WHICH == 2) {                                // + coef3 c   (three-step K-cycle; c arrives in `out2`)
+        const double c3 = S->k[lvl].coef3;
+        const double2 cv = *reinterpret_cast<const double2 *>(third + i);
+        o.x = fma(c3, cv.x, o.x); o.y = fma(c3, cv.y, o.y);
+    }
     *reinterpret_cast<double2 *>(out + i) = o;
 }
 template <int WHICH>
 __global__ void __launch_bounds__(256) k_kcombine(int64_t n_doubles, const double *__restrict__ a, const double *__restrict__ b,
-                                                   double *__restrict__ out, const Scalars *S, int lvl) {
+                                                   double *__restrict__ out, const Scalars *S, int lvl, const double *__restrict__ third) {
     PDL_ENTER();
     if (ld_done(S)) return;
-    kcombine_body<WHICH>(n_doubles, a, b, out, S, lvl, blockIdx.x);
+    kcombine_body<WHICH>(n_doubles, a, b, out, S, lvl, blockIdx.x, third);
 }
 
 // K-cycle, fused: r1 = rhs - alpha_l v1 (the residual after the first inner step) and the pre-smoothing step of the cycle
 // that follows, xa = omega Dinv r1, while r1 is still in registers
-template <int D>
-__global__ void __launch_bounds__(128) k_kresid_dinv(LevelDev L, const double *__restrict__ rhs, const double *__restrict__ v1, double *__restrict__ r1,
+// STEP 2 (three-step K-cycle): r2 = r1 - e2 v2 + e1 v1, in place (rhs == r1), with w = v2
+template <int D, int STEP>
+__global__ void __launch_bounds__(128) k_kresid_dinv(LevelDev L, const double *rhs, const double *__restrict__ v1, const double *__restrict__ w, double *r1,
                                                       double *__restrict__ xa, double omega, const Scalars *S, int lvl) {
     PDL_ENTER();
     if (ld_done(S)) return;
     constexpr int VS = VecStride<D>::value;
     const int64_t row = (int64_t)blockIdx.x * 128 + threadIdx.x;
     if (row >= L.n_pad) return;
-    const double al = S->k[lvl].alpha;
     double a[VS], b[VS], out[VS];
     ld_vec<VS>(rhs + row * VS, a); ld_vec<VS>(v1 + row * VS, b);
+    if (STEP == 1) {
+        const double al = S->k[lvl].alpha;
 #pragma unroll
-    for (int c = 0; c < VS; c++) { a[c] = fma(-al, b[c], a[c]); out[c] = 0.0; }
+        for (int c = 0; c < VS; c++) a[c] = fma(-al, b[c], a[c]);
+    } else {
+        const double e1 = S->k[lvl].e1, e2 = S->k[lvl].e2;
+        double wv[VS];
+        ld_vec<VS>(w + row * VS, wv);
+#pragma unroll
+        for (int c = 0; c < VS; c++) a[c] = fma(e1, b[c], fma(-e2, wv[c], a[c]));
+    }
+#pragma unroll
+    for (int c = 0; c < VS; c++) out[c] = 0.0;
     st_vec<VS>(r1 + row * VS, a);
     const double *di = L.dinv + row;
 #pragma unroll
@@ -949,8 +1006,8 @@ __device__ __forceinline__ void prolong_body(const LevelDev &F, const double *__
 }
 // x_i += P_i (coef1 c1 + coef2 c2)_{agg(i)}: prolongation fused with the final combination of the coarse level's K-cycle
 template <int D>
-__global__ void __launch_bounds__(128) k_prolong_k(LevelDev F, const double *__restrict__ c1, const double *__restrict__ c2, double *__restrict__ x,
-                                                    const Scalars *S, int clvl) {
+__global__ void __launch_bounds__(128) k_prolong_k(LevelDev F, const double *__restrict__ c1, const double *__restrict__ c2, const double *__restrict__ c3,
+                                                    double *__restrict__ x, const Scalars *S, int clvl) {
     PDL_ENTER();
     if (ld_done(S)) return;
     constexpr int VS = VecStride<D>::value;
@@ -964,6 +1021,12 @@ __global__ void __launch_bounds__(128) k_prolong_k(LevelDev F, const double *__r
     ld_vec<VS>(x + i * VS, xi);
 #pragma unroll
     for (int c = 0; c < VS; c++) e[c] = fma(k1, e[c], k2 * e2[c]);
+    if (c3) {                                        // three-step K-cycle
+        const double k3 = S->k[clvl].coef3;
+        ld_vec<VS>(c3 + I * VS, e2);
+#pragma unroll
+        for (int c = 0; c < VS; c++) e[c] = fma(k3, e2[c], e[c]);
+    }
     xfer_prolong(xfer_own<D>(F, i), e, xi);
     st_vec<VS>(x + i * VS, xi);
 }

@@ -59,7 +59,8 @@ struct LevelBuf {
     int64_t n_halo = 0;
     int64_t vec_rows = 0;              // rows (own, padded to the largest partition, + halo) every vector of the level has room for
     double *rhs = nullptr, *sol = nullptr, *xa = nullptr, *res = nullptr;      // cycle work vectors
-    double *c1 = nullptr, *c2 = nullptr, *v1 = nullptr, *v2 = nullptr, *r1 = nullptr;   // K-cycle work vectors
+    double *c1 = nullptr, *c2 = nullptr, *c3 = nullptr, *v1 = nullptr, *v2 = nullptr, *r1 = nullptr;   // K-cycle work vectors
+    int ksteps = 2;                    // inner flexible-CG steps of the K-cycle at this level (2: Notay's; 3: one more, fully orthogonalised)
     double omega = 0.6;
     int grid128 = 0, gridw = 0, gridv = 0, grid8 = 0, grid4 = 0, lpr = 32;
 };
@@ -388,7 +389,7 @@ template <int D, int FINK, bool PRE = false> void cycle(pgo_handle *h, int l, co
     const bool kfold = h->tail_level != l + 1 && l + 1 != last && C.kcycle;
     if (h->tail_level == l + 1) launch_tail<D>(h);   // the whole coarse solve C.rhs -> C.sol in one cooperative launch
     else coarse_solve<D>(h, l + 1, C.rhs, C.sol, kfold);
-    if (kfold) launch_k(h, k_prolong_k<D>, B.grid128, 128, 0, B.d, C.c1, C.c2, B.xa, h->S, l + 1);
+    if (kfold) launch_k(h, k_prolong_k<D>, B.grid128, 128, 0, B.d, C.c1, C.c2, C.ksteps == 3 ? C.c3 : nullptr, B.xa, h->S, l + 1);
     else launch_k(h, k_prolong<D>, B.grid128, 128, 0, B.d, C.sol, B.xa, h->S);
     h->launch_count += 1;
     lbarrier(h, l);
@@ -404,12 +405,21 @@ template <int D> void coarse_solve(pgo_handle *h, int l, const double *rhs, doub
     cycle<D, FIN_NONE>(h, l, rhs, B.c1);
     spmv<D, 0, FIN_K1, true>(h, l, B.c1, nullptr, B.v1, 0.0, rhs, nullptr, 1);
     // r1 = rhs - alpha v1, fused with the pre-smoothing step of the second cycle
-    launch_k(h, k_kresid_dinv<D>, B.grid128, 128, 0, B.d, rhs, B.v1, B.r1, B.xa, B.omega, h->S, l);
+    launch_k(h, k_kresid_dinv<D, 1>, B.grid128, 128, 0, B.d, rhs, B.v1, nullptr, B.r1, B.xa, B.omega, h->S, l);
     h->launch_count += 1;
     cycle<D, FIN_NONE, true>(h, l, B.r1, B.c2);
     spmv<D, 0, FIN_K2, true>(h, l, B.c2, nullptr, B.v2, 0.0, B.v1, B.r1, 1);
-    if (!defer_combine) {                            // else: the caller's prolongation applies coef1 c1 + coef2 c2
-        launch_k(h, k_kcombine<1>, B.gridv, 256, 0, B.d.n_pad * VecStride<D>::value, B.c1, B.c2, out, h->S, l);
+    const double *c3 = nullptr;
+    if (B.ksteps == 3) {                             // third inner step: r2 = r1 - e2 v2 + e1 v1 (in place), c3 = M(r2), dots of c3
+        launch_k(h, k_kresid_dinv<D, 2>, B.grid128, 128, 0, B.d, B.r1, B.v1, B.v2, B.r1, B.xa, B.omega, h->S, l);
+        h->launch_count += 1;
+        cycle<D, FIN_NONE, true>(h, l, B.r1, B.c3);
+        spmv<D, 0, FIN_K3, true>(h, l, B.c3, B.r1, B.res, 0.0, B.v1, B.v2, 1);
+        c3 = B.c3;
+    }
+    if (!defer_combine) {                            // else: the caller's prolongation applies coef1 c1 + coef2 c2 (+ coef3 c3)
+        if (c3) launch_k(h, k_kcombine<2>, B.gridv, 256, 0, B.d.n_pad * VecStride<D>::value, B.c1, B.c2, out, h->S, l, c3);
+        else launch_k(h, k_kcombine<1>, B.gridv, 256, 0, B.d.n_pad * VecStride<D>::value, B.c1, B.c2, out, h->S, l, nullptr);
         h->launch_count += 1;
     }
 }
@@ -740,6 +750,7 @@ void pgo_default_options(pgo_options *o) {
     o->amg_dense_max = 640;
     o->amg_aggregate_size = 16;
     o->amg_kcycle = MAX_LEVELS;
+    o->amg_kcycle3 = -1;
 }
 
 const char *pgo_last_error(const pgo_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -955,10 +966,15 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
             if (l > 0) {
                 arena_request(h, &B.rhs, vec); arena_request(h, &B.sol, vec);
                 arena_request(h, &B.c1, vec); arena_request(h, &B.c2, vec); arena_request(h, &B.v1, vec);
-                arena_request(h, &B.v2, vec); arena_request(h, &B.r1, vec);
+                arena_request(h, &B.v2, vec); arena_request(h, &B.r1, vec); arena_request(h, &B.c3, vec);
             }
         }
         B.kcycle = l > 0 && l <= h->opt.amg_kcycle;
+        // default (-1): level 1 of SE2 / XY graphs.  Measured on B200 (profiles/r01s_kcycle3.log): 1M-pose Manhattan graph 53 -> 41
+        // PCG iterations and 40.3 -> 36.6 ms; on the 250k-pose SE3 sphere 38 -> 32 iterations but 29.4 -> 31.5 ms (its 6x6
+        // coarse levels are the larger share of an iteration), so SE3 graphs keep two steps
+        const int k3 = h->opt.amg_kcycle3 >= 0 ? h->opt.amg_kcycle3 : (D == 3 ? 1 : 0);
+        B.ksteps = (B.kcycle && l <= k3 && !h->opt_tail) ? 3 : 2;
         B.vec_rows = max_pad;
     }
     {
@@ -1065,7 +1081,7 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
         max_grid = std::max<int64_t>(max_grid, grid_for(nm, 256));
     }
     CKC(dalloc(h, &h->S, 1));
-    CKC(dalloc(h, &h->partials, (size_t)3 * max_grid + 8));
+    CKC(dalloc(h, &h->partials, (size_t)4 * max_grid + 8));
     {
         Scalars s{};
         s.world = world;

@@ -33,7 +33,7 @@ BLOCK_JACOBI, AMG = 0, 1
 def Options(**kw) -> pgo_options:
     """pgo_options with the library defaults, overridden by keyword (anchor_weight, pcg_rtol,
     pcg_max_iterations, preconditioner, sort_window, amg_max_levels, device, world, rank, amg_dense_max,
-    amg_aggregate_size, amg_kcycle, amg_fp64_storage)."""
+    amg_aggregate_size, amg_kcycle, amg_kcycle3, amg_fp64_storage)."""
     o = pgo_options()
     lib().pgo_default_options(C.byref(o))
     for k, v in kw.items():
