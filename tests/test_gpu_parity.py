@@ -269,6 +269,43 @@ def test_config4_full_size_properties(built):
     assert abs(m1 - n1) <= 1e-6 * n1 and abs(d1 - c1) <= CHI2_RTOL * c1 and abs(jt1 - it1) <= 0.05 * it1
 
 
+_ORACLE_100K = {}
+
+
+def _oracle_100k():
+    """oracle history / poses of the 100k-pose Manhattan graph (3 GN iterations), computed once per session"""
+    if not _ORACLE_100K:
+        from rustrobotics_b200.synthetic import manhattan_se2
+        g = manhattan_se2(100000)
+        o = _oracle(g)
+        _ORACLE_100K.update(g=g, errs=o.optimize(3), v=o.vertices()[3])
+    return _ORACLE_100K["g"], _ORACLE_100K["errs"], _ORACLE_100K["v"]
+
+
+@pytest.mark.parametrize("variant", [
+    {"amg_fp64_storage": 1},                 # the cycle reads the fp64 blocks (default: fp32 copies)
+    {"amg_kcycle3": 0},                      # two inner steps per K-cycle visit on every level (default: three on level 1)
+    {"amg_kcycle3": 2},
+    {"amg_kcycle": 0},                       # plain V-cycle
+    {"amg_aggregate_size": 8, "amg_dense_max": 256},
+    {"env": {"PGO_SPMV_TMA64": "2", "PGO_SPMV_TMA32": "3"}},     # TMA-staged sliced SpMV
+    {"env": {"PGO_PDL": "0"}},               # plain (non-programmatic) launches
+], ids=lambda v: ",".join(f"{k}={w}" for k, w in v.items()))
+def test_solver_variants_agree_with_the_direct_solve(built, monkeypatch, variant):
+    """every solver configuration converges to the oracle's direct solve: same chi2 history (1e-6) and poses (1e-6)"""
+    g, errs_o, vo = _oracle_100k()
+    variant = dict(variant)
+    for k, w in variant.pop("env", {}).items():
+        monkeypatch.setenv(k, w)
+    pg = _pg(g, **variant)
+    errs_g = pg.optimize(3)
+    np.testing.assert_allclose(errs_g, errs_o, rtol=CHI2_RTOL)
+    dxy, dth = _pose_diff(g, pg.poses(), vo)
+    assert dxy < POSE_ATOL and dth < POSE_ATOL
+    nl = len(pg.level_sizes()[0])
+    assert nl >= 3 and all(pg.time_coarse(l, 3) > 0 for l in range(1, nl))      # the per-level coarse-solve timer runs
+
+
 def test_cpp_example_and_bench_drivers(built, g2o_files, tmp_path):
     """examples/pose_graph_optimization.cpp (reference examples/mapping/pose_graph_optimization.rs:49-50) and
     benches/graph_slam.cpp (reference benches/graph_slam.rs:6-13) through the C++ host mirror"""
