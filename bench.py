@@ -185,7 +185,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "host_cpus": os.cpu_count(),
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -220,8 +220,9 @@ def run_b200(args):
     t0 = time.perf_counter()
     # world > 1: ONE graph sharded by contiguous vertex ranges, one process per GPU; halo rows are read from
     # peer HBM over NVLink inside the kernels, dot products reduced by a device-side peer-memory all-reduce
+    extra = {k: (float(v) if "." in v or "e" in v else int(v)) for k, v in (kv.split("=") for kv in args.opts.split(",") if kv)}
     pg = PoseGraph(graph=g, options=Options(device=local, world=world, rank=rank, pcg_rtol=args.pcg_rtol,
-                                            preconditioner=args.preconditioner))
+                                            preconditioner=args.preconditioner, **extra))
     t_create = time.perf_counter() - t0
     log(f"[rank {rank}] graph {n_poses} poses / {n_edges} edges generated in {t_gen:.1f}s, created in {t_create:.1f}s, {pg.stats()}")
     chi2_0 = pg.global_error()
@@ -308,7 +309,7 @@ def run_b200(args):
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "bundled dataset" if args.workload in BUNDLED else "synthetic",
             "config": {"workload": wl_desc.format(n_poses, n_edges) + "; 1 step = 1 Gauss-Newton iteration from the initial guess",
-                       "poses": n_poses, "edges": n_edges, "pcg_rtol": args.pcg_rtol,
+                       "poses": n_poses, "edges": n_edges, "pcg_rtol": args.pcg_rtol, "option_overrides": args.opts or None,
                        "preconditioner": "aggregation-AMG K-cycle (flexible PCG); the cycle's SpMVs read fp32 copies of the stored blocks and accumulate in fp64, the PCG operator / residual / dot products are fp64" if args.preconditioner == 1 else "block-Jacobi",
                        "parallelism": "single GPU" if world == 1 else
                        f"1 graph sharded over {world} GPUs by contiguous vertex ranges; halo rows read from peer HBM (NVLink), "
@@ -328,14 +329,31 @@ def run_b200(args):
                     "h2d_bytes_per_step": int(init_np.nbytes), "d2h_bytes_per_step": int(out_np.nbytes) + 20 * world},
             "gpu_launches": int(launches), "clocks": clocks, "host_cpus": os.cpu_count(),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     pg.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """the ONE JSON line goes to the process's real stdout; everything else a library prints (e.g. NCCL's version banner)
+    was redirected to stderr by main()"""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                       # fd 1 -> stderr for the rest of the run (C libraries included)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -348,6 +366,7 @@ def main():
     ap.add_argument("--pcg-rtol", type=float, default=1e-8)
     ap.add_argument("--preconditioner", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opts", default="", help="extra pgo_options overrides, k=v,k=v (e.g. amg_kcycle3=0,amg_fp64_storage=1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.poses is None:
