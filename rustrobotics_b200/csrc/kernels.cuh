@@ -567,6 +567,26 @@ __device__ __forceinline__ void spmv_csr_body(const LevelDev &L, const XRef &xr,
     double acc[D];
 #pragma unroll
     for (int a = 0; a < D; a++) acc[a] = 0.0;
+    // the lane that finishes the row requests everything the epilogue needs (own x record, diagonal block, rhs, inverse
+    // diagonal) BEFORE walking the row: these kernels are chains of dependent L2 accesses (row pointer -> column -> x), and
+    // the epilogue's loads would otherwise add one more link after the shuffle reduction
+    double xi[VS], dgv[DD], ri[VS], div[MODE == 2 ? DD : 1];
+#pragma unroll
+    for (int a = 0; a < VS; a++) { xi[a] = 0.0; ri[a] = 0.0; }
+    if (live && sub == 0) {
+        ld_vec<VS>(x + row * VS, xi);
+        const double *dg = L.diag + row;
+#pragma unroll
+        for (int q = 0; q < DD; q++) dgv[q] = dg[(int64_t)q * L.n_pad];
+        if (MODE != 0 || FIN == FIN_K3) ld_vec<VS>(r + row * VS, ri);
+        if (MODE == 2) {
+            const double *di = L.dinv + row;
+#pragma unroll
+            for (int q = 0; q < DD; q++) div[q] = di[(int64_t)q * L.n_pad];
+        }
+    }
+    // (a fixed-stride copy of every row's first column words, so that the x gather would not wait for the row pointer, was
+    // measured and did not help: level-1 solve 319 -> 335 us, profiles/r01z_col0_experiment.log)
     if (live) {
         const int64_t b = L.slice_ptr[row], e = L.slice_ptr[row + 1];
         for (int64_t s = b + sub; s < e; s += LPR) {
@@ -586,15 +606,13 @@ __device__ __forceinline__ void spmv_csr_body(const LevelDev &L, const XRef &xr,
         for (int a = 0; a < D; a++) acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], o);
     }
     if (live && sub == 0) {
-        double xi[VS], out[VS];
+        double out[VS];
 #pragma unroll
         for (int a = 0; a < VS; a++) out[a] = 0.0;
-        ld_vec<VS>(x + row * VS, xi);
-        const double *dg = L.diag + row;
 #pragma unroll
         for (int a = 0; a < D; a++)
 #pragma unroll
-            for (int q = 0; q < D; q++) acc[a] = fma(dg[(int64_t)(a * D + q) * L.n_pad], xi[q], acc[a]);
+            for (int q = 0; q < D; q++) acc[a] = fma(dgv[a * D + q], xi[q], acc[a]);
         if (MODE == 0) {
 #pragma unroll
             for (int a = 0; a < D; a++) out[a] = acc[a];
@@ -610,24 +628,20 @@ __device__ __forceinline__ void spmv_csr_body(const LevelDev &L, const XRef &xr,
 #pragma unroll
                 for (int a = 0; a < D; a++) { dots[0] = fma(xi[a], ui[a], dots[0]); dots[1] = fma(xi[a], acc[a], dots[1]); dots[2] = fma(xi[a], wi[a], dots[2]); }
             } else if (FIN == FIN_K3) {
-                double ui[VS], wi[VS], zi[VS];
+                double ui[VS], wi[VS];
                 ld_vec<VS>(u1 + row * VS, ui);
                 ld_vec<VS>(u2 + row * VS, wi);
-                ld_vec<VS>(r + row * VS, zi);
 #pragma unroll
                 for (int a = 0; a < D; a++) {
                     dots[0] = fma(xi[a], ui[a], dots[0]); dots[1] = fma(xi[a], wi[a], dots[1]);
-                    dots[2] = fma(xi[a], acc[a], dots[2]); dots[3] = fma(xi[a], zi[a], dots[3]);
+                    dots[2] = fma(xi[a], acc[a], dots[2]); dots[3] = fma(xi[a], ri[a], dots[3]);
                 }
             }
         } else {
-            double ri[VS];
-            ld_vec<VS>(r + row * VS, ri);
             if (MODE == 1) {
 #pragma unroll
                 for (int a = 0; a < D; a++) out[a] = ri[a] - acc[a];
             } else {
-                const double *di = L.dinv + row;
                 double t[D];
 #pragma unroll
                 for (int a = 0; a < D; a++) t[a] = ri[a] - acc[a];
@@ -635,7 +649,7 @@ __device__ __forceinline__ void spmv_csr_body(const LevelDev &L, const XRef &xr,
                 for (int a = 0; a < D; a++) {
                     double s = 0.0;
 #pragma unroll
-                    for (int q = 0; q < D; q++) s = fma(di[(int64_t)(a * D + q) * L.n_pad], t[q], s);
+                    for (int q = 0; q < D; q++) s = fma(div[MODE == 2 ? a * D + q : 0], t[q], s);
                     out[a] = fma(omega, s, xi[a]);
                 }
             }

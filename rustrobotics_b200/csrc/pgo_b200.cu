@@ -24,6 +24,7 @@
 #include "kernels.cuh"
 #include "peer.cuh"
 #include "tail.cuh"
+#include "deep.cuh"
 
 using namespace pgo;
 
@@ -101,6 +102,17 @@ struct pgo_handle {
     bool use_amg = false, omega_ready = false;
     int spmv_tma64 = 0, spmv_tma32 = 0; // PGO_SPMV_TMA64 / PGO_SPMV_TMA32: ring depth of the TMA-staged sliced SpMV (0: register-staged kernel)
     int64_t lpr4_min_rows = 16384;     // PGO_LPR4_MIN_ROWS
+    // cluster-resident deep-levels kernel (deep.cuh): levels >= deep_level run as one cluster launch per coarse solve
+    bool opt_deep = false;             // PGO_DEEP=1 enables.  OFF by default: measured on B200 (profiles/r01x_deep_experiment.log) a level-2
+                                       // coarse solve takes 86 us in the cluster kernel vs 53 us as 16 graph-launched kernels -- a stage is a
+                                       // chain of dependent L2 accesses either way, and 16 SMs give each row fewer lanes than a full-grid launch
+    int opt_deep_dense = 0;            // PGO_DEEP_DENSE: 1 = the dense coarsest apply runs inside the cluster kernel, 0 = separate launches
+    int64_t deep_max_rows = 8192;      // PGO_DEEP_MAX_ROWS
+    int deep_level = -1, deep_nc = 0, deep_ops = 0;
+    bool deep_defer = false, deep_dense_inline = true, deep_checked = false;
+    DeepOp *deep_prog = nullptr;
+    LevelDev *deep_lv = nullptr;
+    std::vector<DeepOp> deep_host;
     bool pdl = true;                   // programmatic dependent launch of every kernel (PGO_PDL=0 disables)
     cudaError_t launch_err = cudaSuccess;
     bool lowp = false;                 // the cycle's SpMVs read fp32 copies of the stored blocks (opt.amg_fp64_storage == 0)
@@ -353,6 +365,149 @@ template <int D> void launch_tail(pgo_handle *h) {
     h->launch_count += 1;
 }
 
+// ---- cluster-resident deep levels (deep.cuh): record the stage program of coarse_solve(T, rhs -> sol), launch it
+inline DeepOp deep_op(int type, int lvl) { DeepOp o{}; o.type = type; o.lvl = lvl; o.fin = FIN_NONE; return o; }
+
+template <int D> void drec_solve(pgo_handle *h, int l, const double *rhs, double *out, bool defer, std::vector<DeepOp> &P);
+
+template <int D> void drec_spmv(pgo_handle *h, int l, int mode, int fin, const double *x, const double *r, double *y, double omega,
+                                const double *u1, const double *u2, std::vector<DeepOp> &P) {
+    DeepOp o = deep_op(DOP_SPMV, l);
+    o.mode = mode; o.fin = fin; o.a = x; o.b = r; o.c = u1; o.d = u2; o.out = y; o.omega = omega;
+    P.push_back(o);
+}
+
+template <int D> void drec_cycle(pgo_handle *h, int l, const double *rhs, double *out, bool pre, std::vector<DeepOp> &P) {
+    LevelBuf &B = h->lv[l];
+    const int last = (int)h->lv.size() - 1;
+    if (l == last) { DeepOp o = deep_op(DOP_DENSE, l); o.a = rhs; o.out = out; P.push_back(o); return; }
+    LevelBuf &C = h->lv[l + 1];
+    if (!pre) { DeepOp o = deep_op(DOP_DINV, l); o.a = rhs; o.out = B.xa; o.omega = B.omega; P.push_back(o); }
+    drec_spmv<D>(h, l, 1, FIN_NONE, B.xa, rhs, B.res, 0.0, nullptr, nullptr, P);
+    { DeepOp o = deep_op(DOP_RESTRICT, l); o.a = B.res; o.out = C.rhs; P.push_back(o); }
+    const bool kfold = l + 1 != last && C.kcycle;
+    drec_solve<D>(h, l + 1, C.rhs, C.sol, kfold, P);
+    if (kfold) { DeepOp o = deep_op(DOP_PROLONGK, l); o.a = C.c1; o.b = C.c2; o.c = C.ksteps == 3 ? C.c3 : nullptr; o.out = B.xa; P.push_back(o); }
+    else { DeepOp o = deep_op(DOP_PROLONG, l); o.a = C.sol; o.out = B.xa; P.push_back(o); }
+    drec_spmv<D>(h, l, 2, FIN_NONE, B.xa, rhs, out, B.omega, nullptr, nullptr, P);
+}
+
+template <int D> void drec_solve(pgo_handle *h, int l, const double *rhs, double *out, bool defer, std::vector<DeepOp> &P) {
+    LevelBuf &B = h->lv[l];
+    const int last = (int)h->lv.size() - 1;
+    if (l == last || !B.kcycle) { drec_cycle<D>(h, l, rhs, out, false, P); return; }
+    drec_cycle<D>(h, l, rhs, B.c1, false, P);
+    drec_spmv<D>(h, l, 0, FIN_K1, B.c1, nullptr, B.v1, 0.0, rhs, nullptr, P);
+    { DeepOp o = deep_op(DOP_KRESID, l); o.mode = 1; o.a = rhs; o.b = B.v1; o.out = B.r1; o.d = B.xa; o.omega = B.omega; P.push_back(o); }
+    drec_cycle<D>(h, l, B.r1, B.c2, true, P);
+    drec_spmv<D>(h, l, 0, FIN_K2, B.c2, nullptr, B.v2, 0.0, B.v1, B.r1, P);
+    const double *c3 = nullptr;
+    if (B.ksteps == 3) {
+        { DeepOp o = deep_op(DOP_KRESID, l); o.mode = 2; o.a = B.r1; o.b = B.v1; o.c = B.v2; o.out = B.r1; o.d = B.xa; o.omega = B.omega; P.push_back(o); }
+        drec_cycle<D>(h, l, B.r1, B.c3, true, P);
+        drec_spmv<D>(h, l, 0, FIN_K3, B.c3, B.r1, B.res, 0.0, B.v1, B.v2, P);
+        c3 = B.c3;
+    }
+    if (!defer) { DeepOp o = deep_op(DOP_KCOMBINE, l); o.mode = c3 ? 2 : 1; o.a = B.c1; o.b = B.c2; o.c = c3; o.out = out; P.push_back(o); }
+}
+
+template <int D, bool LOWP> cudaError_t deep_launch_seg(pgo_handle *h, int op0, int op1, size_t smem) {
+    DeepCtx T{};
+    T.prog = h->deep_prog; T.op0 = op0; T.op1 = op1; T.lv = h->deep_lv;
+    T.dense_m = h->dense_m; T.Ainv = h->Ainv; T.S = h->S;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(h->deep_nc); cfg.blockDim = dim3(DEEP_NT); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = h->deep_nc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = h->pdl ? 2 : 1;
+    return cudaLaunchKernelEx(&cfg, k_deep<D, LOWP>, T);
+}
+
+// (re)build the stage program; called whenever the PCG graph is (re)captured (the smoother dampings are baked in)
+template <int D> int build_deep(pgo_handle *h) {
+    h->deep_level = -1;
+    if (!h->use_amg || !h->opt_deep || h->opt_tail || !h->sym.dense_coarsest) return PGO_OK;
+    const int nl = (int)h->lv.size(), last = nl - 1;
+    int T = -1;
+    for (int l = 1; l < last; l++) {
+        bool ok = true;
+        for (int k = l; k < nl && ok; k++)
+            ok = (h->world == 1 || h->lv[k].repl) && !h->lv[k].jds && h->lv[k].d.n <= h->deep_max_rows;
+        if (ok) { T = l; break; }
+    }
+    if (T < 0) return PGO_OK;
+    // cluster size: 16 CTAs (non-portable) when the device can place such a cluster, else 8
+    if (!h->deep_checked) {
+        h->deep_checked = true;
+        h->deep_nc = 0;
+        const size_t smem = sizeof(double) * (size_t)h->dense_m;
+        for (int nc : {16, 8}) {
+            cudaError_t e1, e2;
+            if (h->lowp) {
+                e1 = cudaFuncSetAttribute(k_deep<D, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+                e2 = cudaFuncSetAttribute(k_deep<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024));
+            } else {
+                e1 = cudaFuncSetAttribute(k_deep<D, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+                e2 = cudaFuncSetAttribute(k_deep<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024));
+            }
+            if (e1 != cudaSuccess || e2 != cudaSuccess) { (void)cudaGetLastError(); continue; }
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(nc); cfg.blockDim = dim3(DEEP_NT); cfg.dynamicSmemBytes = smem;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = nc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int n_clusters = 0;
+            cudaError_t e = h->lowp ? cudaOccupancyMaxActiveClusters(&n_clusters, k_deep<D, true>, &cfg)
+                                    : cudaOccupancyMaxActiveClusters(&n_clusters, k_deep<D, false>, &cfg);
+            if (e == cudaSuccess && n_clusters >= 1) { h->deep_nc = nc; break; }
+            (void)cudaGetLastError();
+        }
+    }
+    if (h->deep_nc == 0) return PGO_OK;
+    const bool defer = h->lv[T].kcycle;             // the parent's prolongation folds the final combination (cycle(): kfold)
+    std::vector<DeepOp> P;
+    drec_solve<D>(h, T, h->lv[T].rhs, h->lv[T].sol, defer, P);
+    std::vector<LevelDev> lv(nl);
+    for (int l = 0; l < nl; l++) lv[l] = h->lv[l].d;
+    if (!h->deep_lv) { int rc = dalloc(h, &h->deep_lv, (size_t)nl, false); if (rc) return rc; }
+    CK(cudaMemcpyAsync(h->deep_lv, lv.data(), nl * sizeof(LevelDev), cudaMemcpyHostToDevice, h->stream));
+    if (!h->deep_prog || (int)P.size() > h->deep_ops) { int rc = dalloc(h, &h->deep_prog, P.size(), false); if (rc) return rc; }
+    CK(cudaMemcpyAsync(h->deep_prog, P.data(), P.size() * sizeof(DeepOp), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->deep_ops = (int)P.size();
+    h->deep_host = P;
+    h->deep_defer = defer;
+    // the dense apply is a bandwidth problem (the fp64 inverse, 12 MB at config 4, read by 16 SMs): separate launches by default
+    h->deep_dense_inline = h->opt_deep_dense != 0;
+    h->deep_level = T;
+    return PGO_OK;
+}
+
+template <int D> void dense_apply(pgo_handle *h, int l, const double *rhs, double *out);
+
+template <int D> void launch_deep(pgo_handle *h) {
+    const size_t smem = sizeof(double) * (size_t)h->dense_m;
+    auto seg = [&](int a, int b, size_t sm) {
+        if (a >= b) return;
+        cudaError_t e = h->lowp ? deep_launch_seg<D, true>(h, a, b, sm) : deep_launch_seg<D, false>(h, a, b, sm);
+        if (e != cudaSuccess && h->launch_err == cudaSuccess) h->launch_err = e;
+        h->launch_count += 1;
+    };
+    if (h->deep_dense_inline) { seg(0, h->deep_ops, smem); return; }
+    int a = 0;
+    for (int i = 0; i < h->deep_ops; i++) {
+        if (h->deep_host[i].type != DOP_DENSE) continue;
+        seg(a, i, 0);
+        dense_apply<D>(h, h->deep_host[i].lvl, h->deep_host[i].a, h->deep_host[i].out);
+        a = i + 1;
+    }
+    seg(a, h->deep_ops, 0);
+}
+
 // ---- one multigrid cycle at level l: out = M_l(rhs).  FINK: dots fused into the last kernel (level 0 only).
 // PRE: the pre-smoothing step xa = omega Dinv rhs was already done by the caller (fused into the PCG update kernel)
 template <int D, int FINK, bool PRE = false> void cycle(pgo_handle *h, int l, const double *rhs, double *out) {
@@ -401,6 +556,8 @@ template <int D, int FINK, bool PRE = false> void cycle(pgo_handle *h, int l, co
 template <int D> void coarse_solve(pgo_handle *h, int l, const double *rhs, double *out, bool defer_combine) {
     LevelBuf &B = h->lv[l];
     const int last = (int)h->lv.size() - 1;
+    // the levels from deep_level down run as one cluster launch (the program was recorded for exactly this call)
+    if (l == h->deep_level && rhs == B.rhs && out == B.sol && defer_combine == h->deep_defer) { launch_deep<D>(h); return; }
     if (l == last || !B.kcycle) { cycle<D, FIN_NONE>(h, l, rhs, out); return; }
     cycle<D, FIN_NONE>(h, l, rhs, B.c1);
     spmv<D, 0, FIN_K1, true>(h, l, B.c1, nullptr, B.v1, 0.0, rhs, nullptr, 1);
@@ -457,6 +614,7 @@ template <int D> void pcg_iteration(pgo_handle *h) {
 template <int D> int build_pcg_graph(pgo_handle *h) {
     if (h->pcg_graph) return PGO_OK;
     { int rc = build_tail<D>(h); if (rc) return rc; }
+    { int rc = build_deep<D>(h); if (rc) return rc; }
     cudaGraph_t g = nullptr;
     int64_t before = h->launch_count;
     CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
@@ -474,10 +632,13 @@ template <int D> int build_pcg_graph(pgo_handle *h) {
     if (ie == cudaSuccess && h->launch_err != cudaSuccess) ie = h->launch_err;
     if (ie == cudaSuccess) ie = cudaGraphInstantiate(&h->pcg_graph, g, 0);
     if (g) cudaGraphDestroy(g);
-    if (ie != cudaSuccess && h->pdl) {
-        // programmatic dependent launch edges not accepted by this driver inside a captured graph: plain launches
+    if (ie != cudaSuccess && (h->deep_level >= 0 || h->pdl)) {
+        // a cluster launch / programmatic dependent launch edges not accepted by this driver inside a captured graph:
+        // first give up the cluster-resident deep-levels kernel, then the programmatic launches
         (void)cudaGetLastError();
-        h->pdl = false; h->launch_err = cudaSuccess; h->pcg_graph = nullptr;
+        if (h->deep_level >= 0) { h->opt_deep = false; h->deep_level = -1; }
+        else h->pdl = false;
+        h->launch_err = cudaSuccess; h->pcg_graph = nullptr;
         h->launch_count = before;
         return build_pcg_graph<D>(h);
     }
@@ -700,8 +861,9 @@ template <int D> int time_coarse(pgo_handle *h, int level, int repeats, double *
     cudaGraph_t g = nullptr;
     cudaGraphExec_t ge = nullptr;
     const int64_t before = h->launch_count;
+    if (!h->pcg_graph) { int rc2 = build_pcg_graph<D>(h); if (rc2) return rc2; }
     CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-    coarse_solve<D>(h, level, B.rhs, B.sol);
+    coarse_solve<D>(h, level, B.rhs, B.sol, level == h->deep_level ? h->deep_defer : false);
     CK(cudaStreamEndCapture(h->stream, &g));
     const int64_t per = h->launch_count - before;
     CK(cudaGraphInstantiate(&ge, g, 0));
@@ -807,6 +969,9 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
     if (const char *e = std::getenv("PGO_SPMV_TMA64")) h->spmv_tma64 = std::max(0, std::min(16, std::atoi(e)));
     if (const char *e = std::getenv("PGO_SPMV_TMA32")) h->spmv_tma32 = std::max(0, std::min(16, std::atoi(e)));
     if (const char *e = std::getenv("PGO_LPR4_MIN_ROWS")) h->lpr4_min_rows = std::atoll(e);
+    if (const char *e = std::getenv("PGO_DEEP")) h->opt_deep = std::atoi(e) != 0;
+    if (const char *e = std::getenv("PGO_DEEP_DENSE")) h->opt_deep_dense = std::atoi(e);
+    if (const char *e = std::getenv("PGO_DEEP_MAX_ROWS")) h->deep_max_rows = std::atoll(e);
     if (const char *e = std::getenv("PGO_PDL")) h->pdl = std::atoi(e) != 0;
     if (const char *e = std::getenv("PGO_TAIL")) h->opt_tail = std::atoi(e) != 0;
     if (const char *e = std::getenv("PGO_TAIL_CTAS_PER_SM")) h->tail_ctas_per_sm = std::max(1, std::atoi(e));
@@ -994,6 +1159,7 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
         const int m = h->dense_m;
         CKC(dalloc(h, &h->Ainv, (size_t)m * m));
         CKC(dalloc(h, &h->Awork, (size_t)m * m));
+
         int per_sm = 0, sms = 0;
         CKU(cudaFuncSetAttribute(k_dense_invert, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GJ_SMEM));
         CKU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dense_invert, 256, GJ_SMEM));
