@@ -570,7 +570,10 @@ __device__ __forceinline__ void spmv_csr_body(const LevelDev &L, const XRef &xr,
     // the lane that finishes the row requests everything the epilogue needs (own x record, diagonal block, rhs, inverse
     // diagonal) BEFORE walking the row: these kernels are chains of dependent L2 accesses (row pointer -> column -> x), and
     // the epilogue's loads would otherwise add one more link after the shuffle reduction
-    double xi[VS], dgv[DD], ri[VS], div[MODE == 2 ? DD : 1];
+    // (6x6 blocks: 177 registers, one 256-thread CTA per SM; capping at 128 registers or keeping the inverse diagonal a late load
+    // were both measured slower, profiles/r02a_csr_variants.log)
+    constexpr bool PRE_DINV = MODE == 2;
+    double xi[VS], dgv[DD], ri[VS], div[PRE_DINV ? DD : 1];
 #pragma unroll
     for (int a = 0; a < VS; a++) { xi[a] = 0.0; ri[a] = 0.0; }
     if (live && sub == 0) {
@@ -579,7 +582,7 @@ __device__ __forceinline__ void spmv_csr_body(const LevelDev &L, const XRef &xr,
 #pragma unroll
         for (int q = 0; q < DD; q++) dgv[q] = dg[(int64_t)q * L.n_pad];
         if (MODE != 0 || FIN == FIN_K3) ld_vec<VS>(r + row * VS, ri);
-        if (MODE == 2) {
+        if (PRE_DINV) {
             const double *di = L.dinv + row;
 #pragma unroll
             for (int q = 0; q < DD; q++) div[q] = di[(int64_t)q * L.n_pad];
@@ -589,15 +592,37 @@ __device__ __forceinline__ void spmv_csr_body(const LevelDev &L, const XRef &xr,
     // measured and did not help: level-1 solve 319 -> 335 us, profiles/r01z_col0_experiment.log)
     if (live) {
         const int64_t b = L.slice_ptr[row], e = L.slice_ptr[row + 1];
-        for (int64_t s = b + sub; s < e; s += LPR) {
-            const uint32_t c = __ldg(L.col + s);
-            double xj[VS];
-            ld_vec<VS>(PEER ? xgather<VS>(xr, c) : x + (int64_t)(c & COL_LOCAL_MASK) * VS, xj);
-            const VT *v = level_val<VT>(L) + s * DD;
+        if constexpr (D == 3) {
+            // two entries per trip, all of their loads requested before the first multiply: a row longer than LPR entries
+            // costs one chain col -> x, not one per LPR entries (6x6 blocks: 174 registers, one CTA per SM -- not worth it)
+            for (int64_t s = b + sub; s < e; s += 2 * LPR) {
+                const bool two = s + LPR < e;
+                const uint32_t ca = __ldg(L.col + s), cb = two ? __ldg(L.col + s + LPR) : 0u;
+                double xa[VS], xb[VS];
 #pragma unroll
-            for (int a = 0; a < D; a++)
+                for (int a = 0; a < VS; a++) xb[a] = 0.0;
+                ld_vec<VS>(PEER ? xgather<VS>(xr, ca) : x + (int64_t)(ca & COL_LOCAL_MASK) * VS, xa);
+                if (two) ld_vec<VS>(PEER ? xgather<VS>(xr, cb) : x + (int64_t)(cb & COL_LOCAL_MASK) * VS, xb);
+                const VT *va = level_val<VT>(L) + s * DD;
+                VT ha[DD], hb[DD];
 #pragma unroll
-                for (int q = 0; q < D; q++) acc[a] = fma((double)v[a * D + q], xj[q], acc[a]);
+                for (int q = 0; q < DD; q++) { ha[q] = va[q]; hb[q] = two ? va[(int64_t)LPR * DD + q] : (VT)0; }
+#pragma unroll
+                for (int a = 0; a < D; a++)
+#pragma unroll
+                    for (int q = 0; q < D; q++) acc[a] = fma((double)ha[a * D + q], xa[q], fma((double)hb[a * D + q], xb[q], acc[a]));
+            }
+        } else {
+            for (int64_t s = b + sub; s < e; s += LPR) {
+                const uint32_t c = __ldg(L.col + s);
+                double xj[VS];
+                ld_vec<VS>(PEER ? xgather<VS>(xr, c) : x + (int64_t)(c & COL_LOCAL_MASK) * VS, xj);
+                const VT *v = level_val<VT>(L) + s * DD;
+#pragma unroll
+                for (int a = 0; a < D; a++)
+#pragma unroll
+                    for (int q = 0; q < D; q++) acc[a] = fma((double)v[a * D + q], xj[q], acc[a]);
+            }
         }
     }
 #pragma unroll
@@ -649,7 +674,7 @@ __device__ __forceinline__ void spmv_csr_body(const LevelDev &L, const XRef &xr,
                 for (int a = 0; a < D; a++) {
                     double s = 0.0;
 #pragma unroll
-                    for (int q = 0; q < D; q++) s = fma(div[MODE == 2 ? a * D + q : 0], t[q], s);
+                    for (int q = 0; q < D; q++) s = fma(PRE_DINV ? div[PRE_DINV ? a * D + q : 0] : L.dinv[row + (int64_t)(a * D + q) * L.n_pad], t[q], s);
                     out[a] = fma(omega, s, xi[a]);
                 }
             }
