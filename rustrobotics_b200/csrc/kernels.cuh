@@ -1433,6 +1433,16 @@ __device__ __forceinline__ void dense_apply_body(int64_t n_local, const DenseMap
                                                  const XRef &rr, double *__restrict__ x, unsigned vb) {
     constexpr int VS = VecStride<D>::value;
     extern __shared__ double sr[];
+    const int lane = threadIdx.x & 31;
+    const int64_t srow = (int64_t)vb * 8 + (threadIdx.x >> 5);      // local scalar row
+    const bool live = srow < n_local * D;
+    const double *a = Ainv + ((int64_t)dm.off[rank] * D + (live ? srow : 0)) * m;
+    // a row of the inverse is read in batches of DB independent loads per lane (the first one before the right-hand side
+    // is staged): the kernel is a chain of L2 round trips, one per batch, not a bandwidth problem
+    constexpr int DB = 16;
+    double av[DB];
+#pragma unroll
+    for (int u = 0; u < DB; u++) { const int j = u * 32 + lane; av[u] = (live && j < m) ? __ldg(a + j) : 0.0; }
     for (int t = threadIdx.x; t < m; t += 256) {
         const int g = t / D, c = t - D * g;
         int k = 0;
@@ -1440,12 +1450,17 @@ __device__ __forceinline__ void dense_apply_body(int64_t n_local, const DenseMap
         sr[t] = rr.p[k][(int64_t)(g - dm.off[k]) * VS + c];
     }
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int64_t srow = (int64_t)vb * 8 + (threadIdx.x >> 5);      // local scalar row
-    if (srow >= n_local * D) return;
-    const double *a = Ainv + ((int64_t)dm.off[rank] * D + srow) * m;
+    if (!live) return;
     double s = 0.0;
-    for (int j = lane; j < m; j += 32) s = fma(__ldg(a + j), sr[j], s);
+    for (int j0 = 0; j0 < m; j0 += 32 * DB) {
+        double nv[DB];
+#pragma unroll
+        for (int u = 0; u < DB; u++) { const int j = j0 + 32 * DB + u * 32 + lane; nv[u] = j < m ? __ldg(a + j) : 0.0; }    // next batch
+#pragma unroll
+        for (int u = 0; u < DB; u++) { const int j = j0 + u * 32 + lane; s = fma(av[u], j < m ? sr[j] : 0.0, s); }
+#pragma unroll
+        for (int u = 0; u < DB; u++) av[u] = nv[u];
+    }
     s = warp_sum(s);
     if (lane == 0) x[(srow / D) * VS + (srow % D)] = s;
 }
