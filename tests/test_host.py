@@ -179,3 +179,21 @@ def test_synthetic_sphere_is_well_formed():
     q = g["vertex_values"].reshape(n, 7)[:, 3:]
     np.testing.assert_allclose(np.linalg.norm(q, axis=1), 1.0, atol=1e-12)
     assert 3.8 * n <= len(g["edge_from"]) <= 4 * n
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py --impl reference (the CPU arm: the oracle port on the host cores) runs without a GPU and prints ONE JSON line
+    on stdout with the contract's keys; everything else goes to stderr"""
+    import json
+    import subprocess
+    import sys
+    from conftest import ROOT
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--workload", "pose-landmark", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "gn_edges_per_sec" and d["unit"] == "edges/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
