@@ -175,6 +175,10 @@ int pgo_get_stats(const pgo_handle *h, int64_t *n_block_rows, int64_t *n_offdiag
 int pgo_get_level_sizes(const pgo_handle *h, int32_t max_levels, int64_t *rows, int64_t *blocks);
 
 /* library / device identification, e.g. "pgo_b200 0.1 sm_100a" */
+/* diagnostic (structure-only handles included): the aggregate = row of level `level + 1` (global padded numbering) of every
+ * vertex in lut order (level 0, n = n_vertices) or of every padded row of `level` (level >= 1, n = padded rows, -1 = padding) */
+int pgo_get_aggregates(const pgo_handle *h, int32_t level, int32_t *coarse_row, int64_t n);
+
 const char *pgo_version(void);
 
 #ifdef __cplusplus

@@ -1617,4 +1617,19 @@ int pgo_get_level_sizes(const pgo_handle *h, int32_t max_levels, int64_t *rows, 
     return nl;
 }
 
+int pgo_get_aggregates(const pgo_handle *h, int32_t level, int32_t *coarse_row, int64_t n) {
+    if (!h || !coarse_row) return PGO_ERR_ARG;
+    const Symbolic &S = h->sym;
+    if (level < 0 || level + 1 >= (int)S.levels.size() || S.levels[level].agg.empty()) return PGO_ERR_ARG;
+    const HostLevel &L = S.levels[level];
+    if (level == 0) {                                // per vertex, lut order
+        if (n != S.n) return PGO_ERR_ARG;
+        for (int64_t v = 0; v < S.n; v++) coarse_row[v] = L.agg[S.iperm[v]];
+    } else {                                         // per row of the level (global padded numbering, -1 for padding rows)
+        if (n != L.n_pad) return PGO_ERR_ARG;
+        for (int64_t r = 0; r < L.n_pad; r++) coarse_row[r] = L.agg[r];
+    }
+    return PGO_OK;
+}
+
 } // extern "C"

@@ -14,7 +14,7 @@ ABI_SYMBOLS = [
     "pgo_undo_last_step", "pgo_get_poses", "pgo_set_poses", "pgo_get_dx", "pgo_linearize_and_solve", "pgo_get_pattern",
     "pgo_get_block_structure", "pgo_get_anchor", "pgo_get_system", "pgo_get_timings", "pgo_time_spmv", "pgo_time_coarse", "pgo_get_stats",
     "pgo_version", "pgo_snapshot_poses", "pgo_restore_poses", "pgo_shard_handle_bytes", "pgo_shard_export",
-    "pgo_shard_connect", "pgo_get_partition", "pgo_get_level_sizes",
+    "pgo_shard_connect", "pgo_get_partition", "pgo_get_level_sizes", "pgo_get_aggregates",
 ]
 
 
@@ -58,6 +58,7 @@ def lib():
     L.pgo_shard_connect.argtypes = [P, P, i64]
     L.pgo_get_partition.argtypes = [P, C.POINTER(i32), C.POINTER(i32), P, P]
     L.pgo_get_level_sizes.argtypes = [P, i32, P, P]
+    L.pgo_get_aggregates.argtypes = [P, i32, P, i64]
     L.pgo_restore_poses.argtypes = [P]
     L.pgo_linearize_and_solve.argtypes = [P, C.POINTER(i32)]
     L.pgo_get_pattern.argtypes = [P, C.POINTER(i64), C.POINTER(i64), P, P]

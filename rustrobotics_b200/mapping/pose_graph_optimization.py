@@ -248,6 +248,17 @@ class PoseGraph:
         nl = lib().pgo_get_level_sizes(self._h, 16, ptr(rows), ptr(blocks))
         return rows[:nl].tolist(), blocks[:nl].tolist()
 
+    def aggregates(self, level=0, n=None):
+        """aggregate (row of level + 1, global padded numbering) of every vertex in lut order (level 0) or of every padded
+        row of `level` (n = number of padded rows; -1 marks padding rows)"""
+        if level == 0:
+            nv = C.c_int64(); ne = C.c_int64(); ln = C.c_int64(); nval = C.c_int64()
+            lib().pgo_get_sizes(self._h, C.byref(nv), C.byref(ne), C.byref(ln), C.byref(nval))
+            n = nv.value
+        out = np.zeros(n, np.int32)
+        self._check(lib().pgo_get_aggregates(self._h, level, ptr(out), n), "pgo_get_aggregates")
+        return out
+
     def partition(self):
         w, r = C.c_int32(), C.c_int32()
         lib().pgo_get_partition(self._h, C.byref(w), C.byref(r), None, None)
