@@ -1169,7 +1169,10 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
         CKU(cudaFuncSetAttribute(k_dense_apply<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 6 * 1024)));
         CKU(cudaFuncSetAttribute(k_dense_apply<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 6 * 1024)));
     }
-    h->chunk = h->use_amg ? 4 : 16;
+    // PCG iterations per captured graph: the host keeps two launches in flight, so up to ~2 chunks of early-exit kernels run after
+    // convergence; measured at config 4 (41 AMG iterations): chunk 1 / 2 / 4 / 8 -> PCG 34.17 / 34.19 / 34.70 / 35.79 ms
+    h->chunk = h->use_amg ? 2 : 16;
+    if (const char *e = std::getenv("PGO_CHUNK")) h->chunk = std::max(1, std::atoi(e));   // PCG iterations per captured graph
 
     // ---- level-0 vertex data of the owned rows, in storage order
     const HostLevel &H0 = S.levels[0];
