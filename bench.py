@@ -67,23 +67,36 @@ def log(*a):
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line).  The sampler is started before the warm-up
+    (nvidia-smi needs a few hundred ms to come up), writes line-buffered time-stamped rows every 25 ms, and only the rows whose
+    time stamp falls inside [begin(), end()] -- the timed region -- are reported."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device: int):
         self.device = device
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        self.t0 = self.t1 = None
 
     def start(self):
+        import shutil
+        cmd = ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25", "-i", str(self.device)]
+        if shutil.which("stdbuf"):
+            cmd = ["stdbuf", "-oL"] + cmd
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
-                                       "-i", str(self.device)], stdout=self.f, stderr=subprocess.DEVNULL)
+            self.p = subprocess.Popen(cmd, stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
+
     def stop(self) -> dict:
+        import datetime
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
@@ -94,21 +107,26 @@ class ClockSampler:
         self.f.flush()
         rows = [r.split(",") for r in Path(self.f.name).read_text().splitlines() if r.count(",") >= 8]
         os.unlink(self.f.name)
-        sm, mx, pw, reasons = [], [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        parsed = []
         for r in rows:
             try:
-                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+                ts = datetime.datetime.strptime(r[0].strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                parsed.append((ts, float(r[1]), float(r[2]), float(r[3]), [nm for nm, v in zip(names, r[5:9]) if v.strip().lower().startswith("active")]))
             except ValueError:
                 continue
-            for nm, v in zip(names, r[5:9]):
-                if v.strip().lower().startswith("active"):
-                    reasons.add(nm)
-        if not sm:
+        if rows and not parsed:
+            log(f"[clocks] could not parse nvidia-smi rows, first row: {rows[0]}")
+        inside = [q for q in parsed if self.t0 is not None and self.t1 is not None and self.t0 <= q[0] <= self.t1]
+        window = "timed region"
+        if not inside and parsed:            # a timed region shorter than the sampling period: the nearest rows under load
+            inside = [q for q in parsed if self.t0 is not None and q[0] >= self.t0 - 0.5] or parsed
+            window = "timed region shorter than the 25 ms sampling period: rows from the warm-up + timed region"
+        if not inside:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
-                "reasons": sorted(reasons)}
+        sm = sorted(q[1] for q in inside)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(q[2] for q in inside), "power_w_max": max(q[3] for q in inside),
+                "samples": len(sm), "reasons": sorted({nm for q in inside for nm in q[4]}), "window": window}
 
 
 def measured_peak_hbm():
@@ -234,11 +252,12 @@ def run_b200(args):
         t = pg.timings()
         return r, t
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         one_step()
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
+    sampler.begin()
     w0 = time.perf_counter()
     dev_ms, launches, pcg_its, phases = 0.0, 0, [], {}
     last = None
@@ -253,6 +272,7 @@ def run_b200(args):
             phases[k] = phases.get(k, 0.0) + ms / args.steps
     barrier()
     wall_s = time.perf_counter() - w0
+    sampler.end()
     clocks = sampler.stop()
 
     # ---- dominant kernel: fine-level BSR SpMV, timed live with CUDA events on the library's stream
