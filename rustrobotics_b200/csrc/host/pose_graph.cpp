@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <sys/stat.h>
+#include <utility>
 
 namespace robotics { namespace mapping {
 
@@ -34,6 +35,11 @@ PoseGraph::PoseGraph(const std::string &file_path, PoseGraphSolver solver, const
 
 PoseGraph::PoseGraph(const G2oGraph &graph, const std::string &name, PoseGraphSolver solver, const pgo_options *options)
     : graph_(graph), name_(name), solver_(solver) {
+    init(options);
+}
+
+PoseGraph::PoseGraph(G2oGraph &&graph, const std::string &name, PoseGraphSolver solver, const pgo_options *options)
+    : graph_(std::move(graph)), name_(name), solver_(solver) {
     init(options);
 }
 
@@ -157,7 +163,7 @@ void *pg_from_arrays(const char *name, int solver, const pgo_options *opt,
         g.edge_kind.assign(ekind, ekind + ne); g.edge_from.assign(efrom, efrom + ne); g.edge_to.assign(eto, eto + ne);
         g.edge_meas.assign(emeas, emeas + n_meas); g.edge_info_upper.assign(einfo, einfo + n_info);
         for (int64_t i = 0; i < nv; i++) g.len += vkind[i] == 0 ? 3 : vkind[i] == 1 ? 2 : 6;
-        return new PoseGraph(g, name ? name : "graph", solver ? PoseGraphSolver::LevenbergMarquardt : PoseGraphSolver::GaussNewton, opt);
+        return new PoseGraph(std::move(g), name ? name : "graph", solver ? PoseGraphSolver::LevenbergMarquardt : PoseGraphSolver::GaussNewton, opt);
     } catch (const std::exception &e) { g_err = e.what(); return nullptr; }
 }
 

@@ -26,6 +26,7 @@ public:
     PoseGraph(const std::string &file_path, PoseGraphSolver solver, const pgo_options *options = nullptr);
     // same, from an already loaded graph (synthetic benchmarks)
     PoseGraph(const G2oGraph &graph, const std::string &name, PoseGraphSolver solver, const pgo_options *options = nullptr);
+    PoseGraph(G2oGraph &&graph, const std::string &name, PoseGraphSolver solver, const pgo_options *options = nullptr);
     ~PoseGraph();
     PoseGraph(const PoseGraph &) = delete;
     PoseGraph &operator=(const PoseGraph &) = delete;

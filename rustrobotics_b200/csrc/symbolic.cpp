@@ -7,8 +7,12 @@
 #include "pgo_internal.h"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <thread>
 
 namespace pgo {
 
@@ -16,6 +20,24 @@ static const int KIND_DIM[3] = {3, 2, 6};   // lut stride, g2o.rs:61,68,77
 static const int KIND_NVAL[3] = {3, 2, 7};
 
 static inline int64_t pad32(int64_t x) { return (x + 31) / 32 * 32; }
+
+// The symbolic pass is host work done once per graph, but at BASELINE configs[3] (1M poses / 4M edges) it is seconds of
+// single-threaded index manipulation next to Gauss-Newton steps of 40 ms: the loops whose iterations are independent run
+// on the host's cores.  f(begin, end) is called on disjoint contiguous ranges; results do not depend on the thread count.
+template <typename F> static void parallel_for(int64_t n, int64_t grain, F f) {
+    unsigned nt = std::thread::hardware_concurrency();
+    if (const char *e = std::getenv("PGO_HOST_THREADS")) nt = (unsigned)std::max(1, std::atoi(e));
+    nt = std::min<unsigned>(std::max(1u, nt), 16u);
+    nt = (unsigned)std::min<int64_t>(nt, std::max<int64_t>(1, n / std::max<int64_t>(grain, 1)));
+    if (nt <= 1) { f((int64_t)0, n); return; }
+    std::vector<std::thread> th;
+    th.reserve(nt);
+    for (unsigned t = 0; t < nt; t++) {
+        const int64_t b = n * t / nt, e = n * (t + 1) / nt;
+        th.emplace_back([=]() { f(b, e); });
+    }
+    for (auto &x : th) x.join();
+}
 
 // partitions laid out back to back, each padded to a multiple of 32 rows
 static void layout_partitions(HostLevel &L, const std::vector<int64_t> &counts) {
@@ -40,24 +62,34 @@ static void build_jds(HostLevel &L) {
     const int64_t nent = L.adj_ptr[L.n_pad];
     L.adj_slot.assign(nent, 0);
     L.adj_cnt.assign(nent, 0);
-    int64_t base = 0;
-    for (int64_t s = 0; s < L.n_slices; s++) {
-        L.slice_ptr[s] = base;
-        const int32_t *d = &L.deg[32 * s];
-        const int maxdeg = d[0];
-        int64_t off = 0;
-        for (int k = 0; k < maxdeg; k++) {
-            int cnt = 0;
-            while (cnt < 32 && d[cnt] > k) cnt++;
-            for (int l = 0; l < cnt; l++) {
-                const int64_t row = 32 * s + l;
-                L.adj_slot[L.adj_ptr[row] + k] = base + off + l;
-                L.adj_cnt[L.adj_ptr[row] + k] = cnt;
-            }
-            off += cnt;
+    // slots per slice (even: blobs stay 16-byte aligned) -> prefix sum -> fill
+    parallel_for(L.n_slices, 1024, [&](int64_t s0, int64_t s1) {
+        for (int64_t s = s0; s < s1; s++) {
+            int64_t tot = 0;
+            for (int l = 0; l < 32; l++) tot += L.deg[32 * s + l];
+            L.slice_ptr[s + 1] = (tot + 1) & ~int64_t(1);
         }
-        base += (off + 1) & ~int64_t(1);                   // even slot count: blobs stay 16-byte aligned
-    }
+    });
+    for (int64_t s = 0; s < L.n_slices; s++) L.slice_ptr[s + 1] += L.slice_ptr[s];
+    parallel_for(L.n_slices, 1024, [&](int64_t s0, int64_t s1) {
+        for (int64_t s = s0; s < s1; s++) {
+            const int64_t base = L.slice_ptr[s];
+            const int32_t *d = &L.deg[32 * s];
+            const int maxdeg = d[0];
+            int64_t off = 0;
+            for (int k = 0; k < maxdeg; k++) {
+                int cnt = 0;
+                while (cnt < 32 && d[cnt] > k) cnt++;
+                for (int l = 0; l < cnt; l++) {
+                    const int64_t row = 32 * s + l;
+                    L.adj_slot[L.adj_ptr[row] + k] = base + off + l;
+                    L.adj_cnt[L.adj_ptr[row] + k] = cnt;
+                }
+                off += cnt;
+            }
+        }
+    });
+    const int64_t base = L.slice_ptr[L.n_slices];
     L.slice_ptr[L.n_slices] = base;
     L.n_slots = base;
     L.part_slot.assign(L.part_off.size(), 0);
@@ -75,6 +107,8 @@ static void build_csr(HostLevel &L) {
     for (size_t k = 0; k < L.part_off.size(); k++) L.part_slot[k] = L.adj_ptr[L.part_off[k]];
 }
 
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+#define TICK(name) do { if (getenv("PGO_SYM_TIMING")) { double t_ = now_s(); fprintf(stderr, "[sym] %-28s %.3f s\n", name, t_ - t_last); t_last = t_; } } while (0)
 // ------------------------------------------------------------------------------------------------
 bool build_canonical(Symbolic &S) {
     if (!S.brow_ptr.empty()) return true;
@@ -194,6 +228,7 @@ static int32_t aggregate_partition(const HostLevel &F, int k, int max_size, std:
 // merge: F is sharded over pnc.size() partitions but C becomes one replicated partition (rows of rank k's aggregates at src_off[k])
 static void build_coarse_level(HostLevel &F, HostLevel &C, const std::vector<std::vector<int32_t>> &pagg,
                                const std::vector<int64_t> &pnc, bool jds, bool merge, int DD) {
+    double t_last = now_s();
     const int world = (int)pnc.size();
     std::vector<int64_t> cbase(world, 0);       // coarse row of partition k's aggregate 0
     if (merge) {
@@ -218,28 +253,41 @@ static void build_coarse_level(HostLevel &F, HostLevel &C, const std::vector<std
         std::vector<int64_t> mp(C.mem_ptr.begin(), C.mem_ptr.end() - 1);
         for (int64_t r = 0; r < F.n_pad; r++) if (F.agg[r] >= 0) C.mem_idx[mp[F.agg[r]]++] = (int32_t)r;
     }
+    TICK("  bcl: members");
     // coarse adjacency: I ~ J when any member of I has a stored block towards a member of J
     C.adj_ptr.assign(C.n_pad + 1, 0);
     C.adj_nbr.clear();
-    std::vector<int32_t> tmp;
-    for (int64_t I = 0; I < C.n_pad; I++) {
-        tmp.clear();
-        for (int64_t m = C.mem_ptr[I]; m < C.mem_ptr[I + 1]; m++) {
-            const int64_t r = C.mem_idx[m];
-            for (int64_t p = F.adj_ptr[r]; p < F.adj_ptr[r + 1]; p++) { const int32_t J = F.agg[F.adj_nbr[p]]; if (J != I) tmp.push_back(J); }
-        }
-        std::sort(tmp.begin(), tmp.end());
-        tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
-        C.adj_nbr.insert(C.adj_nbr.end(), tmp.begin(), tmp.end());
-        C.adj_ptr[I + 1] = (int64_t)C.adj_nbr.size();
+    {
+        std::vector<std::vector<int32_t>> lists(C.n_pad);
+        parallel_for(C.n_pad, 256, [&](int64_t I0, int64_t I1) {
+            std::vector<int32_t> tmp;
+            for (int64_t I = I0; I < I1; I++) {
+                tmp.clear();
+                for (int64_t m = C.mem_ptr[I]; m < C.mem_ptr[I + 1]; m++) {
+                    const int64_t r = C.mem_idx[m];
+                    for (int64_t p = F.adj_ptr[r]; p < F.adj_ptr[r + 1]; p++) { const int32_t J = F.agg[F.adj_nbr[p]]; if (J != I) tmp.push_back(J); }
+                }
+                std::sort(tmp.begin(), tmp.end());
+                tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+                lists[I] = tmp;
+            }
+        });
+        for (int64_t I = 0; I < C.n_pad; I++) C.adj_ptr[I + 1] = C.adj_ptr[I] + (int64_t)lists[I].size();
+        C.adj_nbr.resize(C.adj_ptr[C.n_pad]);
+        parallel_for(C.n_pad, 256, [&](int64_t I0, int64_t I1) {
+            for (int64_t I = I0; I < I1; I++) std::copy(lists[I].begin(), lists[I].end(), C.adj_nbr.begin() + C.adj_ptr[I]);
+        });
     }
+    TICK("  bcl: adjacency");
     if (jds) build_jds(C); else build_csr(C);
+    TICK("  bcl: storage");
     // Galerkin targets of every fine block, local to the owning partition: element offset of component 0 of the coarse
     // block inside the partition's val array + the stride between components (CSR: 9 s, 1 ; JDS: component-major)
     F.ctgt.assign(F.n_slots, 0);
     F.cstr.assign(F.n_slots, 1);
     for (int k = 0; k < world; k++)
-        for (int64_t r = F.part_off[k]; r < F.part_off[k] + F.part_real[k]; r++) {
+        parallel_for(F.part_real[k], 4096, [&, k](int64_t i0, int64_t i1) {
+        for (int64_t r = F.part_off[k] + i0; r < F.part_off[k] + i1; r++) {
             const int32_t I = F.agg[r];
             for (int64_t p = F.adj_ptr[r]; p < F.adj_ptr[r + 1]; p++) {
                 const int32_t J = F.agg[F.adj_nbr[p]];
@@ -256,6 +304,8 @@ static void build_coarse_level(HostLevel &F, HostLevel &C, const std::vector<std
                 } else F.ctgt[slot] = (int32_t)(cs * DD);
             }
         }
+        });
+    TICK("  bcl: galerkin targets");
 }
 
 // renumber the aggregates of every partition by decreasing coarse degree inside windows (what the sliced storage needs)
@@ -280,6 +330,7 @@ static void sort_aggregates_by_degree(const HostLevel &C, std::vector<std::vecto
 bool build_symbolic(Symbolic &S, const SymbolicOptions &opt,
                     int64_t nv, const uint32_t *vid, const uint8_t *vkind,
                     int64_t ne, const uint8_t *ekind, const uint32_t *efrom, const uint32_t *eto) {
+    double t_last = now_s();
     if (nv <= 0 || nv > (int64_t)COL_LOCAL_MASK || ne < 0 || ne > 0x7fffffffll) { S.error = "vertex/edge count out of range"; return false; }
     const int world = opt.world;
     if (world < 1 || world > MAX_RANKS) { S.error = "world size must be 1.." + std::to_string(MAX_RANKS); return false; }
@@ -299,12 +350,28 @@ bool build_symbolic(Symbolic &S, const SymbolicOptions &opt,
     if (has2 && has3) { S.error = "SE2/XY and SE3 vertices cannot be mixed in one graph"; return false; }
     S.D = has3 ? 6 : 3;
     S.len = off; S.n_values = vo;
+    TICK("vertex scan");
     // id -> index (the reference's lut, g2o.rs:60)
-    std::vector<std::pair<uint32_t, int32_t>> ids(nv);
-    for (int64_t v = 0; v < nv; v++) ids[v] = {vid[v], (int32_t)v};
-    std::sort(ids.begin(), ids.end());
-    for (int64_t v = 1; v < nv; v++) if (ids[v].first == ids[v - 1].first) { S.error = "duplicate vertex id " + std::to_string(ids[v].first); return false; }
+    // dense ids (the common case: 0..n-1 in some order) resolve through a direct table, anything else by binary search
+    uint32_t max_id = 0;
+    for (int64_t v = 0; v < nv; v++) max_id = std::max(max_id, vid[v]);
+    const bool dense_ids = (uint64_t)max_id < (uint64_t)nv * 4 + 1024;
+    std::vector<int32_t> table;
+    std::vector<std::pair<uint32_t, int32_t>> ids;
+    if (dense_ids) {
+        table.assign((size_t)max_id + 1, -1);
+        for (int64_t v = 0; v < nv; v++) {
+            if (table[vid[v]] >= 0) { S.error = "duplicate vertex id " + std::to_string(vid[v]); return false; }
+            table[vid[v]] = (int32_t)v;
+        }
+    } else {
+        ids.resize(nv);
+        for (int64_t v = 0; v < nv; v++) ids[v] = {vid[v], (int32_t)v};
+        std::sort(ids.begin(), ids.end());
+        for (int64_t v = 1; v < nv; v++) if (ids[v].first == ids[v - 1].first) { S.error = "duplicate vertex id " + std::to_string(ids[v].first); return false; }
+    }
     auto lookup = [&](uint32_t id) -> int32_t {
+        if (dense_ids) return id <= max_id ? table[id] : -1;
         auto it = std::lower_bound(ids.begin(), ids.end(), std::make_pair(id, (int32_t)-1));
         return (it != ids.end() && it->first == id) ? it->second : -1;
     };
@@ -320,6 +387,7 @@ bool build_symbolic(Symbolic &S, const SymbolicOptions &opt,
         S.efrom[k] = i; S.eto[k] = j;
         if (S.anchor < 0 && ekind[k] != 1) S.anchor = i;   // first pose-pose edge's `from` (:330-336)
     }
+    TICK("edge lookup");
     std::vector<int32_t> deg(nv, 0);
     for (int64_t k = 0; k < ne; k++) { deg[S.efrom[k]]++; deg[S.eto[k]]++; }
 
@@ -359,6 +427,7 @@ bool build_symbolic(Symbolic &S, const SymbolicOptions &opt,
             }
             for (int64_t i = 0; i < counts[k]; i++) { S.perm[L0.part_off[k] + i] = idv[i]; S.iperm[idv[i]] = (int32_t)(L0.part_off[k] + i); }
         }
+        TICK("storage order");
         // half edges per storage row, sorted by neighbour row
         L0.adj_ptr.assign(L0.n_pad + 1, 0);
         for (int64_t r = 0; r < L0.n_pad; r++) L0.adj_ptr[r + 1] = L0.adj_ptr[r] + (S.perm[r] >= 0 ? deg[S.perm[r]] : 0);
@@ -372,20 +441,28 @@ bool build_symbolic(Symbolic &S, const SymbolicOptions &opt,
                 he[pos[ri]++] = {rj, (int32_t)k, xy};
                 he[pos[rj]++] = {ri, (int32_t)k, xy | COL_ROLE_TO};
             }
-            for (int64_t r = 0; r < L0.n_pad; r++)
-                std::sort(he.begin() + L0.adj_ptr[r], he.begin() + L0.adj_ptr[r + 1],
-                          [](const HE &a, const HE &b) { return a.nbr != b.nbr ? a.nbr < b.nbr : a.edge < b.edge; });
+            TICK("half-edge fill");
+            parallel_for(L0.n_pad, 4096, [&](int64_t r0, int64_t r1) {
+                for (int64_t r = r0; r < r1; r++)
+                    std::sort(he.begin() + L0.adj_ptr[r], he.begin() + L0.adj_ptr[r + 1],
+                              [](const HE &a, const HE &b) { return a.nbr != b.nbr ? a.nbr < b.nbr : a.edge < b.edge; });
+            });
         }
+        TICK("row sorts");
         build_jds(L0);
+        TICK("build_jds");
         const int64_t nent = L0.adj_ptr[L0.n_pad];
         L0.adj_nbr.resize(nent); L0.adj_flags.resize(nent);
         S.slot_edge.assign(L0.n_slots, -1);
-        for (int64_t q = 0; q < nent; q++) {
-            L0.adj_nbr[q] = he[q].nbr;
-            L0.adj_flags[q] = he[q].flags;
-            S.slot_edge[L0.adj_slot[q]] = he[q].edge;
-        }
+        parallel_for(nent, 65536, [&](int64_t q0, int64_t q1) {
+            for (int64_t q = q0; q < q1; q++) {
+                L0.adj_nbr[q] = he[q].nbr;
+                L0.adj_flags[q] = he[q].flags;
+                S.slot_edge[L0.adj_slot[q]] = he[q].edge;
+            }
+        });
     }
+    TICK("level-0 arrays");
     S.dense_coarsest = false;
     if (!opt.build_amg) return true;
 
@@ -402,11 +479,13 @@ bool build_symbolic(Symbolic &S, const SymbolicOptions &opt,
         std::vector<int64_t> pnc(fworld, 0);
         int64_t nc = 0;
         for (int k = 0; k < fworld; k++) { pnc[k] = aggregate_partition(F, k, opt.agg_size, pagg[k]); nc += pnc[k]; }
+        TICK("aggregate");
         if (nc > 0.8 * F.n) break;                               // coarsening stalled
         const bool merge = fworld > 1 && nc <= repl_max;
         const bool jds = nc >= opt.jds_min_rows && !merge && !F.repl;
         S.levels.emplace_back();
         build_coarse_level(S.levels[lvl], S.levels[lvl + 1], pagg, pnc, false, merge, S.D * S.D);
+        TICK("build_coarse_level");
         if (jds) {
             // a large coarse level is streamed like level 0: one thread per row over the sliced storage
             sort_aggregates_by_degree(S.levels[lvl + 1], pagg, pnc, std::max(32, opt.sort_window / 32 * 32));

@@ -197,3 +197,22 @@ def test_bench_reference_arm_prints_exactly_one_json_line():
     assert d["impl"] == "reference" and d["metric"] == "gn_edges_per_sec" and d["unit"] == "edges/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_symbolic_pass_is_independent_of_the_host_thread_count(built, monkeypatch):
+    """the symbolic pass runs its independent loops on the host's cores: same structure for 1 and for many threads"""
+    import numpy as np
+    from rustrobotics_b200 import Options, PoseGraph
+    from rustrobotics_b200.synthetic import manhattan_se2
+    g = manhattan_se2(20000)
+    out = []
+    for nt in ("1", "7"):
+        monkeypatch.setenv("PGO_HOST_THREADS", nt)
+        pg = PoseGraph(graph=g, options=Options(device=-2))
+        rows, blocks = pg.level_sizes()
+        out.append((rows, blocks, pg.aggregates(0).copy(), [a.copy() for a in pg.block_structure()]))
+        pg.close()
+    assert out[0][0] == out[1][0] and out[0][1] == out[1][1]
+    assert np.array_equal(out[0][2], out[1][2])
+    for a, b in zip(out[0][3], out[1][3]):
+        assert np.array_equal(a, b)
