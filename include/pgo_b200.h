@@ -58,7 +58,7 @@ typedef struct {
     int32_t world;             /* number of ranks (one process per GPU) sharing the graph; 1 = single GPU */
     int32_t rank;              /* this process' rank, 0 .. world-1: it owns a contiguous vertex range */
     int32_t amg_dense_max;     /* a level with at most this many block rows is solved directly (explicit inverse); 0 = default */
-    int32_t amg_aggregate_size;/* upper bound on the members of an aggregate; 0 = default */
+    int32_t amg_aggregate_size;/* upper bound on the members of an aggregate; 0 = default (16 on one GPU, 24 for sharded handles) */
     int32_t amg_kcycle;        /* coarse levels 1..amg_kcycle are solved by a K-cycle (two Krylov-accelerated cycles per
                                 * visit, Notay), deeper ones by a V-cycle; 0 = plain V-cycle; default: all levels */
     int32_t amg_kcycle3;       /* coarse levels 1..amg_kcycle3 run THREE inner flexible-CG steps per K-cycle visit instead of two

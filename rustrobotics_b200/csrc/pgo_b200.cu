@@ -910,7 +910,7 @@ void pgo_default_options(pgo_options *o) {
     o->world = 1;
     o->rank = 0;
     o->amg_dense_max = 640;
-    o->amg_aggregate_size = 16;
+    o->amg_aggregate_size = 0;        // auto: 16 (single GPU), 24 (sharded)
     o->amg_kcycle = MAX_LEVELS;
     o->amg_kcycle3 = -1;
 }
@@ -953,7 +953,12 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
     if (h->opt.world <= 0) h->opt.world = 1;
     if (h->opt.amg_dense_max <= 0) h->opt.amg_dense_max = dflt.amg_dense_max;
     if (h->opt.amg_dense_max > 1024) h->opt.amg_dense_max = 1024;
-    if (h->opt.amg_aggregate_size <= 1) h->opt.amg_aggregate_size = dflt.amg_aggregate_size;
+    // default upper bound on the members of an aggregate: 16 on one GPU (measured optimum at config 4, profiles/r02f_knob_sweep.log).
+    // Sharded handles use 24: the partition-local level-0 aggregation leaves a larger, less regular level 1, and with 16 the
+    // multilevel K-cycle needs 51 PCG iterations at world 2 and 8 where one GPU needs 41; with 24 the scipy prototype fed with
+    // the library's own aggregates (tools/research/hierarchy_study.py, which reproduces 42 / 51 for the old default) gives
+    // 43 (world 2) and 45 (world 8).  On one GPU 24 measures the same as 16 (41 iterations, 34.26 vs 34.19 ms).
+    if (h->opt.amg_aggregate_size <= 1) h->opt.amg_aggregate_size = h->opt.world > 1 ? 24 : 16;
     h->use_amg = h->opt.preconditioner == PGO_PRECOND_AMG;
     h->world = h->opt.world; h->rank = h->opt.rank;
     if (h->rank < 0 || h->rank >= h->world) return fail_create(h, PGO_ERR_ARG, "pgo_create: rank out of range");
