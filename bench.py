@@ -390,7 +390,7 @@ def main():
     os.dup2(2, 1)                       # fd 1 -> stderr for the rest of the run (C libraries included)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="manhattan", choices=["manhattan", "sphere"] + list(BUNDLED),
