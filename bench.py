@@ -65,6 +65,33 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+class TorchComm:
+    """The launcher-side communicator of the process-per-GPU mode (torchrun): torch.distributed is only plumbing here -- one
+    all-gather of a 64-byte CUDA IPC handle per rank at start-up, and the merge of the ranks' pose spans for the getters.
+    The product package imports no torch; its single-process multi-GPU mode (Options(n_gpus=N)) needs none of this."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.world = dist.get_world_size(group)
+
+    def all_gather_bytes(self, mine: bytes) -> bytes:
+        parts = [None] * self.world
+        self.dist.all_gather_object(parts, bytes(mine), group=self.group)
+        return b"".join(parts)
+
+    def all_reduce_sum(self, a):
+        import torch
+        t = torch.from_numpy(a)
+        if self.dist.get_backend(self.group) == "nccl":
+            t = t.cuda()
+        self.dist.all_reduce(t, group=self.group)
+        return t.cpu().numpy()
+
+    def barrier(self):
+        self.dist.barrier(self.group)
+
+
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
     """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line).  The sampler is started before the warm-up
@@ -240,7 +267,7 @@ def run_b200(args):
     # peer HBM over NVLink inside the kernels, dot products reduced by a device-side peer-memory all-reduce
     extra = {k: (float(v) if "." in v or "e" in v else int(v)) for k, v in (kv.split("=") for kv in args.opts.split(",") if kv)}
     pg = PoseGraph(graph=g, options=Options(device=local, world=world, rank=rank, pcg_rtol=args.pcg_rtol,
-                                            preconditioner=args.preconditioner, **extra))
+                                            preconditioner=args.preconditioner, **extra), comm=TorchComm() if world > 1 else None)
     t_create = time.perf_counter() - t0
     log(f"[rank {rank}] graph {n_poses} poses / {n_edges} edges generated in {t_gen:.1f}s, created in {t_create:.1f}s, {pg.stats()}")
     chi2_0 = pg.global_error()

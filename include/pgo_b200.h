@@ -12,8 +12,12 @@
  * Conventions: plain pointers and sizes only; every function returns a status code of enum pgo_status, 0 = ok, and
  * never throws or aborts; pgo_last_error gives the message of the last failure on the handle
  * (or of the last failed pgo_create when handle == NULL).  A handle is single-owner and not
- * thread-safe (PoseGraph::optimize takes &mut self, :247).  Input arrays are borrowed for the
- * duration of the call only.  There is no CPU fallback: without a CUDA device every entry
+ * thread-safe (PoseGraph::optimize takes &mut self, :247): one host thread at a time, every call
+ * blocks until its result is there.  Input arrays are borrowed for the duration of the call only.
+ * Multi-GPU: set pgo_options.n_gpus (and optionally device_ids) and the SAME single handle drives
+ * all GPUs of the box from the one calling thread's point of view (one worker thread per GPU
+ * lives inside the library) -- the reference's `PoseGraph::new(path, solver)?.optimize(n, ..)`
+ * needs no other change.  There is no CPU fallback: without a CUDA device every entry
  * point that computes returns PGO_ERR_CUDA.
  */
 #ifndef PGO_B200_H
@@ -31,7 +35,7 @@ typedef enum {
     PGO_OK = 0,
     PGO_ERR_ARG = 1,        /* bad argument / malformed graph (unknown vertex id, kind mismatch) */
     PGO_ERR_CUDA = 2,       /* CUDA runtime failure, or no device */
-    PGO_ERR_NCCL = 3,       /* NCCL failure (multi-GPU handles) */
+    PGO_ERR_COMM = 3,       /* multi-GPU handles: peer access unavailable, or a cross-GPU synchronisation timed out */
     PGO_ERR_SOLVER = 4,     /* PCG breakdown (p^T H p <= 0 or NaN): H not positive definite */
     PGO_ERR_NOT_CONVERGED = 5, /* PCG hit pcg_max_iterations; dx of that step was still applied */
     PGO_ERR_UNSUPPORTED = 6
@@ -69,6 +73,12 @@ typedef struct {
                                 * is an approximate operator anyway, and half the bytes is half the time of an HBM-bound
                                 * kernel; the PCG operator H p, the residual recurrence, all dot products and the result stay
                                 * fp64, so the solve converges to the same pcg_rtol.  1: everything reads the fp64 blocks */
+    int32_t n_gpus;            /* 0 / 1 (default): one GPU (`device`).  2 .. 8: SINGLE-PROCESS multi-GPU handle -- the graph's block rows
+                                * are split into n_gpus contiguous vertex ranges (lut order), one shard per GPU, and this one handle
+                                * drives all of them; every entry point keeps its single-GPU meaning (world / rank must stay 1 / 0) */
+    const int32_t *device_ids; /* n_gpus CUDA device ordinals, NULL = 0 .. n_gpus-1.  The devices need peer access to each other
+                                * (NVLink / NVSwitch on a B200 box).  An ordinal may appear more than once: those shards then share
+                                * that GPU (how the multi-GPU path is tested on a one-GPU machine).  Borrowed during pgo_create only */
 } pgo_options;
 
 /* fills *opt with the defaults (anchor 1e7, rtol 1e-10, max 200000 iterations, AMG K-cycle, fp32 preconditioner storage, single GPU) */
@@ -80,7 +90,10 @@ void pgo_default_options(pgo_options *opt);
  * Vertices are given in lut order = VERTEX line order (g2o.rs:60,67,76); edges in file order;
  * edge endpoints are g2o ids resolved through vertex_id like the reference's lut (:312-313).
  * vertex_values / edge_measurement / edge_information_upper are packed back to back with the
- * per-kind counts above.  SE2/XY graphs and SE3 graphs cannot be mixed in one handle.
+ * per-kind counts above: the caller guarantees sum(values per vertex kind), sum(measurement values
+ * per edge kind) and sum(information values per edge kind) doubles respectively (the host mirrors
+ * check this before calling; kinds outside 0..2 are rejected here with PGO_ERR_ARG).
+ * SE2/XY graphs and SE3 graphs cannot be mixed in one handle.
  */
 int pgo_create(pgo_handle **out, const pgo_options *opt,
                int64_t n_vertices, const uint32_t *vertex_id, const uint8_t *vertex_kind,
@@ -91,7 +104,8 @@ int pgo_create(pgo_handle **out, const pgo_options *opt,
 void pgo_destroy(pgo_handle *h);
 const char *pgo_last_error(const pgo_handle *h);
 
-/* --- sharded handles (world > 1): one process per GPU, every rank passes the WHOLE graph to pgo_create and keeps the
+/* --- process-per-GPU sharding (world > 1; an alternative to n_gpus for launchers that already run one process per GPU,
+ * e.g. `torchrun bench.py --gpus N`): every rank passes the WHOLE graph to pgo_create and keeps the
  * block rows of its contiguous vertex range.  Neighbour rows on other ranks are read straight from peer HBM over
  * NVLink, so the ranks must exchange one CUDA IPC handle each before the first computing call: every rank exports
  * pgo_shard_handle_bytes() bytes, the caller all-gathers them in rank order (e.g. torch.distributed.all_gather) and

@@ -1,6 +1,7 @@
 #include "g2o.hpp"
 
 #include <cerrno>
+#include <charconv>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -20,10 +21,21 @@ bool parse_u32(const char *t, uint32_t &v) {           // Rust's str::parse::<u3
     v = (uint32_t)a;
     return true;
 }
+// Rust's str::parse::<f64>: decimal / exponent notation, "inf" / "nan", optional sign; no hex floats, and independent of the
+// process locale (std::from_chars, unlike strtod, never looks at LC_NUMERIC)
 bool parse_f64(const char *t, double &v) {
-    char *end = nullptr;
-    v = std::strtod(t, &end);
-    return end != t && *end == 0;
+    const char *end = t + std::strlen(t);
+    if (*t == '+' && t[1] != '+' && t[1] != '-') t++;
+    if (t == end) return false;
+    const std::from_chars_result r = std::from_chars(t, end, v, std::chars_format::general);
+    return r.ec == std::errc() && r.ptr == end;
+}
+// shortest-round-trip-safe %.17g, locale-independent
+void put_f64(FILE *f, double v) {
+    char buf[40];
+    const std::to_chars_result r = std::to_chars(buf, buf + sizeof(buf), v, std::chars_format::general, 17);
+    std::fputc(' ', f);
+    std::fwrite(buf, 1, (size_t)(r.ptr - buf), f);
 }
 } // namespace
 
@@ -81,22 +93,41 @@ bool parse_g2o(const std::string &filename, G2oGraph &g, std::string &error) {
     return true;
 }
 
+bool validate_graph(const G2oGraph &g, std::string &error) {
+    if (g.vertex_kind.size() != g.vertex_id.size()) { error = "graph arrays: vertex_kind and vertex_id differ in length"; return false; }
+    if (g.edge_from.size() != g.edge_kind.size() || g.edge_to.size() != g.edge_kind.size()) { error = "graph arrays: edge_kind / edge_from / edge_to differ in length"; return false; }
+    size_t nval = 0, nmeas = 0, ninfo = 0;
+    for (size_t i = 0; i < g.vertex_kind.size(); i++) {
+        if (g.vertex_kind[i] > 2) { error = "graph arrays: vertex_kind[" + std::to_string(i) + "] = " + std::to_string(g.vertex_kind[i]) + " (must be 0, 1 or 2)"; return false; }
+        nval += (size_t)NVAL[g.vertex_kind[i]];
+    }
+    for (size_t i = 0; i < g.edge_kind.size(); i++) {
+        if (g.edge_kind[i] > 2) { error = "graph arrays: edge_kind[" + std::to_string(i) + "] = " + std::to_string(g.edge_kind[i]) + " (must be 0, 1 or 2)"; return false; }
+        nmeas += (size_t)NMEAS[g.edge_kind[i]]; ninfo += (size_t)NINFO[g.edge_kind[i]];
+    }
+    if (g.vertex_values.size() != nval) { error = "graph arrays: " + std::to_string(g.vertex_values.size()) + " vertex values, the vertex kinds need " + std::to_string(nval); return false; }
+    if (g.edge_meas.size() != nmeas) { error = "graph arrays: " + std::to_string(g.edge_meas.size()) + " edge measurement values, the edge kinds need " + std::to_string(nmeas); return false; }
+    if (g.edge_info_upper.size() != ninfo) { error = "graph arrays: " + std::to_string(g.edge_info_upper.size()) + " edge information values, the edge kinds need " + std::to_string(ninfo); return false; }
+    return true;
+}
+
 bool write_g2o(const std::string &filename, const G2oGraph &g, std::string &error) {
+    if (!validate_graph(g, error)) return false;
     FILE *f = std::fopen(filename.c_str(), "wb");
     if (!f) { error = filename + ": " + std::strerror(errno); return false; }
     const double *v = g.vertex_values.data();
     for (size_t i = 0; i < g.vertex_id.size(); i++) {
         int k = g.vertex_kind[i];
         std::fprintf(f, "%s %u", VTAG[k], g.vertex_id[i]);
-        for (int c = 0; c < NVAL[k]; c++) std::fprintf(f, " %.17g", *v++);
+        for (int c = 0; c < NVAL[k]; c++) put_f64(f, *v++);
         std::fputc('\n', f);
     }
     const double *m = g.edge_meas.data(), *w = g.edge_info_upper.data();
     for (size_t i = 0; i < g.edge_kind.size(); i++) {
         int k = g.edge_kind[i];
         std::fprintf(f, "%s %u %u", ETAG[k], g.edge_from[i], g.edge_to[i]);
-        for (int c = 0; c < NMEAS[k]; c++) std::fprintf(f, " %.17g", *m++);
-        for (int c = 0; c < NINFO[k]; c++) std::fprintf(f, " %.17g", *w++);
+        for (int c = 0; c < NMEAS[k]; c++) put_f64(f, *m++);
+        for (int c = 0; c < NINFO[k]; c++) put_f64(f, *w++);
         std::fputc('\n', f);
     }
     bool ok = std::fclose(f) == 0;

@@ -24,6 +24,9 @@ struct G2oGraph {
 // wrong field count (the todo!() arms).
 bool parse_g2o(const std::string &filename, G2oGraph &out, std::string &error);
 
+// the packed value arrays hold exactly what the per-kind counts say, kinds are 0..2 (what pgo_create reads on the device side)
+bool validate_graph(const G2oGraph &g, std::string &error);
+
 // writes the graph back in g2o text form with round-trip precision (%.17g)
 bool write_g2o(const std::string &filename, const G2oGraph &g, std::string &error);
 

@@ -16,6 +16,8 @@ void PoseGraph::check(int rc, const char *what) const {
 
 void PoseGraph::init(const pgo_options *options) {
     const G2oGraph &g = graph_;
+    std::string verr;
+    if (!validate_graph(g, verr)) throw Error(verr);
     int rc = pgo_create(&h_, options, (int64_t)g.vertex_id.size(), g.vertex_id.data(), g.vertex_kind.data(), g.vertex_values.data(),
                         (int64_t)g.edge_kind.size(), g.edge_kind.data(), g.edge_from.data(), g.edge_to.data(), g.edge_meas.data(),
                         g.edge_info_upper.data());
@@ -162,6 +164,8 @@ void *pg_from_arrays(const char *name, int solver, const pgo_options *opt,
         g.vertex_id.assign(vid, vid + nv); g.vertex_kind.assign(vkind, vkind + nv); g.vertex_values.assign(vval, vval + n_values);
         g.edge_kind.assign(ekind, ekind + ne); g.edge_from.assign(efrom, efrom + ne); g.edge_to.assign(eto, eto + ne);
         g.edge_meas.assign(emeas, emeas + n_meas); g.edge_info_upper.assign(einfo, einfo + n_info);
+        std::string verr;
+        if (!validate_graph(g, verr)) throw Error(verr);
         for (int64_t i = 0; i < nv; i++) g.len += vkind[i] == 0 ? 3 : vkind[i] == 1 ? 2 : 6;
         return new PoseGraph(std::move(g), name ? name : "graph", solver ? PoseGraphSolver::LevenbergMarquardt : PoseGraphSolver::GaussNewton, opt);
     } catch (const std::exception &e) { g_err = e.what(); return nullptr; }

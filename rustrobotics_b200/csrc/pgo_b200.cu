@@ -12,6 +12,11 @@
 // exchanges partial sums through peer memory.
 #include <algorithm>
 #include <cmath>
+#include <condition_variable>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -23,8 +28,6 @@
 #include "../../include/pgo_b200.h"
 #include "kernels.cuh"
 #include "peer.cuh"
-#include "tail.cuh"
-#include "deep.cuh"
 
 using namespace pgo;
 
@@ -70,8 +73,15 @@ struct ArenaReq { double **p; size_t count; };
 
 } // namespace
 
+struct MultiCtx;
+
 struct pgo_handle {
-    Symbolic sym;
+    // the symbolic pass is built once per graph; the shards of a single-process multi-GPU handle share it (read-only)
+    std::shared_ptr<Symbolic> symp;
+    Symbolic &sym;
+    explicit pgo_handle(std::shared_ptr<Symbolic> s = std::make_shared<Symbolic>()) : symp(std::move(s)), sym(*symp) {}
+    MultiCtx *multi = nullptr;         // single-process multi-GPU handle (pgo_options.n_gpus > 1): this handle only dispatches to its shards
+    bool ipc_peer[MAX_RANKS]{};        // peer_base[k] was opened with cudaIpcOpenMemHandle (process-per-GPU mode)
     pgo_options opt{};
     int device = 0, world = 1, rank = 0;
     bool connected = false;
@@ -102,36 +112,12 @@ struct pgo_handle {
     bool use_amg = false, omega_ready = false;
     int spmv_tma64 = 0, spmv_tma32 = 0; // PGO_SPMV_TMA64 / PGO_SPMV_TMA32: ring depth of the TMA-staged sliced SpMV (0: register-staged kernel)
     int64_t lpr4_min_rows = 16384;     // PGO_LPR4_MIN_ROWS
-    // cluster-resident deep-levels kernel (deep.cuh): levels >= deep_level run as one cluster launch per coarse solve
-    bool opt_deep = false;             // PGO_DEEP=1 enables.  OFF by default: measured on B200 (profiles/r01x_deep_experiment.log) a level-2
-                                       // coarse solve takes 86 us in the cluster kernel vs 53 us as 16 graph-launched kernels -- a stage is a
-                                       // chain of dependent L2 accesses either way, and 16 SMs give each row fewer lanes than a full-grid launch
-    int opt_deep_dense = 0;            // PGO_DEEP_DENSE: 1 = the dense coarsest apply runs inside the cluster kernel, 0 = separate launches
-    int64_t deep_max_rows = 8192;      // PGO_DEEP_MAX_ROWS
-    int deep_level = -1, deep_nc = 0, deep_ops = 0;
-    bool deep_defer = false, deep_dense_inline = true, deep_checked = false;
-    DeepOp *deep_prog = nullptr;
-    LevelDev *deep_lv = nullptr;
-    std::vector<DeepOp> deep_host;
     bool pdl = true;                   // programmatic dependent launch of every kernel (PGO_PDL=0 disables)
     cudaError_t launch_err = cudaSuccess;
     bool lowp = false;                 // the cycle's SpMVs read fp32 copies of the stored blocks (opt.amg_fp64_storage == 0)
-    bool tail_fail = false;
-    bool opt_tail = false;             // PGO_TAIL=1 enables the persistent coarse-tail kernel.  OFF by default: measured on B200
-                                       // (profiles/r01j_tail_experiment.log) it is 8 % SLOWER than one graph-launched kernel per
-                                       // stage: a stage is a ~3 us chain of dependent L2 loads either way, a grid-wide barrier
-                                       // costs about what a kernel boundary inside a CUDA graph costs, and the 80-register
-                                       // persistent CTAs hold fewer warps in flight for the 62k-row level than stand-alone launches
-    int tail_ctas_per_sm = 4;          // PGO_TAIL_CTAS_PER_SM
-    int64_t tail_max_rows = 262144;    // a level larger than this is bandwidth-bound on its own: not worth serialising in the tail
     int64_t anchor_row = -1;
     cudaGraphExec_t pcg_graph = nullptr;
     int chunk = 8;
-    // persistent coarse-tail kernel (tail.cuh): levels >= tail_level run as ONE cooperative launch per coarse solve
-    int tail_level = -1, tail_grid = 0, tail_ops = 0;
-    size_t tail_smem = 0;
-    TailOp *tail_prog = nullptr;
-    LevelDev *tail_lv = nullptr;
     int64_t launches_per_iter = 0;
     cudaEvent_t ev[PGO_NUM_PHASES + 2]{}, poll_ev[2]{};
     double ms[PGO_NUM_PHASES]{};
@@ -271,243 +257,6 @@ template <int D> void dense_apply(pgo_handle *h, int l, const double *rhs, doubl
     h->launch_count += 1;
 }
 
-// ---- persistent coarse tail: record the stage program of coarse_solve(T, lv[T].rhs -> lv[T].sol), launch it
-template <int D> void rec_coarse_solve(pgo_handle *h, int l, const double *rhs, double *out, std::vector<TailOp> &P);
-
-inline TailOp tail_op(int type, int lvl, int nvb) { TailOp o{}; o.type = type; o.lvl = lvl; o.nvb = nvb; o.fin = FIN_NONE; return o; }
-
-template <int D> void rec_spmv(pgo_handle *h, int l, int mode, int fin, const double *x, const double *r, double *y, double omega,
-                               const double *u1, const double *u2, std::vector<TailOp> &P) {
-    LevelBuf &B = h->lv[l];
-    TailOp o = tail_op(TOP_SPMV, l, B.lpr == 8 ? B.grid8 : B.gridw);       // the grids of the stand-alone launches
-    o.mode = mode; o.fin = fin; o.lpr = B.lpr == 8 ? 8 : 32;
-    o.a = x; o.b = r; o.c = u1; o.d = u2; o.out = y; o.omega = omega;
-    P.push_back(o);
-}
-
-template <int D> void rec_cycle(pgo_handle *h, int l, const double *rhs, double *out, std::vector<TailOp> &P) {
-    LevelBuf &B = h->lv[l];
-    const int last = (int)h->lv.size() - 1;
-    const int nvb_rows = grid_for(B.d.n_pad, 256);
-    if (l == last) {
-        if (h->sym.dense_coarsest) {
-            TailOp o = tail_op(TOP_DENSE, l, grid_for(B.d.n * D, 8)); o.a = rhs; o.out = out; P.push_back(o);
-        } else {
-            TailOp o = tail_op(TOP_DINV, l, nvb_rows); o.a = rhs; o.out = B.xa; o.omega = B.omega; P.push_back(o);
-            rec_spmv<D>(h, l, 2, FIN_NONE, B.xa, rhs, B.res, B.omega, nullptr, nullptr, P);
-            rec_spmv<D>(h, l, 2, FIN_NONE, B.res, rhs, out, B.omega, nullptr, nullptr, P);
-        }
-        return;
-    }
-    LevelBuf &C = h->lv[l + 1];
-    { TailOp o = tail_op(TOP_DINV, l, nvb_rows); o.a = rhs; o.out = B.xa; o.omega = B.omega; P.push_back(o); }
-    rec_spmv<D>(h, l, 1, FIN_NONE, B.xa, rhs, B.res, 0.0, nullptr, nullptr, P);
-    { TailOp o = tail_op(TOP_RESTRICT, l, C.gridw); o.a = B.res; o.out = C.rhs; P.push_back(o); }
-    rec_coarse_solve<D>(h, l + 1, C.rhs, C.sol, P);
-    { TailOp o = tail_op(TOP_PROLONG, l, nvb_rows); o.a = C.sol; o.out = B.xa; P.push_back(o); }
-    rec_spmv<D>(h, l, 2, FIN_NONE, B.xa, rhs, out, B.omega, nullptr, nullptr, P);
-}
-
-template <int D> void rec_coarse_solve(pgo_handle *h, int l, const double *rhs, double *out, std::vector<TailOp> &P) {
-    LevelBuf &B = h->lv[l];
-    const int last = (int)h->lv.size() - 1;
-    if (l == last || !B.kcycle) { rec_cycle<D>(h, l, rhs, out, P); return; }
-    rec_cycle<D>(h, l, rhs, B.c1, P);
-    rec_spmv<D>(h, l, 0, FIN_K1, B.c1, nullptr, B.v1, 0.0, rhs, nullptr, P);
-    { TailOp o = tail_op(TOP_KCOMBINE, l, B.gridv); o.mode = 0; o.a = rhs; o.b = B.v1; o.out = B.r1; P.push_back(o); }
-    rec_cycle<D>(h, l, B.r1, B.c2, P);
-    rec_spmv<D>(h, l, 0, FIN_K2, B.c2, nullptr, B.v2, 0.0, B.v1, B.r1, P);
-    { TailOp o = tail_op(TOP_KCOMBINE, l, B.gridv); o.mode = 1; o.a = B.c1; o.b = B.c2; o.out = out; P.push_back(o); }
-}
-
-// (re)build the stage program; called whenever the PCG graph is (re)captured (the smoother dampings are baked in)
-template <int D> int build_tail(pgo_handle *h) {
-    h->tail_level = -1;
-    if (!h->use_amg || !h->opt_tail) return PGO_OK;
-    const int nl = (int)h->lv.size(), last = nl - 1;
-    int T = -1;
-    for (int l = 1; l < last; l++) {
-        bool ok = (h->world == 1 || h->lv[l].repl) && h->lv[l].d.n <= h->tail_max_rows;
-        for (int k = l; k < nl && ok; k++) ok = !h->lv[k].jds;
-        if (ok) { T = l; break; }
-    }
-    if (T < 0) return PGO_OK;
-    std::vector<TailOp> P;
-    rec_coarse_solve<D>(h, T, h->lv[T].rhs, h->lv[T].sol, P);
-    std::vector<LevelDev> lv(nl);
-    for (int l = 0; l < nl; l++) lv[l] = h->lv[l].d;
-    if (!h->tail_lv) { int rc = dalloc(h, &h->tail_lv, (size_t)nl, false); if (rc) return rc; }
-    CK(cudaMemcpyAsync(h->tail_lv, lv.data(), nl * sizeof(LevelDev), cudaMemcpyHostToDevice, h->stream));
-    if (!h->tail_prog || (int)P.size() > h->tail_ops) { int rc = dalloc(h, &h->tail_prog, P.size(), false); if (rc) return rc; }
-    CK(cudaMemcpyAsync(h->tail_prog, P.data(), P.size() * sizeof(TailOp), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));          // P / lv are stack-owned
-    h->tail_ops = (int)P.size();
-    h->tail_smem = h->sym.dense_coarsest ? sizeof(double) * (size_t)h->dense_m : 0;
-    int per_sm = 0, sms = 0, coop = 0;
-    CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
-    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
-    CK(cudaFuncSetAttribute(k_tail<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(h->tail_smem, 1024)));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tail<D>, 256, h->tail_smem));
-    if (!coop || per_sm < 1) return PGO_OK;        // no cooperative launch: keep the stage-per-kernel path
-    h->tail_grid = std::min(per_sm, h->tail_ctas_per_sm) * sms;
-    h->tail_level = T;
-    return PGO_OK;
-}
-
-template <int D> void launch_tail(pgo_handle *h) {
-    TailCtx T{};
-    T.prog = h->tail_prog; T.n_ops = h->tail_ops; T.lv = h->tail_lv;
-    T.dmap = h->dmap; T.dense_m = h->dense_m; T.Ainv = h->Ainv;
-    T.S = h->S; T.partials = h->partials;
-    void *args[] = {(void *)&T};
-    cudaError_t e = cudaLaunchCooperativeKernel((void *)k_tail<D>, dim3(h->tail_grid), dim3(256), args, h->tail_smem, h->stream);
-    if (e != cudaSuccess) { h->tail_fail = true; h->err = std::string("cooperative launch of the coarse-tail kernel failed: ") + cudaGetErrorString(e); }
-    h->launch_count += 1;
-}
-
-// ---- cluster-resident deep levels (deep.cuh): record the stage program of coarse_solve(T, rhs -> sol), launch it
-inline DeepOp deep_op(int type, int lvl) { DeepOp o{}; o.type = type; o.lvl = lvl; o.fin = FIN_NONE; return o; }
-
-template <int D> void drec_solve(pgo_handle *h, int l, const double *rhs, double *out, bool defer, std::vector<DeepOp> &P);
-
-template <int D> void drec_spmv(pgo_handle *h, int l, int mode, int fin, const double *x, const double *r, double *y, double omega,
-                                const double *u1, const double *u2, std::vector<DeepOp> &P) {
-    DeepOp o = deep_op(DOP_SPMV, l);
-    o.mode = mode; o.fin = fin; o.a = x; o.b = r; o.c = u1; o.d = u2; o.out = y; o.omega = omega;
-    P.push_back(o);
-}
-
-template <int D> void drec_cycle(pgo_handle *h, int l, const double *rhs, double *out, bool pre, std::vector<DeepOp> &P) {
-    LevelBuf &B = h->lv[l];
-    const int last = (int)h->lv.size() - 1;
-    if (l == last) { DeepOp o = deep_op(DOP_DENSE, l); o.a = rhs; o.out = out; P.push_back(o); return; }
-    LevelBuf &C = h->lv[l + 1];
-    if (!pre) { DeepOp o = deep_op(DOP_DINV, l); o.a = rhs; o.out = B.xa; o.omega = B.omega; P.push_back(o); }
-    drec_spmv<D>(h, l, 1, FIN_NONE, B.xa, rhs, B.res, 0.0, nullptr, nullptr, P);
-    { DeepOp o = deep_op(DOP_RESTRICT, l); o.a = B.res; o.out = C.rhs; P.push_back(o); }
-    const bool kfold = l + 1 != last && C.kcycle;
-    drec_solve<D>(h, l + 1, C.rhs, C.sol, kfold, P);
-    if (kfold) { DeepOp o = deep_op(DOP_PROLONGK, l); o.a = C.c1; o.b = C.c2; o.c = C.ksteps == 3 ? C.c3 : nullptr; o.out = B.xa; P.push_back(o); }
-    else { DeepOp o = deep_op(DOP_PROLONG, l); o.a = C.sol; o.out = B.xa; P.push_back(o); }
-    drec_spmv<D>(h, l, 2, FIN_NONE, B.xa, rhs, out, B.omega, nullptr, nullptr, P);
-}
-
-template <int D> void drec_solve(pgo_handle *h, int l, const double *rhs, double *out, bool defer, std::vector<DeepOp> &P) {
-    LevelBuf &B = h->lv[l];
-    const int last = (int)h->lv.size() - 1;
-    if (l == last || !B.kcycle) { drec_cycle<D>(h, l, rhs, out, false, P); return; }
-    drec_cycle<D>(h, l, rhs, B.c1, false, P);
-    drec_spmv<D>(h, l, 0, FIN_K1, B.c1, nullptr, B.v1, 0.0, rhs, nullptr, P);
-    { DeepOp o = deep_op(DOP_KRESID, l); o.mode = 1; o.a = rhs; o.b = B.v1; o.out = B.r1; o.d = B.xa; o.omega = B.omega; P.push_back(o); }
-    drec_cycle<D>(h, l, B.r1, B.c2, true, P);
-    drec_spmv<D>(h, l, 0, FIN_K2, B.c2, nullptr, B.v2, 0.0, B.v1, B.r1, P);
-    const double *c3 = nullptr;
-    if (B.ksteps == 3) {
-        { DeepOp o = deep_op(DOP_KRESID, l); o.mode = 2; o.a = B.r1; o.b = B.v1; o.c = B.v2; o.out = B.r1; o.d = B.xa; o.omega = B.omega; P.push_back(o); }
-        drec_cycle<D>(h, l, B.r1, B.c3, true, P);
-        drec_spmv<D>(h, l, 0, FIN_K3, B.c3, B.r1, B.res, 0.0, B.v1, B.v2, P);
-        c3 = B.c3;
-    }
-    if (!defer) { DeepOp o = deep_op(DOP_KCOMBINE, l); o.mode = c3 ? 2 : 1; o.a = B.c1; o.b = B.c2; o.c = c3; o.out = out; P.push_back(o); }
-}
-
-template <int D, bool LOWP> cudaError_t deep_launch_seg(pgo_handle *h, int op0, int op1, size_t smem) {
-    DeepCtx T{};
-    T.prog = h->deep_prog; T.op0 = op0; T.op1 = op1; T.lv = h->deep_lv;
-    T.dense_m = h->dense_m; T.Ainv = h->Ainv; T.S = h->S;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(h->deep_nc); cfg.blockDim = dim3(DEEP_NT); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
-    cudaLaunchAttribute at[2];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = h->deep_nc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = h->pdl ? 2 : 1;
-    return cudaLaunchKernelEx(&cfg, k_deep<D, LOWP>, T);
-}
-
-// (re)build the stage program; called whenever the PCG graph is (re)captured (the smoother dampings are baked in)
-template <int D> int build_deep(pgo_handle *h) {
-    h->deep_level = -1;
-    if (!h->use_amg || !h->opt_deep || h->opt_tail || !h->sym.dense_coarsest) return PGO_OK;
-    const int nl = (int)h->lv.size(), last = nl - 1;
-    int T = -1;
-    for (int l = 1; l < last; l++) {
-        bool ok = true;
-        for (int k = l; k < nl && ok; k++)
-            ok = (h->world == 1 || h->lv[k].repl) && !h->lv[k].jds && h->lv[k].d.n <= h->deep_max_rows;
-        if (ok) { T = l; break; }
-    }
-    if (T < 0) return PGO_OK;
-    // cluster size: 16 CTAs (non-portable) when the device can place such a cluster, else 8
-    if (!h->deep_checked) {
-        h->deep_checked = true;
-        h->deep_nc = 0;
-        const size_t smem = sizeof(double) * (size_t)h->dense_m;
-        for (int nc : {16, 8}) {
-            cudaError_t e1, e2;
-            if (h->lowp) {
-                e1 = cudaFuncSetAttribute(k_deep<D, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-                e2 = cudaFuncSetAttribute(k_deep<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024));
-            } else {
-                e1 = cudaFuncSetAttribute(k_deep<D, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-                e2 = cudaFuncSetAttribute(k_deep<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024));
-            }
-            if (e1 != cudaSuccess || e2 != cudaSuccess) { (void)cudaGetLastError(); continue; }
-            cudaLaunchConfig_t cfg{};
-            cfg.gridDim = dim3(nc); cfg.blockDim = dim3(DEEP_NT); cfg.dynamicSmemBytes = smem;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = nc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            cfg.attrs = at; cfg.numAttrs = 1;
-            int n_clusters = 0;
-            cudaError_t e = h->lowp ? cudaOccupancyMaxActiveClusters(&n_clusters, k_deep<D, true>, &cfg)
-                                    : cudaOccupancyMaxActiveClusters(&n_clusters, k_deep<D, false>, &cfg);
-            if (e == cudaSuccess && n_clusters >= 1) { h->deep_nc = nc; break; }
-            (void)cudaGetLastError();
-        }
-    }
-    if (h->deep_nc == 0) return PGO_OK;
-    const bool defer = h->lv[T].kcycle;             // the parent's prolongation folds the final combination (cycle(): kfold)
-    std::vector<DeepOp> P;
-    drec_solve<D>(h, T, h->lv[T].rhs, h->lv[T].sol, defer, P);
-    std::vector<LevelDev> lv(nl);
-    for (int l = 0; l < nl; l++) lv[l] = h->lv[l].d;
-    if (!h->deep_lv) { int rc = dalloc(h, &h->deep_lv, (size_t)nl, false); if (rc) return rc; }
-    CK(cudaMemcpyAsync(h->deep_lv, lv.data(), nl * sizeof(LevelDev), cudaMemcpyHostToDevice, h->stream));
-    if (!h->deep_prog || (int)P.size() > h->deep_ops) { int rc = dalloc(h, &h->deep_prog, P.size(), false); if (rc) return rc; }
-    CK(cudaMemcpyAsync(h->deep_prog, P.data(), P.size() * sizeof(DeepOp), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    h->deep_ops = (int)P.size();
-    h->deep_host = P;
-    h->deep_defer = defer;
-    // the dense apply is a bandwidth problem (the fp64 inverse, 12 MB at config 4, read by 16 SMs): separate launches by default
-    h->deep_dense_inline = h->opt_deep_dense != 0;
-    h->deep_level = T;
-    return PGO_OK;
-}
-
-template <int D> void dense_apply(pgo_handle *h, int l, const double *rhs, double *out);
-
-template <int D> void launch_deep(pgo_handle *h) {
-    const size_t smem = sizeof(double) * (size_t)h->dense_m;
-    auto seg = [&](int a, int b, size_t sm) {
-        if (a >= b) return;
-        cudaError_t e = h->lowp ? deep_launch_seg<D, true>(h, a, b, sm) : deep_launch_seg<D, false>(h, a, b, sm);
-        if (e != cudaSuccess && h->launch_err == cudaSuccess) h->launch_err = e;
-        h->launch_count += 1;
-    };
-    if (h->deep_dense_inline) { seg(0, h->deep_ops, smem); return; }
-    int a = 0;
-    for (int i = 0; i < h->deep_ops; i++) {
-        if (h->deep_host[i].type != DOP_DENSE) continue;
-        seg(a, i, 0);
-        dense_apply<D>(h, h->deep_host[i].lvl, h->deep_host[i].a, h->deep_host[i].out);
-        a = i + 1;
-    }
-    seg(a, h->deep_ops, 0);
-}
-
 // ---- one multigrid cycle at level l: out = M_l(rhs).  FINK: dots fused into the last kernel (level 0 only).
 // PRE: the pre-smoothing step xa = omega Dinv rhs was already done by the caller (fused into the PCG update kernel)
 template <int D, int FINK, bool PRE = false> void cycle(pgo_handle *h, int l, const double *rhs, double *out) {
@@ -541,9 +290,8 @@ template <int D, int FINK, bool PRE = false> void cycle(pgo_handle *h, int l, co
         gather_rows(h, C.rhs, C.src_rows, VecStride<D>::value, 1, 0, 1);
     }
     // a K-cycle level leaves its two search directions in C.c1 / C.c2; their final combination is folded into the prolongation
-    const bool kfold = h->tail_level != l + 1 && l + 1 != last && C.kcycle;
-    if (h->tail_level == l + 1) launch_tail<D>(h);   // the whole coarse solve C.rhs -> C.sol in one cooperative launch
-    else coarse_solve<D>(h, l + 1, C.rhs, C.sol, kfold);
+    const bool kfold = l + 1 != last && C.kcycle;
+    coarse_solve<D>(h, l + 1, C.rhs, C.sol, kfold);
     if (kfold) launch_k(h, k_prolong_k<D>, B.grid128, 128, 0, B.d, C.c1, C.c2, C.ksteps == 3 ? C.c3 : nullptr, B.xa, h->S, l + 1);
     else launch_k(h, k_prolong<D>, B.grid128, 128, 0, B.d, C.sol, B.xa, h->S);
     h->launch_count += 1;
@@ -556,8 +304,6 @@ template <int D, int FINK, bool PRE = false> void cycle(pgo_handle *h, int l, co
 template <int D> void coarse_solve(pgo_handle *h, int l, const double *rhs, double *out, bool defer_combine) {
     LevelBuf &B = h->lv[l];
     const int last = (int)h->lv.size() - 1;
-    // the levels from deep_level down run as one cluster launch (the program was recorded for exactly this call)
-    if (l == h->deep_level && rhs == B.rhs && out == B.sol && defer_combine == h->deep_defer) { launch_deep<D>(h); return; }
     if (l == last || !B.kcycle) { cycle<D, FIN_NONE>(h, l, rhs, out); return; }
     cycle<D, FIN_NONE>(h, l, rhs, B.c1);
     spmv<D, 0, FIN_K1, true>(h, l, B.c1, nullptr, B.v1, 0.0, rhs, nullptr, 1);
@@ -613,31 +359,18 @@ template <int D> void pcg_iteration(pgo_handle *h) {
 
 template <int D> int build_pcg_graph(pgo_handle *h) {
     if (h->pcg_graph) return PGO_OK;
-    { int rc = build_tail<D>(h); if (rc) return rc; }
-    { int rc = build_deep<D>(h); if (rc) return rc; }
     cudaGraph_t g = nullptr;
     int64_t before = h->launch_count;
     CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
     for (int i = 0; i < h->chunk; i++) pcg_iteration<D>(h);
-    cudaError_t ce = cudaStreamEndCapture(h->stream, &g);
-    if (h->tail_fail || (ce != cudaSuccess && h->tail_level >= 0)) {
-        // the cooperative launch cannot be captured on this driver: fall back to one kernel per stage
-        if (g) cudaGraphDestroy(g);
-        (void)cudaGetLastError();
-        h->tail_fail = false; h->opt_tail = false; h->tail_level = -1; h->err.clear();
-        h->launch_count = before;
-        return build_pcg_graph<D>(h);
-    }
-    cudaError_t ie = ce;
+    cudaError_t ie = cudaStreamEndCapture(h->stream, &g);
     if (ie == cudaSuccess && h->launch_err != cudaSuccess) ie = h->launch_err;
     if (ie == cudaSuccess) ie = cudaGraphInstantiate(&h->pcg_graph, g, 0);
     if (g) cudaGraphDestroy(g);
-    if (ie != cudaSuccess && (h->deep_level >= 0 || h->pdl)) {
-        // a cluster launch / programmatic dependent launch edges not accepted by this driver inside a captured graph:
-        // first give up the cluster-resident deep-levels kernel, then the programmatic launches
+    if (ie != cudaSuccess && h->pdl) {
+        // programmatic dependent launch edges not accepted by this driver inside a captured graph: capture again without them
         (void)cudaGetLastError();
-        if (h->deep_level >= 0) { h->opt_deep = false; h->deep_level = -1; }
-        else h->pdl = false;
+        h->pdl = false;
         h->launch_err = cudaSuccess; h->pcg_graph = nullptr;
         h->launch_count = before;
         return build_pcg_graph<D>(h);
@@ -662,7 +395,7 @@ template <int D> int assemble(pgo_handle *h, double lambda, int add_lambda) {
 }
 
 int comm_status(pgo_handle *h, const Scalars &s) {
-    if (s.status == ST_COMM) { h->err = "peer synchronisation timed out (a rank is missing or out of step)"; return PGO_ERR_NCCL; }
+    if (s.status == ST_COMM) { h->err = "peer synchronisation timed out (a rank is missing or out of step)"; return PGO_ERR_COMM; }
     return PGO_OK;
 }
 
@@ -794,7 +527,6 @@ template <int D> int solve(pgo_handle *h, int32_t *iters_out) {
     if (rc) return rc;
     CK(cudaMemsetAsync(h->x, 0, nd * sizeof(double), h->stream));
     precondition<D, FIN_RZ_INIT>(h);
-    if (h->tail_fail) { h->tail_fail = false; return PGO_ERR_CUDA; }
     CK(cudaMemcpyAsync(h->p, h->z, nd * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     xbarrier(h);
     // keep two graph launches in flight; poll the pinned scalars of the older one
@@ -863,7 +595,7 @@ template <int D> int time_coarse(pgo_handle *h, int level, int repeats, double *
     const int64_t before = h->launch_count;
     if (!h->pcg_graph) { int rc2 = build_pcg_graph<D>(h); if (rc2) return rc2; }
     CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-    coarse_solve<D>(h, level, B.rhs, B.sol, level == h->deep_level ? h->deep_defer : false);
+    coarse_solve<D>(h, level, B.rhs, B.sol, false);
     CK(cudaStreamEndCapture(h->stream, &g));
     const int64_t per = h->launch_count - before;
     CK(cudaGraphInstantiate(&ge, g, 0));
@@ -883,6 +615,8 @@ template <int D> int time_coarse(pgo_handle *h, int level, int repeats, double *
 
 // block dimension dispatch: 3 (SE2 / XY graphs) or 6 (SE3 graphs)
 #define BY_D(h, fn, ...) ((h)->sym.D == 6 ? fn<6>(__VA_ARGS__) : fn<3>(__VA_ARGS__))
+
+void multi_shutdown(pgo_handle *h);
 
 int fail_create(pgo_handle *h, int rc, const std::string &msg) {
     g_create_error = msg.empty() ? h->err : msg;
@@ -919,10 +653,11 @@ const char *pgo_last_error(const pgo_handle *h) { return h ? h->err.c_str() : g_
 
 void pgo_destroy(pgo_handle *h) {
     if (!h) return;
+    if (h->multi) multi_shutdown(h);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->pcg_graph) cudaGraphExecDestroy(h->pcg_graph);
     for (int k = 0; k < MAX_RANKS; k++)
-        if (h->peer_base[k] && k != h->rank) cudaIpcCloseMemHandle(h->peer_base[k]);
+        if (h->peer_base[k] && h->ipc_peer[k]) cudaIpcCloseMemHandle(h->peer_base[k]);
     for (void *p : h->allocs) cudaFree(p);
     if (h->hS) cudaFreeHost(h->hS);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
@@ -931,69 +666,21 @@ void pgo_destroy(pgo_handle *h) {
     delete h;
 }
 
-int pgo_create(pgo_handle **out, const pgo_options *opt_in,
-               int64_t nv, const uint32_t *vid, const uint8_t *vkind, const double *vval,
-               int64_t ne, const uint8_t *ekind, const uint32_t *efrom, const uint32_t *eto,
-               const double *emeas, const double *einfo) {
-    if (!out) return PGO_ERR_ARG;
-    *out = nullptr;
-    if (!vid || !vkind || !vval || nv <= 0 || ne < 0 || (ne > 0 && (!ekind || !efrom || !eto || !emeas || !einfo))) {
-        g_create_error = "pgo_create: null or empty input";
-        return PGO_ERR_ARG;
-    }
-    pgo_handle *h = new pgo_handle();
-    if (opt_in) h->opt = *opt_in; else pgo_default_options(&h->opt);
-    pgo_options dflt; pgo_default_options(&dflt);
-    if (h->opt.pcg_rtol <= 0) h->opt.pcg_rtol = dflt.pcg_rtol;
-    if (h->opt.pcg_max_iterations <= 0) h->opt.pcg_max_iterations = dflt.pcg_max_iterations;
-    if (h->opt.sort_window <= 0) h->opt.sort_window = dflt.sort_window;
-    if (h->opt.amg_max_levels <= 0) h->opt.amg_max_levels = dflt.amg_max_levels;
-    if (h->opt.amg_max_levels > MAX_LEVELS) h->opt.amg_max_levels = MAX_LEVELS;
-    if (h->opt.anchor_weight == 0) h->opt.anchor_weight = dflt.anchor_weight;
-    if (h->opt.world <= 0) h->opt.world = 1;
-    if (h->opt.amg_dense_max <= 0) h->opt.amg_dense_max = dflt.amg_dense_max;
-    if (h->opt.amg_dense_max > 1024) h->opt.amg_dense_max = 1024;
-    // default upper bound on the members of an aggregate: 16 on one GPU (measured optimum at config 4, profiles/r02f_knob_sweep.log).
-    // Sharded handles use 24: the partition-local level-0 aggregation leaves a larger, less regular level 1, and with 16 the
-    // multilevel K-cycle needs 51 PCG iterations at world 2 and 8 where one GPU needs 41; with 24 the scipy prototype fed with
-    // the library's own aggregates (tools/research/hierarchy_study.py, which reproduces 42 / 51 for the old default) gives
-    // 43 (world 2) and 45 (world 8).  On one GPU 24 measures the same as 16 (41 iterations, 34.26 vs 34.19 ms).
-    if (h->opt.amg_aggregate_size <= 1) h->opt.amg_aggregate_size = h->opt.world > 1 ? 24 : 16;
-    h->use_amg = h->opt.preconditioner == PGO_PRECOND_AMG;
-    h->world = h->opt.world; h->rank = h->opt.rank;
-    if (h->rank < 0 || h->rank >= h->world) return fail_create(h, PGO_ERR_ARG, "pgo_create: rank out of range");
+} // extern "C"
 
-    SymbolicOptions so;
-    so.world = h->world;
-    so.sort_window = h->opt.sort_window;
-    so.max_levels = h->opt.amg_max_levels;
-    so.agg_size = h->opt.amg_aggregate_size;
-    so.dense_max = h->opt.amg_dense_max;
-    so.build_amg = h->use_amg;
-    if (const char *e = std::getenv("PGO_REPL_MAX_ROWS")) so.repl_max_rows = std::atoll(e);      // tuning knobs
-    if (const char *e = std::getenv("PGO_SPMV_TMA64")) h->spmv_tma64 = std::max(0, std::min(16, std::atoi(e)));
-    if (const char *e = std::getenv("PGO_SPMV_TMA32")) h->spmv_tma32 = std::max(0, std::min(16, std::atoi(e)));
-    if (const char *e = std::getenv("PGO_LPR4_MIN_ROWS")) h->lpr4_min_rows = std::atoll(e);
-    if (const char *e = std::getenv("PGO_DEEP")) h->opt_deep = std::atoi(e) != 0;
-    if (const char *e = std::getenv("PGO_DEEP_DENSE")) h->opt_deep_dense = std::atoi(e);
-    if (const char *e = std::getenv("PGO_DEEP_MAX_ROWS")) h->deep_max_rows = std::atoll(e);
-    if (const char *e = std::getenv("PGO_PDL")) h->pdl = std::atoi(e) != 0;
-    if (const char *e = std::getenv("PGO_TAIL")) h->opt_tail = std::atoi(e) != 0;
-    if (const char *e = std::getenv("PGO_TAIL_CTAS_PER_SM")) h->tail_ctas_per_sm = std::max(1, std::atoi(e));
-    if (const char *e = std::getenv("PGO_TAIL_MAX_ROWS")) h->tail_max_rows = std::atoll(e);
-    h->lowp = h->use_amg && h->opt.amg_fp64_storage == 0 && !h->opt_tail;   // the coarse-tail experiment only knows fp64 blocks
-    if (!build_symbolic(h->sym, so, nv, vid, vkind, ne, ekind, efrom, eto)) return fail_create(h, PGO_ERR_ARG, h->sym.error);
+// device-resident state of one handle (a single-GPU handle, one rank of a process-per-GPU job, or one shard of a single-process
+// multi-GPU handle): h->sym / h->opt / world / rank are set.  Runs on the thread that will own the shard's CUDA device.
+static int create_shard(pgo_handle *h, const double *vval, int64_t ne, const uint8_t *ekind, const double *emeas, const double *einfo) {
     Symbolic &S = h->sym;
     // per-dimension record sizes (kernels.cuh: Dim<D>)
     const int D = S.D, DD = D * D, VS = D == 6 ? 6 : 4, PS = D == 6 ? 8 : 4, NG = D == 6 ? 3 : 2, LS = D == 6 ? 4 : 2, NM = D == 6 ? 28 : 10;
 
-    if (h->opt.device == -2) { *out = h; return PGO_OK; }   // structure-only handle (no device): symbolic-pass queries only
     int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail_create(h, PGO_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
-    if (h->opt.device >= 0) { if (cudaSetDevice(h->opt.device) != cudaSuccess) return fail_create(h, PGO_ERR_CUDA, "cudaSetDevice failed"); }
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { h->err = "no CUDA device available (this library has no CPU fallback)"; return PGO_ERR_CUDA; }
+    if (h->opt.device >= 0) { if (cudaSetDevice(h->opt.device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return PGO_ERR_CUDA; } }
     cudaGetDevice(&h->device);
-#define CKC(call) do { int rc_ = (call); if (rc_) return fail_create(h, rc_, ""); } while (0)
-#define CKU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail_create(h, PGO_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+#define CKC(call) do { int rc_ = (call); if (rc_) return rc_; } while (0)
+#define CKU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return PGO_ERR_CUDA; } } while (0)
     CKU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     for (auto &e : h->ev) CKU(cudaEventCreate(&e));
     for (auto &e : h->poll_ev) CKU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1012,7 +699,7 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
         // a replicated level (sharded handles only) has ONE partition that every rank holds completely
         B.repl = world > 1 && H.repl;
         B.first_repl = B.repl && !S.levels[l - 1].repl;
-        if (B.repl && H.jds) return fail_create(h, PGO_ERR_UNSUPPORTED, "replicated levels must be block CSR");
+        if (B.repl && H.jds) { h->err = "replicated levels must be block CSR"; return PGO_ERR_UNSUPPORTED; }
         const int pk = B.repl ? 0 : rank;              // partition of this level held by this rank
         const int lworld = (int)H.part_real.size();
         const int64_t r0 = H.part_off[pk], r1 = H.part_off[pk + 1];
@@ -1036,7 +723,7 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
         B.grid4 = grid_for(d.n_pad, 64);
         B.lpr = (!H.jds && d.n > 0 && d.n_slots <= 12 * d.n) ? 8 : 32;     // short rows: 8 lanes per row
         // a big level with short rows: 4 lanes per row, so that the whole level is (about) one wave of CTAs
-        if (B.lpr == 8 && d.n >= h->lpr4_min_rows && !h->opt_tail) B.lpr = 4;
+        if (B.lpr == 8 && d.n >= h->lpr4_min_rows) B.lpr = 4;
         B.gridv = grid_for(d.n_pad * (VS / 2), 256);
         max_grid = std::max<int64_t>(max_grid, std::max(B.grid128, B.gridw));
         // row pointers
@@ -1063,7 +750,7 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
             std::vector<uint32_t> hs(std::max<size_t>(halo.size(), 1), 0);
             for (size_t i = 0; i < halo.size(); i++) { const int ow = H.part_of(halo[i]); hs[i] = ((uint32_t)ow << COL_OWNER_SHIFT) | (uint32_t)(halo[i] - H.part_off[ow]); }
             CKC(upload(h, &B.halo_src, hs));
-            if (d.n_pad + max_halo > (int64_t)COL_LOCAL_MASK) return fail_create(h, PGO_ERR_ARG, "level too large for the column word");
+            if (d.n_pad + max_halo > (int64_t)COL_LOCAL_MASK) { h->err = "level too large for the column word"; return PGO_ERR_ARG; }
         }
         max_pad += max_halo;                           // every vector of the level has room for the halo records behind its own rows
         auto local_index = [&](int64_t nb) -> uint32_t {   // index of a neighbour row in this rank's (halo-extended) vectors
@@ -1144,7 +831,7 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
         // PCG iterations and 40.3 -> 36.6 ms; on the 250k-pose SE3 sphere 38 -> 32 iterations but 29.4 -> 31.5 ms (its 6x6
         // coarse levels are the larger share of an iteration), so SE3 graphs keep two steps
         const int k3 = h->opt.amg_kcycle3 >= 0 ? h->opt.amg_kcycle3 : (D == 3 ? 1 : 0);
-        B.ksteps = (B.kcycle && l <= k3 && !h->opt_tail) ? 3 : 2;
+        B.ksteps = (B.kcycle && l <= k3) ? 3 : 2;
         B.vec_rows = max_pad;
     }
     {
@@ -1266,8 +953,221 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
     CKU(cudaStreamSynchronize(h->stream));
 #undef CKC
 #undef CKU
-    // the big transient host arrays are not needed any more
-    for (auto &L : S.levels) { L.ctgt.clear(); L.ctgt.shrink_to_fit(); L.cstr.clear(); L.cstr.shrink_to_fit(); }
+    return PGO_OK;
+}
+
+// ---- single-process multi-GPU handle (pgo_options.n_gpus > 1): one worker thread per shard, bound to the shard's device.
+// Every entry point hands the same call to all workers and waits for them: the kernels of different shards wait for each
+// other on the device (peer.cuh), so the shards' host sides must be able to block independently -- but the caller still sees
+// ONE blocking call on ONE handle from ONE thread, like the reference's `&mut self` methods (pose_graph_optimization.rs:215, :247).
+struct MultiCtx {
+    std::vector<pgo_handle *> shard;
+    std::vector<int> dev;
+    std::vector<std::thread> th;
+    std::mutex m;
+    std::condition_variable cv_go, cv_done;
+    std::function<int(pgo_handle *, int)> job;
+    uint64_t gen = 0;
+    int pending = 0;
+    bool stop = false;
+    std::vector<int> rc;
+};
+
+static void multi_worker(MultiCtx *M, int k) {
+    cudaSetDevice(M->dev[k]);
+    uint64_t seen = 0;
+    for (;;) {
+        std::function<int(pgo_handle *, int)> job;
+        {
+            std::unique_lock<std::mutex> lk(M->m);
+            M->cv_go.wait(lk, [&] { return M->stop || M->gen != seen; });
+            if (M->stop) return;
+            seen = M->gen;
+            job = M->job;
+        }
+        const int rc = job(M->shard[k], k);
+        {
+            std::lock_guard<std::mutex> lk(M->m);
+            M->rc[k] = rc;
+            if (--M->pending == 0) M->cv_done.notify_all();
+        }
+    }
+}
+
+// run fn(shard, k) on every shard's worker; returns the first non-zero status (and copies that shard's message)
+template <typename F> static int multi_run(pgo_handle *h, F &&fn) {
+    MultiCtx *M = h->multi;
+    const int n = (int)M->shard.size();
+    {
+        std::lock_guard<std::mutex> lk(M->m);
+        M->job = std::forward<F>(fn);
+        M->pending = n;
+        M->gen++;
+    }
+    M->cv_go.notify_all();
+    {
+        std::unique_lock<std::mutex> lk(M->m);
+        M->cv_done.wait(lk, [&] { return M->pending == 0; });
+        M->job = nullptr;
+    }
+    for (int k = 0; k < n; k++)
+        if (M->rc[k]) { if (M->shard[k]) h->err = "GPU shard " + std::to_string(k) + ": " + M->shard[k]->err; return M->rc[k]; }
+    return PGO_OK;
+}
+
+namespace { void multi_shutdown(pgo_handle *h) {
+    MultiCtx *M = h->multi;
+    if (!M) return;
+    if (!M->th.empty()) {
+        multi_run(h, [](pgo_handle *s, int) { pgo_destroy(s); return 0; });
+        { std::lock_guard<std::mutex> lk(M->m); M->stop = true; }
+        M->cv_go.notify_all();
+        for (auto &t : M->th) t.join();
+    } else for (pgo_handle *s : M->shard) pgo_destroy(s);
+    delete M;
+    h->multi = nullptr;
+} }
+
+static void normalise_options(pgo_options &o, int world) {
+    pgo_options dflt; pgo_default_options(&dflt);
+    if (o.pcg_rtol <= 0) o.pcg_rtol = dflt.pcg_rtol;
+    if (o.pcg_max_iterations <= 0) o.pcg_max_iterations = dflt.pcg_max_iterations;
+    if (o.sort_window <= 0) o.sort_window = dflt.sort_window;
+    if (o.amg_max_levels <= 0) o.amg_max_levels = dflt.amg_max_levels;
+    if (o.amg_max_levels > MAX_LEVELS) o.amg_max_levels = MAX_LEVELS;
+    if (o.anchor_weight == 0) o.anchor_weight = dflt.anchor_weight;
+    if (o.amg_dense_max <= 0) o.amg_dense_max = dflt.amg_dense_max;
+    if (o.amg_dense_max > 1024) o.amg_dense_max = 1024;
+    // default upper bound on the members of an aggregate: 16 on one GPU (measured optimum at config 4, profiles/r02f_knob_sweep.log).
+    // Sharded handles use 24: the partition-local level-0 aggregation leaves a larger, less regular level 1, and with 16 the
+    // multilevel K-cycle needs 51 PCG iterations at world 2 and 8 where one GPU needs 41; with 24 the scipy prototype fed with
+    // the library's own aggregates (tools/research/hierarchy_study.py, which reproduces 42 / 51 for the old default) gives
+    // 43 (world 2) and 45 (world 8).  On one GPU 24 measures the same as 16 (41 iterations, 34.26 vs 34.19 ms).
+    if (o.amg_aggregate_size <= 1) o.amg_aggregate_size = world > 1 ? 24 : 16;
+}
+
+// options + environment knobs -> handle fields (h->opt, world, rank set)
+static SymbolicOptions configure_handle(pgo_handle *h) {
+    h->use_amg = h->opt.preconditioner == PGO_PRECOND_AMG;
+    SymbolicOptions so;
+    so.world = h->world;
+    so.sort_window = h->opt.sort_window;
+    so.max_levels = h->opt.amg_max_levels;
+    so.agg_size = h->opt.amg_aggregate_size;
+    so.dense_max = h->opt.amg_dense_max;
+    so.build_amg = h->use_amg;
+    if (const char *e = std::getenv("PGO_REPL_MAX_ROWS")) so.repl_max_rows = std::atoll(e);      // tuning knobs
+    if (const char *e = std::getenv("PGO_SPMV_TMA64")) h->spmv_tma64 = std::max(0, std::min(16, std::atoi(e)));
+    if (const char *e = std::getenv("PGO_SPMV_TMA32")) h->spmv_tma32 = std::max(0, std::min(16, std::atoi(e)));
+    if (const char *e = std::getenv("PGO_LPR4_MIN_ROWS")) h->lpr4_min_rows = std::atoll(e);
+    if (const char *e = std::getenv("PGO_PDL")) h->pdl = std::atoi(e) != 0;
+    h->lowp = h->use_amg && h->opt.amg_fp64_storage == 0;
+    return so;
+}
+
+// the packed value arrays must hold exactly what the per-kind counts say (the device copies read that many)
+static bool check_graph_arrays(int64_t nv, const uint8_t *vkind, int64_t ne, const uint8_t *ekind, std::string &err) {
+    for (int64_t i = 0; i < nv; i++) if (vkind[i] > 2) { err = "pgo_create: vertex_kind[" + std::to_string(i) + "] = " + std::to_string(vkind[i]) + " (must be 0, 1 or 2)"; return false; }
+    for (int64_t k = 0; k < ne; k++) if (ekind[k] > 2) { err = "pgo_create: edge_kind[" + std::to_string(k) + "] = " + std::to_string(ekind[k]) + " (must be 0, 1 or 2)"; return false; }
+    return true;
+}
+
+static int create_multi(pgo_handle **out, const pgo_options &opt_in, int64_t nv, const uint32_t *vid, const uint8_t *vkind, const double *vval,
+                        int64_t ne, const uint8_t *ekind, const uint32_t *efrom, const uint32_t *eto, const double *emeas, const double *einfo) {
+    const int n = opt_in.n_gpus;
+    if (n > MAX_RANKS) { g_create_error = "pgo_create: n_gpus > 8"; return PGO_ERR_ARG; }
+    if (opt_in.world > 1 || opt_in.rank != 0) { g_create_error = "pgo_create: n_gpus (single-process multi-GPU) and world / rank (process per GPU) are exclusive"; return PGO_ERR_ARG; }
+    if (opt_in.device == -2) { g_create_error = "pgo_create: a structure-only handle has no GPUs (use world / rank for partition queries)"; return PGO_ERR_ARG; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_create_error = "no CUDA device available (this library has no CPU fallback)"; return PGO_ERR_CUDA; }
+    std::vector<int> dev(n);
+    for (int k = 0; k < n; k++) {
+        dev[k] = opt_in.device_ids ? opt_in.device_ids[k] : k;
+        if (dev[k] < 0 || dev[k] >= ndev) { g_create_error = "pgo_create: device_ids[" + std::to_string(k) + "] = " + std::to_string(dev[k]) + " but the machine has " + std::to_string(ndev) + " CUDA device(s)"; return PGO_ERR_ARG; }
+    }
+    for (int a = 0; a < n; a++)
+        for (int b = 0; b < n; b++) {
+            int ok = 1;
+            if (dev[a] != dev[b] && (cudaDeviceCanAccessPeer(&ok, dev[a], dev[b]) != cudaSuccess || !ok)) {
+                g_create_error = "pgo_create: GPU " + std::to_string(dev[a]) + " has no peer access to GPU " + std::to_string(dev[b]);
+                return PGO_ERR_COMM;
+            }
+        }
+    pgo_handle *h = new pgo_handle();
+    h->opt = opt_in;
+    h->opt.device_ids = nullptr;                    // borrowed during this call only
+    h->opt.world = n; h->opt.rank = 0;
+    normalise_options(h->opt, n);
+    h->world = n; h->rank = 0;
+    const SymbolicOptions so = configure_handle(h);
+    if (!build_symbolic(h->sym, so, nv, vid, vkind, ne, ekind, efrom, eto)) return fail_create(h, PGO_ERR_ARG, h->sym.error);
+    MultiCtx *M = new MultiCtx();
+    h->multi = M;
+    M->dev = dev;
+    M->rc.assign(n, 0);
+    for (int k = 0; k < n; k++) {
+        pgo_handle *s = new pgo_handle(h->symp);
+        s->opt = h->opt; s->opt.rank = k; s->opt.device = dev[k];
+        s->world = n; s->rank = k;
+        configure_handle(s);
+        M->shard.push_back(s);
+    }
+    for (int k = 0; k < n; k++) M->th.emplace_back(multi_worker, M, k);
+    int rc = multi_run(h, [&](pgo_handle *s, int) { return create_shard(s, vval, ne, ekind, emeas, einfo); });
+    if (rc == PGO_OK)
+        rc = multi_run(h, [&](pgo_handle *s, int k) {            // peer access from this shard's device to the others'
+            for (int j = 0; j < n; j++) {
+                if (dev[j] == dev[k]) continue;
+                const cudaError_t e = cudaDeviceEnablePeerAccess(dev[j], 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { s->err = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e); return (int)PGO_ERR_COMM; }
+                (void)cudaGetLastError();
+            }
+            return (int)PGO_OK;
+        });
+    if (rc != PGO_OK) return fail_create(h, rc, h->err);
+    for (int k = 0; k < n; k++) {                     // one address space: a peer's arena is simply its pointer
+        pgo_handle *s = M->shard[k];
+        for (int j = 0; j < MAX_RANKS; j++) {
+            s->peer_base[j] = j < n ? M->shard[j]->arena : nullptr;
+            s->comm_ref.p[j] = (Comm *)M->shard[j < n ? j : k]->arena;
+        }
+        s->connected = true;
+    }
+    for (auto &L : h->sym.levels) { L.ctgt.clear(); L.ctgt.shrink_to_fit(); L.cstr.clear(); L.cstr.shrink_to_fit(); }
+    *out = h;
+    return PGO_OK;
+}
+
+extern "C" {
+
+int pgo_create(pgo_handle **out, const pgo_options *opt_in,
+               int64_t nv, const uint32_t *vid, const uint8_t *vkind, const double *vval,
+               int64_t ne, const uint8_t *ekind, const uint32_t *efrom, const uint32_t *eto,
+               const double *emeas, const double *einfo) {
+    if (!out) return PGO_ERR_ARG;
+    *out = nullptr;
+    if (!vid || !vkind || !vval || nv <= 0 || ne < 0 || (ne > 0 && (!ekind || !efrom || !eto || !emeas || !einfo))) {
+        g_create_error = "pgo_create: null or empty input";
+        return PGO_ERR_ARG;
+    }
+    if (!check_graph_arrays(nv, vkind, ne, ekind, g_create_error)) return PGO_ERR_ARG;
+    if (opt_in && opt_in->n_gpus > 1) return create_multi(out, *opt_in, nv, vid, vkind, vval, ne, ekind, efrom, eto, emeas, einfo);
+    pgo_handle *h = new pgo_handle();
+    if (opt_in) h->opt = *opt_in; else pgo_default_options(&h->opt);
+    h->opt.device_ids = nullptr;
+    if (h->opt.world <= 0) h->opt.world = 1;
+    normalise_options(h->opt, h->opt.world);
+    h->world = h->opt.world; h->rank = h->opt.rank;
+    if (h->rank < 0 || h->rank >= h->world) return fail_create(h, PGO_ERR_ARG, "pgo_create: rank out of range");
+    if (h->world > MAX_RANKS) return fail_create(h, PGO_ERR_ARG, "pgo_create: world > 8");
+    const SymbolicOptions so = configure_handle(h);
+    if (!build_symbolic(h->sym, so, nv, vid, vkind, ne, ekind, efrom, eto)) return fail_create(h, PGO_ERR_ARG, h->sym.error);
+    if (h->opt.device != -2) {                        // -2: structure-only handle (no device): symbolic-pass queries only
+        const int rc = create_shard(h, vval, ne, ekind, emeas, einfo);
+        if (rc != PGO_OK) return fail_create(h, rc, h->err);
+        // the big transient host arrays are not needed any more
+        for (auto &L : h->sym.levels) { L.ctgt.clear(); L.ctgt.shrink_to_fit(); L.cstr.clear(); L.cstr.shrink_to_fit(); }
+    }
     *out = h;
     return PGO_OK;
 }
@@ -1277,6 +1177,7 @@ int pgo_shard_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
 
 int pgo_shard_export(pgo_handle *h, void *buf, int64_t cap) {
     if (!h || !buf || cap < (int64_t)sizeof(cudaIpcMemHandle_t)) return PGO_ERR_ARG;
+    if (h->multi) { h->err = "pgo_shard_export: a single-process multi-GPU handle (n_gpus) connects its shards itself"; return PGO_ERR_ARG; }
     if (!h->stream) { h->err = "structure-only handle"; return PGO_ERR_CUDA; }
     cudaIpcMemHandle_t mh;
     CK(cudaIpcGetMemHandle(&mh, h->arena));
@@ -1286,6 +1187,7 @@ int pgo_shard_export(pgo_handle *h, void *buf, int64_t cap) {
 
 int pgo_shard_connect(pgo_handle *h, const void *all_handles, int64_t n_handles) {
     if (!h || !all_handles || n_handles != h->world) return PGO_ERR_ARG;
+    if (h->multi) { h->err = "pgo_shard_connect: a single-process multi-GPU handle (n_gpus) connects its shards itself"; return PGO_ERR_ARG; }
     if (!h->stream) { h->err = "structure-only handle"; return PGO_ERR_CUDA; }
     for (int k = 0; k < h->world; k++) {
         if (k == h->rank) continue;
@@ -1294,6 +1196,7 @@ int pgo_shard_connect(pgo_handle *h, const void *all_handles, int64_t n_handles)
         void *p = nullptr;
         CK(cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
         h->peer_base[k] = (char *)p;
+        h->ipc_peer[k] = true;
     }
     for (int k = 0; k < MAX_RANKS; k++) h->comm_ref.p[k] = (Comm *)h->peer_base[k < h->world ? k : h->rank];
     h->connected = true;
@@ -1329,6 +1232,12 @@ int pgo_get_sizes(const pgo_handle *h, int64_t *nv, int64_t *ne, int64_t *len, i
 
 int pgo_chi2(pgo_handle *h, double *chi2) {
     if (!h || !chi2) return PGO_ERR_ARG;
+    if (h->multi) {
+        double v[MAX_RANKS];
+        const int rc = multi_run(h, [&](pgo_handle *s, int k) { return pgo_chi2(s, &v[k]); });
+        *chi2 = v[0];
+        return rc;
+    }
     NEED_DEVICE(h);
     int rc = BY_D(h, chi2_launch, h);
     if (rc) return rc;
@@ -1341,6 +1250,16 @@ int pgo_chi2(pgo_handle *h, double *chi2) {
 
 int pgo_gn_step(pgo_handle *h, double lambda, int add_lambda, double *norm_dx, double *chi2, int32_t *pcg_iterations) {
     if (!h) return PGO_ERR_ARG;
+    if (h->multi) {                                  // scalars come back identical on every shard
+        double nd[MAX_RANKS], c2[MAX_RANKS]; int32_t it[MAX_RANKS];
+        const int rc = multi_run(h, [&](pgo_handle *s, int k) { return pgo_gn_step(s, lambda, add_lambda, &nd[k], &c2[k], &it[k]); });
+        if (rc != PGO_OK && rc != PGO_ERR_NOT_CONVERGED) return rc;
+        if (norm_dx) *norm_dx = nd[0];
+        if (chi2) *chi2 = c2[0];
+        if (pcg_iterations) *pcg_iterations = it[0];
+        h->have_step = true;
+        return rc;
+    }
     NEED_DEVICE(h);
     auto mark = [&](int i) { cudaEventRecord(h->ev[i], h->stream); };
     int64_t lc[6];
@@ -1378,17 +1297,26 @@ int pgo_gn_step(pgo_handle *h, double lambda, int add_lambda, double *norm_dx, d
 
 int pgo_undo_last_step(pgo_handle *h) {
     if (!h) return PGO_ERR_ARG;
+    if (h->multi) return multi_run(h, [&](pgo_handle *s, int) { return pgo_undo_last_step(s); });
     NEED_DEVICE(h);
     if (!h->have_step) { h->err = "pgo_undo_last_step: no step to undo"; return PGO_ERR_ARG; }
     int rc = BY_D(h, retract, h, -1.0);
     if (rc) return rc;
     CK(cudaStreamSynchronize(h->stream));
+    h->have_step = false;                            // a step can be undone once
     return PGO_OK;
 }
 
 int pgo_linearize_and_solve(pgo_handle *h, int32_t *pcg_iterations) {
     if (!h) return PGO_ERR_ARG;
+    if (h->multi) {
+        int32_t it[MAX_RANKS];
+        const int rc = multi_run(h, [&](pgo_handle *s, int k) { return pgo_linearize_and_solve(s, &it[k]); });
+        if (pcg_iterations) *pcg_iterations = it[0];
+        return rc;
+    }
     NEED_DEVICE(h);
+    h->have_step = false;                            // h->x is overwritten: the last step's dx is gone
     int rc = BY_D(h, assemble, h, 0.0, 0);
     if (rc) return rc;
     rc = BY_D(h, amg_setup, h);
@@ -1405,6 +1333,7 @@ static void owned_span(const pgo_handle *h, int64_t *o0, int64_t *o1) {
 
 int pgo_get_poses(pgo_handle *h, double *out, int64_t n_values) {
     if (!h || !out) return PGO_ERR_ARG;
+    if (h->multi) return multi_run(h, [&](pgo_handle *s, int) { return pgo_get_poses(s, out, n_values); });   // disjoint spans of `out`
     NEED_DEVICE(h);
     const Symbolic &S = h->sym;
     if (n_values != S.n_values) { h->err = "pgo_get_poses: wrong buffer length"; return PGO_ERR_ARG; }
@@ -1421,6 +1350,7 @@ int pgo_get_poses(pgo_handle *h, double *out, int64_t n_values) {
 
 int pgo_set_poses(pgo_handle *h, const double *in, int64_t n_values) {
     if (!h || !in) return PGO_ERR_ARG;
+    if (h->multi) return multi_run(h, [&](pgo_handle *s, int) { return pgo_set_poses(s, in, n_values); });
     NEED_DEVICE(h);
     const Symbolic &S = h->sym;
     if (n_values != S.n_values) { h->err = "pgo_set_poses: wrong buffer length"; return PGO_ERR_ARG; }
@@ -1438,6 +1368,7 @@ int pgo_set_poses(pgo_handle *h, const double *in, int64_t n_values) {
 
 int pgo_snapshot_poses(pgo_handle *h) {
     if (!h) return PGO_ERR_ARG;
+    if (h->multi) return multi_run(h, [&](pgo_handle *s, int) { return pgo_snapshot_poses(s); });
     NEED_DEVICE(h);
     const size_t cnt = (size_t)(h->sym.D == 6 ? 8 : 4) * h->n_pad_loc;
     if (!h->poses_saved) { int rc = dalloc(h, &h->poses_saved, cnt, false); if (rc) return rc; }
@@ -1448,6 +1379,7 @@ int pgo_snapshot_poses(pgo_handle *h) {
 
 int pgo_restore_poses(pgo_handle *h) {
     if (!h) return PGO_ERR_ARG;
+    if (h->multi) return multi_run(h, [&](pgo_handle *s, int) { return pgo_restore_poses(s); });
     NEED_DEVICE(h);
     if (!h->poses_saved) { h->err = "pgo_restore_poses: no snapshot"; return PGO_ERR_ARG; }
     CK(cudaMemcpyAsync(h->poses, h->poses_saved, (size_t)(h->sym.D == 6 ? 8 : 4) * h->n_pad_loc * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
@@ -1458,6 +1390,7 @@ int pgo_restore_poses(pgo_handle *h) {
 
 int pgo_get_dx(pgo_handle *h, double *out, int64_t len) {
     if (!h || !out) return PGO_ERR_ARG;
+    if (h->multi) return multi_run(h, [&](pgo_handle *s, int) { return pgo_get_dx(s, out, len); });           // disjoint entries of `out`
     NEED_DEVICE(h);
     const Symbolic &S = h->sym;
     if (len != S.len) { h->err = "pgo_get_dx: wrong buffer length"; return PGO_ERR_ARG; }
@@ -1505,6 +1438,11 @@ int pgo_get_anchor(const pgo_handle *h, int64_t *v) {
 // so the caller can merge the ranks' outputs (they are disjoint).
 int pgo_get_system(pgo_handle *h, double lambda, int add_lambda, double *csc_values, double *b) {
     if (!h) return PGO_ERR_ARG;
+    if (h->multi) {
+        // the lazily built structures live in the shared symbolic pass: build them once, here, before the shards read them
+        if (!build_csc_pattern(h->sym)) { h->err = h->sym.error; return PGO_ERR_UNSUPPORTED; }
+        return multi_run(h, [&](pgo_handle *s, int) { return pgo_get_system(s, lambda, add_lambda, csc_values, b); });   // disjoint block rows
+    }
     NEED_DEVICE(h);
     Symbolic &S = h->sym;
     if (!build_csc_pattern(S)) { h->err = S.error; return PGO_ERR_UNSUPPORTED; }
@@ -1565,6 +1503,15 @@ int pgo_get_system(pgo_handle *h, double lambda, int add_lambda, double *csc_val
 
 int pgo_get_timings(pgo_handle *h, double *ms, int64_t *launches, int32_t n) {
     if (!h) return PGO_ERR_ARG;
+    if (h->multi) {                                  // per phase: the slowest shard's time, the launches of all shards
+        for (int i = 0; i < n && i < PGO_NUM_PHASES; i++) {
+            double m = 0; int64_t c = 0;
+            for (pgo_handle *s : h->multi->shard) { m = std::max(m, s->ms[i]); c += s->launches[i]; }
+            if (ms) ms[i] = m;
+            if (launches) launches[i] = c;
+        }
+        return PGO_OK;
+    }
     for (int i = 0; i < n && i < PGO_NUM_PHASES; i++) {
         if (ms) ms[i] = h->ms[i];
         if (launches) launches[i] = h->launches[i];
@@ -1574,6 +1521,12 @@ int pgo_get_timings(pgo_handle *h, double *ms, int64_t *launches, int32_t n) {
 
 int pgo_time_spmv(pgo_handle *h, int32_t repeats, double *avg_ms) {
     if (!h || !avg_ms || repeats <= 0) return PGO_ERR_ARG;
+    if (h->multi) {
+        double v[MAX_RANKS] = {0};
+        const int rc = multi_run(h, [&](pgo_handle *s, int k) { return pgo_time_spmv(s, repeats, &v[k]); });
+        *avg_ms = *std::max_element(v, v + h->multi->shard.size());
+        return rc;
+    }
     NEED_DEVICE(h);
     LevelBuf &B = h->lv[0];
     // p -> q with the PCG SpMV; done-flag test disabled so the launches always do the work, no cross-rank reduction
@@ -1598,6 +1551,12 @@ int pgo_time_spmv(pgo_handle *h, int32_t repeats, double *avg_ms) {
 
 int pgo_time_coarse(pgo_handle *h, int32_t level, int32_t repeats, double *avg_ms) {
     if (!h || !avg_ms || repeats <= 0) return PGO_ERR_ARG;
+    if (h->multi) {
+        double v[MAX_RANKS] = {0};
+        const int rc = multi_run(h, [&](pgo_handle *s, int k) { return pgo_time_coarse(s, level, repeats, &v[k]); });
+        *avg_ms = *std::max_element(v, v + h->multi->shard.size());
+        return rc;
+    }
     NEED_DEVICE(h);
     if (!h->have_step) { h->err = "pgo_time_coarse: run a Gauss-Newton step first (the hierarchy must be set up)"; return PGO_ERR_ARG; }
     return BY_D(h, time_coarse, h, level, repeats, avg_ms);
@@ -1605,6 +1564,13 @@ int pgo_time_coarse(pgo_handle *h, int32_t level, int32_t repeats, double *avg_m
 
 int pgo_get_stats(const pgo_handle *h, int64_t *rows, int64_t *offdiag, int64_t *levels, int64_t *bytes) {
     if (!h) return PGO_ERR_ARG;
+    if (h->multi) {                                  // totals over the shards
+        if (rows) *rows = h->sym.n;
+        if (offdiag) *offdiag = 2 * h->sym.n_edges;
+        if (levels) *levels = (int64_t)h->sym.levels.size();
+        if (bytes) { *bytes = 0; for (pgo_handle *s : h->multi->shard) *bytes += (int64_t)s->device_bytes; }
+        return PGO_OK;
+    }
     if (rows) *rows = h->stream ? h->n_loc : h->sym.n;
     if (offdiag) {
         const HostLevel &H = h->sym.levels[0];

@@ -45,4 +45,5 @@ def write_g2o(filename, graph):
                         ptr(a["edge_from"]), ptr(a["edge_to"]), ptr(a["edge_meas"]), len(a["edge_meas"]),
                         ptr(a["edge_info_upper"]), len(a["edge_info_upper"]))
     if rc != 0:
-        raise OSError("write_g2o: " + L.pg_last_error().decode())
+        msg = L.pg_last_error().decode()
+        raise (ValueError if msg.startswith("graph arrays") else OSError)("write_g2o: " + msg)

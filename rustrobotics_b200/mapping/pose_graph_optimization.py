@@ -25,7 +25,7 @@ class PoseGraphSolver(enum.IntEnum):   # :28-32
     LevenbergMarquardt = 1
 
 
-STATUS = {0: "ok", 1: "bad argument", 2: "CUDA error", 3: "NCCL error", 4: "solver breakdown", 5: "PCG not converged",
+STATUS = {0: "ok", 1: "bad argument", 2: "CUDA error", 3: "multi-GPU communication error", 4: "solver breakdown", 5: "PCG not converged",
           6: "unsupported"}
 BLOCK_JACOBI, AMG = 0, 1
 
@@ -33,29 +33,32 @@ BLOCK_JACOBI, AMG = 0, 1
 def Options(**kw) -> pgo_options:
     """pgo_options with the library defaults, overridden by keyword (anchor_weight, pcg_rtol,
     pcg_max_iterations, preconditioner, sort_window, amg_max_levels, device, world, rank, amg_dense_max,
-    amg_aggregate_size, amg_kcycle, amg_kcycle3, amg_fp64_storage)."""
+    amg_aggregate_size, amg_kcycle, amg_kcycle3, amg_fp64_storage, n_gpus, device_ids).
+
+    Multi-GPU from ONE process: `Options(n_gpus=8)` (devices 0..7) or `Options(n_gpus=2, device_ids=[0, 0])`
+    (two shards sharing GPU 0: the multi-GPU path on a one-GPU machine)."""
     o = pgo_options()
     lib().pgo_default_options(C.byref(o))
     for k, v in kw.items():
         if not hasattr(o, k):
             raise TypeError(f"unknown option {k}")
+        if k == "device_ids" and v is not None:
+            ids = (C.c_int32 * len(v))(*[int(d) for d in v])
+            o._device_ids_keepalive = ids          # pgo_create borrows the array
+            v = C.cast(ids, C.POINTER(C.c_int32))
+            if "n_gpus" not in kw:
+                o.n_gpus = len(ids)
         setattr(o, k, v)
     return o
 
 
-def gather_handles(mine: bytes, world: int, group=None) -> bytes:
-    """all-gather one fixed-size byte string per rank, concatenated in rank order"""
-    import torch.distributed as dist
-    parts = [None] * world
-    dist.all_gather_object(parts, bytes(mine), group=group)
-    if any(p is None or len(p) != len(mine) for p in parts):
-        raise PgoError("shard handle exchange failed")
-    return b"".join(parts)
-
-
 class PoseGraph:
     def __init__(self, file_path=None, solver=PoseGraphSolver.GaussNewton, *, graph=None, name="graph", options=None,
-                 process_group=None):
+                 comm=None):
+        """`comm` is only for the process-per-GPU mode (options.world > 1, e.g. under torchrun): an object with
+        `all_gather_bytes(bytes) -> bytes` (rank order), `all_reduce_sum(ndarray) -> ndarray` and `barrier()`, supplied by
+        the launcher (bench.py's TorchComm).  This package itself imports no torch; the single-process multi-GPU mode
+        (options.n_gpus) needs no comm at all."""
         L = lib()
         self._pg = None
         self.solver = PoseGraphSolver(solver)
@@ -79,7 +82,7 @@ class PoseGraph:
         self.pcg_iterations: list[int] = []
         self.world = int(options.world) if options is not None else 1
         self.rank = int(options.rank) if options is not None else 0
-        self._group = process_group
+        self._comm = comm
         if self.world > 1 and options.device != -2:
             self.connect_shards()
 
@@ -99,33 +102,27 @@ class PoseGraph:
         except Exception:
             pass
 
-    # ---- sharded handles (one process per GPU) ------------------------------------------
+    # ---- process-per-GPU sharding (options.world > 1; the launcher supplies `comm`) -----------------------------
     def connect_shards(self):
-        """Exchange the ranks' peer-memory handles (torch.distributed is only the plumbing: one all-gather of
-        64 bytes per rank at start-up) and connect the shards.  Afterwards every computing call is collective."""
-        import torch.distributed as dist
-        if not dist.is_initialized():
-            raise PgoError("sharded PoseGraph (options.world > 1) needs an initialised torch.distributed process group")
-        if dist.get_world_size(self._group) != self.world or dist.get_rank(self._group) != self.rank:
-            raise PgoError("options.world / options.rank do not match the process group")
+        """Exchange the ranks' peer-memory handles (one all-gather of 64 bytes per rank at start-up, moved by the launcher's
+        `comm`) and connect the shards.  Afterwards every computing call is collective."""
+        if self._comm is None:
+            raise PgoError("process-per-GPU PoseGraph (options.world > 1) needs comm=<launcher's communicator>; "
+                           "for multi-GPU from one process use options.n_gpus instead")
         n = lib().pgo_shard_handle_bytes()
         buf = C.create_string_buffer(n)
         self._check(lib().pgo_shard_export(self._h, buf, n), "pgo_shard_export")
-        blob = gather_handles(buf.raw, self.world, self._group)
+        blob = self._comm.all_gather_bytes(buf.raw)
+        if len(blob) != n * self.world:
+            raise PgoError("shard handle exchange failed")
         self._check(lib().pgo_shard_connect(self._h, blob, self.world), "pgo_shard_connect")
-        dist.barrier(self._group)      # every rank has opened every arena before the first peer read
+        self._comm.barrier()           # every rank has opened every arena before the first peer read
 
     def _merge_owned(self, out):
-        """sharded getters fill the span this rank owns: sum the (disjoint, zero elsewhere) spans over ranks"""
+        """process-per-GPU getters fill the span this rank owns: sum the (disjoint, zero elsewhere) spans over ranks"""
         if self.world == 1:
             return out
-        import torch
-        import torch.distributed as dist
-        t = torch.from_numpy(out)
-        if dist.get_backend(self._group) == "nccl":
-            t = t.cuda()
-        dist.all_reduce(t, group=self._group)
-        return t.cpu().numpy()
+        return self._comm.all_reduce_sum(out)
 
     # ---- reference API ----------------------------------------------------------------------
     def optimize(self, num_iterations, log=False, plot=False):

@@ -20,6 +20,7 @@ CHI2_RTOL, POSE_ATOL = 1e-6, 1e-6
 def main():
     import torch
     import torch.distributed as dist
+    from bench import TorchComm
     from conftest import graph_of, load_golden
     from oracle.oracle import OraclePoseGraph
     from rustrobotics_b200 import Options, PoseGraph
@@ -51,7 +52,7 @@ def main():
         errs_o = o.optimize(its)
         _, _, _, vo = o.vertices()
         dist.barrier()
-        pg = PoseGraph(graph=g, options=Options(device=local, world=world, rank=rank, preconditioner=precond))
+        pg = PoseGraph(graph=g, options=Options(device=local, world=world, rank=rank, preconditioner=precond), comm=TorchComm())
         part = pg.partition()
         assert part["world"] == world and part["rank"] == rank
         c_g = pg.global_error()

@@ -65,6 +65,110 @@ def test_parse_g2o_errors(tmp_path, text, what):
         OraclePoseGraph.from_g2o(p)
 
 
+def test_parse_g2o_rejects_hex_floats_and_ignores_the_locale(tmp_path, built):
+    """Rust's str::parse::<f64> (g2o.rs:24-32) knows no hex floats and no locale; neither does the C++ loader"""
+    import locale
+    from rustrobotics_b200 import parse_g2o, write_g2o
+    p = tmp_path / "hex.g2o"
+    p.write_text("VERTEX_SE2 0 0x10 1 0\n")
+    with pytest.raises(ValueError, match="bad number"):
+        parse_g2o(p)
+    p.write_text("VERTEX_SE2 0 +1.5 -2.5e-1 1E2\nVERTEX_XY 1 inf .5\n")
+    _, g = parse_g2o(p)
+    assert g["vertex_values"].tolist() == [1.5, -0.25, 100.0, float("inf"), 0.5]
+    old = locale.setlocale(locale.LC_NUMERIC)
+    try:
+        for loc in ("de_DE.UTF-8", "fr_FR.UTF-8", "de_DE", "C.UTF-8"):       # whichever decimal-comma locale the image has
+            try:
+                locale.setlocale(locale.LC_NUMERIC, loc)
+                break
+            except locale.Error:
+                continue
+        p.write_text("VERTEX_SE2 0 1.5 2.25 0.125\n")
+        _, g = parse_g2o(p)
+        assert g["vertex_values"].tolist() == [1.5, 2.25, 0.125]
+        q = tmp_path / "out.g2o"
+        write_g2o(q, g)
+        assert q.read_text() == "VERTEX_SE2 0 1.5 2.25 0.125\n"
+    finally:
+        locale.setlocale(locale.LC_NUMERIC, old)
+
+
+def test_raw_reference_lines_parse_like_the_oracle(tmp_path, built):
+    """the reference's own bytes (committed excerpts of dataset/g2o/sphere2500.g2o -- every line ends in a space, fields separated
+    by two spaces before the information block -- and dlr.g2o), not text re-written by write_g2o: g2o.rs:52"""
+    from rustrobotics_b200 import parse_g2o
+    for name in ("sphere2500_head", "dlr_head"):
+        p = ROOT / "tests" / "golden" / "raw" / f"{name}.g2o"
+        assert name != "sphere2500_head" or p.read_bytes().split(b"\n")[0].endswith(b" ")
+        ln, g = parse_g2o(p)
+        oa = OraclePoseGraph.from_g2o(p).arrays()
+        for k in KEYS:
+            if k in ("vertex_values", "edge_meas"):    # the oracle hands back its stored state (unit complex / normalised quaternion)
+                np.testing.assert_allclose(g[k], oa[k], atol=2e-6 if name == "sphere2500_head" else 1e-12)
+            else:
+                assert np.array_equal(g[k], oa[k]), (name, k)
+        # every number exactly as Python's (correctly rounded) float() reads the same token
+        toks = [ln_.split() for ln_ in p.read_text().splitlines()]
+        want_v = [float(t) for tk in toks if tk[0].startswith("VERTEX") for t in tk[2:]]
+        want_e = [float(t) for tk in toks if tk[0].startswith("EDGE") for t in tk[3:]]
+        assert g["vertex_values"].tolist() == want_v
+        nm = {0: 3, 1: 2, 2: 7}
+        got_e, im, ii = [], 0, 0
+        for kind in g["edge_kind"]:
+            m, w = nm[int(kind)], {0: 6, 1: 3, 2: 21}[int(kind)]
+            got_e += g["edge_meas"][im:im + m].tolist() + g["edge_info_upper"][ii:ii + w].tolist()
+            im += m; ii += w
+        assert got_e == want_e
+        assert ln == int(np.sum(np.array([3, 2, 6])[g["vertex_kind"]]))
+
+
+@pytest.mark.parametrize("name", SE2_GRAPHS + ["sphere2500", "parking-garage"])
+def test_raw_reference_files_parse_to_the_committed_fixtures(built, name):
+    """the whole raw files, when the reference checkout is present (authoring container; skipped on the GPU box)"""
+    from rustrobotics_b200 import parse_g2o
+    p = Path("/root/reference/dataset/g2o") / f"{name}.g2o"
+    if not p.exists():
+        pytest.skip("reference checkout not present")
+    ln, g = parse_g2o(p)
+    gold = load_golden(name)
+    assert ln == int(gold["len"])
+    se3 = name in ("sphere2500", "parking-garage")
+    for k in KEYS:
+        if k in ("vertex_values", "edge_meas"):   # the fixtures hold the oracle's stored state (theta through atan2(sin, cos); normalised quaternions)
+            np.testing.assert_allclose(g[k], gold[k], atol=5e-6 if se3 else 1e-12)
+        else:
+            assert np.array_equal(g[k], gold[k]), k
+
+
+def test_graph_arrays_are_validated(tmp_path, built):
+    """kinds outside 0..2 and value arrays that do not match the per-kind counts are rejected before anything reads them"""
+    from rustrobotics_b200 import Options, PgoError, PoseGraph, write_g2o
+    g = graph_of(load_golden("simulation-pose-landmark"))
+    for key, val, what in (("vertex_kind", 200, "vertex_kind"), ("edge_kind", 7, "edge_kind")):
+        bad = dict(g); bad[key] = g[key].copy(); bad[key][0] = val
+        with pytest.raises(PgoError, match=what):
+            PoseGraph(graph=bad, options=Options(device=-2))
+        with pytest.raises(ValueError, match=what):
+            write_g2o(tmp_path / "bad.g2o", bad)
+    for key, what in (("vertex_values", "vertex values"), ("edge_meas", "measurement values"), ("edge_info_upper", "information values")):
+        bad = dict(g); bad[key] = g[key][:-1]
+        with pytest.raises(PgoError, match=what):
+            PoseGraph(graph=bad, options=Options(device=-2))
+        with pytest.raises(ValueError, match=what):
+            write_g2o(tmp_path / "bad.g2o", bad)
+    # the C ABI itself rejects bad kinds (it cannot know the array lengths: documented caller contract)
+    from rustrobotics_b200.mapping._lib import lib, ptr
+    L = lib()
+    a = {k: np.ascontiguousarray(g[k]) for k in KEYS}
+    a["vertex_kind"] = a["vertex_kind"].copy(); a["vertex_kind"][3] = 9
+    h = C.c_void_p()
+    o = Options(device=-2)
+    rc = L.pgo_create(C.byref(h), C.byref(o), len(a["vertex_id"]), ptr(a["vertex_id"]), ptr(a["vertex_kind"]), ptr(a["vertex_values"]),
+                      len(a["edge_kind"]), ptr(a["edge_kind"]), ptr(a["edge_from"]), ptr(a["edge_to"]), ptr(a["edge_meas"]), ptr(a["edge_info_upper"]))
+    assert rc == 1 and b"vertex_kind[3]" in L.pgo_last_error(None)
+
+
 def test_missing_file_is_an_error(tmp_path, built):                # fs::read_to_string(...)? -> Err, g2o.rs:51
     from rustrobotics_b200 import PgoError, PoseGraph, parse_g2o
     with pytest.raises(ValueError):

@@ -70,13 +70,14 @@ def _gloo_worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
+        from bench import TorchComm
         from rustrobotics_b200 import Options, PgoError, PoseGraph
-        from rustrobotics_b200.mapping.pose_graph_optimization import gather_handles
+        comm = TorchComm()
         mine = bytes([rank + 1]) * 64
-        blob = gather_handles(mine, world)
+        blob = comm.all_gather_bytes(mine)
         ok = blob == b"".join(bytes([r + 1]) * 64 for r in range(world))
         g = graph_of(load_golden("simulation-pose-pose"))
-        pg = PoseGraph(graph=g, options=Options(device=-2, world=world, rank=rank))
+        pg = PoseGraph(graph=g, options=Options(device=-2, world=world, rank=rank), comm=comm)
         part = pg.partition()
         # the merge of owned spans: every rank contributes its (disjoint) slice, zero elsewhere
         vr = part["vertex_range"]
