@@ -34,6 +34,7 @@ sys.path.insert(0, str(ROOT))
 
 METRIC = "gn_edges_per_sec"
 UNIT = "edges/s"
+DEFAULT_PCG_RTOL = 1e-8             # the tolerance the golden parity test of the headline config runs at (tests/test_gpu_parity.py)
 CPU_SAMPLE_POSES = 100_000          # Manhattan SE2 sample of the CPU arm
 CPU_SAMPLE_POSES_SE3 = 25_000       # sphere SE3 sample (50 levels x 500)
 
@@ -424,7 +425,7 @@ def main():
                     help="manhattan = BASELINE configs[3] (the headline, default); sphere = configs[4] (SE3, 6x6 blocks); "
                          "pose-pose / pose-landmark / intel / dlr / m3500 / sphere2500 / garage = the reference's bundled g2o graphs")
     ap.add_argument("--poses", type=int, default=None, help="default: 1M (manhattan) / 250k (sphere)")
-    ap.add_argument("--pcg-rtol", type=float, default=1e-8)
+    ap.add_argument("--pcg-rtol", type=float, default=DEFAULT_PCG_RTOL)
     ap.add_argument("--preconditioner", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--opts", default="", help="extra pgo_options overrides, k=v,k=v (e.g. amg_kcycle3=0,amg_fp64_storage=1)")

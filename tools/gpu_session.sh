@@ -1,0 +1,23 @@
+#!/bin/bash
+# 1-GPU measurement session on the B200 box:  gpurun --timeout 2400 -- 'bash tools/gpu_session.sh TAG [parts]'
+# parts (default all): tests sweep bench traffic sanitize
+tag=${1:-r03}; parts=${2:-"tests sweep bench traffic sanitize"}
+mkdir -p gpurun_out
+for part in $parts; do case $part in
+tests)
+  timeout 2400 python -m pytest tests -m gpu -q -rs --durations=8 > gpurun_out/pytest_gpu_$tag.log 2>&1; echo "pytest rc=$?"; tail -25 gpurun_out/pytest_gpu_$tag.log;;
+sweep)
+  timeout 900 python tools/rtol_sweep.py 1e-8 1e-9 1e-10 1e-11 1e-12 1e-13 > gpurun_out/rtol_sweep_$tag.log 2>&1; echo "sweep rc=$?"; cat gpurun_out/rtol_sweep_$tag.log;;
+bench)
+  timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err; echo "bench rc=$?"; cut -c1-2500 gpurun_out/bench_$tag.json;;
+traffic)
+  timeout 1200 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --cache-control none \
+      --profile-from-start off --csv --log-file gpurun_out/step_traffic_$tag.csv python tools/step_traffic.py > gpurun_out/step_traffic_$tag.log 2>&1; echo "traffic rc=$?"
+  tail -2 gpurun_out/step_traffic_$tag.log; python tools/summarize_traffic.py gpurun_out/step_traffic_$tag.csv gpurun_out/step_traffic_$tag.json | head -30;;
+sanitize)
+  for tool in memcheck racecheck; do for n in 1 2; do
+    timeout 600 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize.py $n > gpurun_out/sanitize_${tool}_n${n}_$tag.log 2>&1; echo "$tool n=$n rc=$?"
+    grep -E "sanitize |ERROR SUMMARY|RACECHECK SUMMARY|Error|hazard" gpurun_out/sanitize_${tool}_n${n}_$tag.log | head -14
+  done; done;;
+esac; done
+ls -la gpurun_out | tail -12
