@@ -58,6 +58,7 @@ struct LevelDev {
     const double *quat;          // level 0 of an SE3 graph: the (halo-extended) pose records, 8 doubles per row, unit
                                  // quaternion (w,x,y,z) at +4 (the rotation unknown is body-frame); nullptr otherwise
     const int32_t *agg; const int32_t *ctgt; const int32_t *cstr;   // towards the coarser level (local indices)
+    const int32_t *gptr; const int32_t *gsrc; int64_t n_gblk;       // deterministic Galerkin product: contributors of every coarse block
     const int64_t *mem_ptr; const int32_t *mem_idx;                 // members in the finer level (local rows)
 };
 
@@ -1195,6 +1196,116 @@ __global__ void __launch_bounds__(256) k_galerkin_csr(LevelDev F, LevelDev C, co
         for (int q = 0; q < DD; q++) h[q] = v[q];
         xfer_ptap(h, Pi, Pj, g);
         galerkin_scatter<DD>(C, F.ctgt[s], F.cstr[s], g);
+    }
+}
+
+// ---- deterministic Galerkin product (default; the atomic kernels above remain for coarse levels in sliced storage) --------------
+// Step 1: every fine block is projected, g = P_i^T H_ij P_j, into a staging buffer in STORAGE order, block-major (DD doubles per
+// block: stored block s at s, diagonal block of row r at n_slots + r) -- the same streaming pass as above, all stores coalesced.
+// Step 2: one group of lanes per coarse block sums its contributors in the fixed order of the symbolic pass' lists.  No atomics,
+// a single writer per coarse block: two runs give bit-identical hierarchies (and hence bit-identical Gauss-Newton steps).
+template <int D>
+__global__ void __launch_bounds__(128) k_galerkin_stage_jds(LevelDev F, const __grid_constant__ XRef levr, double *__restrict__ stage) {
+    PDL_ENTER();
+    constexpr int DD = D * D;
+    __shared__ double sm[4][32 * DD];
+    const int64_t row = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int64_t slice = row >> 5;
+    if (slice >= F.n_slices) return;
+    double *my = sm[threadIdx.x >> 5];
+    const int mydeg = F.deg[row];
+    const int maxdeg = __shfl_sync(0xffffffffu, mydeg, 0);
+    const bool real = row < F.n;
+    Xfer<D> Pi = xfer_own<D>(F, real ? row : 0);
+    {
+        double h[DD], g[DD];
+#pragma unroll
+        for (int q = 0; q < DD; q++) { h[q] = real ? F.diag[(int64_t)q * F.n_pad + row] : 0.0; g[q] = 0.0; }
+        if (real) xfer_ptap(h, Pi, Pi, g);
+#pragma unroll
+        for (int q = 0; q < DD; q++) my[lane * DD + q] = g[q];
+        __syncwarp();
+        double *dst = stage + (F.n_slots + slice * 32) * DD;
+        for (int t = lane; t < 32 * DD; t += 32) dst[t] = my[t];
+        __syncwarp();
+    }
+    const int64_t base = F.slice_ptr[slice];
+    int64_t off = 0;
+    for (int k = 0; k < maxdeg; k++) {
+        const bool active = k < mydeg;
+        const int cnt = __popc(__ballot_sync(0xffffffffu, active));
+        if (active) {
+            const uint32_t cw = F.col[base + off + lane];
+            const Xfer<D> Pj = xfer_nbr<D>(F, levr, cw);
+            const double *v = F.val + (base + off) * DD + lane;
+            double h[DD], g[DD];
+#pragma unroll
+            for (int q = 0; q < DD; q++) h[q] = v[(int64_t)q * cnt];
+            xfer_ptap(h, Pi, Pj, g);
+#pragma unroll
+            for (int q = 0; q < DD; q++) my[lane * DD + q] = g[q];
+        }
+        __syncwarp();
+        double *dst = stage + (base + off) * DD;
+        for (int t = lane; t < cnt * DD; t += 32) dst[t] = my[t];
+        __syncwarp();
+        off += cnt;
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) k_galerkin_stage_csr(LevelDev F, const __grid_constant__ XRef levr, double *__restrict__ stage) {
+    PDL_ENTER();
+    constexpr int DD = D * D;
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= F.n) return;
+    const Xfer<D> Pi = xfer_own<D>(F, row);
+    if (lane == 0) {
+        double h[DD], g[DD];
+#pragma unroll
+        for (int q = 0; q < DD; q++) h[q] = F.diag[(int64_t)q * F.n_pad + row];
+        xfer_ptap(h, Pi, Pi, g);
+        double *dst = stage + (F.n_slots + row) * DD;
+#pragma unroll
+        for (int q = 0; q < DD; q++) dst[q] = g[q];
+    }
+    for (int64_t s = F.slice_ptr[row] + lane; s < F.slice_ptr[row + 1]; s += 32) {
+        const Xfer<D> Pj = xfer_nbr<D>(F, levr, F.col[s]);
+        const double *v = F.val + s * DD;
+        double h[DD], g[DD];
+#pragma unroll
+        for (int q = 0; q < DD; q++) h[q] = v[q];
+        xfer_ptap(h, Pi, Pj, g);
+        double *dst = stage + s * DD;
+#pragma unroll
+        for (int q = 0; q < DD; q++) dst[q] = g[q];
+    }
+}
+
+template <int D> struct GalerkinLanes { static constexpr int value = D * D <= 16 ? 16 : 32; };   // lanes per coarse block
+
+template <int D>
+__global__ void __launch_bounds__(256) k_galerkin_reduce(LevelDev F, LevelDev C, const double *__restrict__ stage) {
+    PDL_ENTER();
+    constexpr int DD = D * D, LPB = GalerkinLanes<D>::value;
+    const int64_t b = ((int64_t)blockIdx.x * 256 + threadIdx.x) / LPB;
+    const int q0 = threadIdx.x % LPB;
+    if (b >= F.n_gblk) return;
+    const int32_t p0 = F.gptr[b], p1 = F.gptr[b + 1];
+    if (p0 == p1) return;                           // a block of the first replicated level built by another rank: gathered later
+    for (int q = q0; q < DD; q += LPB) {
+        double s = 0.0;
+        int32_t p = p0;
+        for (; p + 4 <= p1; p += 4) {               // four independent loads in flight, summed in list order
+            const double a0 = stage[(int64_t)F.gsrc[p] * DD + q], a1 = stage[(int64_t)F.gsrc[p + 1] * DD + q];
+            const double a2 = stage[(int64_t)F.gsrc[p + 2] * DD + q], a3 = stage[(int64_t)F.gsrc[p + 3] * DD + q];
+            s += a0; s += a1; s += a2; s += a3;
+        }
+        for (; p < p1; p++) s += stage[(int64_t)F.gsrc[p] * DD + q];
+        if (b < C.n_pad) C.diag[(int64_t)q * C.n_pad + b] = s;
+        else C.val[(b - C.n_pad) * DD + q] = s;
     }
 }
 

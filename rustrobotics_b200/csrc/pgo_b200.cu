@@ -10,6 +10,9 @@
 // Sharded mode (world > 1): every rank owns a contiguous vertex range of every level; neighbour rows are read
 // directly from peer HBM over NVLink (CUDA IPC), dot products and stage barriers are one tiny kernel that
 // exchanges partial sums through peer memory.
+#include <cuda.h>
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cmath>
 #include <condition_variable>
@@ -106,6 +109,7 @@ struct pgo_handle {
     double *x = nullptr, *r = nullptr, *p = nullptr, *q = nullptr, *z = nullptr;
     Scalars *S = nullptr, *hS = nullptr;   // device / pinned host (2 slots)
     double *partials = nullptr;
+    double *gstage = nullptr;          // staging buffer of the deterministic Galerkin product (largest level)
     double *Ainv = nullptr, *Awork = nullptr;   // explicit inverse of the coarsest matrix; second buffer of the ping-pong inversion
     DenseMap dmap{};
     int dense_m = 0, invert_grid = 0;
@@ -468,7 +472,12 @@ template <int D> int amg_setup(pgo_handle *h) {
         CK(cudaMemsetAsync(C.d.diag, 0, sizeof(double) * DD * C.d.n_pad, h->stream));
         lbarrier(h, l, 0);                           // lever arms of neighbour rows on other ranks
         halo_pull(h, l, F.d.lev, LS, 0);
-        if (F.jds) launch_k(h, k_galerkin_jds<D>, F.grid128, 128, 0, F.d, C.d, xref(h, F.d.lev, true));
+        if (F.d.gptr) {      // deterministic: project every fine block into the staging buffer, then one writer per coarse block
+            if (F.jds) launch_k(h, k_galerkin_stage_jds<D>, F.grid128, 128, 0, F.d, xref(h, F.d.lev, true), h->gstage);
+            else launch_k(h, k_galerkin_stage_csr<D>, F.gridw, 256, 0, F.d, xref(h, F.d.lev, true), h->gstage);
+            launch_k(h, k_galerkin_reduce<D>, grid_for(F.d.n_gblk * GalerkinLanes<D>::value, 256), 256, 0, F.d, C.d, (const double *)h->gstage);
+            h->launch_count += 1;
+        } else if (F.jds) launch_k(h, k_galerkin_jds<D>, F.grid128, 128, 0, F.d, C.d, xref(h, F.d.lev, true));
         else launch_k(h, k_galerkin_csr<D>, F.gridw, 256, 0, F.d, C.d, xref(h, F.d.lev, true));
         h->launch_count += 3;
         if (C.first_repl) {                          // every rank built the coarse rows of its own aggregates: all-gather them
@@ -690,7 +699,7 @@ static int create_shard(pgo_handle *h, const double *vval, int64_t ne, const uin
     const int rank = h->rank, world = h->world;
     const int nl = (int)S.levels.size();
     h->lv.resize(nl);
-    int64_t max_grid = 1;
+    int64_t max_grid = 1, max_stage = 0;
     // ---- pass 1: local structure of every level + arena requests (sizes from the largest partition: same layout on all ranks)
     for (int l = 0; l < nl; l++) {
         HostLevel &H = S.levels[l];
@@ -794,11 +803,21 @@ static int create_shard(pgo_handle *h, const double *vval, int64_t ne, const uin
             const int64_t c0 = Cn.part_off[(world > 1 && Cn.repl) ? 0 : rank];
             std::vector<int32_t> ag(d.n_pad, -1);
             for (int64_t r = r0; r < r1; r++) if (H.agg[r] >= 0) ag[r - r0] = (int32_t)(H.agg[r] - c0);
-            std::vector<int32_t> ct(H.ctgt.begin() + s0, H.ctgt.begin() + s1), cs(H.cstr.begin() + s0, H.cstr.begin() + s1);
-            if (ct.empty()) { ct.push_back(0); cs.push_back(1); }
-            int32_t *dag, *dct, *dcs;
-            CKC(upload(h, &dag, ag)); CKC(upload(h, &dct, ct)); CKC(upload(h, &dcs, cs));
-            d.agg = dag; d.ctgt = dct; d.cstr = dcs;
+            int32_t *dag;
+            CKC(upload(h, &dag, ag));
+            d.agg = dag;
+            if ((int)H.gal_ptr.size() > pk && !H.gal_ptr[pk].empty()) {     // deterministic Galerkin product: contributor lists
+                int32_t *dgp, *dgs;
+                CKC(upload(h, &dgp, H.gal_ptr[pk])); CKC(upload(h, &dgs, H.gal_src[pk]));
+                d.gptr = dgp; d.gsrc = dgs; d.n_gblk = (int64_t)H.gal_ptr[pk].size() - 1;
+                max_stage = std::max<int64_t>(max_stage, (int64_t)DD * (d.n_slots + d.n_pad));
+            } else {                                                        // coarse level in sliced storage: atomic scatter
+                std::vector<int32_t> ct(H.ctgt.begin() + s0, H.ctgt.begin() + s1), cs(H.cstr.begin() + s0, H.cstr.begin() + s1);
+                if (ct.empty()) { ct.push_back(0); cs.push_back(1); }
+                int32_t *dct, *dcs;
+                CKC(upload(h, &dct, ct)); CKC(upload(h, &dcs, cs));
+                d.ctgt = dct; d.cstr = dcs;
+            }
         }
         if (!H.mem_ptr.empty()) {
             HostLevel &Fn = S.levels[l - 1];
@@ -847,6 +866,7 @@ static int create_shard(pgo_handle *h, const double *vval, int64_t ne, const uin
         h->dense_m = (int)HL.n * D;
     }
     CKC(arena_commit(h));
+    if (max_stage > 0) CKC(dalloc(h, &h->gstage, (size_t)max_stage, false));
     if (h->use_amg && S.dense_coarsest) {
         const int m = h->dense_m;
         CKC(dalloc(h, &h->Ainv, (size_t)m * m));
@@ -972,6 +992,34 @@ struct MultiCtx {
     bool stop = false;
     std::vector<int> rc;
 };
+
+// CUDA loads a kernel's code lazily, at its first launch, and that load may synchronise the whole context.  Shards that share
+// ONE device also share one context, and their kernels wait for each other on the device (peer.cuh): a shard's host thread
+// blocked in such a load, behind a peer's spinning kernel that waits for the very kernel being loaded, is a deadlock (the
+// "concurrent kernels" caveat of lazy loading).  So a multi-GPU handle loads every kernel of this library up front, through the
+// driver's module enumeration (libcuda is only dlopen'ed: no link-time dependency, nothing happens on a machine without a driver).
+static bool preload_all_kernels(std::string &err) {
+    void *lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) { err = "dlopen(libcuda.so.1) failed"; return false; }
+    typedef CUresult (*fn_get_module)(CUmodule *, CUfunction);
+    typedef CUresult (*fn_count)(unsigned int *, CUmodule);
+    typedef CUresult (*fn_enum)(CUfunction *, unsigned int, CUmodule);
+    typedef CUresult (*fn_load)(CUfunction);
+    fn_get_module get_module = (fn_get_module)dlsym(lib, "cuFuncGetModule");
+    fn_count count = (fn_count)dlsym(lib, "cuModuleGetFunctionCount");
+    fn_enum enumerate = (fn_enum)dlsym(lib, "cuModuleEnumerateFunctions");
+    fn_load load = (fn_load)dlsym(lib, "cuFuncLoad");
+    if (!get_module || !count || !enumerate || !load) { err = "this CUDA driver has no cuModuleEnumerateFunctions / cuFuncLoad"; return false; }
+    cudaFunction_t f = nullptr;
+    if (cudaGetFuncBySymbol(&f, (const void *)k_scale) != cudaSuccess || !f) { (void)cudaGetLastError(); err = "cudaGetFuncBySymbol failed"; return false; }
+    CUmodule mod = nullptr;
+    unsigned int n = 0;
+    if (get_module(&mod, (CUfunction)f) != CUDA_SUCCESS || count(&n, mod) != CUDA_SUCCESS || n == 0) { err = "module enumeration failed"; return false; }
+    std::vector<CUfunction> fs(n);
+    if (enumerate(fs.data(), n, mod) != CUDA_SUCCESS) { err = "cuModuleEnumerateFunctions failed"; return false; }
+    for (CUfunction g : fs) if (load(g) != CUDA_SUCCESS) { err = "cuFuncLoad failed"; return false; }
+    return true;
+}
 
 static void multi_worker(MultiCtx *M, int k) {
     cudaSetDevice(M->dev[k]);
@@ -1113,7 +1161,20 @@ static int create_multi(pgo_handle **out, const pgo_options &opt_in, int64_t nv,
         M->shard.push_back(s);
     }
     for (int k = 0; k < n; k++) M->th.emplace_back(multi_worker, M, k);
-    int rc = multi_run(h, [&](pgo_handle *s, int) { return create_shard(s, vval, ne, ekind, emeas, einfo); });
+    bool shared_device = false;
+    for (int a = 0; a < n; a++) for (int b = a + 1; b < n; b++) shared_device |= dev[a] == dev[b];
+    int rc = multi_run(h, [&](pgo_handle *s, int k) {
+        const int rc1 = create_shard(s, vval, ne, ekind, emeas, einfo);
+        if (rc1 != PGO_OK) return rc1;
+        bool first_on_device = true;                     // one load per context
+        for (int j = 0; j < k; j++) first_on_device &= dev[j] != dev[k];
+        std::string perr;
+        if (first_on_device && !preload_all_kernels(perr) && shared_device) {
+            s->err = "shards share GPU " + std::to_string(dev[k]) + " and the kernels cannot be pre-loaded (" + perr + "): set CUDA_MODULE_LOADING=EAGER";
+            return (int)PGO_ERR_CUDA;
+        }
+        return (int)PGO_OK;
+    });
     if (rc == PGO_OK)
         rc = multi_run(h, [&](pgo_handle *s, int k) {            // peer access from this shard's device to the others'
             for (int j = 0; j < n; j++) {
@@ -1133,7 +1194,7 @@ static int create_multi(pgo_handle **out, const pgo_options &opt_in, int64_t nv,
         }
         s->connected = true;
     }
-    for (auto &L : h->sym.levels) { L.ctgt.clear(); L.ctgt.shrink_to_fit(); L.cstr.clear(); L.cstr.shrink_to_fit(); }
+    for (auto &L : h->sym.levels) { L.ctgt.clear(); L.ctgt.shrink_to_fit(); L.cstr.clear(); L.cstr.shrink_to_fit(); L.gal_ptr.clear(); L.gal_ptr.shrink_to_fit(); L.gal_src.clear(); L.gal_src.shrink_to_fit(); }
     *out = h;
     return PGO_OK;
 }
@@ -1166,7 +1227,7 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
         const int rc = create_shard(h, vval, ne, ekind, emeas, einfo);
         if (rc != PGO_OK) return fail_create(h, rc, h->err);
         // the big transient host arrays are not needed any more
-        for (auto &L : h->sym.levels) { L.ctgt.clear(); L.ctgt.shrink_to_fit(); L.cstr.clear(); L.cstr.shrink_to_fit(); }
+        for (auto &L : h->sym.levels) { L.ctgt.clear(); L.ctgt.shrink_to_fit(); L.cstr.clear(); L.cstr.shrink_to_fit(); L.gal_ptr.clear(); L.gal_ptr.shrink_to_fit(); L.gal_src.clear(); L.gal_src.shrink_to_fit(); }
     }
     *out = h;
     return PGO_OK;

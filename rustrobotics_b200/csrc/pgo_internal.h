@@ -55,6 +55,10 @@ struct HostLevel {
     std::vector<int32_t> ctgt;        // [n_slots] Galerkin target of each stored block, LOCAL to the owning partition:
                                       //   >= 0: element offset of component 0 in the coarse val array ; < 0: diagonal of coarse row (-1 - row)
     std::vector<int32_t> cstr;        // [n_slots] stride between the 9 components of that target (1: CSR ; cnt: sliced storage)
+    // deterministic Galerkin product (coarse level stored as block CSR): per partition k, the contributors of every coarse block in a
+    // FIXED order.  Coarse block ids are local to the coarse partition: [0, rows) = diagonal blocks, rows + s = stored block s;
+    // a contributor is an index into the fine partition's staging buffer: [0, slots) = stored block, slots + r = diagonal block of row r.
+    std::vector<std::vector<int32_t>> gal_ptr, gal_src;
     // this level seen as the coarse side of the finer level: members (finer global padded rows) of each row
     std::vector<int64_t> mem_ptr;     // [n_pad + 1]
     std::vector<int32_t> mem_idx;

@@ -306,6 +306,35 @@ static void build_coarse_level(HostLevel &F, HostLevel &C, const std::vector<std
         }
         });
     TICK("  bcl: galerkin targets");
+    // Contributor lists of the deterministic (atomics-free) Galerkin product: every fine block is first projected into a staging
+    // buffer in storage order (coalesced), then ONE group of lanes per coarse block sums its contributors in this fixed order.
+    F.gal_ptr.assign(world, {});
+    F.gal_src.assign(world, {});
+    if (!jds) {
+        parallel_for(world, 1, [&](int64_t k0, int64_t k1) {
+            for (int64_t k = k0; k < k1; k++) {
+                const int kc = merge ? 0 : (int)k;
+                const int64_t crows = C.part_off[kc + 1] - C.part_off[kc], cslots = C.part_slot[kc + 1] - C.part_slot[kc];
+                const int64_t fr0 = F.part_off[k], fs0 = F.part_slot[k], fslots = F.part_slot[k + 1] - fs0;
+                const int64_t nblk = crows + cslots;
+                std::vector<int32_t> &ptr = F.gal_ptr[k], &src = F.gal_src[k];
+                ptr.assign(nblk + 1, 0);
+                auto target = [&](int32_t ct) -> int64_t { return ct < 0 ? (int64_t)(-1 - ct) : crows + ct / DD; };
+                // stage order: stored blocks by slot, then the diagonal blocks by row
+                std::vector<int32_t> slot_tgt(fslots, -1);                 // padding slots of the sliced storage have no block
+                for (int64_t r = fr0; r < fr0 + F.part_real[k]; r++)
+                    for (int64_t q = F.adj_ptr[r]; q < F.adj_ptr[r + 1]; q++) slot_tgt[F.adj_slot[q] - fs0] = (int32_t)target(F.ctgt[F.adj_slot[q]]);
+                for (int64_t sl = 0; sl < fslots; sl++) if (slot_tgt[sl] >= 0) ptr[slot_tgt[sl] + 1]++;
+                for (int64_t i = 0; i < F.part_real[k]; i++) ptr[(F.agg[fr0 + i] - C.part_off[kc]) + 1]++;
+                for (int64_t b = 0; b < nblk; b++) ptr[b + 1] += ptr[b];
+                src.resize(ptr[nblk]);
+                std::vector<int32_t> pos(ptr.begin(), ptr.end() - 1);
+                for (int64_t sl = 0; sl < fslots; sl++) if (slot_tgt[sl] >= 0) src[pos[slot_tgt[sl]]++] = (int32_t)sl;
+                for (int64_t i = 0; i < F.part_real[k]; i++) src[pos[F.agg[fr0 + i] - C.part_off[kc]]++] = (int32_t)(fslots + i);
+            }
+        });
+    }
+    TICK("  bcl: galerkin contributor lists");
 }
 
 // renumber the aggregates of every partition by decreasing coarse degree inside windows (what the sliced storage needs)

@@ -183,3 +183,82 @@ def test_config5_sphere_full_size_properties(built):
     cgt = pg.global_error()
     assert 0.9 < cgt / (6 * ne) < 1.1
     assert c2 < 1.2 * cgt
+
+
+# ---- the GPU's own Jacobians against finite differences of the GPU's own chi2 (no oracle involved) ----------------------------
+def _quat_mul(a, b):      # (x, y, z, w) convention of the g2o files
+    ax, ay, az, aw = a; bx, by, bz, bw = b
+    return np.array([aw * bx + ax * bw + ay * bz - az * by, aw * by - ax * bz + ay * bw + az * bx,
+                     aw * bz + ax * by - ay * bx + az * bw, aw * bw - ax * bx - ay * by - az * bz])
+
+
+def _quat_exp(w):
+    th = np.linalg.norm(w)
+    s = np.sin(th / 2) / th if th > 1e-12 else 0.5
+    return np.array([s * w[0], s * w[1], s * w[2], np.cos(th / 2)])
+
+
+def _retract(values, d):
+    """the solver's retraction on packed (x y z qx qy qz qw) poses: t += dt (global frame), q <- q Exp(dw) (body frame)"""
+    v = values.reshape(-1, 7).copy(); d = d.reshape(-1, 6)
+    for i in range(len(v)):
+        v[i, :3] += d[i, :3]
+        v[i, 3:] = _quat_mul(v[i, 3:], _quat_exp(d[i, 3:]))
+    return v.ravel()
+
+
+def _quat_rot(q, t):
+    x, y, z, w = q
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                  [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                  [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    return R @ t
+
+
+def test_se3_gpu_jacobians_match_finite_differences_of_gpu_chi2(built):
+    """2-vertex SE3 graph through the C ABI.  (1) generic measurement: b = -J^T Omega e must equal minus half the central-difference
+    gradient of the GPU's chi2 along its own retraction.  (2) measurement = the exact relative pose (e = 0): the Gauss-Newton matrix
+    J^T Omega J the GPU assembles (pgo_get_system, anchor weight removed) must equal half the finite-difference Hessian of chi2."""
+    rng = np.random.default_rng(7)
+    q1 = rng.standard_normal(4); q1 /= np.linalg.norm(q1)
+    q2 = rng.standard_normal(4); q2 /= np.linalg.norm(q2)
+    t1, t2 = rng.standard_normal(3), rng.standard_normal(3) * 2
+    vals = np.concatenate([t1, q1, t2, q2])
+    q1c = q1 * np.array([-1, -1, -1, 1])
+    z_exact = np.concatenate([_quat_rot(q1c, t2 - t1), _quat_mul(q1c, q2)])
+    A = rng.standard_normal((6, 6)); W = A @ A.T + 6 * np.eye(6)
+    iu = np.triu_indices(6)
+
+    def graph(z):
+        return dict(vertex_id=np.array([0, 1], np.uint32), vertex_kind=np.full(2, 2, np.uint8), vertex_values=vals,
+                    edge_kind=np.full(1, 2, np.uint8), edge_from=np.array([0], np.uint32), edge_to=np.array([1], np.uint32),
+                    edge_meas=z, edge_info_upper=W[iu])
+
+    def chi2_at(pg, d):
+        pg.set_poses(_retract(vals, d))
+        return pg.global_error()
+
+    # (1) gradient, generic residual
+    zq = _quat_mul(z_exact[3:], _quat_exp(np.array([0.2, -0.1, 0.15])))
+    pg = _pg(graph(np.concatenate([z_exact[:3] + [0.3, -0.2, 0.1], zq])))
+    _, _, _, b = pg.system()
+    h = 1e-6
+    grad = np.zeros(12)
+    for k in range(12):
+        e = np.zeros(12); e[k] = h
+        grad[k] = (chi2_at(pg, e) - chi2_at(pg, -e)) / (2 * h)
+    assert np.abs(-0.5 * grad - b).max() <= 1e-6 * max(np.abs(b).max(), 1.0), (grad, b)
+    # (2) Gauss-Newton matrix at zero residual
+    pg = _pg(graph(z_exact))
+    cp, ri, v, _ = pg.system()
+    import scipy.sparse as sp
+    H = sp.csc_matrix((v, ri, cp), shape=(12, 12)).toarray()
+    H[:6, :6] -= 1e7 * np.eye(6)                                  # the anchor on the first edge's `from`
+    assert chi2_at(pg, np.zeros(12)) <= 1e-20
+    h = 1e-4
+    Hfd = np.zeros((12, 12))
+    for a in range(12):
+        for c in range(a, 12):
+            ea = np.zeros(12); ea[a] = h; ec = np.zeros(12); ec[c] = h
+            Hfd[a, c] = Hfd[c, a] = (chi2_at(pg, ea + ec) - chi2_at(pg, ea - ec) - chi2_at(pg, ec - ea) + chi2_at(pg, -ea - ec)) / (4 * h * h)
+    assert np.abs(0.5 * Hfd - H).max() <= 2e-5 * np.abs(H).max(), np.abs(0.5 * Hfd - H).max()
