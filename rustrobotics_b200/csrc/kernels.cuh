@@ -21,6 +21,13 @@ namespace cg = cooperative_groups;
 // ------------------------------------------------------------------------------------------------
 constexpr int MAX_LEVELS = 12;
 struct KScal { double alpha, coef1, coef2, coef3, rho1, a1, rho2, gam21, alpha2, e1, e2; int steps, pad_; };
+// Cross-rank synchronisation block (sharded handles): one per rank at the start of its peer-visible arena, see xrank_exchange
+struct Comm {
+    unsigned long long flags[MAX_RANKS];
+    double vals[2][MAX_RANKS][4];
+};
+struct CommRef { Comm *p[MAX_RANKS]; };
+
 struct Scalars {
     double rz, rz0, pq, alpha, beta, tol2;
     double norm2_dx, chi2;
@@ -29,7 +36,8 @@ struct Scalars {
     int world, repl_from;           // sharded handles: levels >= repl_from are replicated (their sums are already global)
     unsigned long long epoch;       // cross-rank barrier epoch (peer.cuh)
     KScal k[MAX_LEVELS];
-    double loc[4];                  // sharded mode: this rank's partial sums, reduced across ranks by k_xreduce
+    double loc[4];                  // (unused since the cross-rank reduction is fused into the producing kernel)
+    Comm *comm_mine; Comm *comm_peer[MAX_RANKS]; int rank, pad2_;   // sharded handles: where the last block of a reducing kernel meets its peers
 };
 enum { ST_OK = 0, ST_BREAKDOWN = 1, ST_MAXIT = 2, ST_COMM = 3 };
 enum { FIN_NONE = 0, FIN_PQ = 1, FIN_RZ = 2, FIN_RZ_INIT = 3, FIN_NORM = 4, FIN_CHI2 = 5, FIN_K1 = 6, FIN_K2 = 7, FIN_K3 = 8 };
@@ -157,9 +165,57 @@ template <int NT, int NV> __device__ bool block_sum_last(const double *v, double
             for (int w = 0; w < NT / 32; w++) t += sm[k][w];
             total[k] = t;
         }
-        return true;
     }
-    return false;
+    return true;                                   // every thread of the last block; `total` is valid in thread 0
+}
+
+// Cross-rank all-reduce / barrier over NVLink peer memory, executed by ONE CTA per rank (the last block of a reducing kernel, or
+// the single block of k_xreduce): thread t < world stores this rank's NV partial sums and then the new epoch into rank t's Comm
+// block (st.release.sys), and spins on its own Comm until rank t's epoch arrives (ld.acquire.sys); thread 0 then adds the
+// partials in rank order (identical bits on every rank).  Kernels of one stream run in order, so every later kernel sees the
+// peers' earlier writes; no peer can be more than one epoch ahead (values are double-buffered by epoch parity).  A spin of
+// more than ~20 s sets ST_COMM and ends the solve instead of hanging.  Called by all threads of the block; returns false on time-out.
+template <int NV> __device__ bool xrank_exchange(Scalars *S, double *total) {
+    __shared__ unsigned long long ep;
+    __shared__ int bad;
+    __shared__ double mine_v[NV > 0 ? NV : 1];
+    const int t = threadIdx.x, world = S->world, rank = S->rank;
+    if (t == 0) {
+        ep = S->epoch + 1; S->epoch = ep; bad = 0;
+#pragma unroll
+        for (int k = 0; k < NV; k++) mine_v[k] = total[k];
+    }
+    __syncthreads();
+    const unsigned long long epoch = ep;
+    const int slot = (int)(epoch & 1);
+    Comm *mine = S->comm_mine;
+    if (t < world) {
+        Comm *p = S->comm_peer[t];
+#pragma unroll
+        for (int k = 0; k < NV; k++) *((volatile double *)&p->vals[slot][rank][k]) = mine_v[k];
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&p->flags[rank]), "l"(epoch) : "memory");
+        const long long t0 = clock64();
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(&mine->flags[t]) : "memory");
+            if (v < epoch && clock64() - t0 > 40000000000ll) { bad = 1; break; }
+        } while (v < epoch);
+    }
+    __syncthreads();
+    if (bad) {
+        if (t == 0) { S->status = ST_COMM; S->done = 1; __threadfence(); }
+        return false;
+    }
+    if (t == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            double s = 0.0;
+            for (int r = 0; r < world; r++) s += *((volatile double *)&mine->vals[slot][r][k]);
+            total[k] = s;
+        }
+    }
+    return true;
 }
 
 // what the owner of a global sum does with it (PCG / flexible-CG / K-cycle scalar recurrences)
@@ -231,13 +287,10 @@ template <int NT, int FIN> __device__ __forceinline__ void reduce_and_finalize(c
     if (FIN == FIN_NONE) return;
     constexpr int NV = fin_ndot(FIN) > 0 ? fin_ndot(FIN) : 1;
     double total[NV];
-    if (block_sum_last<NT, NV>(dots, partials, &S->counter[FIN], total, vb, nvb)) {
-        if (S->world > 1 && lvl < S->repl_from) {
-#pragma unroll
-            for (int k = 0; k < NV; k++) S->loc[k] = total[k];
-            __threadfence();
-        } else finalize(FIN, S, total, lvl);
-    }
+    if (!block_sum_last<NT, NV>(dots, partials, &S->counter[FIN], total, vb, nvb)) return;
+    // the last block of this rank: on a sharded level it meets the other ranks' last blocks right here (no separate kernel)
+    if (S->world > 1 && lvl < S->repl_from && !xrank_exchange<NV>(S, total)) return;
+    if (threadIdx.x == 0) finalize(FIN, S, total, lvl);
 }
 
 // Tail of the sliced SpMV of one block row (shared by k_spmv and k_spmv_tma): adds the diagonal block, applies the MODE,
@@ -324,7 +377,10 @@ __device__ __forceinline__ void spmv_row_finish(const LevelDev &L, int64_t row, 
 //   MODE 1: y = r - H x                  (residual)
 //   MODE 2: y = x + omega Dinv (r - H x) (damped block-Jacobi sweep; + r.y -> FIN_RZ_INIT, + {r.y, y.u1} -> FIN_RZ)
 // Large coarse levels use the same kernel (K-cycle dots FIN_K1 / FIN_K2 as in k_spmv_csr).
-template <int D, int MODE, int FIN, bool PEER, typename VT = double, int U = 1>
+// CS: the block values -- a pure stream, every byte used once per launch -- are loaded with the evict-first policy (ld.global.cs),
+// so that they do not push the data that IS re-used out of L2: the gathered x records and, between the three fine-level products
+// of a PCG iteration, the L2-resident coarse levels.
+template <int D, int MODE, int FIN, bool PEER, typename VT = double, int U = 1, bool CS = false>
 __global__ void __launch_bounds__(128) k_spmv(LevelDev L, const __grid_constant__ XRef xr, const double *__restrict__ x, const double *__restrict__ r,
                                                double *__restrict__ y, double omega, const double *__restrict__ u1, const double *__restrict__ u2,
                                                Scalars *S, double *partials, int lvl, int check_done) {
@@ -387,7 +443,7 @@ __global__ void __launch_bounds__(128) k_spmv(LevelDev L, const __grid_constant_
                     ld_vec<VS>(PEER ? xgather<VS>(xr, cw[j]) : x + (int64_t)(cw[j] & COL_LOCAL_MASK) * VS, xj[j]);
                     const VT *v = vals + of[j] * DD;
 #pragma unroll
-                    for (int q = 0; q < DD; q++) hv[j][q] = __ldg(v + (int64_t)q * cn[j]);
+                    for (int q = 0; q < DD; q++) hv[j][q] = CS ? __ldcs(v + (int64_t)q * cn[j]) : __ldg(v + (int64_t)q * cn[j]);
                 }
             }
             {
@@ -1727,10 +1783,15 @@ __global__ void __launch_bounds__(128) k_assemble_se2(LevelDev L, const __grid_c
             for (int q = 0; q < 9; q++) Hd[q] += Own[q];
             g[0] += gi[0]; g[1] += gi[1]; g[2] += gi[2];
             double *v = L.val + (base + off) * 9 + lane;
+            float *vf = L.valf ? L.valf + (base + off) * 9 + lane : nullptr;      // fp32 copy for the cycle's products, written in the same pass
 #pragma unroll
             for (int r = 0; r < 3; r++)
 #pragma unroll
-                for (int c = 0; c < 3; c++) v[(int64_t)(3 * r + c) * cnt] = to_side ? T[3 * c + r] : T[3 * r + c];
+                for (int c = 0; c < 3; c++) {
+                    const double t = to_side ? T[3 * c + r] : T[3 * r + c];
+                    v[(int64_t)(3 * r + c) * cnt] = t;
+                    if (vf) vf[(int64_t)(3 * r + c) * cnt] = (float)t;
+                }
         }
         off += cnt;
     }
@@ -1750,6 +1811,7 @@ __global__ void __launch_bounds__(128) k_assemble_se2(LevelDev L, const __grid_c
     for (int q = 0; q < 9; q++) {
         L.diag[(int64_t)q * L.n_pad + row] = Hd[q];
         L.dinv[(int64_t)q * L.n_pad + row] = Di[q];
+        if (L.diagf) { L.diagf[(int64_t)q * L.n_pad + row] = (float)Hd[q]; L.dinvf[(int64_t)q * L.n_pad + row] = (float)Di[q]; }
     }
     double out[4] = {-g[0], -g[1], -g[2], 0.0};                                                 // b = -g (:361)
     st_vec<4>(rvec + row * 4, out);
@@ -2010,6 +2072,7 @@ __global__ void __launch_bounds__(128) k_assemble_se3(LevelDev L, const double *
 #pragma unroll
                     for (int q = 0; q < 6; q++) h = fma(WJ[6 * q + r], K[6 * q + c], h);
                     v[(int64_t)(6 * r + c) * cnt] = h;
+                    if (L.valf) L.valf[(base + off) * 36 + lane + (int64_t)(6 * r + c) * cnt] = (float)h;
                 }
         }
         off += cnt;
@@ -2029,6 +2092,7 @@ __global__ void __launch_bounds__(128) k_assemble_se3(LevelDev L, const double *
     for (int q = 0; q < 36; q++) {
         L.diag[(int64_t)q * L.n_pad + row] = Hd[q];
         L.dinv[(int64_t)q * L.n_pad + row] = Di[q];
+        if (L.diagf) { L.diagf[(int64_t)q * L.n_pad + row] = (float)Hd[q]; L.dinvf[(int64_t)q * L.n_pad + row] = (float)Di[q]; }
     }
     double out[6] = {-g[0], -g[1], -g[2], -g[3], -g[4], -g[5]};
     st_vec<6>(rvec + row * 6, out);

@@ -99,7 +99,6 @@ struct pgo_handle {
     char *peer_base[MAX_RANKS]{};
     std::vector<ArenaReq> arena_reqs;
     Comm *comm = nullptr;
-    CommRef comm_ref{};
     // level-0 state (local rows)
     int64_t n_loc = 0, n_pad_loc = 0, n_edges_loc = 0, row0 = 0;
     double *poses = nullptr, *poses_saved = nullptr, *hz = nullptr, *ed = nullptr;
@@ -116,6 +115,7 @@ struct pgo_handle {
     bool use_amg = false, omega_ready = false;
     int spmv_tma64 = 0, spmv_tma32 = 0; // PGO_SPMV_TMA64 / PGO_SPMV_TMA32: ring depth of the TMA-staged sliced SpMV (0: register-staged kernel)
     int64_t lpr4_min_rows = 16384;     // PGO_LPR4_MIN_ROWS
+    bool stream_cs = false;            // PGO_STREAM_CS=1: evict-first loads of the fine-level block values (experiment)
     bool pdl = true;                   // programmatic dependent launch of every kernel (PGO_PDL=0 disables)
     cudaError_t launch_err = cudaSuccess;
     bool lowp = false;                 // the cycle's SpMVs read fp32 copies of the stored blocks (opt.amg_fp64_storage == 0)
@@ -195,9 +195,11 @@ XRef xref(const pgo_handle *h, const double *local, bool repl = false) {
 }
 
 // ---- cross-rank stage barrier / all-reduce of the partial sums a kernel left in S->loc (world > 1 only)
+// All-reduces (FIN != FIN_NONE) happen inside the kernel that produced the partial sums: its last block exchanges them with the
+// peers' last blocks (kernels.cuh: reduce_and_finalize), which is also a barrier.  Only the plain barrier is a kernel of its own.
 template <int FIN> void xreduce(pgo_handle *h, int lvl, int check_done) {
-    if (h->world == 1 || h->lv[lvl].repl) return;
-    launch_k(h, k_xreduce<FIN>, 1, 32, 0, h->comm, h->comm_ref, h->rank, h->world, h->S, lvl, check_done);
+    if (FIN != FIN_NONE || h->world == 1 || h->lv[lvl].repl) return;
+    launch_k(h, k_xbarrier, 1, 32, 0, h->S, check_done);
     h->launch_count += 1;
 }
 inline void xbarrier(pgo_handle *h, int check_done = 1) { xreduce<FIN_NONE>(h, 0, check_done); }
@@ -232,7 +234,8 @@ template <int D, int MODE, int FIN, typename VT> void spmv_launch(pgo_handle *h,
             const size_t smem = spmv_tma_smem<D, VT>(ns);
             if (smem > 48 * 1024) cudaFuncSetAttribute(k_spmv_tma<D, MODE, FIN, VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             launch_k(h, k_spmv_tma<D, MODE, FIN, VT>, B.grid128, 128, smem, B.d, x, r, y, omega, u1, u2, h->S, h->partials, l, check, ns);
-        } else launch_k(h, k_spmv<D, MODE, FIN, false, VT>, B.grid128, 128, 0, B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
+        } else if (h->stream_cs) launch_k(h, k_spmv<D, MODE, FIN, false, VT, 1, true>, B.grid128, 128, 0, B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
+        else launch_k(h, k_spmv<D, MODE, FIN, false, VT>, B.grid128, 128, 0, B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
     }
     else if (B.lpr == 4) launch_k(h, k_spmv_csr<D, MODE, FIN, false, 4, VT>, B.grid4, 256, 0, B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
     else if (B.lpr == 8) launch_k(h, k_spmv_csr<D, MODE, FIN, false, 8, VT>, B.grid8, 256, 0, B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
@@ -240,13 +243,16 @@ template <int D, int MODE, int FIN, typename VT> void spmv_launch(pgo_handle *h,
 }
 // CYC: the product belongs to the multigrid cycle (the preconditioner), which may read the fp32 copy of the blocks;
 // the PCG operator product, the setup and the diagnostics always read the fp64 blocks
-template <int D, int MODE, int FIN, bool CYC = false> void spmv(pgo_handle *h, int l, const double *x, const double *r, double *y, double omega,
-                                                                const double *u1, const double *u2, int check) {
-    halo_pull(h, l, x, VecStride<D>::value, check);  // the caller's barrier made the peers' x final
+// Sharded levels: the product gathers neighbour rows of x from the halo slots behind the rank's own rows.  PULL: fetch them from the
+// peers first (the caller's barrier / all-reduce made the peers' x final); false when the caller keeps the halo slots current itself.
+// A fused all-reduce (FIN != FIN_NONE) is also a barrier between the ranks; with FIN_NONE the CALLER places the barriers its data
+// hazards need (peers may still be pulling x when this returns).
+template <int D, int MODE, int FIN, bool CYC = false, bool PULL = true> void spmv(pgo_handle *h, int l, const double *x, const double *r, double *y, double omega,
+                                                                                  const double *u1, const double *u2, int check) {
+    if (PULL) halo_pull(h, l, x, VecStride<D>::value, check);
     if (CYC && h->lowp) spmv_launch<D, MODE, FIN, float>(h, l, x, r, y, omega, u1, u2, check);
     else spmv_launch<D, MODE, FIN, double>(h, l, x, r, y, omega, u1, u2, check);
     h->launch_count += 1;
-    xreduce<FIN>(h, l, check);
 }
 template <int D, int MODE, bool CYC = false> void spmv_any(pgo_handle *h, int l, const double *x, const double *r, double *y, double omega, int check) {
     spmv<D, MODE, FIN_NONE, CYC>(h, l, x, r, y, omega, nullptr, nullptr, check);
@@ -285,7 +291,9 @@ template <int D, int FINK, bool PRE = false> void cycle(pgo_handle *h, int l, co
         launch_k(h, k_dinv_apply<D, FIN_NONE>, B.grid128, 128, 0, B.d, rhs, B.xa, B.omega, nullptr, h->S, h->partials, 1);
         h->launch_count += 1;
     }
-    lbarrier(h, l);
+    lbarrier(h, l);                                  // the peers' xa rows are final before the halo pull
+    // no barrier behind this product: xa is only overwritten by the prolongation, and every path to it crosses a barrier (the
+    // gather of the first replicated level's right-hand side, or the barriers inside a sharded coarse solve)
     spmv_any<D, 1, true>(h, l, B.xa, rhs, B.res, 0.0, 1);
     launch_k(h, k_restrict<D>, C.gridw, 256, 0, B.d, C.d, B.res, C.rhs, h->S);
     h->launch_count += 1;
@@ -299,9 +307,9 @@ template <int D, int FINK, bool PRE = false> void cycle(pgo_handle *h, int l, co
     if (kfold) launch_k(h, k_prolong_k<D>, B.grid128, 128, 0, B.d, C.c1, C.c2, C.ksteps == 3 ? C.c3 : nullptr, B.xa, h->S, l + 1);
     else launch_k(h, k_prolong<D>, B.grid128, 128, 0, B.d, C.sol, B.xa, h->S);
     h->launch_count += 1;
-    lbarrier(h, l);
+    lbarrier(h, l);                                  // the peers' xa rows are final before the halo pull
     spmv<D, 2, FINK, true>(h, l, B.xa, rhs, out, B.omega, FINK == FIN_RZ ? h->q : nullptr, nullptr, 1);
-    if (FINK == FIN_NONE) lbarrier(h, l);            // FINK != NONE: the all-reduce is the barrier
+    if (FINK == FIN_NONE) lbarrier(h, l);            // `out` is final everywhere (FINK != NONE: the fused all-reduce is the barrier)
 }
 
 // K-cycle: the coarse system of level l is solved by two flexible-CG steps preconditioned by the cycle of level l
@@ -346,9 +354,20 @@ template <int D, int FINK, bool PRE = false> void precondition(pgo_handle *h) { 
     }
 }
 
+// p = z + beta p on the rank's own rows AND on the halo slots: the peers' z rows are pulled (z is final everywhere once the r.z
+// all-reduce inside the preconditioner's last kernel has completed), so the halo of p never has to be exchanged and no barrier
+// is needed between the update and the next product H p
+template <int D> void update_p(pgo_handle *h) {
+    LevelBuf &B = h->lv[0];
+    halo_pull(h, 0, h->z, VecStride<D>::value, 1);
+    const int64_t rows = B.d.n_pad + (h->world > 1 ? B.n_halo : 0);
+    launch_k(h, k_update_p<D>, grid_for(rows * (VecStride<D>::value / 2), 256), 256, 0, rows, h->p, h->z, h->S);
+    h->launch_count += 1;
+}
+
 template <int D> void pcg_iteration(pgo_handle *h) {
     LevelBuf &B = h->lv[0];
-    spmv<D, 0, FIN_PQ>(h, 0, h->p, nullptr, h->q, 0.0, nullptr, nullptr, 1);
+    spmv<D, 0, FIN_PQ, false, false>(h, 0, h->p, nullptr, h->q, 0.0, nullptr, nullptr, 1);
     if (h->use_amg && h->lv.size() > 1) {
         launch_k(h, k_update_xr_dinv<D>, B.grid128, 128, 0, B.d, h->x, h->r, h->p, h->q, B.xa, B.omega, h->S);
         precondition<D, FIN_RZ, true>(h);
@@ -356,9 +375,8 @@ template <int D> void pcg_iteration(pgo_handle *h) {
         launch_k(h, k_update_xr<D>, B.gridv, 256, 0, B.d.n_pad, h->x, h->r, h->p, h->q, h->S);
         precondition<D, FIN_RZ>(h);
     }
-    launch_k(h, k_update_p<D>, B.gridv, 256, 0, B.d.n_pad, h->p, h->z, h->S);
-    h->launch_count += 2;
-    xbarrier(h);                                     // p complete on every rank before the next SpMV reads it
+    h->launch_count += 1;
+    update_p<D>(h);
 }
 
 template <int D> int build_pcg_graph(pgo_handle *h) {
@@ -398,6 +416,14 @@ template <int D> int assemble(pgo_handle *h, double lambda, int add_lambda) {
     return PGO_OK;
 }
 
+// the peers' Comm blocks (= the start of their arenas) into the device-side scalars, once the shards are connected
+int upload_comm_peers(pgo_handle *h) {
+    Comm *peers[MAX_RANKS];
+    for (int k = 0; k < MAX_RANKS; k++) peers[k] = (Comm *)h->peer_base[k < h->world ? k : h->rank];
+    CK(cudaMemcpy(&h->S->comm_peer[0], peers, sizeof(peers), cudaMemcpyHostToDevice));
+    return PGO_OK;
+}
+
 int comm_status(pgo_handle *h, const Scalars &s) {
     if (s.status == ST_COMM) { h->err = "peer synchronisation timed out (a rank is missing or out of step)"; return PGO_ERR_COMM; }
     return PGO_OK;
@@ -428,6 +454,7 @@ template <int D> int estimate_omega(pgo_handle *h, int l) {
         // b = H a ; a' = Dinv b ; rho ~ |a'| / |a|
         lbarrier(h, l, 0);
         spmv_any<D, 0>(h, l, a, nullptr, b, 0.0, 0);
+        lbarrier(h, l, 0);                           // every peer has pulled its halo of `a` before it is overwritten
         launch_k(h, k_dinv_apply<D, FIN_NONE>, B.grid128, 128, 0, B.d, b, a, 1.0, nullptr, h->S, h->partials, 0);
         launch_k(h, k_dots<D, FIN_NORM>, B.grid128, 128, 0, B.d.n_pad, a, a, nullptr, h->S, h->partials, l, 0);
         xreduce<FIN_NORM>(h, l, 0);
@@ -463,7 +490,7 @@ template <int D> int amg_setup(pgo_handle *h) {
             h->launch_count += 2;
         }
     };
-    to_float(h->lv[0]);
+    // level 0: the assembly kernel wrote the fp32 copies (blocks, diagonal blocks, their inverses) in the same pass
     for (int l = 0; l < last; l++) {
         LevelBuf &F = h->lv[l], &C = h->lv[l + 1];
         launch_k(h, k_coarse_pos<NG>, C.gridw, 256, 0, F.d, C.d);
@@ -536,8 +563,8 @@ template <int D> int solve(pgo_handle *h, int32_t *iters_out) {
     if (rc) return rc;
     CK(cudaMemsetAsync(h->x, 0, nd * sizeof(double), h->stream));
     precondition<D, FIN_RZ_INIT>(h);
-    CK(cudaMemcpyAsync(h->p, h->z, nd * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    xbarrier(h);
+    halo_pull(h, 0, h->z, VecStride<D>::value, 1);   // p = z, halo slots included (pcg_iteration keeps them current from here on)
+    CK(cudaMemcpyAsync(h->p, h->z, (nd + (h->world > 1 ? B.n_halo * VecStride<D>::value : 0)) * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     // keep two graph launches in flight; poll the pinned scalars of the older one
     int slot = 0, inflight = 0;
     int64_t launched = 0;
@@ -966,6 +993,9 @@ static int create_shard(pgo_handle *h, const double *vval, int64_t ne, const uin
     {
         Scalars s{};
         s.world = world;
+        s.rank = rank;
+        s.comm_mine = (Comm *)h->arena;
+        for (int k = 0; k < MAX_RANKS; k++) s.comm_peer[k] = (Comm *)h->arena;    // the peers' blocks are filled in when the shards connect
         s.repl_from = nl;
         for (int l = nl - 1; l >= 1; l--) if (h->lv[l].repl) s.repl_from = l;
         CKU(cudaMemcpyAsync(h->S, &s, sizeof(Scalars), cudaMemcpyHostToDevice, h->stream));
@@ -1109,6 +1139,7 @@ static SymbolicOptions configure_handle(pgo_handle *h) {
     if (const char *e = std::getenv("PGO_SPMV_TMA32")) h->spmv_tma32 = std::max(0, std::min(16, std::atoi(e)));
     if (const char *e = std::getenv("PGO_LPR4_MIN_ROWS")) h->lpr4_min_rows = std::atoll(e);
     if (const char *e = std::getenv("PGO_PDL")) h->pdl = std::atoi(e) != 0;
+    if (const char *e = std::getenv("PGO_STREAM_CS")) h->stream_cs = std::atoi(e) != 0;
     h->lowp = h->use_amg && h->opt.amg_fp64_storage == 0;
     return so;
 }
@@ -1188,12 +1219,10 @@ static int create_multi(pgo_handle **out, const pgo_options &opt_in, int64_t nv,
     if (rc != PGO_OK) return fail_create(h, rc, h->err);
     for (int k = 0; k < n; k++) {                     // one address space: a peer's arena is simply its pointer
         pgo_handle *s = M->shard[k];
-        for (int j = 0; j < MAX_RANKS; j++) {
-            s->peer_base[j] = j < n ? M->shard[j]->arena : nullptr;
-            s->comm_ref.p[j] = (Comm *)M->shard[j < n ? j : k]->arena;
-        }
-        s->connected = true;
+        for (int j = 0; j < MAX_RANKS; j++) s->peer_base[j] = j < n ? M->shard[j]->arena : nullptr;
     }
+    rc = multi_run(h, [&](pgo_handle *s, int) { const int r = upload_comm_peers(s); s->connected = r == PGO_OK; return r; });
+    if (rc != PGO_OK) return fail_create(h, rc, h->err);
     for (auto &L : h->sym.levels) { L.ctgt.clear(); L.ctgt.shrink_to_fit(); L.cstr.clear(); L.cstr.shrink_to_fit(); L.gal_ptr.clear(); L.gal_ptr.shrink_to_fit(); L.gal_src.clear(); L.gal_src.shrink_to_fit(); }
     *out = h;
     return PGO_OK;
@@ -1259,7 +1288,7 @@ int pgo_shard_connect(pgo_handle *h, const void *all_handles, int64_t n_handles)
         h->peer_base[k] = (char *)p;
         h->ipc_peer[k] = true;
     }
-    for (int k = 0; k < MAX_RANKS; k++) h->comm_ref.p[k] = (Comm *)h->peer_base[k < h->world ? k : h->rank];
+    { int rc = upload_comm_peers(h); if (rc) return rc; }
     h->connected = true;
     return PGO_OK;
 }

@@ -301,6 +301,26 @@ def test_config4_first_step_matches_the_golden_solution_at_the_benchmark_toleran
     assert e_dx[:, :2].max() <= tol_xy and e_dx[:, 2].max() <= POSE_ATOL
 
 
+@pytest.mark.parametrize("n_gpus", [1, 2])
+def test_repeat_runs_are_bit_identical(built, n_gpus):
+    """deterministic mode is the only mode: no atomics anywhere on the path (segmented assembly, single-writer Galerkin product,
+    two-stage reductions summed in a fixed order, cross-GPU sums in rank order), so two handles on the same graph produce the same
+    BITS -- chi2, |dx|, every component of dx and of the poses -- on one GPU and with the graph sharded over two"""
+    import torch
+    from rustrobotics_b200 import Options, PoseGraph
+    from rustrobotics_b200.synthetic import manhattan_se2
+    g = manhattan_se2(100000)
+    runs = []
+    for _ in range(2):
+        kw = {} if n_gpus == 1 else dict(device_ids=[k % max(torch.cuda.device_count(), 1) for k in range(n_gpus)])
+        pg = PoseGraph(graph=g, options=Options(**kw))
+        steps = [pg.gn_step() for _ in range(2)]
+        runs.append((steps, pg.dx().copy(), pg.poses().copy()))
+        pg.close()
+    assert runs[0][0] == runs[1][0]
+    assert np.array_equal(runs[0][1], runs[1][1]) and np.array_equal(runs[0][2], runs[1][2])
+
+
 _ORACLE_100K = {}
 
 
