@@ -172,26 +172,37 @@ bool build_csc_pattern(Symbolic &S) {
 // Root + neighbours aggregation (Vanek-style, three passes) of the rows of ONE partition of a level, restricted to
 // edges inside the partition (aggregates never straddle ranks, so restriction, prolongation and the Galerkin
 // product need no communication).  agg[row - r0] = aggregate id in creation order.
-static int32_t aggregate_partition(const HostLevel &F, int k, int max_size, std::vector<int32_t> &agg) {
+//
+// Graphs with landmarks (level 0 only; landmark[row - r0] != 0 marks a VERTEX_XY row): a landmark is a star -- observed from
+// dozens of poses, with no edge to another landmark -- and a star centre as aggregation root collects poses from all over the
+// trajectory (dlr.g2o: 250 PCG iterations).  So only the POSES are aggregated, over the pose-pose edges; every landmark then
+// joins the aggregate that holds most of its observing poses, and when the pose graph is chain-like (odometry only: aggregates
+// of ~3 poses) neighbouring aggregates are paired once more.  Same hierarchy, 6x fewer iterations on dlr (tools/research/).
+static int32_t aggregate_partition(const HostLevel &F, int k, int max_size, std::vector<int32_t> &agg, const uint8_t *landmark = nullptr) {
     const int64_t r0 = F.part_off[k], n = F.part_real[k];
     agg.assign(n, -1);
     if (n == 0) return 0;
+    bool mixed = false;
+    if (landmark) for (int64_t i = 0; i < n && !mixed; i++) mixed = landmark[i] != 0;
+    if (!mixed) landmark = nullptr;
     std::vector<int64_t> ptr(n + 1, 0);
     std::vector<int32_t> nbr;
     nbr.reserve(F.adj_ptr[r0 + n] - F.adj_ptr[r0]);
     for (int64_t i = 0; i < n; i++) {
         const size_t start = nbr.size();
-        for (int64_t p = F.adj_ptr[r0 + i]; p < F.adj_ptr[r0 + i + 1]; p++) {
-            const int64_t j = F.adj_nbr[p] - r0;
-            if (j >= 0 && j < n && j != i) nbr.push_back((int32_t)j);
-        }
+        if (!(landmark && landmark[i]))
+            for (int64_t p = F.adj_ptr[r0 + i]; p < F.adj_ptr[r0 + i + 1]; p++) {
+                const int64_t j = F.adj_nbr[p] - r0;
+                if (j >= 0 && j < n && j != i && !(landmark && landmark[j])) nbr.push_back((int32_t)j);
+            }
         std::sort(nbr.begin() + start, nbr.end());
         nbr.erase(std::unique(nbr.begin() + start, nbr.end()), nbr.end());
         ptr[i + 1] = (int64_t)nbr.size();
     }
+    if (landmark) for (int64_t i = 0; i < n; i++) if (landmark[i]) agg[i] = -2;      // not a candidate in the three passes below
     int32_t nc = 0;
     for (int64_t i = 0; i < n; i++) {
-        if (agg[i] >= 0) continue;
+        if (agg[i] != -1) continue;
         bool free_nb = true;
         for (int64_t p = ptr[i]; p < ptr[i + 1] && free_nb; p++) free_nb = agg[nbr[p]] < 0;
         if (!free_nb) continue;
@@ -202,7 +213,7 @@ static int32_t aggregate_partition(const HostLevel &F, int k, int max_size, std:
     }
     std::vector<int32_t> snap(agg), cand;
     for (int64_t i = 0; i < n; i++) {
-        if (agg[i] >= 0) continue;
+        if (agg[i] != -1) continue;
         cand.clear();
         for (int64_t p = ptr[i]; p < ptr[i + 1]; p++) if (snap[nbr[p]] >= 0) cand.push_back(snap[nbr[p]]);
         if (cand.empty()) continue;
@@ -215,11 +226,49 @@ static int32_t aggregate_partition(const HostLevel &F, int k, int max_size, std:
         agg[i] = best;
     }
     for (int64_t i = 0; i < n; i++) {
-        if (agg[i] >= 0) continue;
+        if (agg[i] >= 0 || agg[i] == -2) continue;
         agg[i] = nc;
         int sz = 1;
-        for (int64_t p = ptr[i]; p < ptr[i + 1] && sz < max_size; p++) if (agg[nbr[p]] < 0) { agg[nbr[p]] = nc; sz++; }
+        for (int64_t p = ptr[i]; p < ptr[i + 1] && sz < max_size; p++) if (agg[nbr[p]] == -1) { agg[nbr[p]] = nc; sz++; }
         nc++;
+    }
+    if (!landmark) return nc;
+    // ---- landmark graphs: pair up the aggregates of a chain-like pose graph, then attach the landmarks
+    int64_t n_pose = 0;
+    for (int64_t i = 0; i < n; i++) n_pose += !landmark[i];
+    if (nc > 1 && (int64_t)nc * 4 > n_pose) {
+        std::vector<std::vector<int32_t>> cadj(nc);
+        for (int64_t i = 0; i < n; i++) {
+            if (landmark[i]) continue;
+            for (int64_t p = ptr[i]; p < ptr[i + 1]; p++) if (agg[nbr[p]] != agg[i]) cadj[agg[i]].push_back(agg[nbr[p]]);
+        }
+        std::vector<int32_t> pair(nc, -1);
+        int32_t np = 0;
+        for (int32_t a = 0; a < nc; a++) {
+            if (pair[a] >= 0) continue;
+            pair[a] = np;
+            std::sort(cadj[a].begin(), cadj[a].end());
+            for (int32_t c : cadj[a]) if (pair[c] < 0) { pair[c] = np; break; }
+            np++;
+        }
+        for (int64_t i = 0; i < n; i++) if (agg[i] >= 0) agg[i] = pair[agg[i]];
+        nc = np;
+    }
+    for (int64_t i = 0; i < n; i++) {
+        if (!landmark[i]) continue;
+        cand.clear();
+        for (int64_t p = F.adj_ptr[r0 + i]; p < F.adj_ptr[r0 + i + 1]; p++) {
+            const int64_t j = F.adj_nbr[p] - r0;
+            if (j >= 0 && j < n && agg[j] >= 0 && !landmark[j]) cand.push_back(agg[j]);
+        }
+        if (cand.empty()) { agg[i] = nc++; continue; }        // all its poses live on other ranks (or none at all)
+        std::sort(cand.begin(), cand.end());
+        int32_t best = cand[0]; int bc = 0, run = 0;
+        for (size_t q = 0; q < cand.size(); q++) {
+            run = (q > 0 && cand[q] == cand[q - 1]) ? run + 1 : 1;
+            if (run > bc) { bc = run; best = cand[q]; }
+        }
+        agg[i] = best;
     }
     return nc;
 }
@@ -507,7 +556,16 @@ bool build_symbolic(Symbolic &S, const SymbolicOptions &opt,
         std::vector<std::vector<int32_t>> pagg(fworld);
         std::vector<int64_t> pnc(fworld, 0);
         int64_t nc = 0;
-        for (int k = 0; k < fworld; k++) { pnc[k] = aggregate_partition(F, k, opt.agg_size, pagg[k]); nc += pnc[k]; }
+        std::vector<uint8_t> lm;                                  // level 0 of an SE2 graph with landmarks: VERTEX_XY rows
+        if (lvl == 0 && S.D == 3) {
+            bool any = false;
+            for (int64_t v = 0; v < nv && !any; v++) any = vkind[v] == 1;
+            if (any) { lm.assign(F.n_pad, 0); for (int64_t r = 0; r < F.n_pad; r++) if (S.perm[r] >= 0) lm[r] = vkind[S.perm[r]] == 1; }
+        }
+        for (int k = 0; k < fworld; k++) {
+            pnc[k] = aggregate_partition(F, k, opt.agg_size, pagg[k], lm.empty() ? nullptr : lm.data() + F.part_off[k]);
+            nc += pnc[k];
+        }
         TICK("aggregate");
         if (nc > 0.8 * F.n) break;                               // coarsening stalled
         const bool merge = fworld > 1 && nc <= repl_max;

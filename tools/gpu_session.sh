@@ -14,6 +14,13 @@ traffic)
   timeout 1200 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --cache-control none \
       --profile-from-start off --csv --log-file gpurun_out/step_traffic_$tag.csv python tools/step_traffic.py > gpurun_out/step_traffic_$tag.log 2>&1; echo "traffic rc=$?"
   tail -2 gpurun_out/step_traffic_$tag.log; python tools/summarize_traffic.py gpurun_out/step_traffic_$tag.csv gpurun_out/step_traffic_$tag.json | head -30;;
+abcs)
+  for v in 0 1; do PGO_STREAM_CS=$v timeout 300 python tools/quick_perf.py --opts pcg_rtol=1e-9 2>&1 | tail -1 | sed "s/^/STREAM_CS=$v /"; done | tee gpurun_out/stream_cs_$tag.log;;
+sanitize2)
+  for tool in memcheck racecheck; do
+    timeout 240 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize.py 2 > gpurun_out/sanitize_${tool}_n2_$tag.log 2>&1; echo "$tool n=2 rc=$?"
+    grep -E "sanitize |ERROR SUMMARY|RACECHECK SUMMARY|Error|hazard" gpurun_out/sanitize_${tool}_n2_$tag.log | head -14
+  done;;
 sanitize)
   for tool in memcheck racecheck; do for n in 1 2; do
     timeout 600 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize.py $n > gpurun_out/sanitize_${tool}_n${n}_$tag.log 2>&1; echo "$tool n=$n rc=$?"
