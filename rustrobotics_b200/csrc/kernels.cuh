@@ -1595,6 +1595,169 @@ __global__ void __launch_bounds__(256) k_dense_invert(int m, double *__restrict_
 }
 
 // x_own = Ainv[own rows, :] r  on the coarsest level; r is gathered from all ranks.  One warp per scalar row.
+// ---- second generation of the same inversion (default): same panel algebra and ping-pong buffers, restructured for latency.
+//   * the 32x32 pivot inverse of panel p+1 is produced DURING panel p (look-ahead): the CTA that owns the diagonal tile holding the
+//     next pivot block updates that tile first, inverts the block right away and publishes it, so after the barrier every CTA only
+//     loads 8 KB instead of running 32 dependent elimination steps itself;
+//   * the grid barrier is one atomic arrive + an acquire spin on a counter (the cooperative launch only guarantees co-residency),
+//     ~1 us instead of the cooperative-groups grid.sync();
+//   * one 64x64 tile per CTA when the grid allows it.
+constexpr size_t GJ2_SMEM = GJ_SMEM + sizeof(double) * 2 * GJ_W * (GJ_W + 1);
+
+__device__ __forceinline__ void gj_grid_barrier(unsigned *bar, unsigned target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        unsigned v;
+        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory"); } while ((int)(v - target) < 0);
+    }
+    __syncthreads();
+}
+
+// P (in Pb[0]) <- P^-1 by 32 unblocked Gauss-Jordan steps ping-ponging Pb[0] <-> Pb[1]; all 256 threads; result in Pb[0]
+__device__ __forceinline__ void gj_invert32(double (*Pb)[GJ_W][GJ_W + 1]) {
+    const int tid = threadIdx.x;
+    const int i = tid >> 3, j0 = (tid & 7) * 4;
+    for (int k = 0; k < GJ_W; k++) {
+        const double (*Pi)[GJ_W + 1] = Pb[k & 1];
+        double (*Po)[GJ_W + 1] = Pb[(k & 1) ^ 1];
+        const double ikk = 1.0 / Pi[k][k];
+        const double pik = Pi[i][k];
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) {
+            const int j = j0 + jj;
+            double v;
+            if (i == k) v = (j == k) ? ikk : Pi[k][j] * ikk;
+            else if (j == k) v = -pik * ikk;
+            else v = Pi[i][j] - pik * Pi[k][j] * ikk;
+            Po[i][j] = v;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) k_dense_invert2(int m, double *__restrict__ bufA, double *__restrict__ bufB, double *__restrict__ pnext,
+                                                        unsigned *bar, unsigned bar_base) {
+    PDL_ENTER();
+    extern __shared__ double gj_smem[];
+    double (*Pb)[GJ_W][GJ_W + 1] = reinterpret_cast<double (*)[GJ_W][GJ_W + 1]>(gj_smem);                      // [2][32][33] current pivot inverse
+    double (*Xr)[GJ_T] = reinterpret_cast<double (*)[GJ_T]>(gj_smem + 2 * GJ_W * (GJ_W + 1));                 // [32][64] raw panel rows
+    double (*Xb)[GJ_T] = reinterpret_cast<double (*)[GJ_T]>(gj_smem + 2 * GJ_W * (GJ_W + 1) + GJ_W * GJ_T);   // [32][64] R (or P^-1 columns)
+    double (*Cb)[GJ_W + 1] = reinterpret_cast<double (*)[GJ_W + 1]>(gj_smem + 2 * GJ_W * (GJ_W + 1) + 2 * GJ_W * GJ_T);   // [64][33]
+    double (*Pn)[GJ_W][GJ_W + 1] = reinterpret_cast<double (*)[GJ_W][GJ_W + 1]>(gj_smem + GJ_SMEM / sizeof(double));        // [2][32][33] look-ahead block
+    const int tid = threadIdx.x;
+    const int nt = (m + GJ_T - 1) / GJ_T, n_panels = (m + GJ_W - 1) / GJ_W;
+    const double *src = bufA;
+    double *dst = bufB;
+    for (int pi = 0; pi < n_panels; pi++) {
+        const int p0 = pi * GJ_W;
+        if (pi == 0) {
+            for (int t = tid; t < GJ_W * GJ_W; t += 256) {
+                const int i = t / GJ_W, j = t % GJ_W;
+                Pb[0][i][j] = (i < m && j < m) ? __ldcg(src + (int64_t)i * m + j) : (i == j ? 1.0 : 0.0);
+            }
+            __syncthreads();
+            gj_invert32(Pb);
+        } else {
+            const double *pn = pnext + (size_t)(pi & 1) * GJ_W * GJ_W;
+            for (int t = tid; t < GJ_W * GJ_W; t += 256) Pb[0][t / GJ_W][t % GJ_W] = __ldcg(pn + t);
+            __syncthreads();
+        }
+        const double (*Pinv)[GJ_W + 1] = Pb[0];
+        // the diagonal tile that holds the NEXT pivot block goes first on the CTA that owns it
+        const int np0 = p0 + GJ_W;
+        const bool has_next = pi + 1 < n_panels;
+        const int ntile = (np0 / GJ_T) * nt + np0 / GJ_T;
+        const int first = (has_next && ntile % (int)gridDim.x == (int)blockIdx.x) ? ntile : -1;
+        for (int k = first >= 0 ? -1 : 0; ; k++) {      // k = -1: the priority tile; then the CTA's other tiles in order
+            int tile = first;
+            if (k >= 0) {
+                tile = (int)blockIdx.x + k * (int)gridDim.x;
+                if (tile >= nt * nt) break;
+                if (tile == first) continue;
+            }
+            const int i0 = (tile / nt) * GJ_T, j0 = (tile % nt) * GJ_T;
+            __syncthreads();                              // the previous tile's shared arrays are free
+            for (int t = tid; t < GJ_W * GJ_T; t += 256) {       // panel rows of this column block
+                const int l = t / GJ_T, jj = t % GJ_T;
+                const int gi = p0 + l, gj = j0 + jj;
+                Xr[l][jj] = (gi < m && gj < m) ? __ldcg(src + (int64_t)gi * m + gj) : 0.0;
+            }
+            for (int t = tid; t < GJ_T * GJ_W; t += 256) {       // panel columns of this row block
+                const int ii = t / GJ_W, l = t % GJ_W;
+                const int gi = i0 + ii, gj = p0 + l;
+                Cb[ii][l] = (gi < m && gj < m) ? __ldcg(src + (int64_t)gi * m + gj) : 0.0;
+            }
+            const int ty = tid >> 4, tx = tid & 15;
+            double aij[4][4];                             // the tile's own entries: requested before the products need them
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const int gi = i0 + ty * 4 + a, gj = j0 + tx + 16 * c;
+                    aij[a][c] = (gi < m && gj < m) ? __ldcg(src + (int64_t)gi * m + gj) : 0.0;
+                }
+            __syncthreads();
+            for (int t = tid; t < GJ_W * GJ_T; t += 256) {       // X[l][j] = (P^-1 A[p, j])[l] outside the panel columns, P^-1[l][j - p0] inside
+                const int l = t / GJ_T, jj = t % GJ_T;
+                const int gj = j0 + jj;
+                double v;
+                if (gj >= p0 && gj < p0 + GJ_W) v = Pinv[l][gj - p0];
+                else {
+                    v = 0.0;
+#pragma unroll 8
+                    for (int q = 0; q < GJ_W; q++) v = fma(Pinv[l][q], Xr[q][jj], v);
+                }
+                Xb[l][jj] = v;
+            }
+            __syncthreads();
+            double acc[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) acc[a][c] = 0.0;
+#pragma unroll 4
+            for (int l = 0; l < GJ_W; l++) {
+                double cv[4], xv[4];
+#pragma unroll
+                for (int a = 0; a < 4; a++) cv[a] = Cb[ty * 4 + a][l];
+#pragma unroll
+                for (int c = 0; c < 4; c++) xv[c] = Xb[l][tx + 16 * c];
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) acc[a][c] = fma(cv[a], xv[c], acc[a][c]);
+            }
+#pragma unroll
+            for (int a = 0; a < 4; a++) {
+                const int gi = i0 + ty * 4 + a;
+                const bool iin = gi >= p0 && gi < p0 + GJ_W;
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const int gj = j0 + tx + 16 * c;
+                    const bool jin = gj >= p0 && gj < p0 + GJ_W;
+                    double v;
+                    if (iin) v = Xb[gi - p0][tx + 16 * c];            // P^-1 (jin) or R
+                    else if (jin) v = -acc[a][c];
+                    else v = aij[a][c] - acc[a][c];
+                    if (gi < m && gj < m) dst[(int64_t)gi * m + gj] = v;
+                    if (tile == first && gi >= np0 && gi < np0 + GJ_W && gj >= np0 && gj < np0 + GJ_W)     // the next pivot block, as updated by this panel
+                        Pn[0][gi - np0][gj - np0] = (gi < m && gj < m) ? v : (gi == gj ? 1.0 : 0.0);
+                }
+            }
+            if (tile == first) {                          // look-ahead: invert the next pivot block now and publish it
+                __syncthreads();
+                gj_invert32(Pn);
+                double *pn = pnext + (size_t)((pi + 1) & 1) * GJ_W * GJ_W;
+                for (int t = tid; t < GJ_W * GJ_W; t += 256) pn[t] = Pn[0][t / GJ_W][t % GJ_W];
+            }
+        }
+        gj_grid_barrier(bar, bar_base + (unsigned)(pi + 1) * gridDim.x);
+        const double *t = src; src = dst; dst = const_cast<double *>(t);
+    }
+}
+
 template <int D>
 __device__ __forceinline__ void dense_apply_body(int64_t n_local, const DenseMap &dm, int rank, int world, int m, const double *__restrict__ Ainv,
                                                  const XRef &rr, double *__restrict__ x, unsigned vb) {

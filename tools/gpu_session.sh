@@ -14,6 +14,9 @@ traffic)
   timeout 1200 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --cache-control none \
       --profile-from-start off --csv --log-file gpurun_out/step_traffic_$tag.csv python tools/step_traffic.py > gpurun_out/step_traffic_$tag.log 2>&1; echo "traffic rc=$?"
   tail -2 gpurun_out/step_traffic_$tag.log; python tools/summarize_traffic.py gpurun_out/step_traffic_$tag.csv gpurun_out/step_traffic_$tag.json | head -30;;
+abgj)
+  for v in 1 0; do PGO_GJ_OLD=$v timeout 300 python tools/quick_perf.py --opts pcg_rtol=1e-9 2>&1 | tail -1 | sed "s/^/GJ_OLD=$v /"; done | tee gpurun_out/gj_$tag.log
+  for v in 1 0; do PGO_GJ_OLD=$v timeout 300 python tools/quick_perf.py --se3 --poses 250000 --opts pcg_rtol=1e-9 2>&1 | tail -1 | sed "s/^/SE3 GJ_OLD=$v /"; done | tee -a gpurun_out/gj_$tag.log;;
 abcs)
   for v in 0 1; do PGO_STREAM_CS=$v timeout 300 python tools/quick_perf.py --opts pcg_rtol=1e-9 2>&1 | tail -1 | sed "s/^/STREAM_CS=$v /"; done | tee gpurun_out/stream_cs_$tag.log;;
 sanitize2)
