@@ -1837,6 +1837,34 @@ __global__ void __launch_bounds__(256) k_gather_peer(double *__restrict__ v, con
 // SE(2) linearisation (restated from pose_graph_optimization.rs:434-486, 516-535; closed forms in
 // SURVEY.md Appendix A).  Poses are (x, y, cos, sin): the reference stores the heading as a unit
 // complex (g2o.rs:14-16), so no sincos per edge, one atan2.
+// One-time (pgo_create): the half-edge measurement stream hz -- laid out exactly like val, NM components per stored block -- is
+// gathered on the device from the edge-ordered records `ed` ([NM][ed_stride] planes) through the slot -> edge map, instead of being
+// packed on the host and uploaded (640 MB at 1M poses).  One thread per block row, walking its slice like the assembly kernel.
+template <int NM>
+__global__ void __launch_bounds__(128) k_build_hz(LevelDev L, const int32_t *__restrict__ slot_edge, const double *__restrict__ ed, int64_t ed_stride,
+                                                   double *__restrict__ hz) {
+    PDL_ENTER();
+    const int64_t row = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int64_t slice = row >> 5;
+    if (slice >= L.n_slices) return;
+    const int mydeg = L.deg[row];
+    const int maxdeg = __shfl_sync(0xffffffffu, mydeg, 0);
+    const int64_t base = L.slice_ptr[slice];
+    int64_t off = 0;
+    for (int k = 0; k < maxdeg; k++) {
+        const bool active = k < mydeg;
+        const int cnt = __popc(__ballot_sync(0xffffffffu, active));
+        if (active) {
+            const int64_t e = slot_edge[base + off + lane];
+            double *dst = hz + (base + off) * NM + lane;
+#pragma unroll
+            for (int c = 0; c < NM; c++) dst[(int64_t)c * cnt] = __ldg(ed + (int64_t)c * ed_stride + e);
+        }
+        off += cnt;
+    }
+}
+
 struct PP { double e[3]; double m11, m12, a0, a1; };
 
 __device__ __forceinline__ void pose_pose(const double *x1, const double *x2, const double *z, PP &o) {
@@ -1985,7 +2013,7 @@ __global__ void __launch_bounds__(128) k_assemble_se2(LevelDev L, const __grid_c
 // edge-ordered SoA copy of the measurements.
 // ed: [10][n_edges] planes (z: x y cos sin ; Omega upper 6 -- for XY edges w11 w12 w22 in the first three)
 // ends: .x = local row of `from`, .y = column word of `to` (COL_EDGE_XY marks a pose-landmark edge)
-__global__ void __launch_bounds__(256) k_chi2_se2(int64_t n_edges, const uint2 *__restrict__ ends, const double *__restrict__ ed,
+__global__ void __launch_bounds__(256) k_chi2_se2(int64_t n_edges, int64_t ed_stride, const uint2 *__restrict__ ends, const double *__restrict__ ed,
                                                    const double *__restrict__ poses, const __grid_constant__ XRef posr, Scalars *S, double *partials) {
     PDL_ENTER();
     const int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x;
@@ -1997,9 +2025,9 @@ __global__ void __launch_bounds__(256) k_chi2_se2(int64_t n_edges, const uint2 *
         ld_vec<4>(poses + (int64_t)en.x * 4, x1);
         ld_vec<4>(xgather<4>(posr, en.y), x2);
 #pragma unroll
-        for (int q = 0; q < 4; q++) z[q] = __ldg(ed + (int64_t)q * n_edges + k);
+        for (int q = 0; q < 4; q++) z[q] = __ldg(ed + (int64_t)q * ed_stride + k);
 #pragma unroll
-        for (int q = 0; q < 6; q++) w[q] = __ldg(ed + (int64_t)(4 + q) * n_edges + k);
+        for (int q = 0; q < 6; q++) w[q] = __ldg(ed + (int64_t)(4 + q) * ed_stride + k);
         if (!xy) {
             PP p;
             pose_pose(x1, x2, z, p);
@@ -2263,7 +2291,7 @@ __global__ void __launch_bounds__(128) k_assemble_se3(LevelDev L, const double *
 }
 
 // chi2 of an SE3 graph: ed = [28][n_edges] planes, ends as in k_chi2_se2
-__global__ void __launch_bounds__(256) k_chi2_se3(int64_t n_edges, const uint2 *__restrict__ ends, const double *__restrict__ ed,
+__global__ void __launch_bounds__(256) k_chi2_se3(int64_t n_edges, int64_t ed_stride, const uint2 *__restrict__ ends, const double *__restrict__ ed,
                                                    const double *__restrict__ poses, Scalars *S, double *partials) {
     PDL_ENTER();
     const int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x;
@@ -2274,9 +2302,9 @@ __global__ void __launch_bounds__(256) k_chi2_se3(int64_t n_edges, const uint2 *
         ld_vec<8>(poses + (int64_t)en.x * 8, x1);
         ld_vec<8>(poses + (int64_t)(en.y & COL_LOCAL_MASK) * 8, x2);
 #pragma unroll
-        for (int q = 0; q < 7; q++) z[q] = __ldg(ed + (int64_t)q * n_edges + k);
+        for (int q = 0; q < 7; q++) z[q] = __ldg(ed + (int64_t)q * ed_stride + k);
 #pragma unroll
-        for (int q = 0; q < 21; q++) wu[q] = __ldg(ed + (int64_t)(7 + q) * n_edges + k);
+        for (int q = 0; q < 21; q++) wu[q] = __ldg(ed + (int64_t)(7 + q) * ed_stride + k);
         se3_edge<false>(x1, x2, z, e, nullptr, nullptr, nullptr, nullptr);
         sym6_expand(wu, W);
 #pragma unroll

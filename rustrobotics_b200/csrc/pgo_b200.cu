@@ -101,6 +101,7 @@ struct pgo_handle {
     Comm *comm = nullptr;
     // level-0 state (local rows)
     int64_t n_loc = 0, n_pad_loc = 0, n_edges_loc = 0, row0 = 0;
+    int64_t ed_stride = 1;             // edges whose records `ed` holds (the n_edges_loc owned ones first): plane stride of ed
     double *poses = nullptr, *poses_saved = nullptr, *hz = nullptr, *ed = nullptr;
     double *vstage = nullptr;          // g2o-layout vertex values (n_values) for set/get_poses
     int64_t *row_valofs = nullptr;     // [n_loc] offset of each local row's values in vstage
@@ -621,8 +622,8 @@ template <int D> int retract(pgo_handle *h, double sign) {
 template <int D> int chi2_launch(pgo_handle *h) {
     xbarrier(h, 0);
     halo_pull(h, 0, h->poses, Dim<D>::PS, 0);
-    if (D == 3) launch_k(h, k_chi2_se2, grid_for(h->n_edges_loc, 256), 256, 0, h->n_edges_loc, h->ends, h->ed, h->poses, xref(h, h->poses, true), h->S, h->partials);
-    else launch_k(h, k_chi2_se3, grid_for(h->n_edges_loc, 256), 256, 0, h->n_edges_loc, h->ends, h->ed, h->poses, h->S, h->partials);
+    if (D == 3) launch_k(h, k_chi2_se2, grid_for(h->n_edges_loc, 256), 256, 0, h->n_edges_loc, h->ed_stride, h->ends, h->ed, h->poses, xref(h, h->poses, true), h->S, h->partials);
+    else launch_k(h, k_chi2_se3, grid_for(h->n_edges_loc, 256), 256, 0, h->n_edges_loc, h->ed_stride, h->ends, h->ed, h->poses, h->S, h->partials);
     h->launch_count += 1;
     xreduce<FIN_CHI2>(h, 0, 0);
     CK(cudaGetLastError()); CK(h->launch_err);
@@ -805,17 +806,21 @@ static int create_shard(pgo_handle *h, const double *vval, int64_t ne, const uin
         };
         std::vector<int32_t> dg(d.n_pad, 0);
         std::vector<uint32_t> cl(std::max<int64_t>(d.n_slots, 1), 0);
-        for (int64_t r = r0; r < r1; r++) {
-            dg[r - r0] = (int32_t)(H.adj_ptr[r + 1] - H.adj_ptr[r]);
-            for (int64_t q = H.adj_ptr[r]; q < H.adj_ptr[r + 1]; q++)
-                cl[H.adj_slot[q] - s0] = local_index(H.adj_nbr[q]) | (H.adj_flags.empty() ? 0u : H.adj_flags[q]);
-        }
+        parallel_for(r1 - r0, 8192, [&](int64_t a0, int64_t a1) {
+            for (int64_t r = r0 + a0; r < r0 + a1; r++) {
+                dg[r - r0] = (int32_t)(H.adj_ptr[r + 1] - H.adj_ptr[r]);
+                for (int64_t q = H.adj_ptr[r]; q < H.adj_ptr[r + 1]; q++)
+                    cl[H.adj_slot[q] - s0] = local_index(H.adj_nbr[q]) | (H.adj_flags.empty() ? 0u : H.adj_flags[q]);
+            }
+        });
         if (l == 0) {   // the chi2 edge list addresses the `to` pose the same way
             h->to_index.resize(S.n_edges);
-            for (int64_t e = 0; e < S.n_edges; e++) {
-                const int64_t a = S.iperm[S.efrom[e]], b = S.iperm[S.eto[e]];
-                h->to_index[e] = (a >= r0 && a < r1) ? local_index(b) : 0u;
-            }
+            parallel_for(S.n_edges, 65536, [&](int64_t e0, int64_t e1) {
+                for (int64_t e = e0; e < e1; e++) {
+                    const int64_t a = S.iperm[S.efrom[e]], b = S.iperm[S.eto[e]];
+                    h->to_index[e] = (a >= r0 && a < r1) ? local_index(b) : 0u;
+                }
+            });
         }
         int64_t *drp; int32_t *ddg; uint32_t *dcl;
         CKC(upload(h, &drp, rp)); CKC(upload(h, &ddg, dg)); CKC(upload(h, &dcl, cl));
@@ -951,57 +956,79 @@ static int create_shard(pgo_handle *h, const double *vval, int64_t ne, const uin
         const int64_t ag = S.anchor >= 0 ? S.iperm[S.anchor] : -1;
         h->anchor_row = (ag >= r0 && ag < r1) ? ag - r0 : -1;
     }
-    // ---- measurements: per-edge packed offsets
-    std::vector<int64_t> mofs(ne + 1, 0), iofs(ne + 1, 0);
-    static const int NMEAS[3] = {3, 2, 7}, NINFO[3] = {6, 3, 21};
-    for (int64_t k = 0; k < ne; k++) { mofs[k + 1] = mofs[k] + NMEAS[ekind[k]]; iofs[k + 1] = iofs[k] + NINFO[ekind[k]]; }
-    auto edge_rec = [&](int64_t k, double *o) {   // SE2: z = x y cos sin ; Omega upper (6).  SE3: z = t(3) q(w,x,y,z) normalised ; Omega upper (21)
-        const double *m = emeas + mofs[k], *w = einfo + iofs[k];
-        for (int c = 0; c < NM; c++) o[c] = 0.0;
-        if (ekind[k] == 2) {
-            const double nq = std::sqrt(m[3] * m[3] + m[4] * m[4] + m[5] * m[5] + m[6] * m[6]);
-            o[0] = m[0]; o[1] = m[1]; o[2] = m[2]; o[3] = m[6] / nq; o[4] = m[3] / nq; o[5] = m[4] / nq; o[6] = m[5] / nq;
-            for (int c = 0; c < 21; c++) o[7 + c] = w[c];
-            return;
-        }
-        o[0] = m[0]; o[1] = m[1];
-        if (ekind[k] == 0) { o[2] = std::cos(m[2]); o[3] = std::sin(m[2]); for (int c = 0; c < 6; c++) o[4 + c] = w[c]; }
-        else { for (int c = 0; c < 3; c++) o[4 + c] = w[c]; }
-    };
-    {   // half-edge stream, laid out like val with 10 components
-        std::vector<double> hz((size_t)NM * std::max<int64_t>(s1 - s0, 1), 0.0);
-        double rec[28];
-        for (int64_t r = r0; r < r0 + h->n_loc; r++) {
-            const int lane = (int)(r & 31);
-            for (int64_t qi = H0.adj_ptr[r]; qi < H0.adj_ptr[r + 1]; qi++) {
-                const int64_t slot = H0.adj_slot[qi] - s0;
-                const int64_t cnt = H0.adj_cnt[qi];
-                edge_rec(S.slot_edge[H0.adj_slot[qi]], rec);
-                double *dst = hz.data() + (slot - lane) * NM + lane;
-                for (int c = 0; c < NM; c++) dst[c * cnt] = rec[c];
+    // ---- measurements.  Edges incident to the rows of this rank: first the ones it owns (owner = the rank of `from`; these are the
+    // edges its chi2 kernel sums), then the ones it only sees from the `to` side.  Their records -- SE2: z = x y cos sin, Omega upper (6);
+    // SE3: z = t(3) q(w,x,y,z) normalised, Omega upper (21) -- go to the device once, edge-ordered ([NM][n_inc] planes, `ed`); the
+    // half-edge stream hz the assembly kernel reads is gathered from them ON the device (k_build_hz).
+    {
+        std::vector<int64_t> mofs(ne + 1, 0), iofs(ne + 1, 0);
+        static const int NMEAS[3] = {3, 2, 7}, NINFO[3] = {6, 3, 21};
+        for (int64_t k = 0; k < ne; k++) { mofs[k + 1] = mofs[k] + NMEAS[ekind[k]]; iofs[k + 1] = iofs[k] + NINFO[ekind[k]]; }
+        std::vector<int32_t> inc, inc_of;
+        int64_t nm = ne, n_inc = ne;
+        if (world > 1) {
+            inc_of.assign(ne, -1);
+            for (int64_t k = 0; k < ne; k++) { const int64_t a = S.iperm[S.efrom[k]]; if (a >= r0 && a < r1) inc.push_back((int32_t)k); }
+            nm = (int64_t)inc.size();
+            for (int64_t k = 0; k < ne; k++) {
+                const int64_t a = S.iperm[S.efrom[k]], b = S.iperm[S.eto[k]];
+                if (!(a >= r0 && a < r1) && b >= r0 && b < r1) inc.push_back((int32_t)k);
             }
+            n_inc = (int64_t)inc.size();
+            for (int64_t i = 0; i < n_inc; i++) inc_of[inc[i]] = (int32_t)i;
         }
-        CKC(upload(h, &h->hz, hz));
-    }
-    {   // edge-ordered copy of the edges this rank owns (owner = the rank of `from`) for chi2
-        std::vector<int64_t> mine;
-        for (int64_t k = 0; k < ne; k++) { const int64_t a = S.iperm[S.efrom[k]]; if (a >= r0 && a < r1) mine.push_back(k); }
-        const int64_t nm = (int64_t)mine.size();
         h->n_edges_loc = nm;
+        h->ed_stride = std::max<int64_t>(n_inc, 1);
+        const int64_t stride = h->ed_stride;
         std::vector<uint2> ends(std::max<int64_t>(nm, 1));
-        std::vector<double> ed((size_t)NM * std::max<int64_t>(nm, 1), 0.0);
-        double rec[28];
-        for (int64_t i = 0; i < nm; i++) {
-            const int64_t k = mine[i];
-            const int64_t a = S.iperm[S.efrom[k]];
-            ends[i] = make_uint2((uint32_t)(a - r0), h->to_index[k] | (ekind[k] == 1 ? COL_EDGE_XY : 0u));
-            edge_rec(k, rec);
-            for (int c = 0; c < NM; c++) ed[(size_t)c * nm + i] = rec[c];
-        }
+        std::vector<double> ed((size_t)NM * stride, 0.0);
+        parallel_for(n_inc, 16384, [&](int64_t i0, int64_t i1) {
+            for (int64_t i = i0; i < i1; i++) {
+                const int64_t k = world > 1 ? inc[i] : i;
+                const double *m = emeas + mofs[k], *w = einfo + iofs[k];
+                double *o = ed.data() + i;
+                if (ekind[k] == 2) {
+                    const double nq = std::sqrt(m[3] * m[3] + m[4] * m[4] + m[5] * m[5] + m[6] * m[6]);
+                    o[0] = m[0]; o[stride] = m[1]; o[2 * stride] = m[2];
+                    o[3 * stride] = m[6] / nq; o[4 * stride] = m[3] / nq; o[5 * stride] = m[4] / nq; o[6 * stride] = m[5] / nq;
+                    for (int c = 0; c < 21; c++) o[(size_t)(7 + c) * stride] = w[c];
+                } else {
+                    o[0] = m[0]; o[stride] = m[1];
+                    if (ekind[k] == 0) { o[2 * stride] = std::cos(m[2]); o[3 * stride] = std::sin(m[2]); for (int c = 0; c < 6; c++) o[(size_t)(4 + c) * stride] = w[c]; }
+                    else { for (int c = 0; c < 3; c++) o[(size_t)(4 + c) * stride] = w[c]; }
+                }
+                if (i < nm) {
+                    const int64_t a = S.iperm[S.efrom[k]];
+                    ends[i] = make_uint2((uint32_t)(a - r0), h->to_index[k] | (ekind[k] == 1 ? COL_EDGE_XY : 0u));
+                }
+            }
+        });
         CKC(upload(h, &h->ends, ends));
         CKC(upload(h, &h->ed, ed));
         h->to_index.clear(); h->to_index.shrink_to_fit();
         max_grid = std::max<int64_t>(max_grid, grid_for(nm, 256));
+        // slot -> index into `ed` of the edge the stored block comes from
+        const int64_t nsl = std::max<int64_t>(s1 - s0, 1);
+        std::vector<int32_t> se(nsl, 0);
+        parallel_for(s1 - s0, 65536, [&](int64_t a, int64_t b) {
+            for (int64_t q = a; q < b; q++) {
+                const int32_t e = S.slot_edge[s0 + q];                     // -1: padding slot of the sliced storage (never read)
+                se[q] = e < 0 ? 0 : (world > 1 ? inc_of[e] : e);
+            }
+        });
+        int32_t *dse = nullptr;
+        CKU(cudaMalloc((void **)&dse, nsl * sizeof(int32_t)));
+        cudaError_t ce = cudaMemcpyAsync(dse, se.data(), nsl * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream);
+        if (ce == cudaSuccess) {
+            int rc = dalloc(h, &h->hz, (size_t)NM * nsl);
+            if (rc) { cudaFree(dse); return rc; }
+            if (D == 6) launch_k(h, k_build_hz<28>, h->lv[0].grid128, 128, 0, h->lv[0].d, (const int32_t *)dse, (const double *)h->ed, stride, h->hz);
+            else launch_k(h, k_build_hz<10>, h->lv[0].grid128, 128, 0, h->lv[0].d, (const int32_t *)dse, (const double *)h->ed, stride, h->hz);
+            ce = cudaStreamSynchronize(h->stream);
+            if (ce == cudaSuccess) ce = h->launch_err;
+        }
+        cudaFree(dse);
+        CKU(ce);
     }
     CKC(dalloc(h, &h->S, 1));
     CKC(dalloc(h, &h->partials, (size_t)4 * max_grid + 8));

@@ -1,8 +1,11 @@
 // Internal data structures shared by the host symbolic pass and the CUDA solver.
 // Not part of the ABI (include/pgo_b200.h is).
 #pragma once
+#include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace pgo {
@@ -106,6 +109,24 @@ bool build_symbolic(Symbolic &sym, const SymbolicOptions &opt,
                     int64_t n_vertices, const uint32_t *vertex_id, const uint8_t *vertex_kind,
                     int64_t n_edges, const uint8_t *edge_kind, const uint32_t *edge_from_id,
                     const uint32_t *edge_to_id);
+
+// Host-side set-up is seconds of index manipulation at 1M poses next to Gauss-Newton steps of 40 ms: loops whose iterations are
+// independent run on the host's cores.  f(begin, end) is called on disjoint contiguous ranges; results do not depend on the
+// thread count (PGO_HOST_THREADS overrides it).
+template <typename F> inline void parallel_for(int64_t n, int64_t grain, F f) {
+    unsigned nt = std::thread::hardware_concurrency();
+    if (const char *e = std::getenv("PGO_HOST_THREADS")) nt = (unsigned)std::max(1, std::atoi(e));
+    nt = std::min<unsigned>(std::max(1u, nt), 16u);
+    nt = (unsigned)std::min<int64_t>(nt, std::max<int64_t>(1, n / std::max<int64_t>(grain, 1)));
+    if (nt <= 1) { f((int64_t)0, n); return; }
+    std::vector<std::thread> th;
+    th.reserve(nt);
+    for (unsigned t = 0; t < nt; t++) {
+        const int64_t b = n * t / nt, e = n * (t + 1) / nt;
+        th.emplace_back([=]() { f(b, e); });
+    }
+    for (auto &x : th) x.join();
+}
 
 // lazily computed (only the structure checks and pgo_get_system need them)
 bool build_canonical(Symbolic &sym);      // brow_ptr / bcol / edge_slots

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <numeric>
 #include <thread>
 
@@ -20,24 +21,6 @@ static const int KIND_DIM[3] = {3, 2, 6};   // lut stride, g2o.rs:61,68,77
 static const int KIND_NVAL[3] = {3, 2, 7};
 
 static inline int64_t pad32(int64_t x) { return (x + 31) / 32 * 32; }
-
-// The symbolic pass is host work done once per graph, but at BASELINE configs[3] (1M poses / 4M edges) it is seconds of
-// single-threaded index manipulation next to Gauss-Newton steps of 40 ms: the loops whose iterations are independent run
-// on the host's cores.  f(begin, end) is called on disjoint contiguous ranges; results do not depend on the thread count.
-template <typename F> static void parallel_for(int64_t n, int64_t grain, F f) {
-    unsigned nt = std::thread::hardware_concurrency();
-    if (const char *e = std::getenv("PGO_HOST_THREADS")) nt = (unsigned)std::max(1, std::atoi(e));
-    nt = std::min<unsigned>(std::max(1u, nt), 16u);
-    nt = (unsigned)std::min<int64_t>(nt, std::max<int64_t>(1, n / std::max<int64_t>(grain, 1)));
-    if (nt <= 1) { f((int64_t)0, n); return; }
-    std::vector<std::thread> th;
-    th.reserve(nt);
-    for (unsigned t = 0; t < nt; t++) {
-        const int64_t b = n * t / nt, e = n * (t + 1) / nt;
-        th.emplace_back([=]() { f(b, e); });
-    }
-    for (auto &x : th) x.join();
-}
 
 // partitions laid out back to back, each padded to a multiple of 32 rows
 static void layout_partitions(HostLevel &L, const std::vector<int64_t> &counts) {
@@ -360,8 +343,8 @@ static void build_coarse_level(HostLevel &F, HostLevel &C, const std::vector<std
     F.gal_ptr.assign(world, {});
     F.gal_src.assign(world, {});
     if (!jds) {
-        parallel_for(world, 1, [&](int64_t k0, int64_t k1) {
-            for (int64_t k = k0; k < k1; k++) {
+        {
+            for (int64_t k = 0; k < world; k++) {
                 const int kc = merge ? 0 : (int)k;
                 const int64_t crows = C.part_off[kc + 1] - C.part_off[kc], cslots = C.part_slot[kc + 1] - C.part_slot[kc];
                 const int64_t fr0 = F.part_off[k], fs0 = F.part_slot[k], fslots = F.part_slot[k + 1] - fs0;
@@ -369,19 +352,39 @@ static void build_coarse_level(HostLevel &F, HostLevel &C, const std::vector<std
                 std::vector<int32_t> &ptr = F.gal_ptr[k], &src = F.gal_src[k];
                 ptr.assign(nblk + 1, 0);
                 auto target = [&](int32_t ct) -> int64_t { return ct < 0 ? (int64_t)(-1 - ct) : crows + ct / DD; };
-                // stage order: stored blocks by slot, then the diagonal blocks by row
+                // contributors of every coarse block in ascending stage order (stored blocks by slot, then the diagonal blocks by row):
+                // counted and scattered by all cores, then every segment is sorted, so the lists do not depend on the thread count
                 std::vector<int32_t> slot_tgt(fslots, -1);                 // padding slots of the sliced storage have no block
-                for (int64_t r = fr0; r < fr0 + F.part_real[k]; r++)
-                    for (int64_t q = F.adj_ptr[r]; q < F.adj_ptr[r + 1]; q++) slot_tgt[F.adj_slot[q] - fs0] = (int32_t)target(F.ctgt[F.adj_slot[q]]);
-                for (int64_t sl = 0; sl < fslots; sl++) if (slot_tgt[sl] >= 0) ptr[slot_tgt[sl] + 1]++;
-                for (int64_t i = 0; i < F.part_real[k]; i++) ptr[(F.agg[fr0 + i] - C.part_off[kc]) + 1]++;
-                for (int64_t b = 0; b < nblk; b++) ptr[b + 1] += ptr[b];
+                parallel_for(F.part_real[k], 8192, [&](int64_t a, int64_t b2) {
+                    for (int64_t r = fr0 + a; r < fr0 + b2; r++)
+                        for (int64_t q = F.adj_ptr[r]; q < F.adj_ptr[r + 1]; q++) slot_tgt[F.adj_slot[q] - fs0] = (int32_t)target(F.ctgt[F.adj_slot[q]]);
+                });
+                std::vector<std::atomic<int32_t>> cnt(nblk);
+                parallel_for(nblk, 65536, [&](int64_t a, int64_t b2) { for (int64_t q = a; q < b2; q++) cnt[q].store(0, std::memory_order_relaxed); });
+                parallel_for(fslots, 65536, [&](int64_t a, int64_t b2) {
+                    for (int64_t sl = a; sl < b2; sl++) if (slot_tgt[sl] >= 0) cnt[slot_tgt[sl]].fetch_add(1, std::memory_order_relaxed);
+                });
+                parallel_for(F.part_real[k], 65536, [&](int64_t a, int64_t b2) {
+                    for (int64_t i = a; i < b2; i++) cnt[F.agg[fr0 + i] - C.part_off[kc]].fetch_add(1, std::memory_order_relaxed);
+                });
+                for (int64_t q = 0; q < nblk; q++) ptr[q + 1] = ptr[q] + cnt[q].load(std::memory_order_relaxed);
                 src.resize(ptr[nblk]);
-                std::vector<int32_t> pos(ptr.begin(), ptr.end() - 1);
-                for (int64_t sl = 0; sl < fslots; sl++) if (slot_tgt[sl] >= 0) src[pos[slot_tgt[sl]]++] = (int32_t)sl;
-                for (int64_t i = 0; i < F.part_real[k]; i++) src[pos[F.agg[fr0 + i] - C.part_off[kc]]++] = (int32_t)(fslots + i);
+                parallel_for(nblk, 65536, [&](int64_t a, int64_t b2) { for (int64_t q = a; q < b2; q++) cnt[q].store(0, std::memory_order_relaxed); });
+                parallel_for(fslots, 65536, [&](int64_t a, int64_t b2) {
+                    for (int64_t sl = a; sl < b2; sl++) {
+                        const int32_t t = slot_tgt[sl];
+                        if (t >= 0) src[ptr[t] + cnt[t].fetch_add(1, std::memory_order_relaxed)] = (int32_t)sl;
+                    }
+                });
+                parallel_for(F.part_real[k], 65536, [&](int64_t a, int64_t b2) {
+                    for (int64_t i = a; i < b2; i++) {
+                        const int64_t t = F.agg[fr0 + i] - C.part_off[kc];
+                        src[ptr[t] + cnt[t].fetch_add(1, std::memory_order_relaxed)] = (int32_t)(fslots + i);
+                    }
+                });
+                parallel_for(nblk, 4096, [&](int64_t a, int64_t b2) { for (int64_t q = a; q < b2; q++) std::sort(src.begin() + ptr[q], src.begin() + ptr[q + 1]); });
             }
-        });
+        }
     }
     TICK("  bcl: galerkin contributor lists");
 }
@@ -512,13 +515,17 @@ bool build_symbolic(Symbolic &S, const SymbolicOptions &opt,
         struct HE { int32_t nbr, edge; uint32_t flags; };
         std::vector<HE> he(L0.adj_ptr[L0.n_pad]);
         {
-            std::vector<int64_t> pos(L0.adj_ptr.begin(), L0.adj_ptr.end() - 1);
-            for (int64_t k = 0; k < ne; k++) {
-                const int32_t ri = S.iperm[S.efrom[k]], rj = S.iperm[S.eto[k]];
-                const uint32_t xy = ekind[k] == 1 ? COL_EDGE_XY : 0u;
-                he[pos[ri]++] = {rj, (int32_t)k, xy};
-                he[pos[rj]++] = {ri, (int32_t)k, xy | COL_ROLE_TO};
-            }
+            // filled by all cores: the order inside a row does not matter here, the row sort below fixes it (thread-count independent)
+            std::vector<std::atomic<int32_t>> fill(L0.n_pad);
+            parallel_for(L0.n_pad, 65536, [&](int64_t a, int64_t b) { for (int64_t r = a; r < b; r++) fill[r].store(0, std::memory_order_relaxed); });
+            parallel_for(ne, 65536, [&](int64_t k0, int64_t k1) {
+                for (int64_t k = k0; k < k1; k++) {
+                    const int32_t ri = S.iperm[S.efrom[k]], rj = S.iperm[S.eto[k]];
+                    const uint32_t xy = ekind[k] == 1 ? COL_EDGE_XY : 0u;
+                    he[L0.adj_ptr[ri] + fill[ri].fetch_add(1, std::memory_order_relaxed)] = {rj, (int32_t)k, xy};
+                    he[L0.adj_ptr[rj] + fill[rj].fetch_add(1, std::memory_order_relaxed)] = {ri, (int32_t)k, xy | COL_ROLE_TO};
+                }
+            });
             TICK("half-edge fill");
             parallel_for(L0.n_pad, 4096, [&](int64_t r0, int64_t r1) {
                 for (int64_t r = r0; r < r1; r++)
