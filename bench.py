@@ -271,6 +271,9 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # `python bench.py --gpus N` WITHOUT torchrun: the single-process multi-GPU handle (Options(n_gpus=N)): one process, one PoseGraph,
+    # N shards.  Under torchrun (what the driver does for N > 1) the same shards are one process each (Options(world, rank)).
+    n_shards = args.gpus if (world == 1 and args.gpus > 1) else 1
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
@@ -294,6 +297,9 @@ def run_b200(args):
     # world > 1: ONE graph sharded by contiguous vertex ranges, one process per GPU; halo rows are read from
     # peer HBM over NVLink inside the kernels, dot products reduced by a device-side peer-memory all-reduce
     extra = {k: (float(v) if "." in v or "e" in v else int(v)) for k, v in (kv.split("=") for kv in args.opts.split(",") if kv)}
+    if n_shards > 1:
+        nd = torch.cuda.device_count()
+        extra = dict(extra, device_ids=[k % nd for k in range(n_shards)])       # fewer GPUs than shards: shards share devices (functional test only)
     pg = PoseGraph(graph=g, options=Options(device=local, world=world, rank=rank, pcg_rtol=args.pcg_rtol,
                                             preconditioner=args.preconditioner, **extra), comm=TorchComm() if world > 1 else None)
     t_create = time.perf_counter() - t0
@@ -384,10 +390,11 @@ def run_b200(args):
     else:     # 6x6 blocks: 72 -> 288 per block, 24 -> 48 per vector record, 56-byte poses, 21-value information triangle
         step_bytes = ((8 + 56 + 168) * E_ + 16 * E_ + 288 * (N_ + 2 * E_) + (56 + 48) * N_) + 2 * 288 * N_ + \
                      k_its * ((288 + 4) * (N_ + 2 * E_) + (4 + 96 + 288 + 96 + 6 * 48) * N_) + (56 * 2 + 48) * N_ + ((8 + 56 + 168) * E_ + 56 * N_)
+    part = pg.partition() if world * n_shards > 1 else None
     step_tr = (ncu_traffic("step_traffic.json") or {}) if (D == 3 and world == 1 and n_poses == 1_000_000 and args.preconditioner == 1) else {}
     # ---- the reference's benches/graph_slam.rs shape (:7-11): PoseGraph::new + optimize(5) per sample, host set-up included
     new_opt5 = None
-    if world == 1 and not args.no_secondary:
+    if world == 1 and n_shards == 1 and not args.no_secondary:
         pg.close()
         t0 = time.perf_counter()
         pg2 = PoseGraph(graph=g, options=Options(device=local, pcg_rtol=args.pcg_rtol, preconditioner=args.preconditioner, **extra))
@@ -399,7 +406,7 @@ def run_b200(args):
         pg2.close()
     # ---- BASELINE configs[4] (SE3 sphere, 250k poses / 1M edges; repo-defined SE3 semantics, parity unpinned) as a secondary line
     secondary = None
-    if world == 1 and args.workload == "manhattan" and n_poses == 1_000_000 and not args.no_secondary:
+    if world == 1 and n_shards == 1 and args.workload == "manhattan" and n_poses == 1_000_000 and not args.no_secondary:
         g3, _, d3 = make_graph("sphere", 250_000)
         p3 = PoseGraph(graph=g3, options=Options(device=local, pcg_rtol=args.pcg_rtol))
         p3.snapshot_poses()
@@ -416,35 +423,37 @@ def run_b200(args):
     line = None
     if rank == 0:
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and n_shards == 1 and not args.no_cpu_baseline:
             v, sec, sample, cores = cpu_reference_run(CPU_SAMPLE_POSES_SE3 if D == 6 else CPU_SAMPLE_POSES, 1 if args.workload == "manhattan" else 2, 0,
                                                       args.workload)   # bundled graphs ignore the size
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "s_per_gn_iteration": sec,
                    "extrapolation": CPU_EXTRAPOLATION if args.workload == "manhattan" and n_poses > CPU_SAMPLE_POSES else None}
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world * n_shards, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "bundled dataset" if args.workload in BUNDLED else "synthetic",
             "config": {"workload": wl_desc.format(n_poses, n_edges) + "; 1 step = 1 Gauss-Newton iteration from the initial guess",
                        "poses": n_poses, "edges": n_edges, "pcg_rtol": args.pcg_rtol, "option_overrides": args.opts or None,
                        "preconditioner": "aggregation-AMG K-cycle (flexible PCG); the cycle's SpMVs read fp32 copies of the stored blocks and accumulate in fp64, the PCG operator / residual / dot products are fp64" if args.preconditioner == 1 else "block-Jacobi",
-                       "parallelism": "single GPU" if world == 1 else
+                       "parallelism": "single GPU" if world * n_shards == 1 else
+                       f"1 graph sharded over {n_shards} GPUs by contiguous vertex ranges, ONE process / one PoseGraph handle (pgo_options.n_gpus); halo rows read "
+                       f"from peer HBM (NVLink), all-reduces fused into the producing kernels' last blocks" if n_shards > 1 else
                        f"1 graph sharded over {world} GPUs by contiguous vertex ranges; halo rows read from peer HBM (NVLink), "
                        f"device-side peer-memory all-reduce for the dot products",
                        "l2": (f"working set {st['device_bytes'] * world / 1e9:.1f} GB >> 126 MB L2, no flush needed" if st['device_bytes'] * world > 1e9 else
                               f"working set {st['device_bytes'] * world / 1e6:.1f} MB fits the 126 MB L2 (small bundled graph: L2-resident by nature, not flushed)")},
             "gn_iterations_per_sec": 1e3 / step_ms, "pcg_iterations_per_step": sum(pcg_its) / len(pcg_its),
             "wall_ms_per_step": wall_ms, "phase_ms": phases, "create_s": t_create, "e2e_new_plus_optimize5": new_opt5,
-            "partition": pg.partition() if world > 1 else None,
+            "partition": part,
             "chi2": {"initial": chi2_0, "after_step": last[1], "norm_dx": last[0]},
-            "roofline": {"bound": "hbm", "kernel": f"k_spmv<{D},0> (fine-level BSR SpMV)" + ("" if world == 1 else ", rank 0's shard"), "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": f"k_spmv<{D},0> (fine-level BSR SpMV)" + ("" if world * n_shards == 1 else ", the largest shard"), "achieved": achieved, "peak": peak,
                          "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "ms_per_launch": spmv_ms,
                          "algorithmic_bytes_per_launch": spmv_bytes,
                          "traffic": (tr or {}).get("dram_bytes_per_launch") if (D == 3 and world == 1 and n_poses == 1_000_000) else None,
                          "traffic_source": (tr or {}).get("source") if (D == 3 and world == 1 and n_poses == 1_000_000) else None},
             "step_roofline": {"definition": "SURVEY 8(d): compulsory bytes of assemble + block-Jacobi setup + k block-Jacobi-form PCG iterations + retract + chi2, k = PCG iterations run; a lower bound for the AMG path",
-                              "bytes_per_step": step_bytes, "achieved": step_bytes / (step_ms * 1e-3) / 1e9 / world, "unit": "GB/s per GPU",
-                              "frac": step_bytes / (step_ms * 1e-3) / 1e9 / world / peak,
+                              "bytes_per_step": step_bytes, "achieved": step_bytes / (step_ms * 1e-3) / 1e9 / (world * n_shards), "unit": "GB/s per GPU",
+                              "frac": step_bytes / (step_ms * 1e-3) / 1e9 / (world * n_shards) / peak,
                               # what the step REALLY moves: ncu dram__bytes over every kernel of one converged GN step (profiles/)
                               "traffic": step_tr.get("dram_bytes_per_step"), "traffic_source": step_tr.get("source"),
                               "traffic_pcg_iterations": step_tr.get("pcg_iterations"),
