@@ -373,6 +373,11 @@ def test_cpp_example_and_bench_drivers(built, g2o_files, tmp_path):
     want, eps = KAT.FINAL_ERROR["intel"]
     assert abs(final - want) <= eps
     assert list((tmp_path / "img").glob("*.svg"))                       # plot=true writes img/*.svg (:375-431)
+    # the same example, ONE PoseGraph driving two shards (here both on GPU 0): same result
+    r = subprocess.run([str(ROOT / "examples" / "pose_graph_optimization"), str(g2o_files["intel"]), "GaussNewton", "noplot", "--devices", "0,0"],
+                       capture_output=True, text=True, cwd=tmp_path, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert abs(float(r.stdout.strip().splitlines()[-1].split()[2]) - want) <= eps
     r = subprocess.run([str(ROOT / "examples" / "graph_slam"), str(g2o_files["intel"]), "3"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
     out = json.loads(r.stdout.strip().splitlines()[-1])
