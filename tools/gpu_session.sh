@@ -14,6 +14,12 @@ traffic)
   timeout 1200 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --cache-control none \
       --profile-from-start off --csv --log-file gpurun_out/step_traffic_$tag.csv python tools/step_traffic.py > gpurun_out/step_traffic_$tag.log 2>&1; echo "traffic rc=$?"
   tail -2 gpurun_out/step_traffic_$tag.log; python tools/summarize_traffic.py gpurun_out/step_traffic_$tag.csv gpurun_out/step_traffic_$tag.json | head -30;;
+multi)   # on a box with N >= 2 GPUs:  gpurun --gpus N -- 'bash tools/gpu_session.sh TAG multi'
+  N=$(nvidia-smi -L | wc -l)
+  timeout 900 python -m pytest tests/test_multi_gpu.py tests/test_sharded.py -m gpu -q -rs > gpurun_out/pytest_multi_n${N}_$tag.log 2>&1; echo "pytest multi rc=$?"; tail -4 gpurun_out/pytest_multi_n${N}_$tag.log
+  timeout 600 python bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/bench_sp_n${N}_$tag.json 2> gpurun_out/bench_sp_n${N}_$tag.err; echo "bench single-process N=$N rc=$?"; cut -c1-1800 gpurun_out/bench_sp_n${N}_$tag.json
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 5 --warmup 3 \
+      > gpurun_out/bench_tr_n${N}_$tag.json 2> gpurun_out/bench_tr_n${N}_$tag.err; echo "bench torchrun N=$N rc=$?"; cut -c1-1800 gpurun_out/bench_tr_n${N}_$tag.json;;
 abgj)
   for v in 1 0; do PGO_GJ_OLD=$v timeout 300 python tools/quick_perf.py --opts pcg_rtol=1e-9 2>&1 | tail -1 | sed "s/^/GJ_OLD=$v /"; done | tee gpurun_out/gj_$tag.log
   for v in 1 0; do PGO_GJ_OLD=$v timeout 300 python tools/quick_perf.py --se3 --poses 250000 --opts pcg_rtol=1e-9 2>&1 | tail -1 | sed "s/^/SE3 GJ_OLD=$v /"; done | tee -a gpurun_out/gj_$tag.log;;

@@ -15,7 +15,9 @@ for name, g in (("intel", graph_of(load_golden("intel"))), ("simulation-pose-lan
     for pre in (1, 0):
         kw = dict(preconditioner=pre, pcg_max_iterations=400)
         if n > 1:
-            kw.update(device_ids=[0] * n)
+            import torch
+            nd = torch.cuda.device_count()
+            kw.update(device_ids=[k % nd for k in range(n)])      # distinct GPUs when the box has them, else shards share GPU 0
         pg = PoseGraph(graph=g, options=Options(**kw))
         errs = pg.optimize(2)
         v = pg.poses()
