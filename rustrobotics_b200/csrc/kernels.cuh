@@ -377,10 +377,10 @@ __device__ __forceinline__ void spmv_row_finish(const LevelDev &L, int64_t row, 
 //   MODE 1: y = r - H x                  (residual)
 //   MODE 2: y = x + omega Dinv (r - H x) (damped block-Jacobi sweep; + r.y -> FIN_RZ_INIT, + {r.y, y.u1} -> FIN_RZ)
 // Large coarse levels use the same kernel (K-cycle dots FIN_K1 / FIN_K2 as in k_spmv_csr).
-// CS: the block values -- a pure stream, every byte used once per launch -- are loaded with the evict-first policy (ld.global.cs),
-// so that they do not push the data that IS re-used out of L2: the gathered x records and, between the three fine-level products
-// of a PCG iteration, the L2-resident coarse levels.
-template <int D, int MODE, int FIN, bool PEER, typename VT = double, int U = 1, bool CS = false>
+// (Loading the block values -- a pure stream -- with the evict-first policy, ld.global.cs, so that they do not push the gathered x
+// records and the L2-resident coarse levels out of L2, was measured and does not pay: 135 vs 130 us per launch, the same PCG time;
+// profiles/r03b_stream_cs.log.)
+template <int D, int MODE, int FIN, bool PEER, typename VT = double, int U = 1>
 __global__ void __launch_bounds__(128) k_spmv(LevelDev L, const __grid_constant__ XRef xr, const double *__restrict__ x, const double *__restrict__ r,
                                                double *__restrict__ y, double omega, const double *__restrict__ u1, const double *__restrict__ u2,
                                                Scalars *S, double *partials, int lvl, int check_done) {
@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(128) k_spmv(LevelDev L, const __grid_constant_
                     ld_vec<VS>(PEER ? xgather<VS>(xr, cw[j]) : x + (int64_t)(cw[j] & COL_LOCAL_MASK) * VS, xj[j]);
                     const VT *v = vals + of[j] * DD;
 #pragma unroll
-                    for (int q = 0; q < DD; q++) hv[j][q] = CS ? __ldcs(v + (int64_t)q * cn[j]) : __ldg(v + (int64_t)q * cn[j]);
+                    for (int q = 0; q < DD; q++) hv[j][q] = __ldg(v + (int64_t)q * cn[j]);
                 }
             }
             {
@@ -1699,17 +1699,29 @@ __global__ void __launch_bounds__(256) k_dense_invert2(int m, double *__restrict
                     aij[a][c] = (gi < m && gj < m) ? __ldcg(src + (int64_t)gi * m + gj) : 0.0;
                 }
             __syncthreads();
-            for (int t = tid; t < GJ_W * GJ_T; t += 256) {       // X[l][j] = (P^-1 A[p, j])[l] outside the panel columns, P^-1[l][j - p0] inside
-                const int l = t / GJ_T, jj = t % GJ_T;
-                const int gj = j0 + jj;
-                double v;
-                if (gj >= p0 && gj < p0 + GJ_W) v = Pinv[l][gj - p0];
-                else {
-                    v = 0.0;
+            {   // X[l][j] = (P^-1 A[p, j])[l] outside the panel columns, P^-1[l][j - p0] inside.  Register-blocked: a warp owns four rows l
+                // (its P^-1 operands are warp-uniform shared-memory broadcasts), a lane two columns: 6 shared loads per 8 FMAs
+                const int l0 = (tid >> 5) * 4, jj0 = tid & 31;
+                double xa[4][2];
+#pragma unroll
+                for (int a = 0; a < 4; a++) xa[a][0] = xa[a][1] = 0.0;
 #pragma unroll 8
-                    for (int q = 0; q < GJ_W; q++) v = fma(Pinv[l][q], Xr[q][jj], v);
+                for (int q = 0; q < GJ_W; q++) {
+                    const double x0 = Xr[q][jj0], x1 = Xr[q][jj0 + 32];
+#pragma unroll
+                    for (int a = 0; a < 4; a++) {
+                        const double pv = Pinv[l0 + a][q];
+                        xa[a][0] = fma(pv, x0, xa[a][0]);
+                        xa[a][1] = fma(pv, x1, xa[a][1]);
+                    }
                 }
-                Xb[l][jj] = v;
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    const int jj = jj0 + 32 * c, gj = j0 + jj;
+                    const bool jin = gj >= p0 && gj < p0 + GJ_W;
+#pragma unroll
+                    for (int a = 0; a < 4; a++) Xb[l0 + a][jj] = jin ? Pinv[l0 + a][gj - p0] : xa[a][c];
+                }
             }
             __syncthreads();
             double acc[4][4];

@@ -14,6 +14,12 @@ __global__ void __launch_bounds__(32) k_xbarrier(Scalars *S, int check_done) {
     xrank_exchange<0>(S, none);
 }
 
+// last node of the body of the device-side PCG loop (a CUDA-graph WHILE node): keep iterating until a kernel has set `done`
+__global__ void __launch_bounds__(32) k_loop_cond(cudaGraphConditionalHandle hnd, const Scalars *S) {
+    PDL_ENTER();
+    if (threadIdx.x == 0) cudaGraphSetConditional(hnd, ld_done(S) ? 0u : 1u);
+}
+
 // {a.b (, b.c)} over the local rows -> FIN (used when the preconditioner itself has no kernel to fuse the dots into)
 template <int D, int FIN>
 __global__ void __launch_bounds__(128) k_dots(int64_t n_pad, const double *__restrict__ a, const double *__restrict__ b,

@@ -120,12 +120,13 @@ struct pgo_handle {
     bool use_amg = false, omega_ready = false;
     int spmv_tma64 = 0, spmv_tma32 = 0; // PGO_SPMV_TMA64 / PGO_SPMV_TMA32: ring depth of the TMA-staged sliced SpMV (0: register-staged kernel)
     int64_t lpr4_min_rows = 16384;     // PGO_LPR4_MIN_ROWS
-    bool stream_cs = false;            // PGO_STREAM_CS=1: evict-first loads of the fine-level block values (experiment)
     bool pdl = true;                   // programmatic dependent launch of every kernel (PGO_PDL=0 disables)
     cudaError_t launch_err = cudaSuccess;
     bool lowp = false;                 // the cycle's SpMVs read fp32 copies of the stored blocks (opt.amg_fp64_storage == 0)
     int64_t anchor_row = -1;
     cudaGraphExec_t pcg_graph = nullptr;
+    bool opt_while = false;            // PGO_WHILE=1: the whole PCG loop is ONE graph launch, a WHILE conditional node iterating on the device
+    bool pcg_while = false;            // ... and that is what pcg_graph holds
     int chunk = 8;
     int64_t launches_per_iter = 0;
     cudaEvent_t ev[PGO_NUM_PHASES + 2]{}, poll_ev[2]{};
@@ -239,8 +240,7 @@ template <int D, int MODE, int FIN, typename VT> void spmv_launch(pgo_handle *h,
             const size_t smem = spmv_tma_smem<D, VT>(ns);
             if (smem > 48 * 1024) cudaFuncSetAttribute(k_spmv_tma<D, MODE, FIN, VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             launch_k(h, k_spmv_tma<D, MODE, FIN, VT>, B.grid128, 128, smem, B.d, x, r, y, omega, u1, u2, h->S, h->partials, l, check, ns);
-        } else if (h->stream_cs) launch_k(h, k_spmv<D, MODE, FIN, false, VT, 1, true>, B.grid128, 128, 0, B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
-        else launch_k(h, k_spmv<D, MODE, FIN, false, VT>, B.grid128, 128, 0, B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
+        } else launch_k(h, k_spmv<D, MODE, FIN, false, VT>, B.grid128, 128, 0, B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
     }
     else if (B.lpr == 4) launch_k(h, k_spmv_csr<D, MODE, FIN, false, 4, VT>, B.grid4, 256, 0, B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
     else if (B.lpr == 8) launch_k(h, k_spmv_csr<D, MODE, FIN, false, 8, VT>, B.grid8, 256, 0, B.d, xr, x, r, y, omega, u1, u2, h->S, h->partials, l, check);
@@ -384,8 +384,52 @@ template <int D> void pcg_iteration(pgo_handle *h) {
     update_p<D>(h);
 }
 
+// The PCG loop as a device-side loop: a graph with one WHILE conditional node whose body is one PCG iteration followed by
+// k_loop_cond (loop again unless a kernel has set `done`).  One graph launch per solve, no host polling, no iterations launched
+// behind the convergence flag.  Returns false when this driver / toolkit cannot build it (the caller falls back to the chunked graph).
+template <int D> bool build_pcg_while(pgo_handle *h) {
+    cudaGraph_t g = nullptr;
+    cudaGraphExec_t ge = nullptr;
+    const int64_t before = h->launch_count;
+    bool capturing = false, ok = false;
+    do {
+        if (cudaGraphCreate(&g, 0) != cudaSuccess) break;
+        cudaGraphConditionalHandle hnd;
+        if (cudaGraphConditionalHandleCreate(&hnd, g, 1, cudaGraphCondAssignDefault) != cudaSuccess) break;
+        cudaGraphNodeParams p = {cudaGraphNodeTypeConditional};
+        p.type = cudaGraphNodeTypeConditional;
+        p.conditional.handle = hnd;
+        p.conditional.type = cudaGraphCondTypeWhile;
+        p.conditional.size = 1;
+        cudaGraphNode_t node;
+        if (cudaGraphAddNode(&node, g, nullptr, 0, &p) != cudaSuccess) break;
+        cudaGraph_t body = p.conditional.phGraph_out[0];
+        if (cudaStreamBeginCaptureToGraph(h->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) != cudaSuccess) break;
+        capturing = true;
+        pcg_iteration<D>(h);
+        launch_k(h, k_loop_cond, 1, 32, 0, hnd, (const Scalars *)h->S);
+        h->launch_count += 1;
+        cudaGraph_t out = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(h->stream, &out);
+        capturing = false;
+        if (ce != cudaSuccess || h->launch_err != cudaSuccess) break;
+        if (cudaGraphInstantiate(&ge, g, 0) != cudaSuccess) break;
+        ok = true;
+    } while (false);
+    if (capturing) { cudaGraph_t out = nullptr; cudaStreamEndCapture(h->stream, &out); }
+    if (g) cudaGraphDestroy(g);
+    if (!ok) { (void)cudaGetLastError(); h->launch_err = cudaSuccess; h->launch_count = before; return false; }
+    h->pcg_graph = ge;
+    h->pcg_while = true;
+    h->launches_per_iter = h->launch_count - before;
+    h->launch_count = before;
+    return true;
+}
+
 template <int D> int build_pcg_graph(pgo_handle *h) {
     if (h->pcg_graph) return PGO_OK;
+    h->pcg_while = false;
+    if (h->opt_while && build_pcg_while<D>(h)) return PGO_OK;
     cudaGraph_t g = nullptr;
     int64_t before = h->launch_count;
     CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
@@ -576,11 +620,17 @@ template <int D> int solve(pgo_handle *h, int32_t *iters_out) {
     precondition<D, FIN_RZ_INIT>(h);
     halo_pull(h, 0, h->z, VecStride<D>::value, 1);   // p = z, halo slots included (pcg_iteration keeps them current from here on)
     CK(cudaMemcpyAsync(h->p, h->z, (nd + (h->world > 1 ? B.n_halo * VecStride<D>::value : 0)) * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    if (h->pcg_while) {                              // the loop runs on the device: one launch, the host only waits for the end
+        CK(cudaGraphLaunch(h->pcg_graph, h->stream));
+        CK(cudaMemcpyAsync(&h->hS[0], h->S, sizeof(Scalars), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        h->launch_count += h->launches_per_iter * std::max(h->hS[0].iters, 1);
+    }
     // keep two graph launches in flight; poll the pinned scalars of the older one
     int slot = 0, inflight = 0;
     int64_t launched = 0;
     const int64_t max_graphs = (int64_t)h->opt.pcg_max_iterations / h->chunk + 2;
-    bool done = false;
+    bool done = h->pcg_while;
     while (!done) {
         if (launched < max_graphs) {
             CK(cudaGraphLaunch(h->pcg_graph, h->stream));
@@ -1181,7 +1231,7 @@ static SymbolicOptions configure_handle(pgo_handle *h) {
     if (const char *e = std::getenv("PGO_SPMV_TMA32")) h->spmv_tma32 = std::max(0, std::min(16, std::atoi(e)));
     if (const char *e = std::getenv("PGO_LPR4_MIN_ROWS")) h->lpr4_min_rows = std::atoll(e);
     if (const char *e = std::getenv("PGO_PDL")) h->pdl = std::atoi(e) != 0;
-    if (const char *e = std::getenv("PGO_STREAM_CS")) h->stream_cs = std::atoi(e) != 0;
+    if (const char *e = std::getenv("PGO_WHILE")) h->opt_while = std::atoi(e) != 0;
     h->lowp = h->use_amg && h->opt.amg_fp64_storage == 0;
     return so;
 }

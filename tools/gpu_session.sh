@@ -23,8 +23,13 @@ multi)   # on a box with N >= 2 GPUs:  gpurun --gpus N -- 'bash tools/gpu_sessio
 abgj)
   for v in 1 0; do PGO_GJ_OLD=$v timeout 300 python tools/quick_perf.py --opts pcg_rtol=1e-9 2>&1 | tail -1 | sed "s/^/GJ_OLD=$v /"; done | tee gpurun_out/gj_$tag.log
   for v in 1 0; do PGO_GJ_OLD=$v timeout 300 python tools/quick_perf.py --se3 --poses 250000 --opts pcg_rtol=1e-9 2>&1 | tail -1 | sed "s/^/SE3 GJ_OLD=$v /"; done | tee -a gpurun_out/gj_$tag.log;;
-abcs)
+abcs_removed)
   for v in 0 1; do PGO_STREAM_CS=$v timeout 300 python tools/quick_perf.py --opts pcg_rtol=1e-9 2>&1 | tail -1 | sed "s/^/STREAM_CS=$v /"; done | tee gpurun_out/stream_cs_$tag.log;;
+setup)   # what the hierarchy set-up of one GN step consists of (launch list of everything that is not the PCG loop)
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none --profile-from-start off --csv \
+      -k regex:'galerkin|dense|to_float|coarse_pos|lever|invert_diag|assemble|build_hz|chi2|retract' \
+      --log-file gpurun_out/setup_launches_$tag.csv python tools/step_traffic.py > gpurun_out/setup_launches_$tag.log 2>&1; echo "setup rc=$?"
+  python tools/summarize_launches.py gpurun_out/setup_launches_$tag.csv | tee gpurun_out/setup_launches_$tag.md | head -40;;
 sanitize2)
   for tool in memcheck racecheck; do
     timeout 240 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize.py 2 > gpurun_out/sanitize_${tool}_n2_$tag.log 2>&1; echo "$tool n=2 rc=$?"
