@@ -25,6 +25,9 @@ abgj)
   for v in 1 0; do PGO_GJ_OLD=$v timeout 300 python tools/quick_perf.py --se3 --poses 250000 --opts pcg_rtol=1e-9 2>&1 | tail -1 | sed "s/^/SE3 GJ_OLD=$v /"; done | tee -a gpurun_out/gj_$tag.log;;
 abcs_removed)
   for v in 0 1; do PGO_STREAM_CS=$v timeout 300 python tools/quick_perf.py --opts pcg_rtol=1e-9 2>&1 | tail -1 | sed "s/^/STREAM_CS=$v /"; done | tee gpurun_out/stream_cs_$tag.log;;
+abwhile)
+  for v in 0 1; do PGO_WHILE=$v timeout 300 python tools/quick_perf.py --opts pcg_rtol=1e-9 2>&1 | tail -1 | sed "s/^/WHILE=$v /"; done | tee gpurun_out/while_$tag.log
+  for v in 0 1; do PGO_WHILE=$v timeout 300 python tools/quick_perf.py --poses 100000 --opts pcg_rtol=1e-9 2>&1 | tail -1 | sed "s/^/100k WHILE=$v /"; done | tee -a gpurun_out/while_$tag.log;;
 setup)   # what the hierarchy set-up of one GN step consists of (launch list of everything that is not the PCG loop)
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none --profile-from-start off --csv \
       -k regex:'galerkin|dense|to_float|coarse_pos|lever|invert_diag|assemble|build_hz|chi2|retract' \
