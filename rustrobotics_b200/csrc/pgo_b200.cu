@@ -267,7 +267,7 @@ template <int D> void coarse_solve(pgo_handle *h, int l, const double *rhs, doub
 
 template <int D> void dense_apply(pgo_handle *h, int l, const double *rhs, double *out) {
     LevelBuf &B = h->lv[l];      // always a local (single-GPU or replicated) level
-    launch_k(h, k_dense_apply<D>, grid_for(B.d.n * D, 8), 256, sizeof(double) * h->dense_m, B.d.n, h->dmap, 0, 1, h->dense_m,
+    launch_k(h, k_dense_apply<D>, grid_for(B.d.n * D, 8 / DENSE_KS), 256, sizeof(double) * (h->dense_m + 8), B.d.n, h->dmap, 0, 1, h->dense_m,
                                                                                              h->Ainv, xref(h, rhs, true), out, h->S);
     h->launch_count += 1;
 }
@@ -975,8 +975,8 @@ static int create_shard(pgo_handle *h, const double *vval, int64_t ne, const uin
         CKU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
         const int nt = (m + GJ_T - 1) / GJ_T;
         h->invert_grid = std::max(1, std::min(std::max(per_sm, 1) * sms, nt * nt));
-        CKU(cudaFuncSetAttribute(k_dense_apply<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 6 * 1024)));
-        CKU(cudaFuncSetAttribute(k_dense_apply<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 6 * 1024)));
+        CKU(cudaFuncSetAttribute(k_dense_apply<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (6 * 1024 + 8))));
+        CKU(cudaFuncSetAttribute(k_dense_apply<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (6 * 1024 + 8))));
     }
     // PCG iterations per captured graph: the host keeps two launches in flight, so up to ~2 chunks of early-exit kernels run after
     // convergence; measured at config 4 (41 AMG iterations): chunk 1 / 2 / 4 / 8 -> PCG 34.17 / 34.19 / 34.70 / 35.79 ms

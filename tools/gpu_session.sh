@@ -25,6 +25,18 @@ abgj)
   for v in 1 0; do PGO_GJ_OLD=$v timeout 300 python tools/quick_perf.py --se3 --poses 250000 --opts pcg_rtol=1e-9 2>&1 | tail -1 | sed "s/^/SE3 GJ_OLD=$v /"; done | tee -a gpurun_out/gj_$tag.log;;
 abcs_removed)
   for v in 0 1; do PGO_STREAM_CS=$v timeout 300 python tools/quick_perf.py --opts pcg_rtol=1e-9 2>&1 | tail -1 | sed "s/^/STREAM_CS=$v /"; done | tee gpurun_out/stream_cs_$tag.log;;
+bundled)  # the reference's own datasets (BASELINE configs[0..2]) + configs[4]
+  : > gpurun_out/bench_bundled_$tag.jsonl
+  for w in pose-pose pose-landmark intel dlr m3500 sphere2500 garage; do
+    timeout 300 python bench.py --workload $w --steps 10 --warmup 3 >> gpurun_out/bench_bundled_$tag.jsonl 2>> gpurun_out/bench_bundled_$tag.err; echo "bench $w rc=$?"
+  done
+  python - <<PY
+import json
+for l in open("gpurun_out/bench_bundled_$tag.jsonl"):
+    d = json.loads(l); c = d["cpu_baseline"] or {}
+    print(d["config"]["workload"][:60], "| ms/step %.3f | pcg its %.0f | cpu s/GN it %s" % (d["ms_per_step"], d["pcg_iterations_per_step"], c.get("s_per_gn_iteration")))
+PY
+  ;;
 abwhile)
   for v in 0 1; do PGO_WHILE=$v timeout 300 python tools/quick_perf.py --opts pcg_rtol=1e-9 2>&1 | tail -1 | sed "s/^/WHILE=$v /"; done | tee gpurun_out/while_$tag.log
   for v in 0 1; do PGO_WHILE=$v timeout 300 python tools/quick_perf.py --poses 100000 --opts pcg_rtol=1e-9 2>&1 | tail -1 | sed "s/^/100k WHILE=$v /"; done | tee -a gpurun_out/while_$tag.log;;
