@@ -834,13 +834,26 @@ __global__ void __launch_bounds__(128) k_update_xr_dinv(LevelDev L, double *__re
     for (int c = 0; c < VS; c++) { xv[c] = fma(a, pv[c], xv[c]); rv[c] = fma(-a, qv[c], rv[c]); out[c] = 0.0; }
     st_vec<VS>(x + row * VS, xv);
     st_vec<VS>(r + row * VS, rv);
-    const double *di = L.dinv + row;
+    // xa = omega Dinv r is the first step of the PRECONDITIONER: with reduced-precision preconditioner storage it reads the fp32
+    // copy of the inverse diagonal blocks like the cycle's other kernels (half the bytes of this term)
+    if (L.dinvf) {
+        const float *di = L.dinvf + row;
 #pragma unroll
-    for (int c = 0; c < D; c++) {
-        double s = 0.0;
+        for (int c = 0; c < D; c++) {
+            double s = 0.0;
 #pragma unroll
-        for (int b = 0; b < D; b++) s = fma(__ldg(di + (int64_t)(c * D + b) * L.n_pad), rv[b], s);
-        out[c] = omega * s;
+            for (int b = 0; b < D; b++) s = fma((double)__ldg(di + (int64_t)(c * D + b) * L.n_pad), rv[b], s);
+            out[c] = omega * s;
+        }
+    } else {
+        const double *di = L.dinv + row;
+#pragma unroll
+        for (int c = 0; c < D; c++) {
+            double s = 0.0;
+#pragma unroll
+            for (int b = 0; b < D; b++) s = fma(__ldg(di + (int64_t)(c * D + b) * L.n_pad), rv[b], s);
+            out[c] = omega * s;
+        }
     }
     st_vec<VS>(xa + row * VS, out);
 }
@@ -1637,7 +1650,7 @@ __device__ __forceinline__ void gj_invert32(double (*Pb)[GJ_W][GJ_W + 1]) {
     }
 }
 
-__global__ void __launch_bounds__(256, 3) k_dense_invert2(int m, double *__restrict__ bufA, double *__restrict__ bufB, double *__restrict__ pnext,
+__global__ void __launch_bounds__(256) k_dense_invert2(int m, double *__restrict__ bufA, double *__restrict__ bufB, double *__restrict__ pnext,
                                                         unsigned *bar, unsigned bar_base) {
     PDL_ENTER();
     extern __shared__ double gj_smem[];
@@ -1770,29 +1783,24 @@ __global__ void __launch_bounds__(256, 3) k_dense_invert2(int m, double *__restr
     }
 }
 
-// x = Ainv r on the coarsest level.  The kernel is a chain of L2 round trips, not a bandwidth problem (the fp64 inverse, 12 MB at
-// config 4, is L2-resident): a row of the inverse is split over DENSE_KS warps, so that each lane has ALL its loads of the row in
-// flight at once (one round trip instead of three) and four times as many warps keep the L2 busy; the DENSE_KS partial sums of a row
-// are added in a fixed order.  6.9 -> (see profiles/) us per application, ~300 applications per Gauss-Newton step.
-constexpr int DENSE_KS = 4;
+// (Splitting a row of the inverse over four warps, so that every lane has all its loads of the row in flight at once, was measured
+// and LOSES: 8.8 vs 6.9 us per application -- four times as many CTAs each stage the whole right-hand side before they can start;
+// profiles/r03d_setup_launches.md.)
 template <int D>
-__global__ void __launch_bounds__(256) k_dense_apply(int64_t n_local, DenseMap dm, int rank, int world, int m, const double *__restrict__ Ainv,
-                                                      const __grid_constant__ XRef rr, double *__restrict__ x, const Scalars *S) {
-    PDL_ENTER();
-    if (ld_done(S)) return;
-    constexpr int VS = VecStride<D>::value, RPC = 8 / DENSE_KS;      // rows per CTA
-    extern __shared__ double sr[];                                   // [m] right-hand side, then [8] partial sums
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int part = w % DENSE_KS;
-    const int64_t srow = (int64_t)blockIdx.x * RPC + w / DENSE_KS;   // local scalar row
+__device__ __forceinline__ void dense_apply_body(int64_t n_local, const DenseMap &dm, int rank, int world, int m, const double *__restrict__ Ainv,
+                                                 const XRef &rr, double *__restrict__ x, unsigned vb) {
+    constexpr int VS = VecStride<D>::value;
+    extern __shared__ double sr[];
+    const int lane = threadIdx.x & 31;
+    const int64_t srow = (int64_t)vb * 8 + (threadIdx.x >> 5);      // local scalar row
     const bool live = srow < n_local * D;
-    const int seg = ((m + DENSE_KS - 1) / DENSE_KS + 31) / 32 * 32;
-    const int jb = part * seg, je = min(m, jb + seg);
     const double *a = Ainv + ((int64_t)dm.off[rank] * D + (live ? srow : 0)) * m;
+    // a row of the inverse is read in batches of DB independent loads per lane (the first one before the right-hand side
+    // is staged): the kernel is a chain of L2 round trips, one per batch, not a bandwidth problem
     constexpr int DB = 16;
     double av[DB];
 #pragma unroll
-    for (int u = 0; u < DB; u++) { const int j = jb + u * 32 + lane; av[u] = (live && j < je) ? __ldg(a + j) : 0.0; }
+    for (int u = 0; u < DB; u++) { const int j = u * 32 + lane; av[u] = (live && j < m) ? __ldg(a + j) : 0.0; }
     for (int t = threadIdx.x; t < m; t += 256) {
         const int g = t / D, c = t - D * g;
         int k = 0;
@@ -1800,27 +1808,26 @@ __global__ void __launch_bounds__(256) k_dense_apply(int64_t n_local, DenseMap d
         sr[t] = rr.p[k][(int64_t)(g - dm.off[k]) * VS + c];
     }
     __syncthreads();
+    if (!live) return;
     double s = 0.0;
-    if (live)
-        for (int j0 = jb; j0 < je; j0 += 32 * DB) {
-            double nv[DB];
+    for (int j0 = 0; j0 < m; j0 += 32 * DB) {
+        double nv[DB];
 #pragma unroll
-            for (int u = 0; u < DB; u++) { const int j = j0 + 32 * DB + u * 32 + lane; nv[u] = j < je ? __ldg(a + j) : 0.0; }    // next batch
+        for (int u = 0; u < DB; u++) { const int j = j0 + 32 * DB + u * 32 + lane; nv[u] = j < m ? __ldg(a + j) : 0.0; }    // next batch
 #pragma unroll
-            for (int u = 0; u < DB; u++) { const int j = j0 + u * 32 + lane; s = fma(av[u], j < je ? sr[j] : 0.0, s); }
+        for (int u = 0; u < DB; u++) { const int j = j0 + u * 32 + lane; s = fma(av[u], j < m ? sr[j] : 0.0, s); }
 #pragma unroll
-            for (int u = 0; u < DB; u++) av[u] = nv[u];
-        }
-    s = warp_sum(s);
-    double *part_sum = sr + m;
-    if (lane == 0) part_sum[w] = s;
-    __syncthreads();
-    if (live && part == 0 && lane == 0) {
-        double t = 0.0;
-#pragma unroll
-        for (int q = 0; q < DENSE_KS; q++) t += part_sum[w + q];
-        x[(srow / D) * VS + (srow % D)] = t;
+        for (int u = 0; u < DB; u++) av[u] = nv[u];
     }
+    s = warp_sum(s);
+    if (lane == 0) x[(srow / D) * VS + (srow % D)] = s;
+}
+template <int D>
+__global__ void __launch_bounds__(256) k_dense_apply(int64_t n_local, DenseMap dm, int rank, int world, int m, const double *__restrict__ Ainv,
+                                                      const __grid_constant__ XRef rr, double *__restrict__ x, const Scalars *S) {
+    PDL_ENTER();
+    if (ld_done(S)) return;
+    dense_apply_body<D>(n_local, dm, rank, world, m, Ainv, rr, x, blockIdx.x);
 }
 
 // Halo exchange: v[(n_pad + i) * stride ...] <- the record of row halo_src[i] in its owner's copy of v (peer HBM, NVLink).

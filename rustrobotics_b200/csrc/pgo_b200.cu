@@ -125,7 +125,8 @@ struct pgo_handle {
     bool lowp = false;                 // the cycle's SpMVs read fp32 copies of the stored blocks (opt.amg_fp64_storage == 0)
     int64_t anchor_row = -1;
     cudaGraphExec_t pcg_graph = nullptr;
-    bool opt_while = false;            // PGO_WHILE=1: the whole PCG loop is ONE graph launch, a WHILE conditional node iterating on the device
+    bool opt_while = true;             // the whole PCG loop is ONE graph launch, a WHILE conditional node iterating on the device (PGO_WHILE=0:
+                                       // chunks of `chunk` iterations per launch, the host polling a pinned copy of the scalars)
     bool pcg_while = false;            // ... and that is what pcg_graph holds
     int chunk = 8;
     int64_t launches_per_iter = 0;
@@ -267,7 +268,7 @@ template <int D> void coarse_solve(pgo_handle *h, int l, const double *rhs, doub
 
 template <int D> void dense_apply(pgo_handle *h, int l, const double *rhs, double *out) {
     LevelBuf &B = h->lv[l];      // always a local (single-GPU or replicated) level
-    launch_k(h, k_dense_apply<D>, grid_for(B.d.n * D, 8 / DENSE_KS), 256, sizeof(double) * (h->dense_m + 8), B.d.n, h->dmap, 0, 1, h->dense_m,
+    launch_k(h, k_dense_apply<D>, grid_for(B.d.n * D, 8), 256, sizeof(double) * h->dense_m, B.d.n, h->dmap, 0, 1, h->dense_m,
                                                                                              h->Ainv, xref(h, rhs, true), out, h->S);
     h->launch_count += 1;
 }

@@ -91,6 +91,25 @@ def test_multi_gpu_handle_matches_the_oracle(built, case, n_gpus):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("case", ["manhattan100000", "sphere40x50"])
+def test_multi_gpu_handle_with_sharded_coarse_levels(built, monkeypatch, case):
+    """what a graph too large to replicate level 1 looks like (8M poses on 8 GPUs), forced on a small one: PGO_REPL_MAX_ROWS makes the
+    coarse levels above 700 rows SHARDED too, so the K-cycle's inner products, halo pulls and barriers cross the GPUs on every level"""
+    from rustrobotics_b200 import Options, PoseGraph
+    from test_gpu_parity import _pose_diff
+    from test_gpu_se3 import se3_pose_diff
+    monkeypatch.setenv("PGO_REPL_MAX_ROWS", "700")
+    g, c0, errs_o, vo = _oracle_run(case, 3 if case == "manhattan100000" else 8)
+    pg = PoseGraph(graph=g, options=Options(device_ids=_device_ids(3)))
+    errs_g = pg.optimize(len(errs_o) - 1)
+    np.testing.assert_allclose(errs_g, errs_o[:len(errs_g)], rtol=CHI2_RTOL)
+    se3 = int(g["vertex_kind"][0]) == 2
+    dxy, dth = se3_pose_diff(pg.poses(), vo) if se3 else _pose_diff(g, pg.poses(), vo)
+    assert dxy < POSE_ATOL and dth < POSE_ATOL
+    pg.close()
+
+
+@pytest.mark.gpu
 def test_multi_gpu_handle_assembles_the_same_system_and_same_api(built):
     """pattern / H / b bit-identical in structure and 1e-12 in value to the oracle, set/get/snapshot/undo behave like 1 GPU"""
     from oracle.oracle import OraclePoseGraph
