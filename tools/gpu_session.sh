@@ -46,8 +46,8 @@ setup)   # what the hierarchy set-up of one GN step consists of (launch list of 
       --log-file gpurun_out/setup_launches_$tag.csv python tools/step_traffic.py > gpurun_out/setup_launches_$tag.log 2>&1; echo "setup rc=$?"
   python tools/summarize_launches.py gpurun_out/setup_launches_$tag.csv | tee gpurun_out/setup_launches_$tag.md | head -40;;
 sanitize2)
-  for tool in memcheck racecheck; do
-    timeout 240 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize.py 2 > gpurun_out/sanitize_${tool}_n2_$tag.log 2>&1; echo "$tool n=2 rc=$?"
+  for tool in ${SAN_TOOLS:-memcheck racecheck}; do
+    timeout 200 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize.py 2 > gpurun_out/sanitize_${tool}_n2_$tag.log 2>&1; echo "$tool n=2 rc=$?"
     grep -E "sanitize |ERROR SUMMARY|RACECHECK SUMMARY|Error|hazard" gpurun_out/sanitize_${tool}_n2_$tag.log | head -14
   done;;
 sanitize)
