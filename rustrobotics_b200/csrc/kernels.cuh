@@ -38,6 +38,7 @@ struct Scalars {
     KScal k[MAX_LEVELS];
     double loc[4];                  // (unused since the cross-rank reduction is fused into the producing kernel)
     Comm *comm_mine; Comm *comm_peer[MAX_RANKS]; int rank, pad2_;   // sharded handles: where the last block of a reducing kernel meets its peers
+    long long spin_limit;           // clock cycles a rank waits for its peers before it gives up with ST_COMM (~20 s; PGO_COMM_TIMEOUT_S)
 };
 enum { ST_OK = 0, ST_BREAKDOWN = 1, ST_MAXIT = 2, ST_COMM = 3 };
 enum { FIN_NONE = 0, FIN_PQ = 1, FIN_RZ = 2, FIN_RZ_INIT = 3, FIN_NORM = 4, FIN_CHI2 = 5, FIN_K1 = 6, FIN_K2 = 7, FIN_K3 = 8 };
@@ -199,7 +200,7 @@ template <int NV> __device__ bool xrank_exchange(Scalars *S, double *total) {
         unsigned long long v;
         do {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(&mine->flags[t]) : "memory");
-            if (v < epoch && clock64() - t0 > 40000000000ll) { bad = 1; break; }
+            if (v < epoch && clock64() - t0 > S->spin_limit) { bad = 1; break; }
         } while (v < epoch);
     }
     __syncthreads();

@@ -1088,6 +1088,8 @@ static int create_shard(pgo_handle *h, const double *vval, int64_t ne, const uin
         s.world = world;
         s.rank = rank;
         s.comm_mine = (Comm *)h->arena;
+        s.spin_limit = 40000000000ll;
+        if (const char *e = std::getenv("PGO_COMM_TIMEOUT_S")) s.spin_limit = (long long)(std::max(0.01, std::atof(e)) * 2.0e9);
         for (int k = 0; k < MAX_RANKS; k++) s.comm_peer[k] = (Comm *)h->arena;    // the peers' blocks are filled in when the shards connect
         s.repl_from = nl;
         for (int l = nl - 1; l >= 1; l--) if (h->lv[l].repl) s.repl_from = l;
