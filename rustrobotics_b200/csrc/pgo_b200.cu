@@ -127,6 +127,7 @@ struct pgo_handle {
     cudaGraphExec_t pcg_graph = nullptr;
     bool opt_while = true;             // the whole PCG loop is ONE graph launch, a WHILE conditional node iterating on the device (PGO_WHILE=0:
                                        // chunks of `chunk` iterations per launch, the host polling a pinned copy of the scalars)
+    bool opt_while_sharded = false;    // PGO_WHILE=2
     bool pcg_while = false;            // ... and that is what pcg_graph holds
     int chunk = 8;
     int64_t launches_per_iter = 0;
@@ -430,7 +431,10 @@ template <int D> bool build_pcg_while(pgo_handle *h) {
 template <int D> int build_pcg_graph(pgo_handle *h) {
     if (h->pcg_graph) return PGO_OK;
     h->pcg_while = false;
-    if (h->opt_while && build_pcg_while<D>(h)) return PGO_OK;
+    // Sharded handles keep the chunked graph: with SHARDED coarse levels the combination "WHILE body + programmatic dependent launch +
+    // kernels that wait for another GPU's kernels" stalls (measured, r03 debug session: either ingredient alone is fine) -- not understood,
+    // so not used; per-iteration cross-GPU synchronisation dominates there anyway.  PGO_WHILE=2 forces it for experiments.
+    if (h->opt_while && (h->world == 1 || h->opt_while_sharded) && build_pcg_while<D>(h)) return PGO_OK;
     cudaGraph_t g = nullptr;
     int64_t before = h->launch_count;
     CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
@@ -1234,7 +1238,7 @@ static SymbolicOptions configure_handle(pgo_handle *h) {
     if (const char *e = std::getenv("PGO_SPMV_TMA32")) h->spmv_tma32 = std::max(0, std::min(16, std::atoi(e)));
     if (const char *e = std::getenv("PGO_LPR4_MIN_ROWS")) h->lpr4_min_rows = std::atoll(e);
     if (const char *e = std::getenv("PGO_PDL")) h->pdl = std::atoi(e) != 0;
-    if (const char *e = std::getenv("PGO_WHILE")) h->opt_while = std::atoi(e) != 0;
+    if (const char *e = std::getenv("PGO_WHILE")) { h->opt_while = std::atoi(e) != 0; h->opt_while_sharded = std::atoi(e) == 2; }
     h->lowp = h->use_amg && h->opt.amg_fp64_storage == 0;
     return so;
 }
