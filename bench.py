@@ -344,6 +344,8 @@ def run_b200(args):
     nb = st["block_rows"] + st["offdiag_blocks"]          # blocks of H incl. diagonal
     # 8 D^2 B (values) + 4B (col) + 4N (row ptr) + 8 D N (x) + 8 D N (y)  [D = 3: 76B + 52N]
     spmv_bytes = (8 * D * D + 4) * nb + (4 + 16 * D) * st["block_rows"]
+    if n_shards > 1:                                      # one handle, N shards: the handle reports totals, the kernel time is the slowest shard's
+        spmv_bytes /= n_shards                            # (the partition balances stored blocks, so this is the mean = about the largest shard)
     peak, peak_src = measured_peak_hbm()
     achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9
     tr = ncu_traffic()
