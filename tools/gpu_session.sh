@@ -20,6 +20,22 @@ multi)   # on a box with N >= 2 GPUs:  gpurun --gpus N -- 'bash tools/gpu_sessio
   timeout 600 python bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/bench_sp_n${N}_$tag.json 2> gpurun_out/bench_sp_n${N}_$tag.err; echo "bench single-process N=$N rc=$?"; cut -c1-1800 gpurun_out/bench_sp_n${N}_$tag.json
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 5 --warmup 3 \
       > gpurun_out/bench_tr_n${N}_$tag.json 2> gpurun_out/bench_tr_n${N}_$tag.err; echo "bench torchrun N=$N rc=$?"; cut -c1-1800 gpurun_out/bench_tr_n${N}_$tag.json;;
+scale)   # strong scaling (1M poses) as the driver runs it (torchrun) + weak scaling (1M poses per GPU) through the single-process handle
+  N=$(nvidia-smi -L | wc -l)
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 5 --warmup 3 \
+      > gpurun_out/bench_tr_n${N}_$tag.json 2> gpurun_out/bench_tr_n${N}_$tag.err; echo "bench torchrun N=$N rc=$?"; cut -c1-300 gpurun_out/bench_tr_n${N}_$tag.json
+  timeout 900 python bench.py --gpus $N --poses $((N * 1000000)) --steps 3 --warmup 2 --no-secondary --no-cpu-baseline \
+      > gpurun_out/bench_weak_n${N}_$tag.json 2> gpurun_out/bench_weak_n${N}_$tag.err; echo "bench weak N=$N rc=$?"; cut -c1-300 gpurun_out/bench_weak_n${N}_$tag.json
+  python - <<PY
+import json
+for f in ("bench_tr_n${N}_$tag", "bench_weak_n${N}_$tag"):
+    try:
+        d = json.load(open("gpurun_out/%s.json" % f))
+        print(f, "poses", d["config"]["poses"], "ms/step %.2f" % d["ms_per_step"], "its", d["pcg_iterations_per_step"], "phases", {k: round(v, 2) for k, v in d["phase_ms"].items()}, "create_s %.1f" % d["create_s"], "parity", d.get("parity"))
+    except Exception as e:
+        print(f, "unreadable:", e)
+PY
+  ;;
 abgj)
   for v in 1 0; do PGO_GJ_OLD=$v timeout 300 python tools/quick_perf.py --opts pcg_rtol=1e-9 2>&1 | tail -1 | sed "s/^/GJ_OLD=$v /"; done | tee gpurun_out/gj_$tag.log
   for v in 1 0; do PGO_GJ_OLD=$v timeout 300 python tools/quick_perf.py --se3 --poses 250000 --opts pcg_rtol=1e-9 2>&1 | tail -1 | sed "s/^/SE3 GJ_OLD=$v /"; done | tee -a gpurun_out/gj_$tag.log;;
