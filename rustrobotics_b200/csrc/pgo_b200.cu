@@ -113,6 +113,7 @@ struct pgo_handle {
     double *Ainv = nullptr, *Awork = nullptr;   // explicit inverse of the coarsest matrix; second buffer of the ping-pong inversion
     DenseMap dmap{};
     int dense_m = 0, invert_grid = 0;
+    double omega_rho = 1.5;            // PGO_OMEGA_RHO: damping of the Jacobi smoother times the estimated spectral radius
     bool gj_old = false;               // PGO_GJ_OLD=1: first-generation inversion kernel (cooperative-groups grid.sync per panel)
     double *gj_pnext = nullptr;        // look-ahead pivot inverses [2][32 x 32]
     unsigned *gj_bar = nullptr;        // arrival counter of the inversion kernel's grid barrier (monotonic)
@@ -521,7 +522,11 @@ template <int D> int estimate_omega(pgo_handle *h, int l) {
         if (it > 0) rho = nrm;                                   // |a| was normalised to 1 by the previous pass
         launch_k(h, k_scale, grid_for(nd / 2, 256), 256, 0, nd, a, 1.0 / nrm);
     }
-    B.omega = 4.0 / (3.0 * 1.1 * std::max(rho, 1.0));
+    // damping of the block-Jacobi smoother: omega = c / rho(Dinv H).  c = 4/3.3 = 1.21 (the textbook 4/3 with a 10 % margin on the
+    // power-iteration estimate) was round 1's choice; the PCG count keeps falling up to c ~ 1.5 and is flat from there to 1.75 on every
+    // graph tried (SciPy prototype: manhattan 100k 49 -> 43, 300k 47 -> 43, intel 28 -> 26, M3500 54 -> 52; tools/research/), and the
+    // smoother stays convergent / the cycle SPD up to c = 2, so c = 1.5 leaves a 33 % margin for an under-estimated or drifting rho.
+    B.omega = h->omega_rho / std::max(rho, 1.0);
     if (B.omega > 1.0) B.omega = 1.0;
     return PGO_OK;
 }
@@ -946,7 +951,11 @@ static int create_shard(pgo_handle *h, const double *vval, int64_t ne, const uin
         // default (-1): level 1 of SE2 / XY graphs.  Measured on B200 (profiles/r01s_kcycle3.log): 1M-pose Manhattan graph 53 -> 41
         // PCG iterations and 40.3 -> 36.6 ms; on the 250k-pose SE3 sphere 38 -> 32 iterations but 29.4 -> 31.5 ms (its 6x6
         // coarse levels are the larger share of an iteration), so SE3 graphs keep two steps
-        const int k3 = h->opt.amg_kcycle3 >= 0 ? h->opt.amg_kcycle3 : (D == 3 ? 1 : 0);
+        // Hierarchies of five or more levels (SE2 graphs beyond ~1.5M poses) lose convergence through the recursion -- the two-grid rate of
+        // this aggregation (~0.6) is outside the regime where two inner steps keep a K-cycle level-independent: 47 / 117 / 368 PCG
+        // iterations at 1M / 2M / 4M poses -- so there every K-cycle level runs three steps: 66 / 178 iterations, 182 -> 126 ms and
+        // 971 -> 539 ms per GN step on one GPU (profiles/r03h_size_scaling.log).  Four levels: level 1 only (46 vs 47 iterations, slower).
+        const int k3 = h->opt.amg_kcycle3 >= 0 ? h->opt.amg_kcycle3 : (D == 3 ? (nl >= 5 ? nl : 1) : 0);
         B.ksteps = (B.kcycle && l <= k3) ? 3 : 2;
         B.vec_rows = max_pad;
     }
@@ -1238,6 +1247,7 @@ static SymbolicOptions configure_handle(pgo_handle *h) {
     if (const char *e = std::getenv("PGO_SPMV_TMA32")) h->spmv_tma32 = std::max(0, std::min(16, std::atoi(e)));
     if (const char *e = std::getenv("PGO_LPR4_MIN_ROWS")) h->lpr4_min_rows = std::atoll(e);
     if (const char *e = std::getenv("PGO_PDL")) h->pdl = std::atoi(e) != 0;
+    if (const char *e = std::getenv("PGO_OMEGA_RHO")) h->omega_rho = std::min(1.9, std::max(0.5, std::atof(e)));
     if (const char *e = std::getenv("PGO_WHILE")) { h->opt_while = std::atoi(e) != 0; h->opt_while_sharded = std::atoi(e) == 2; }
     h->lowp = h->use_amg && h->opt.amg_fp64_storage == 0;
     return so;
