@@ -22,9 +22,9 @@ multi)   # on a box with N >= 2 GPUs:  gpurun --gpus N -- 'bash tools/gpu_sessio
       > gpurun_out/bench_tr_n${N}_$tag.json 2> gpurun_out/bench_tr_n${N}_$tag.err; echo "bench torchrun N=$N rc=$?"; cut -c1-1800 gpurun_out/bench_tr_n${N}_$tag.json;;
 scale)   # strong scaling (1M poses) as the driver runs it (torchrun) + weak scaling (1M poses per GPU) through the single-process handle
   N=$(nvidia-smi -L | wc -l)
-  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 5 --warmup 3 \
+  timeout ${T1:-600} python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 5 --warmup 3 \
       > gpurun_out/bench_tr_n${N}_$tag.json 2> gpurun_out/bench_tr_n${N}_$tag.err; echo "bench torchrun N=$N rc=$?"; cut -c1-300 gpurun_out/bench_tr_n${N}_$tag.json
-  timeout 900 python bench.py --gpus $N --poses $((N * 1000000)) --steps 3 --warmup 2 --no-secondary --no-cpu-baseline \
+  timeout ${T2:-900} python bench.py --gpus $N --poses $((N * 1000000)) --steps 3 --warmup 2 --no-secondary --no-cpu-baseline \
       > gpurun_out/bench_weak_n${N}_$tag.json 2> gpurun_out/bench_weak_n${N}_$tag.err; echo "bench weak N=$N rc=$?"; cut -c1-300 gpurun_out/bench_weak_n${N}_$tag.json
   python - <<PY
 import json
