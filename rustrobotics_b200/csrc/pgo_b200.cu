@@ -1471,6 +1471,17 @@ int pgo_gn_step(pgo_handle *h, double lambda, int add_lambda, double *norm_dx, d
     mark(2); lc[2] = h->launch_count;
     int32_t iters = 0;
     int src = BY_D(h, solve, h, &iters);
+    if (src == PGO_ERR_SOLVER && h->use_amg && h->omega_ready) {
+        // The smoother dampings were estimated once, on the first H of this handle.  H is re-linearised every step (and the caller may
+        // have moved the poses far away with pgo_set_poses): if rho(Dinv H) has grown past the margin the cycle stops being positive
+        // definite and PCG reports a breakdown.  Re-estimate on the current H and solve once more before giving up.
+        h->omega_ready = false;
+        rc = BY_D(h, assemble, h, lambda, add_lambda);          // the solve consumed b
+        if (rc) return rc;
+        rc = BY_D(h, amg_setup, h);
+        if (rc) return rc;
+        src = BY_D(h, solve, h, &iters);
+    }
     if (src != PGO_OK && src != PGO_ERR_NOT_CONVERGED) return src;
     mark(3); lc[3] = h->launch_count;
     rc = BY_D(h, retract, h, 1.0);
