@@ -29,7 +29,11 @@ def graph_of(gold):
 @pytest.fixture(scope="session")
 def built():
     """build (if stale) and return the product library; the oracle is built on first use."""
+    import shutil
     from rustrobotics_b200 import _build
+    if not _build.LIB.exists() and not (shutil.which("nvcc") or Path("/usr/local/cuda/bin/nvcc").exists()):
+        pytest.skip("libpgo_b200.so is not built and there is no nvcc to build it: the host-side tests (g2o loader, symbolic pass, C ABI "
+                    "surface) live in the same CUDA library as the kernels -- there is no CPU-only build, as there is no CPU fallback")
     _build.build()
     from rustrobotics_b200.mapping import _lib
     return _lib.lib()

@@ -304,6 +304,25 @@ def test_config4_first_step_matches_the_golden_solution_at_the_benchmark_toleran
     assert e_dx[:, :2].max() <= tol_xy and e_dx[:, 2].max() <= POSE_ATOL
 
 
+def test_a_step_can_be_undone_once(built):
+    """update_nodes(&(-dx)) (:277) through pgo_undo_last_step: the poses come back; a second undo, or an undo after
+    linearize_and_solve (which overwrites dx), is refused instead of moving the poses by a stale vector"""
+    from rustrobotics_b200 import PgoError
+    g = graph_of(load_golden("intel"))
+    pg = _pg(g)
+    v0 = pg.poses()
+    pg.gn_step()
+    pg.undo_last_step()
+    dxy, dth = _pose_diff(g, pg.poses(), v0)
+    assert dxy < 1e-9 and dth < 1e-9
+    with pytest.raises(PgoError, match="no step to undo"):
+        pg.undo_last_step()
+    pg.gn_step()
+    pg.linearize_and_solve()
+    with pytest.raises(PgoError, match="no step to undo"):
+        pg.undo_last_step()
+
+
 @pytest.mark.parametrize("n_gpus", [1, 2])
 def test_repeat_runs_are_bit_identical(built, n_gpus):
     """deterministic mode is the only mode: no atomics anywhere on the path (segmented assembly, single-writer Galerkin product,
