@@ -2218,9 +2218,12 @@ __global__ void __launch_bounds__(128) k_assemble_se3(LevelDev L, const double *
     const int maxdeg = __shfl_sync(0xffffffffu, mydeg, 0);
     double xi[8];
     ld_vec<8>(poses + row * 8, xi);
-    double Hd[36], g[6];
+    // the diagonal block accumulates in shared memory (component-major: conflict-free), not in 72 registers: the edge loop's
+    // 6x6 algebra needs them (255 registers + 0.5 KB of spills before)
+    __shared__ double sHd[36][128];
+    double g[6];
 #pragma unroll
-    for (int q = 0; q < 36; q++) Hd[q] = 0.0;
+    for (int q = 0; q < 36; q++) sHd[q][threadIdx.x] = 0.0;
 #pragma unroll
     for (int q = 0; q < 6; q++) g[q] = 0.0;
     const int64_t base = L.slice_ptr[slice];
@@ -2280,7 +2283,7 @@ __global__ void __launch_bounds__(128) k_assemble_se3(LevelDev L, const double *
                     double h = 0.0;
 #pragma unroll
                     for (int q = 0; q < 6; q++) h = fma(J[6 * q + r], WJ[6 * q + c], h);
-                    Hd[6 * r + c] += h;
+                    sHd[6 * r + c][threadIdx.x] += h;
                 }
             }
             double *v = L.val + (base + off) * 36 + lane;
@@ -2298,6 +2301,9 @@ __global__ void __launch_bounds__(128) k_assemble_se3(LevelDev L, const double *
         off += cnt;
     }
     const bool real = row < L.n;
+    double Hd[36];
+#pragma unroll
+    for (int q = 0; q < 36; q++) Hd[q] = sHd[q][threadIdx.x];
     if (real) {
 #pragma unroll
         for (int a = 0; a < 6; a++) Hd[7 * a] += lambda + (row == anchor_row ? anchor_w : 0.0);
