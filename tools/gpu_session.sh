@@ -21,6 +21,21 @@ multi)   # on a box with N >= 2 GPUs:  gpurun --gpus N -- 'bash tools/gpu_sessio
   timeout 600 python bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/bench_sp_n${N}_$tag.json 2> gpurun_out/bench_sp_n${N}_$tag.err; echo "bench single-process N=$N rc=$?"; cut -c1-1800 gpurun_out/bench_sp_n${N}_$tag.json
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 5 --warmup 3 \
       > gpurun_out/bench_tr_n${N}_$tag.json 2> gpurun_out/bench_tr_n${N}_$tag.err; echo "bench torchrun N=$N rc=$?"; cut -c1-1800 gpurun_out/bench_tr_n${N}_$tag.json;;
+strong)  # strong scaling of the 1M-pose graph on all GPUs of the box, both launch modes
+  N=$(nvidia-smi -L | wc -l)
+  timeout ${T1:-300} python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $N --steps 10 --warmup 3 \
+      > gpurun_out/bench_tr_n${N}_$tag.json 2> gpurun_out/bench_tr_n${N}_$tag.err; echo "bench torchrun N=$N rc=$?"
+  timeout ${T1:-300} python bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/bench_sp_n${N}_$tag.json 2> gpurun_out/bench_sp_n${N}_$tag.err; echo "bench single-process N=$N rc=$?"
+  python - <<PY
+import json
+for f in ("bench_tr_n${N}_$tag", "bench_sp_n${N}_$tag"):
+    try:
+        d = json.load(open("gpurun_out/%s.json" % f))
+        print(f, "ms/step %.2f" % d["ms_per_step"], "its", d["pcg_iterations_per_step"], "phases", {k: round(v, 2) for k, v in d["phase_ms"].items()}, "e2e %.2f" % d["e2e"]["ms_per_step"], "parity", {k: v for k, v in (d.get("parity") or {}).items() if "err" in k})
+    except Exception as e:
+        print(f, "unreadable:", e)
+PY
+  ;;
 scale)   # strong scaling (1M poses) as the driver runs it (torchrun) + weak scaling (1M poses per GPU) through the single-process handle
   N=$(nvidia-smi -L | wc -l)
   timeout ${T1:-600} python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 5 --warmup 3 \
