@@ -43,7 +43,7 @@ CPU_SAMPLE_POSES = 300_000          # cpu_baseline leg of the default run: one G
 CPU_REF_SAMPLE_POSES = 500_000      # --impl reference: ~35 s per GN iteration, at most 1 warm-up + 2 timed steps
 CPU_SAMPLE_POSES_SE3 = 25_000       # sphere SE3 sample (50 levels x 500)
 CPU_EXTRAPOLATION = ("same_config false: the oracle's SuperLU cannot factorise the 1M-pose system here; measured 2.4 / 16.7 / 33 s per GN "
-                     "iteration at 100k / 300k / 500k poses (1 core) => about 100 s at 1M poses (SURVEY App. C probe: 105 s), i.e. ~4e4 edges/s")
+                     "iteration at 100k / 300k / 500k poses (1 core, authoring container; the GPU box's host is ~1.7x faster) => about 100 s at 1M poses (SURVEY App. C probe: 105 s), i.e. ~4e4 edges/s")
 
 
 BUNDLED = {   # the reference's bundled datasets (dataset/g2o/*.g2o), shipped as parsed arrays in tests/golden/*.npz (make_golden.py)
