@@ -1787,6 +1787,150 @@ __global__ void __launch_bounds__(256) k_dense_invert2(int m, double *__restrict
 // (Splitting a row of the inverse over four warps, so that every lane has all its loads of the row in flight at once, was measured
 // and LOSES: 8.8 vs 6.9 us per application -- four times as many CTAs each stage the whole right-hand side before they can start;
 // profiles/r03d_setup_launches.md.)
+// ---- third generation: the panel step in TWO phases, so that the product R = P^-1 A[p, :] is computed once per column block
+// instead of once per tile (it was twice the work of the rank-32 update itself):
+//   phase A  CTA c < nt:  dst[p, block c] <- P^-1 src[p, block c]   (and P^-1 itself inside the panel columns)          | barrier
+//   phase B  every tile outside the panel rows:  dst[i, j] <- src[i, j] - src[i, p] dst[p, j]   (-src[i, p] P^-1 inside the panel columns);
+//            the CTA owning the diagonal tile with the next pivot block goes first and inverts it right away (look-ahead)   | barrier
+__global__ void __launch_bounds__(256) k_dense_invert3(int m, double *__restrict__ bufA, double *__restrict__ bufB, double *__restrict__ pnext,
+                                                        unsigned *bar, unsigned bar_base) {
+    PDL_ENTER();
+    extern __shared__ double gj_smem[];
+    double (*Pb)[GJ_W][GJ_W + 1] = reinterpret_cast<double (*)[GJ_W][GJ_W + 1]>(gj_smem);                      // [2][32][33]
+    double (*Xr)[GJ_T] = reinterpret_cast<double (*)[GJ_T]>(gj_smem + 2 * GJ_W * (GJ_W + 1));                 // [32][64]
+    double (*Xb)[GJ_T] = reinterpret_cast<double (*)[GJ_T]>(gj_smem + 2 * GJ_W * (GJ_W + 1) + GJ_W * GJ_T);   // [32][64]
+    double (*Cb)[GJ_W + 1] = reinterpret_cast<double (*)[GJ_W + 1]>(gj_smem + 2 * GJ_W * (GJ_W + 1) + 2 * GJ_W * GJ_T);   // [64][33]
+    double (*Pn)[GJ_W][GJ_W + 1] = reinterpret_cast<double (*)[GJ_W][GJ_W + 1]>(gj_smem + GJ_SMEM / sizeof(double));        // [2][32][33]
+    const int tid = threadIdx.x;
+    const int nt = (m + GJ_T - 1) / GJ_T, n_panels = (m + GJ_W - 1) / GJ_W;
+    const double *src = bufA;
+    double *dst = bufB;
+    unsigned phase = 0;
+    for (int pi = 0; pi < n_panels; pi++) {
+        const int p0 = pi * GJ_W;
+        // ---- phase A: the panel rows of dst
+        if ((int)blockIdx.x < nt) {
+            if (pi == 0) {
+                for (int t = tid; t < GJ_W * GJ_W; t += 256) {
+                    const int i = t / GJ_W, j = t % GJ_W;
+                    Pb[0][i][j] = (i < m && j < m) ? __ldcg(src + (int64_t)i * m + j) : (i == j ? 1.0 : 0.0);
+                }
+                __syncthreads();
+                gj_invert32(Pb);
+            } else {
+                const double *pn = pnext + (size_t)(pi & 1) * GJ_W * GJ_W;
+                for (int t = tid; t < GJ_W * GJ_W; t += 256) Pb[0][t / GJ_W][t % GJ_W] = __ldcg(pn + t);
+            }
+            const int j0 = (int)blockIdx.x * GJ_T;
+            for (int t = tid; t < GJ_W * GJ_T; t += 256) {
+                const int l = t / GJ_T, jj = t % GJ_T;
+                const int gi = p0 + l, gj = j0 + jj;
+                Xr[l][jj] = (gi < m && gj < m) ? __ldcg(src + (int64_t)gi * m + gj) : 0.0;
+            }
+            __syncthreads();
+            const int l0 = (tid >> 5) * 4, jj0 = tid & 31;
+            double xa[4][2];
+#pragma unroll
+            for (int a = 0; a < 4; a++) xa[a][0] = xa[a][1] = 0.0;
+#pragma unroll 8
+            for (int q = 0; q < GJ_W; q++) {
+                const double x0 = Xr[q][jj0], x1 = Xr[q][jj0 + 32];
+#pragma unroll
+                for (int a = 0; a < 4; a++) {
+                    const double pv = Pb[0][l0 + a][q];
+                    xa[a][0] = fma(pv, x0, xa[a][0]);
+                    xa[a][1] = fma(pv, x1, xa[a][1]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                const int gj = j0 + jj0 + 32 * c;
+                const bool jin = gj >= p0 && gj < p0 + GJ_W;
+#pragma unroll
+                for (int a = 0; a < 4; a++) {
+                    const int gi = p0 + l0 + a;
+                    if (gi < m && gj < m) dst[(int64_t)gi * m + gj] = jin ? Pb[0][l0 + a][gj - p0] : xa[a][c];
+                }
+            }
+        }
+        gj_grid_barrier(bar, bar_base + (++phase) * gridDim.x);
+        // ---- phase B: every tile, rows outside the panel
+        const int np0 = p0 + GJ_W;
+        const bool has_next = pi + 1 < n_panels;
+        const int ntile = (np0 / GJ_T) * nt + np0 / GJ_T;
+        const int first = (has_next && ntile % (int)gridDim.x == (int)blockIdx.x) ? ntile : -1;
+        for (int k = first >= 0 ? -1 : 0; ; k++) {
+            int tile = first;
+            if (k >= 0) {
+                tile = (int)blockIdx.x + k * (int)gridDim.x;
+                if (tile >= nt * nt) break;
+                if (tile == first) continue;
+            }
+            const int i0 = (tile / nt) * GJ_T, j0 = (tile % nt) * GJ_T;
+            __syncthreads();
+            for (int t = tid; t < GJ_W * GJ_T; t += 256) {       // R (or P^-1) rows of this column block, from phase A
+                const int l = t / GJ_T, jj = t % GJ_T;
+                const int gi = p0 + l, gj = j0 + jj;
+                Xb[l][jj] = (gi < m && gj < m) ? __ldcg(dst + (int64_t)gi * m + gj) : 0.0;
+            }
+            for (int t = tid; t < GJ_T * GJ_W; t += 256) {       // panel columns of this row block
+                const int ii = t / GJ_W, l = t % GJ_W;
+                const int gi = i0 + ii, gj = p0 + l;
+                Cb[ii][l] = (gi < m && gj < m) ? __ldcg(src + (int64_t)gi * m + gj) : 0.0;
+            }
+            const int ty = tid >> 4, tx = tid & 15;
+            double aij[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const int gi = i0 + ty * 4 + a, gj = j0 + tx + 16 * c;
+                    aij[a][c] = (gi < m && gj < m) ? __ldcg(src + (int64_t)gi * m + gj) : 0.0;
+                }
+            __syncthreads();
+            double acc[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) acc[a][c] = 0.0;
+#pragma unroll 4
+            for (int l = 0; l < GJ_W; l++) {
+                double cv[4], xv[4];
+#pragma unroll
+                for (int a = 0; a < 4; a++) cv[a] = Cb[ty * 4 + a][l];
+#pragma unroll
+                for (int c = 0; c < 4; c++) xv[c] = Xb[l][tx + 16 * c];
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) acc[a][c] = fma(cv[a], xv[c], acc[a][c]);
+            }
+#pragma unroll
+            for (int a = 0; a < 4; a++) {
+                const int gi = i0 + ty * 4 + a;
+                const bool iin = gi >= p0 && gi < p0 + GJ_W;
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const int gj = j0 + tx + 16 * c;
+                    const bool jin = gj >= p0 && gj < p0 + GJ_W;
+                    const double v = jin ? -acc[a][c] : aij[a][c] - acc[a][c];
+                    if (!iin && gi < m && gj < m) dst[(int64_t)gi * m + gj] = v;      // the panel rows were written by phase A
+                    if (tile == first && gi >= np0 && gi < np0 + GJ_W && gj >= np0 && gj < np0 + GJ_W)
+                        Pn[0][gi - np0][gj - np0] = (gi < m && gj < m) ? v : (gi == gj ? 1.0 : 0.0);
+                }
+            }
+            if (tile == first) {
+                __syncthreads();
+                gj_invert32(Pn);
+                double *pn = pnext + (size_t)((pi + 1) & 1) * GJ_W * GJ_W;
+                for (int t = tid; t < GJ_W * GJ_W; t += 256) pn[t] = Pn[0][t / GJ_W][t % GJ_W];
+            }
+        }
+        gj_grid_barrier(bar, bar_base + (++phase) * gridDim.x);
+        const double *t = src; src = dst; dst = const_cast<double *>(t);
+    }
+}
+
 template <int D>
 __device__ __forceinline__ void dense_apply_body(int64_t n_local, const DenseMap &dm, int rank, int world, int m, const double *__restrict__ Ainv,
                                                  const XRef &rr, double *__restrict__ x, unsigned vb) {

@@ -69,6 +69,12 @@ for l in open("gpurun_out/bench_bundled_$tag.jsonl"):
     print(d["config"]["workload"][:60], "| ms/step %.3f | pcg its %.0f | cpu s/GN it %s" % (d["ms_per_step"], d["pcg_iterations_per_step"], c.get("s_per_gn_iteration")))
 PY
   ;;
+abgj3)
+  for v in 2 3; do PGO_GJ=$v timeout 300 python tools/quick_perf.py --opts pcg_rtol=1e-9 2>&1 | tail -1 | sed "s/^/GJ=$v /"; done | tee gpurun_out/gj3_$tag.log
+  for v in 2 3; do PGO_GJ=$v timeout 300 python tools/quick_perf.py --se3 --poses 250000 --opts pcg_rtol=1e-9 2>&1 | tail -1 | sed "s/^/SE3 GJ=$v /"; done | tee -a gpurun_out/gj3_$tag.log
+  PGO_GJ=3 timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_se3.py -m gpu -q -x 2>&1 | tail -3 | tee -a gpurun_out/gj3_$tag.log
+  PGO_GJ=3 timeout 300 python bench.py --workload dlr --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('dlr GJ=3 ms/step', d['ms_per_step'], d['phase_ms'])" | tee -a gpurun_out/gj3_$tag.log
+  timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1;;
 abwhile)
   for v in 0 1; do PGO_WHILE=$v timeout 300 python tools/quick_perf.py --opts pcg_rtol=1e-9 2>&1 | tail -1 | sed "s/^/WHILE=$v /"; done | tee gpurun_out/while_$tag.log
   for v in 0 1; do PGO_WHILE=$v timeout 300 python tools/quick_perf.py --poses 100000 --opts pcg_rtol=1e-9 2>&1 | tail -1 | sed "s/^/100k WHILE=$v /"; done | tee -a gpurun_out/while_$tag.log;;
