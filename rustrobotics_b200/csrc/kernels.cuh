@@ -10,13 +10,11 @@
 // finalises") with all PCG / K-cycle scalars resident on the device; no host in the PCG loop.
 #pragma once
 #include <cstdint>
-#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include "pgo_internal.h"
 
 namespace pgo {
-namespace cg = cooperative_groups;
 
 // ------------------------------------------------------------------------------------------------
 constexpr int MAX_LEVELS = 12;
@@ -1482,140 +1480,26 @@ __global__ void __launch_bounds__(128) k_dense_assemble(LevelDev L, DenseMap dm,
     }
 }
 
-// In-place blocked Gauss-Jordan inversion of the SPD matrix A (m x m, row-major), no pivoting; cooperative launch.
-// Panels of GJ_W = 24 scalars (8 block rows): per panel p (two grid syncs)
-//   phase 0  every CTA inverts the pivot block A_pp in shared memory (redundantly: cheaper than a third sync)
-//   phase 1  R = A_pp^-1 A_p: (w x m) and Cp = A_:p (m x w) go to scratch
-//   phase 2  A_pp <- A_pp^-1 ; A_pj <- R_j ; A_ip <- -Cp_i A_pp^-1 ; A_ij <- A_ij - Cp_i R_j   (tiles of 8 rows x 256 columns)
-// In-place-style inverse of the dense coarsest matrix (symmetric positive definite, m <= 3 * 1024 + ...): right-looking
-// BLOCKED Gauss-Jordan without pivoting, panel width 32, as a persistent cooperative kernel with ONE grid barrier per
-// panel.  With pivot block P = A[pp] the panel step is
+// Inverse of the dense coarsest matrix (symmetric positive definite, m <= 6 * 1024): right-looking BLOCKED Gauss-Jordan without
+// pivoting, panel width 32, as a persistent cooperative kernel with ONE grid barrier per panel.  With pivot block P = A[pp] the
+// panel step is
 //     A[pp] <- P^-1        A[p,r] <- P^-1 A[p,r] (= R)        A[r,p] <- -A[r,p] P^-1        A[r,r] <- A[r,r] - A[r,p] R
-// Every CTA inverts the 32x32 pivot block itself (shared memory, 32 unblocked steps) and recomputes the slice of R its
-// 64x64 tiles need, so nothing has to be exchanged inside a panel step; the step reads `src` and writes the whole
-// matrix to `dst` (ping-pong, both L2-resident), which removes every read-after-write hazard between tiles.  The matrix
-// is treated as padded with an identity block up to a multiple of 32.  The host passes the buffers such that the
-// result of the last panel lands in the caller's Ainv.
+// Every CTA recomputes the slice of R its 64x64 tiles need, so nothing has to be exchanged inside a panel step; the step reads `src`
+// and writes the whole matrix to `dst` (ping-pong, both L2-resident), which removes every read-after-write hazard between tiles.
+// The matrix is treated as padded with an identity block up to a multiple of 32.  The host passes the buffers such that the result
+// of the last panel lands in the caller's Ainv.
 constexpr int GJ_W = 32, GJ_T = 64;
 constexpr size_t GJ_SMEM = sizeof(double) * (2 * GJ_W * (GJ_W + 1) + 2 * GJ_W * GJ_T + GJ_T * (GJ_W + 1));
-__global__ void __launch_bounds__(256) k_dense_invert(int m, double *__restrict__ bufA, double *__restrict__ bufB) {
-    PDL_ENTER();
-    cg::grid_group grid = cg::this_grid();
-    extern __shared__ double gj_smem[];
-    double (*Pb)[GJ_W][GJ_W + 1] = reinterpret_cast<double (*)[GJ_W][GJ_W + 1]>(gj_smem);                      // [2][32][33]
-    double (*Xr)[GJ_T] = reinterpret_cast<double (*)[GJ_T]>(gj_smem + 2 * GJ_W * (GJ_W + 1));                 // [32][64] raw panel rows
-    double (*Xb)[GJ_T] = reinterpret_cast<double (*)[GJ_T]>(gj_smem + 2 * GJ_W * (GJ_W + 1) + GJ_W * GJ_T);   // [32][64] R (or P^-1 columns)
-    double (*Cb)[GJ_W + 1] = reinterpret_cast<double (*)[GJ_W + 1]>(gj_smem + 2 * GJ_W * (GJ_W + 1) + 2 * GJ_W * GJ_T);   // [64][33]
-    const int tid = threadIdx.x;
-    const int nt = (m + GJ_T - 1) / GJ_T;
-    const double *src = bufA;
-    double *dst = bufB;
-    for (int p0 = 0; p0 < m; p0 += GJ_W) {
-        // ---- pivot block -> Pb[0], inverted by 32 unblocked Gauss-Jordan steps ping-ponging Pb[0] <-> Pb[1]
-        for (int t = tid; t < GJ_W * GJ_W; t += 256) {
-            const int i = t / GJ_W, j = t % GJ_W;
-            const int gi = p0 + i, gj = p0 + j;
-            Pb[0][i][j] = (gi < m && gj < m) ? __ldcg(src + (int64_t)gi * m + gj) : (i == j ? 1.0 : 0.0);
-        }
-        __syncthreads();
-        {
-            const int i = tid >> 3, j0 = (tid & 7) * 4;
-            for (int k = 0; k < GJ_W; k++) {
-                const double (*Pi)[GJ_W + 1] = Pb[k & 1];
-                double (*Po)[GJ_W + 1] = Pb[(k & 1) ^ 1];
-                const double ikk = 1.0 / Pi[k][k];
-                const double pik = Pi[i][k];
-#pragma unroll
-                for (int jj = 0; jj < 4; jj++) {
-                    const int j = j0 + jj;
-                    double v;
-                    if (i == k) v = (j == k) ? ikk : Pi[k][j] * ikk;
-                    else if (j == k) v = -pik * ikk;
-                    else v = Pi[i][j] - pik * Pi[k][j] * ikk;
-                    Po[i][j] = v;
-                }
-                __syncthreads();
-            }
-        }
-        const double (*Pinv)[GJ_W + 1] = Pb[0];          // 32 steps: the result is back in Pb[0]
-        // ---- tiles
-        for (int tile = blockIdx.x; tile < nt * nt; tile += gridDim.x) {
-            const int i0 = (tile / nt) * GJ_T, j0 = (tile % nt) * GJ_T;
-            __syncthreads();                              // the previous tile's shared arrays are free
-            for (int t = tid; t < GJ_W * GJ_T; t += 256) {       // panel rows of this column block
-                const int l = t / GJ_T, jj = t % GJ_T;
-                const int gi = p0 + l, gj = j0 + jj;
-                Xr[l][jj] = (gi < m && gj < m) ? __ldcg(src + (int64_t)gi * m + gj) : 0.0;
-            }
-            for (int t = tid; t < GJ_T * GJ_W; t += 256) {       // panel columns of this row block
-                const int ii = t / GJ_W, l = t % GJ_W;
-                const int gi = i0 + ii, gj = p0 + l;
-                Cb[ii][l] = (gi < m && gj < m) ? __ldcg(src + (int64_t)gi * m + gj) : 0.0;
-            }
-            __syncthreads();
-            // X[l][j] = (P^-1 A[p, j])[l] outside the panel columns, P^-1[l][j - p0] inside them
-            for (int t = tid; t < GJ_W * GJ_T; t += 256) {
-                const int l = t / GJ_T, jj = t % GJ_T;
-                const int gj = j0 + jj;
-                double v;
-                if (gj >= p0 && gj < p0 + GJ_W) v = Pinv[l][gj - p0];
-                else {
-                    v = 0.0;
-#pragma unroll 8
-                    for (int q = 0; q < GJ_W; q++) v = fma(Pinv[l][q], Xr[q][jj], v);
-                }
-                Xb[l][jj] = v;
-            }
-            __syncthreads();
-            const int ty = tid >> 4, tx = tid & 15;
-            double acc[4][4];
-#pragma unroll
-            for (int a = 0; a < 4; a++)
-#pragma unroll
-                for (int c = 0; c < 4; c++) acc[a][c] = 0.0;
-#pragma unroll 4
-            for (int l = 0; l < GJ_W; l++) {
-                double cv[4], xv[4];
-#pragma unroll
-                for (int a = 0; a < 4; a++) cv[a] = Cb[ty * 4 + a][l];
-#pragma unroll
-                for (int c = 0; c < 4; c++) xv[c] = Xb[l][tx + 16 * c];
-#pragma unroll
-                for (int a = 0; a < 4; a++)
-#pragma unroll
-                    for (int c = 0; c < 4; c++) acc[a][c] = fma(cv[a], xv[c], acc[a][c]);
-            }
-#pragma unroll
-            for (int a = 0; a < 4; a++) {
-                const int gi = i0 + ty * 4 + a;
-                if (gi >= m) continue;
-                const bool iin = gi >= p0 && gi < p0 + GJ_W;
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    const int gj = j0 + tx + 16 * c;
-                    if (gj >= m) continue;
-                    const bool jin = gj >= p0 && gj < p0 + GJ_W;
-                    double v;
-                    if (iin) v = Xb[gi - p0][tx + 16 * c];            // P^-1 (jin) or R
-                    else if (jin) v = -acc[a][c];
-                    else v = __ldcg(src + (int64_t)gi * m + gj) - acc[a][c];
-                    dst[(int64_t)gi * m + gj] = v;
-                }
-            }
-        }
-        grid.sync();
-        const double *t = src; src = dst; dst = const_cast<double *>(t);
-    }
-}
-
-// x_own = Ainv[own rows, :] r  on the coarsest level; r is gathered from all ranks.  One warp per scalar row.
-// ---- second generation of the same inversion (default): same panel algebra and ping-pong buffers, restructured for latency.
+// Second generation (round 2; the first one ran 32 redundant elimination steps per CTA and panel and used grid.sync(): 2.13 ms for the
+// 1221^2 matrix of config 4, this one 1.20 ms): same panel algebra and ping-pong buffers, restructured for latency.
 //   * the 32x32 pivot inverse of panel p+1 is produced DURING panel p (look-ahead): the CTA that owns the diagonal tile holding the
 //     next pivot block updates that tile first, inverts the block right away and publishes it, so after the barrier every CTA only
 //     loads 8 KB instead of running 32 dependent elimination steps itself;
 //   * the grid barrier is one atomic arrive + an acquire spin on a counter (the cooperative launch only guarantees co-residency),
 //     ~1 us instead of the cooperative-groups grid.sync();
-//   * one 64x64 tile per CTA when the grid allows it.
+//   * the panel product is register-blocked (6 shared loads per 8 FMAs).
+// A two-phase variant (R = P^-1 A[p, :] computed once per column block instead of once per tile, a second barrier per panel) measured
+// the same (profiles/r03n_gj3.log): the step is bound by its barriers and dependent L2 loads, ~31 us per panel, not by the flops.
 constexpr size_t GJ2_SMEM = GJ_SMEM + sizeof(double) * 2 * GJ_W * (GJ_W + 1);
 
 __device__ __forceinline__ void gj_grid_barrier(unsigned *bar, unsigned target) {
@@ -1787,150 +1671,6 @@ __global__ void __launch_bounds__(256) k_dense_invert2(int m, double *__restrict
 // (Splitting a row of the inverse over four warps, so that every lane has all its loads of the row in flight at once, was measured
 // and LOSES: 8.8 vs 6.9 us per application -- four times as many CTAs each stage the whole right-hand side before they can start;
 // profiles/r03d_setup_launches.md.)
-// ---- third generation: the panel step in TWO phases, so that the product R = P^-1 A[p, :] is computed once per column block
-// instead of once per tile (it was twice the work of the rank-32 update itself):
-//   phase A  CTA c < nt:  dst[p, block c] <- P^-1 src[p, block c]   (and P^-1 itself inside the panel columns)          | barrier
-//   phase B  every tile outside the panel rows:  dst[i, j] <- src[i, j] - src[i, p] dst[p, j]   (-src[i, p] P^-1 inside the panel columns);
-//            the CTA owning the diagonal tile with the next pivot block goes first and inverts it right away (look-ahead)   | barrier
-__global__ void __launch_bounds__(256) k_dense_invert3(int m, double *__restrict__ bufA, double *__restrict__ bufB, double *__restrict__ pnext,
-                                                        unsigned *bar, unsigned bar_base) {
-    PDL_ENTER();
-    extern __shared__ double gj_smem[];
-    double (*Pb)[GJ_W][GJ_W + 1] = reinterpret_cast<double (*)[GJ_W][GJ_W + 1]>(gj_smem);                      // [2][32][33]
-    double (*Xr)[GJ_T] = reinterpret_cast<double (*)[GJ_T]>(gj_smem + 2 * GJ_W * (GJ_W + 1));                 // [32][64]
-    double (*Xb)[GJ_T] = reinterpret_cast<double (*)[GJ_T]>(gj_smem + 2 * GJ_W * (GJ_W + 1) + GJ_W * GJ_T);   // [32][64]
-    double (*Cb)[GJ_W + 1] = reinterpret_cast<double (*)[GJ_W + 1]>(gj_smem + 2 * GJ_W * (GJ_W + 1) + 2 * GJ_W * GJ_T);   // [64][33]
-    double (*Pn)[GJ_W][GJ_W + 1] = reinterpret_cast<double (*)[GJ_W][GJ_W + 1]>(gj_smem + GJ_SMEM / sizeof(double));        // [2][32][33]
-    const int tid = threadIdx.x;
-    const int nt = (m + GJ_T - 1) / GJ_T, n_panels = (m + GJ_W - 1) / GJ_W;
-    const double *src = bufA;
-    double *dst = bufB;
-    unsigned phase = 0;
-    for (int pi = 0; pi < n_panels; pi++) {
-        const int p0 = pi * GJ_W;
-        // ---- phase A: the panel rows of dst
-        if ((int)blockIdx.x < nt) {
-            if (pi == 0) {
-                for (int t = tid; t < GJ_W * GJ_W; t += 256) {
-                    const int i = t / GJ_W, j = t % GJ_W;
-                    Pb[0][i][j] = (i < m && j < m) ? __ldcg(src + (int64_t)i * m + j) : (i == j ? 1.0 : 0.0);
-                }
-                __syncthreads();
-                gj_invert32(Pb);
-            } else {
-                const double *pn = pnext + (size_t)(pi & 1) * GJ_W * GJ_W;
-                for (int t = tid; t < GJ_W * GJ_W; t += 256) Pb[0][t / GJ_W][t % GJ_W] = __ldcg(pn + t);
-            }
-            const int j0 = (int)blockIdx.x * GJ_T;
-            for (int t = tid; t < GJ_W * GJ_T; t += 256) {
-                const int l = t / GJ_T, jj = t % GJ_T;
-                const int gi = p0 + l, gj = j0 + jj;
-                Xr[l][jj] = (gi < m && gj < m) ? __ldcg(src + (int64_t)gi * m + gj) : 0.0;
-            }
-            __syncthreads();
-            const int l0 = (tid >> 5) * 4, jj0 = tid & 31;
-            double xa[4][2];
-#pragma unroll
-            for (int a = 0; a < 4; a++) xa[a][0] = xa[a][1] = 0.0;
-#pragma unroll 8
-            for (int q = 0; q < GJ_W; q++) {
-                const double x0 = Xr[q][jj0], x1 = Xr[q][jj0 + 32];
-#pragma unroll
-                for (int a = 0; a < 4; a++) {
-                    const double pv = Pb[0][l0 + a][q];
-                    xa[a][0] = fma(pv, x0, xa[a][0]);
-                    xa[a][1] = fma(pv, x1, xa[a][1]);
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < 2; c++) {
-                const int gj = j0 + jj0 + 32 * c;
-                const bool jin = gj >= p0 && gj < p0 + GJ_W;
-#pragma unroll
-                for (int a = 0; a < 4; a++) {
-                    const int gi = p0 + l0 + a;
-                    if (gi < m && gj < m) dst[(int64_t)gi * m + gj] = jin ? Pb[0][l0 + a][gj - p0] : xa[a][c];
-                }
-            }
-        }
-        gj_grid_barrier(bar, bar_base + (++phase) * gridDim.x);
-        // ---- phase B: every tile, rows outside the panel
-        const int np0 = p0 + GJ_W;
-        const bool has_next = pi + 1 < n_panels;
-        const int ntile = (np0 / GJ_T) * nt + np0 / GJ_T;
-        const int first = (has_next && ntile % (int)gridDim.x == (int)blockIdx.x) ? ntile : -1;
-        for (int k = first >= 0 ? -1 : 0; ; k++) {
-            int tile = first;
-            if (k >= 0) {
-                tile = (int)blockIdx.x + k * (int)gridDim.x;
-                if (tile >= nt * nt) break;
-                if (tile == first) continue;
-            }
-            const int i0 = (tile / nt) * GJ_T, j0 = (tile % nt) * GJ_T;
-            __syncthreads();
-            for (int t = tid; t < GJ_W * GJ_T; t += 256) {       // R (or P^-1) rows of this column block, from phase A
-                const int l = t / GJ_T, jj = t % GJ_T;
-                const int gi = p0 + l, gj = j0 + jj;
-                Xb[l][jj] = (gi < m && gj < m) ? __ldcg(dst + (int64_t)gi * m + gj) : 0.0;
-            }
-            for (int t = tid; t < GJ_T * GJ_W; t += 256) {       // panel columns of this row block
-                const int ii = t / GJ_W, l = t % GJ_W;
-                const int gi = i0 + ii, gj = p0 + l;
-                Cb[ii][l] = (gi < m && gj < m) ? __ldcg(src + (int64_t)gi * m + gj) : 0.0;
-            }
-            const int ty = tid >> 4, tx = tid & 15;
-            double aij[4][4];
-#pragma unroll
-            for (int a = 0; a < 4; a++)
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    const int gi = i0 + ty * 4 + a, gj = j0 + tx + 16 * c;
-                    aij[a][c] = (gi < m && gj < m) ? __ldcg(src + (int64_t)gi * m + gj) : 0.0;
-                }
-            __syncthreads();
-            double acc[4][4];
-#pragma unroll
-            for (int a = 0; a < 4; a++)
-#pragma unroll
-                for (int c = 0; c < 4; c++) acc[a][c] = 0.0;
-#pragma unroll 4
-            for (int l = 0; l < GJ_W; l++) {
-                double cv[4], xv[4];
-#pragma unroll
-                for (int a = 0; a < 4; a++) cv[a] = Cb[ty * 4 + a][l];
-#pragma unroll
-                for (int c = 0; c < 4; c++) xv[c] = Xb[l][tx + 16 * c];
-#pragma unroll
-                for (int a = 0; a < 4; a++)
-#pragma unroll
-                    for (int c = 0; c < 4; c++) acc[a][c] = fma(cv[a], xv[c], acc[a][c]);
-            }
-#pragma unroll
-            for (int a = 0; a < 4; a++) {
-                const int gi = i0 + ty * 4 + a;
-                const bool iin = gi >= p0 && gi < p0 + GJ_W;
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    const int gj = j0 + tx + 16 * c;
-                    const bool jin = gj >= p0 && gj < p0 + GJ_W;
-                    const double v = jin ? -acc[a][c] : aij[a][c] - acc[a][c];
-                    if (!iin && gi < m && gj < m) dst[(int64_t)gi * m + gj] = v;      // the panel rows were written by phase A
-                    if (tile == first && gi >= np0 && gi < np0 + GJ_W && gj >= np0 && gj < np0 + GJ_W)
-                        Pn[0][gi - np0][gj - np0] = (gi < m && gj < m) ? v : (gi == gj ? 1.0 : 0.0);
-                }
-            }
-            if (tile == first) {
-                __syncthreads();
-                gj_invert32(Pn);
-                double *pn = pnext + (size_t)((pi + 1) & 1) * GJ_W * GJ_W;
-                for (int t = tid; t < GJ_W * GJ_W; t += 256) pn[t] = Pn[0][t / GJ_W][t % GJ_W];
-            }
-        }
-        gj_grid_barrier(bar, bar_base + (++phase) * gridDim.x);
-        const double *t = src; src = dst; dst = const_cast<double *>(t);
-    }
-}
-
 template <int D>
 __device__ __forceinline__ void dense_apply_body(int64_t n_local, const DenseMap &dm, int rank, int world, int m, const double *__restrict__ Ainv,
                                                  const XRef &rr, double *__restrict__ x, unsigned vb) {

@@ -114,8 +114,6 @@ struct pgo_handle {
     DenseMap dmap{};
     int dense_m = 0, invert_grid = 0;
     double omega_rho = 1.5;            // PGO_OMEGA_RHO: damping of the Jacobi smoother times the estimated spectral radius
-    int gj_gen = 2;                    // PGO_GJ=3: two-phase panel step (k_dense_invert3), experiment
-    bool gj_old = false;               // PGO_GJ_OLD=1: first-generation inversion kernel (cooperative-groups grid.sync per panel)
     double *gj_pnext = nullptr;        // look-ahead pivot inverses [2][32 x 32]
     unsigned *gj_bar = nullptr;        // arrival counter of the inversion kernel's grid barrier (monotonic)
     unsigned gj_bar_base = 0;
@@ -587,19 +585,9 @@ template <int D> int amg_setup(pgo_handle *h) {
         if (C.jds) launch_k(h, k_dense_assemble<D, true>, C.grid128, 128, 0, C.d, h->dmap, 0, m, first);
         else launch_k(h, k_dense_assemble<D, false>, C.grid128, 128, 0, C.d, h->dmap, 0, m, first);
         h->launch_count += 1;
-        if (h->gj_old) {
-            void *args[] = {(void *)&h->dense_m, (void *)&first, (void *)&second};
-            CK(cudaLaunchCooperativeKernel((void *)k_dense_invert, dim3(h->invert_grid), dim3(256), args, GJ_SMEM, h->stream));
-        } else {
-            void *args[] = {(void *)&h->dense_m, (void *)&first, (void *)&second, (void *)&h->gj_pnext, (void *)&h->gj_bar, (void *)&h->gj_bar_base};
-            if (h->gj_gen == 3) {
-                CK(cudaLaunchCooperativeKernel((void *)k_dense_invert3, dim3(h->invert_grid), dim3(256), args, GJ2_SMEM, h->stream));
-                h->gj_bar_base += 2u * (unsigned)n_panels * (unsigned)h->invert_grid;
-            } else {
-                CK(cudaLaunchCooperativeKernel((void *)k_dense_invert2, dim3(h->invert_grid), dim3(256), args, GJ2_SMEM, h->stream));
-                h->gj_bar_base += (unsigned)n_panels * (unsigned)h->invert_grid;
-            }
-        }
+        void *args[] = {(void *)&h->dense_m, (void *)&first, (void *)&second, (void *)&h->gj_pnext, (void *)&h->gj_bar, (void *)&h->gj_bar_base};
+        CK(cudaLaunchCooperativeKernel((void *)k_dense_invert2, dim3(h->invert_grid), dim3(256), args, GJ2_SMEM, h->stream));
+        h->gj_bar_base += (unsigned)n_panels * (unsigned)h->invert_grid;
         h->launch_count += 1;
     }
     CK(cudaGetLastError()); CK(h->launch_err);
@@ -985,15 +973,10 @@ static int create_shard(pgo_handle *h, const double *vval, int64_t ne, const uin
         CKC(dalloc(h, &h->Awork, (size_t)m * m));
 
         int per_sm = 0, sms = 0;
-        if (const char *e = std::getenv("PGO_GJ_OLD")) h->gj_old = std::atoi(e) != 0;
-        if (const char *e = std::getenv("PGO_GJ")) h->gj_gen = std::atoi(e) == 3 ? 3 : 2;
-        CKU(cudaFuncSetAttribute(k_dense_invert3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GJ2_SMEM));
         CKC(dalloc(h, &h->gj_pnext, (size_t)2 * GJ_W * GJ_W));
         CKC(dalloc(h, &h->gj_bar, 1));
-        CKU(cudaFuncSetAttribute(k_dense_invert, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GJ_SMEM));
         CKU(cudaFuncSetAttribute(k_dense_invert2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GJ2_SMEM));
-        if (h->gj_old) CKU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dense_invert, 256, GJ_SMEM));
-        else CKU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dense_invert2, 256, GJ2_SMEM));
+        CKU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dense_invert2, 256, GJ2_SMEM));
         CKU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
         const int nt = (m + GJ_T - 1) / GJ_T;
         h->invert_grid = std::max(1, std::min(std::max(per_sm, 1) * sms, nt * nt));
