@@ -364,6 +364,7 @@ def _oracle_100k():
     {"amg_aggregate_size": 8, "amg_dense_max": 256},
     {"env": {"PGO_SPMV_TMA64": "2", "PGO_SPMV_TMA32": "3"}},     # TMA-staged sliced SpMV
     {"env": {"PGO_PDL": "0"}},               # plain (non-programmatic) launches
+    {"env": {"PGO_WHILE": "0"}},             # chunked PCG graph + host polling instead of the device-side WHILE loop
 ], ids=lambda v: ",".join(f"{k}={w}" for k, w in v.items()))
 def test_solver_variants_agree_with_the_direct_solve(built, monkeypatch, variant):
     """every solver configuration converges to the oracle's direct solve: same chi2 history (1e-6) and poses (1e-6)"""

@@ -236,6 +236,31 @@ def test_create_rejects_malformed_graphs(built):
         PoseGraph(graph=bad, options=Options(device=-2))
 
 
+def test_landmark_graphs_aggregate_poses_and_attach_landmarks(built):
+    """level-0 aggregation of a graph with VERTEX_XY: poses are aggregated over pose-pose edges (pairs of chain aggregates), every
+    landmark joins the aggregate of most of its observers -- never a landmark-rooted star (dlr: 250 -> 41 PCG iterations)"""
+    g = graph_of(load_golden("dlr"))
+    pg = _structure_handle(g)
+    rows, _ = pg.level_sizes()
+    assert rows[0] == 3873 and 400 <= rows[1] <= 640            # ~6 poses per aggregate, and the dense coarsest level right below
+    agg = pg.aggregates(0)
+    kind = g["vertex_kind"]
+    lut = {int(v): i for i, v in enumerate(g["vertex_id"])}
+    # every landmark sits in the aggregate that holds the plurality of its observing poses
+    obs = {}
+    for a, b, k in zip(g["edge_from"], g["edge_to"], g["edge_kind"]):
+        if k == 1:
+            obs.setdefault(lut[int(b)], []).append(agg[lut[int(a)]])
+    for lm, aggs in obs.items():
+        vals, cnt = np.unique(aggs, return_counts=True)
+        assert cnt[vals == agg[lm]].sum() == cnt.max(), lm
+    # no aggregate consists of landmarks only (unless the landmark has no observer at all)
+    pose_aggs = set(agg[kind == 0].tolist())
+    assert all(a in pose_aggs for a in agg[kind == 1].tolist())
+    sizes = np.bincount(agg[kind == 0])
+    assert sizes.max() <= 2 * 16
+
+
 def test_structure_only_handle_refuses_to_compute(built):
     from rustrobotics_b200 import PgoError
     pg = _structure_handle(graph_of(load_golden("simulation-pose-landmark")))
