@@ -406,6 +406,22 @@ def run_b200(args):
         new_opt5 = {"new_s": t_new, "new_plus_optimize5_s": t_all, "gn_iterations_run": len(errs) - 1, "final_chi2": errs[-1],
                     "what": "PoseGraph(graph) + optimize(5) through the public API, host symbolic pass and uploads included (reference benches/graph_slam.rs:7-11 shape)"}
         pg2.close()
+    # ---- the same step with pgo_options.refine = 1 (one refinement round on a double-double residual): the mode that pins the poses of
+    # this 1M-pose step to 1e-6 m (tests/test_gpu_parity.py::test_config4_refined_step_is_within_1e_6_m_of_the_golden)
+    refined = None
+    if world == 1 and n_shards == 1 and args.workload == "manhattan" and not args.no_secondary:
+        pg3 = PoseGraph(graph=g, options=Options(device=local, pcg_rtol=args.pcg_rtol, preconditioner=args.preconditioner, refine=1, **extra))
+        pg3.snapshot_poses()
+        msr, itr = [], []
+        for i in range(2 + 3):
+            pg3.restore_poses()
+            ndr, c2r, kr = pg3.gn_step(allow_not_converged=False)
+            if i >= 2:
+                msr.append(sum(v[0] for kk, v in pg3.timings().items() if kk != "spmv_fine")); itr.append(kr)
+        refined = {"ms_per_step": sum(msr) / len(msr), "pcg_iterations_per_step": sum(itr) / len(itr), "steps": 3, "warmup": 2,
+                   "parity": golden_check(c2r, ndr, n_poses, args.workload),
+                   "what": "same step with pgo_options.refine = 1: + one round of iterative refinement, residual in double-double arithmetic"}
+        pg3.close()
     # ---- BASELINE configs[4] (SE3 sphere, 250k poses / 1M edges; repo-defined SE3 semantics, parity unpinned) as a secondary line
     secondary = None
     if world == 1 and n_shards == 1 and args.workload == "manhattan" and n_poses == 1_000_000 and not args.no_secondary:
@@ -462,7 +478,7 @@ def run_b200(args):
                               "hbm_utilisation": (step_tr["dram_bytes_per_step"] * (k_its / step_tr["pcg_iterations"] if step_tr.get("pcg_iterations") else 1.0)
                                                   / (step_ms * 1e-3) / 1e9 / peak) if step_tr.get("dram_bytes_per_step") else None},
             "parity": golden_check(last[1], last[0], n_poses, args.workload),
-            "secondary": secondary,
+            "secondary": secondary, "refined": refined,
             "cpu_baseline": cpu,
             "e2e": {"value": total_edges / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(init_np.nbytes), "d2h_bytes_per_step": int(out_np.nbytes) + 20 * world},

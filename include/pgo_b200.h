@@ -79,6 +79,11 @@ typedef struct {
     const int32_t *device_ids; /* n_gpus CUDA device ordinals, NULL = 0 .. n_gpus-1.  The devices need peer access to each other
                                 * (NVLink / NVSwitch on a B200 box).  An ordinal may appear more than once: those shards then share
                                 * that GPU (how the multi-GPU path is tested on a one-GPU machine).  Borrowed during pgo_create only */
+    int32_t refine;            /* 0 (default): dx = the PCG solution.  1: one round of iterative refinement on top of it, with the residual
+                                * b - H dx evaluated in double-double arithmetic and the correction solved to refine_rtol.  On graphs of
+                                * ~1M poses the first Gauss-Newton step cannot be pinned below ~1e-5 m by ANY plain-fp64 solver (direct
+                                * ones included); this mode reaches the 1e-6 m of small graphs there, for ~40 % more time */
+    double refine_rtol;        /* relative tolerance of the correction solve; 0 = default 2e-4 */
 } pgo_options;
 
 /* fills *opt with the defaults (anchor 1e7, rtol 1e-10, max 200000 iterations, AMG K-cycle, fp32 preconditioner storage, single GPU) */

@@ -466,6 +466,81 @@ __global__ void __launch_bounds__(128) k_spmv(LevelDev L, const __grid_constant_
     reduce_and_finalize<128, FIN>(dots, S, partials, lvl, blockIdx.x, gridDim.x);
 }
 
+// ---- residual in extended precision (pgo_options.refine) -----------------------------------------------------------------------
+// r = b - H x with every product and sum carried in double-double (error-free two_prod via FMA, two_sum), rounded to fp64 once at the
+// end.  At 1M poses the first Gauss-Newton step is ~80 m per pose and cond(H) ~ 1e9: a plain fp64 residual is itself wrong at the level
+// of the 1e-6 m pose tolerance, which is why NO fp64 solver gets there; one refinement round x += H^-1 r with THIS
+// residual does.  Same streaming pass over the sliced storage as k_spmv (one thread per block row); ~10x the flops, still memory-bound.
+struct dd { double hi, lo; };
+// (__dadd_rn / __dmul_rn: never contracted into an FMA by the compiler -- the error-free transformations rely on the individual roundings)
+__device__ __forceinline__ dd dd_add(dd a, double bh, double bl) {        // a + (bh + bl)
+    const double s = __dadd_rn(a.hi, bh), v = __dadd_rn(s, -a.hi);
+    const double e = __dadd_rn(__dadd_rn(__dadd_rn(a.hi, -__dadd_rn(s, -v)), __dadd_rn(bh, -v)), __dadd_rn(a.lo, bl));   // TwoSum + the low parts
+    dd o; o.hi = __dadd_rn(s, e); o.lo = __dadd_rn(e, -__dadd_rn(o.hi, -s));
+    return o;
+}
+__device__ __forceinline__ dd dd_sub_prod(dd a, double h, double x) {     // a - h * x, the product exact (TwoProduct by FMA)
+    const double p = __dmul_rn(h, x), pe = __fma_rn(h, x, -p);
+    return dd_add(a, -p, -pe);
+}
+template <int D>
+__global__ void __launch_bounds__(128) k_residual_dd(LevelDev L, const double *__restrict__ x, const double *__restrict__ b, double *__restrict__ r) {
+    PDL_ENTER();
+    constexpr int DD = D * D, VS = VecStride<D>::value;
+    const int64_t row = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int64_t slice = row >> 5;
+    if (slice >= L.n_slices) return;
+    const int mydeg = L.deg[row];
+    const int maxdeg = __shfl_sync(0xffffffffu, mydeg, 0);
+    double xi[VS], bi[VS];
+    ld_vec<VS>(x + row * VS, xi);
+    ld_vec<VS>(b + row * VS, bi);
+    dd acc[D];
+#pragma unroll
+    for (int a = 0; a < D; a++) { acc[a].hi = bi[a]; acc[a].lo = 0.0; }
+    const int64_t base = L.slice_ptr[slice];
+    int64_t off = 0;
+    for (int k = 0; k < maxdeg; k++) {
+        const bool active = k < mydeg;
+        const int cnt = __popc(__ballot_sync(0xffffffffu, active));
+        if (active) {
+            const uint32_t cw = __ldg(L.col + base + off + lane);
+            double xj[VS];
+            ld_vec<VS>(x + (int64_t)(cw & COL_LOCAL_MASK) * VS, xj);
+            const double *v = L.val + (base + off) * DD + lane;
+#pragma unroll
+            for (int a = 0; a < D; a++)
+#pragma unroll
+                for (int c = 0; c < D; c++) acc[a] = dd_sub_prod(acc[a], __ldg(v + (int64_t)(a * D + c) * cnt), xj[c]);
+        }
+        off += cnt;
+    }
+    double out[VS];
+#pragma unroll
+    for (int a = 0; a < VS; a++) out[a] = 0.0;
+    if (row < L.n) {
+#pragma unroll
+        for (int a = 0; a < D; a++) {
+#pragma unroll
+            for (int c = 0; c < D; c++) acc[a] = dd_sub_prod(acc[a], L.diag[(int64_t)(a * D + c) * L.n_pad + row], xi[c]);
+            out[a] = acc[a].hi + acc[a].lo;
+        }
+    }
+    st_vec<VS>(r + row * VS, out);
+}
+
+// x += y (vector records)
+__global__ void __launch_bounds__(256) k_add_to(int64_t n_doubles, double *__restrict__ x, const double *__restrict__ y) {
+    PDL_ENTER();
+    const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 2;
+    if (i >= n_doubles) return;
+    double2 a = *reinterpret_cast<double2 *>(x + i);
+    const double2 c = *reinterpret_cast<const double2 *>(y + i);
+    a.x += c.x; a.y += c.y;
+    *reinterpret_cast<double2 *>(x + i) = a;
+}
+
 // ---- TMA-staged variant of the sliced SpMV -----------------------------------------------------------------------
 // Same mapping (one thread per block row, one warp per 32-row slice), but the block values -- >= 90 % of the bytes -- do
 // not pass through registers while in flight: lane 0 of every warp streams the slice's columns with 1-D bulk copies

@@ -107,6 +107,7 @@ struct pgo_handle {
     int64_t *row_valofs = nullptr;     // [n_loc] offset of each local row's values in vstage
     uint2 *ends = nullptr;
     double *x = nullptr, *r = nullptr, *p = nullptr, *q = nullptr, *z = nullptr;
+    double *b0 = nullptr, *xs = nullptr;   // pgo_options.refine: the right-hand side b (the solve consumes h->r) and the first solution
     Scalars *S = nullptr, *hS = nullptr;   // device / pinned host (2 slots)
     double *partials = nullptr;
     double *gstage = nullptr;          // staging buffer of the deterministic Galerkin product (largest level)
@@ -663,6 +664,38 @@ template <int D> int solve(pgo_handle *h, int32_t *iters_out) {
     return PGO_OK;
 }
 
+// pgo_options.refine: dx = x1 + d with x1 the PCG solution and d the PCG solution of H d = b - H x1, the residual evaluated in
+// double-double arithmetic (k_residual_dd) -- one round of iterative refinement with an extended-precision residual
+template <int D> int solve_refined(pgo_handle *h, int32_t *iters_out) {
+    if (!h->opt.refine) return solve<D>(h, iters_out);
+    constexpr int VS = VecStride<D>::value;
+    LevelBuf &B = h->lv[0];
+    const int64_t nd = B.d.n_pad * VS;
+    if (!h->b0) {
+        int rc = dalloc(h, &h->b0, (size_t)nd); if (rc) return rc;
+        rc = dalloc(h, &h->xs, (size_t)nd); if (rc) return rc;
+    }
+    CK(cudaMemcpyAsync(h->b0, h->r, nd * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    int32_t it1 = 0, it2 = 0;
+    int rc = solve<D>(h, &it1);
+    if (iters_out) *iters_out = it1;
+    if (rc != PGO_OK) return rc;
+    xbarrier(h, 0);                                  // every shard's x is final before its halo rows are pulled
+    halo_pull(h, 0, h->x, VS, 0);
+    launch_k(h, k_residual_dd<D>, B.grid128, 128, 0, B.d, (const double *)h->x, (const double *)h->b0, h->r);
+    h->launch_count += 1;
+    CK(cudaMemcpyAsync(h->xs, h->x, nd * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    const double rtol = h->opt.pcg_rtol;
+    h->opt.pcg_rtol = h->opt.refine_rtol;
+    rc = solve<D>(h, &it2);                          // H d = r ; d lands in h->x
+    h->opt.pcg_rtol = rtol;
+    launch_k(h, k_add_to, grid_for(nd / 2, 256), 256, 0, nd, h->x, (const double *)h->xs);
+    h->launch_count += 1;
+    CK(cudaGetLastError()); CK(h->launch_err);
+    if (iters_out) *iters_out = it1 + it2;
+    return rc;
+}
+
 template <int D> int retract(pgo_handle *h, double sign) {
     LevelBuf &B = h->lv[0];
     if (D == 3) launch_k(h, k_retract_se2, grid_for(B.d.n, 256), 256, 0, B.d, h->poses, h->x, sign, h->S, h->partials);
@@ -1215,6 +1248,7 @@ static void normalise_options(pgo_options &o, int world) {
     if (o.anchor_weight == 0) o.anchor_weight = dflt.anchor_weight;
     if (o.amg_dense_max <= 0) o.amg_dense_max = dflt.amg_dense_max;
     if (o.amg_dense_max > 1024) o.amg_dense_max = 1024;
+    if (o.refine_rtol <= 0) o.refine_rtol = 2e-4;
     // default upper bound on the members of an aggregate: 16 on one GPU (measured optimum at config 4, profiles/r02f_knob_sweep.log).
     // Sharded handles use 24: the partition-local level-0 aggregation leaves a larger, less regular level 1, and with 16 the
     // multilevel K-cycle needs 51 PCG iterations at world 2 and 8 where one GPU needs 41; with 24 the scipy prototype fed with
@@ -1461,7 +1495,7 @@ int pgo_gn_step(pgo_handle *h, double lambda, int add_lambda, double *norm_dx, d
     if (rc) return rc;
     mark(2); lc[2] = h->launch_count;
     int32_t iters = 0;
-    int src = BY_D(h, solve, h, &iters);
+    int src = BY_D(h, solve_refined, h, &iters);
     if (src == PGO_ERR_SOLVER && h->use_amg && h->omega_ready) {
         // The smoother dampings were estimated once, on the first H of this handle.  H is re-linearised every step (and the caller may
         // have moved the poses far away with pgo_set_poses): if rho(Dinv H) has grown past the margin the cycle stops being positive
@@ -1471,7 +1505,7 @@ int pgo_gn_step(pgo_handle *h, double lambda, int add_lambda, double *norm_dx, d
         if (rc) return rc;
         rc = BY_D(h, amg_setup, h);
         if (rc) return rc;
-        src = BY_D(h, solve, h, &iters);
+        src = BY_D(h, solve_refined, h, &iters);
     }
     if (src != PGO_OK && src != PGO_ERR_NOT_CONVERGED) return src;
     mark(3); lc[3] = h->launch_count;
@@ -1522,7 +1556,7 @@ int pgo_linearize_and_solve(pgo_handle *h, int32_t *pcg_iterations) {
     if (rc) return rc;
     rc = BY_D(h, amg_setup, h);
     if (rc) return rc;
-    return BY_D(h, solve, h, pcg_iterations);
+    return BY_D(h, solve_refined, h, pcg_iterations);
 }
 
 // vertex values of the rows this rank owns are a contiguous span of the packed array (contiguous vertex ranges)

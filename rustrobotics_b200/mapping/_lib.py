@@ -23,7 +23,7 @@ class pgo_options(C.Structure):
                 ("preconditioner", C.c_int32), ("sort_window", C.c_int32), ("amg_max_levels", C.c_int32),
                 ("device", C.c_int32), ("world", C.c_int32), ("rank", C.c_int32), ("amg_dense_max", C.c_int32),
                 ("amg_aggregate_size", C.c_int32), ("amg_kcycle", C.c_int32), ("amg_kcycle3", C.c_int32), ("amg_fp64_storage", C.c_int32),
-                ("n_gpus", C.c_int32), ("device_ids", C.POINTER(C.c_int32))]
+                ("n_gpus", C.c_int32), ("device_ids", C.POINTER(C.c_int32)), ("refine", C.c_int32), ("refine_rtol", C.c_double)]
 
 
 def lib_path() -> Path:

@@ -33,7 +33,7 @@ BLOCK_JACOBI, AMG = 0, 1
 def Options(**kw) -> pgo_options:
     """pgo_options with the library defaults, overridden by keyword (anchor_weight, pcg_rtol,
     pcg_max_iterations, preconditioner, sort_window, amg_max_levels, device, world, rank, amg_dense_max,
-    amg_aggregate_size, amg_kcycle, amg_kcycle3, amg_fp64_storage, n_gpus, device_ids).
+    amg_aggregate_size, amg_kcycle, amg_kcycle3, amg_fp64_storage, n_gpus, device_ids, refine, refine_rtol).
 
     Multi-GPU from ONE process: `Options(n_gpus=8)` (devices 0..7) or `Options(n_gpus=2, device_ids=[0, 0])`
     (two shards sharing GPU 0: the multi-GPU path on a one-GPU machine)."""

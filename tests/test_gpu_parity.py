@@ -323,6 +323,26 @@ def test_a_step_can_be_undone_once(built):
         pg.undo_last_step()
 
 
+def test_config4_refined_step_is_within_1e_6_m_of_the_golden(built):
+    """pgo_options.refine = 1: one round of iterative refinement with the residual b - H dx in double-double arithmetic.  THIS meets the
+    1e-6 m / 1e-6 rad of the small graphs on the 1M-pose graph too -- closer to the true solution than any plain-fp64 solve, the
+    reference's UMFPACK included"""
+    import bench
+    from rustrobotics_b200.synthetic import manhattan_se2
+    gold = load_golden("manhattan_1m_step1")
+    g = manhattan_se2(int(gold["n_poses"]))
+    pg = _pg(g, pcg_rtol=bench.DEFAULT_PCG_RTOL, refine=1)
+    nd, c1, it = pg.gn_step(allow_not_converged=False)
+    s = gold["sample"]
+    got = pg.poses().reshape(-1, 3)[s]
+    e_xy = np.abs(got[:, :2] - gold["values_sample"][:, :2]).max()
+    e_th = _angle_diff(got[:, 2], gold["values_sample"][:, 2]).max()
+    e_dx = np.abs(pg.dx().reshape(-1, 3)[s] - gold["dx_sample"]).max()
+    print(f"config 4 refined: {it} PCG iterations, pose err xy {e_xy:.2e} theta {e_th:.2e}, dx err {e_dx:.2e}, | |dx| - truth | {abs(nd - float(gold['norm_dx'])):.2e}")
+    assert abs(c1 - float(gold["chi2_1"])) <= 1e-9 * c1
+    assert e_xy <= POSE_ATOL and e_th <= POSE_ATOL and e_dx <= POSE_ATOL
+
+
 @pytest.mark.parametrize("n_gpus", [1, 2])
 def test_repeat_runs_are_bit_identical(built, n_gpus):
     """deterministic mode is the only mode: no atomics anywhere on the path (segmented assembly, single-writer Galerkin product,
@@ -365,6 +385,7 @@ def _oracle_100k():
     {"env": {"PGO_SPMV_TMA64": "2", "PGO_SPMV_TMA32": "3"}},     # TMA-staged sliced SpMV
     {"env": {"PGO_PDL": "0"}},               # plain (non-programmatic) launches
     {"env": {"PGO_WHILE": "0"}},             # chunked PCG graph + host polling instead of the device-side WHILE loop
+    {"refine": 1},                           # + one refinement round with the double-double residual
 ], ids=lambda v: ",".join(f"{k}={w}" for k, w in v.items()))
 def test_solver_variants_agree_with_the_direct_solve(built, monkeypatch, variant):
     """every solver configuration converges to the oracle's direct solve: same chi2 history (1e-6) and poses (1e-6)"""

@@ -142,3 +142,8 @@ def test_multi_gpu_handle_assembles_the_same_system_and_same_api(built):
     assert dxy <= 1e-12 and dth <= 1e-12
     assert pg.stats()["block_rows"] == len(g["vertex_id"]) and pg.time_spmv(3) > 0
     pg.close()
+    # the refinement round (double-double residual over the halo-extended x) on a sharded handle
+    pr = PoseGraph(graph=g, options=Options(device_ids=_device_ids(3), refine=1))
+    dxr, _ = pr.linearize_and_solve()
+    assert np.abs(dxr - sls.solve()).max() <= 1e-8 * np.abs(dxr).max()
+    pr.close()

@@ -75,6 +75,11 @@ abgj3)
   PGO_GJ=3 timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_se3.py -m gpu -q -x 2>&1 | tail -3 | tee -a gpurun_out/gj3_$tag.log
   PGO_GJ=3 timeout 300 python bench.py --workload dlr --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('dlr GJ=3 ms/step', d['ms_per_step'], d['phase_ms'])" | tee -a gpurun_out/gj3_$tag.log
   timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1;;
+refine)
+  timeout 300 python tools/rtol_sweep.py 1e-9 1e-8 --opts=refine=1 2>&1 | tee gpurun_out/refine_$tag.log
+  timeout 300 python tools/rtol_sweep.py 1e-9 --opts=refine=1,refine_rtol=1e-3 2>&1 | tail -1 | tee -a gpurun_out/refine_$tag.log
+  timeout 300 python tools/rtol_sweep.py 1e-9 --opts=refine=1,refine_rtol=1e-5 2>&1 | tail -1 | tee -a gpurun_out/refine_$tag.log
+  timeout 900 python -m pytest tests -m gpu -q -x -k "refine or variants or multi_gpu_handle_assembles" 2>&1 | tail -3 | tee -a gpurun_out/refine_$tag.log;;
 abwhile)
   for v in 0 1; do PGO_WHILE=$v timeout 300 python tools/quick_perf.py --opts pcg_rtol=1e-9 2>&1 | tail -1 | sed "s/^/WHILE=$v /"; done | tee gpurun_out/while_$tag.log
   for v in 0 1; do PGO_WHILE=$v timeout 300 python tools/quick_perf.py --poses 100000 --opts pcg_rtol=1e-9 2>&1 | tail -1 | sed "s/^/100k WHILE=$v /"; done | tee -a gpurun_out/while_$tag.log;;
