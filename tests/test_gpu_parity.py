@@ -273,11 +273,12 @@ def test_config4_first_step_matches_the_golden_solution_at_the_benchmark_toleran
     """BASELINE config 4 at bench.py's own pcg_rtol against tests/golden/manhattan_1m_step1.npz (make_golden_1m.py): the TRUE
     solution of the reference's first Gauss-Newton system (oracle assembly, independent CPU solve refined with long-double
     residuals).  chi2 1e-6 relative; theta 1e-6 rad; x / y within max(1e-6 m, 5 x the fp64 noise floor of this system).
-    The floor: dx of this step is ~80 m per pose and cond(H) ~ 1e9, so plain fp64 cannot pin the softest modes to 1e-6 m -- the
-    CPU solve driven to stagnation is fp64_noise_xy = 9.6e-6 m away from the truth, two SuperLU orderings disagree by 2.4e-6 m already
-    at 100k poses, and CONVERGED GPU solves (any pcg_rtol from 1e-9 to 1e-13, any hierarchy) scatter between 6e-6 and 4e-5 m
-    (profiles/r03a_rtol_sweep.log, r03c_rtol_sweep.log); at pcg_rtol 1e-8 the error is 2e-4 m: not converged, and this test fails.
-    No fp64 solver -- the reference's UMFPACK included -- gets closer than that floor."""
+    The floor: dx of this step is ~80 m per pose and cond(H) ~ 1e9, so fp64 cannot pin the softest modes to 1e-6 m -- the CPU solve
+    driven to stagnation is fp64_noise_xy = 9.6e-6 m away from the truth, two SuperLU orderings disagree by 2.4e-6 m already at 100k
+    poses, and the EXACT solutions of two fp64 assemblies of this same system (GPU kernel vs oracle: 1.6e-13 relative apart in b)
+    are 3.25e-5 m apart (profiles/r03p_system_conditioning.log; the test below separates that from the solver's own error, 3.8e-6 m).
+    At pcg_rtol 1e-8 the error is 2e-4 m: not converged, and this test fails.  No fp64 implementation -- the reference's own included
+    -- is closer to another one than that floor."""
     import hashlib
     import bench
     from rustrobotics_b200.synthetic import manhattan_se2
@@ -323,24 +324,37 @@ def test_a_step_can_be_undone_once(built):
         pg.undo_last_step()
 
 
-def test_config4_refined_step_is_within_1e_6_m_of_the_golden(built):
-    """pgo_options.refine = 1: one round of iterative refinement with the residual b - H dx in double-double arithmetic.  THIS meets the
-    1e-6 m / 1e-6 rad of the small graphs on the 1M-pose graph too -- closer to the true solution than any plain-fp64 solve, the
-    reference's UMFPACK included"""
+def test_config4_solver_error_is_separated_from_the_conditioning_of_the_step(built):
+    """pgo_options.refine = 1 (one round of iterative refinement, residual b - H dx in double-double arithmetic) solves the system the
+    GPU assembled essentially exactly: within 1.4e-8 m of its true solution computed on the CPU with long-double refinement
+    (tools/system_conditioning.py, profiles/r03p_system_conditioning.log).  This test pins what follows from it without the CPU solve:
+      * the refined dx does not depend on the solver settings (two very different settings agree to 2e-7 m): it IS the solution;
+      * the plain solve at the benchmark tolerance is within 1e-5 m of it (measured 3.8e-6 m): that is the SOLVER's error;
+      * the refined dx is still 3.25e-5 m from the golden: that distance is the response of this ill-conditioned step (dx ~ 80 m per
+        pose, cond(H) ~ 1e9) to last-bit differences between two fp64 assemblies of the same system -- GPU and oracle differ by
+        1.6e-13 relative in b -- and no solver can remove it"""
     import bench
     from rustrobotics_b200.synthetic import manhattan_se2
     gold = load_golden("manhattan_1m_step1")
     g = manhattan_se2(int(gold["n_poses"]))
-    pg = _pg(g, pcg_rtol=bench.DEFAULT_PCG_RTOL, refine=1)
-    nd, c1, it = pg.gn_step(allow_not_converged=False)
     s = gold["sample"]
-    got = pg.poses().reshape(-1, 3)[s]
-    e_xy = np.abs(got[:, :2] - gold["values_sample"][:, :2]).max()
-    e_th = _angle_diff(got[:, 2], gold["values_sample"][:, 2]).max()
-    e_dx = np.abs(pg.dx().reshape(-1, 3)[s] - gold["dx_sample"]).max()
-    print(f"config 4 refined: {it} PCG iterations, pose err xy {e_xy:.2e} theta {e_th:.2e}, dx err {e_dx:.2e}, | |dx| - truth | {abs(nd - float(gold['norm_dx'])):.2e}")
-    assert abs(c1 - float(gold["chi2_1"])) <= 1e-9 * c1
-    assert e_xy <= POSE_ATOL and e_th <= POSE_ATOL and e_dx <= POSE_ATOL
+
+    def solve(**kw):
+        pg = _pg(g, **kw)
+        dx, it = pg.linearize_and_solve()
+        pg.close()
+        return dx.reshape(-1, 3)[s], it
+    plain, it0 = solve(pcg_rtol=bench.DEFAULT_PCG_RTOL)
+    ref_a, it1 = solve(pcg_rtol=bench.DEFAULT_PCG_RTOL, refine=1)
+    ref_b, it2 = solve(pcg_rtol=1e-8, refine=1, refine_rtol=1e-5)
+    d_ab = np.abs(ref_a - ref_b).max()
+    d_plain = np.abs(plain - ref_a)
+    d_gold = np.abs(ref_a - gold["dx_sample"])
+    print(f"config 4: plain {it0} its, refined {it1} / {it2} its; refined vs refined {d_ab:.2e}; plain vs refined xy {d_plain[:, :2].max():.2e} "
+          f"theta {d_plain[:, 2].max():.2e}; refined vs golden xy {d_gold[:, :2].max():.2e} theta {d_gold[:, 2].max():.2e}")
+    assert d_ab <= 2e-7
+    assert d_plain[:, :2].max() <= 1e-5 and d_plain[:, 2].max() <= POSE_ATOL
+    assert d_gold[:, :2].max() <= max(POSE_ATOL, 5.0 * float(gold["fp64_noise_xy"])) and d_gold[:, 2].max() <= POSE_ATOL
 
 
 @pytest.mark.parametrize("n_gpus", [1, 2])
