@@ -86,6 +86,9 @@ typedef struct {
     double refine_rtol;        /* relative tolerance of the correction solve; 0 = default 2e-4 */
 } pgo_options;
 
+/* pgo_options grows at its END between versions of the library (n_gpus / device_ids and refine / refine_rtol are round-2 additions):
+ * a caller must be compiled against the header that ships with the library it loads (pgo_default_options writes sizeof(pgo_options)
+ * bytes); pgo_version() lets a binding check. */
 /* fills *opt with the defaults (anchor 1e7, rtol 1e-10, max 200000 iterations, AMG K-cycle, fp32 preconditioner storage, single GPU) */
 void pgo_default_options(pgo_options *opt);
 
