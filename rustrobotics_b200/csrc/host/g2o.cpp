@@ -93,22 +93,28 @@ bool parse_g2o(const std::string &filename, G2oGraph &g, std::string &error) {
     return true;
 }
 
+bool validate_graph_arrays(size_t n_vertices, const uint8_t *vertex_kind, size_t n_values, size_t n_edges, const uint8_t *edge_kind,
+                           size_t n_meas, size_t n_info, std::string &error) {
+    size_t nval = 0, nmeas = 0, ninfo = 0;
+    for (size_t i = 0; i < n_vertices; i++) {
+        if (vertex_kind[i] > 2) { error = "graph arrays: vertex_kind[" + std::to_string(i) + "] = " + std::to_string(vertex_kind[i]) + " (must be 0, 1 or 2)"; return false; }
+        nval += (size_t)NVAL[vertex_kind[i]];
+    }
+    for (size_t i = 0; i < n_edges; i++) {
+        if (edge_kind[i] > 2) { error = "graph arrays: edge_kind[" + std::to_string(i) + "] = " + std::to_string(edge_kind[i]) + " (must be 0, 1 or 2)"; return false; }
+        nmeas += (size_t)NMEAS[edge_kind[i]]; ninfo += (size_t)NINFO[edge_kind[i]];
+    }
+    if (n_values != nval) { error = "graph arrays: " + std::to_string(n_values) + " vertex values, the vertex kinds need " + std::to_string(nval); return false; }
+    if (n_meas != nmeas) { error = "graph arrays: " + std::to_string(n_meas) + " edge measurement values, the edge kinds need " + std::to_string(nmeas); return false; }
+    if (n_info != ninfo) { error = "graph arrays: " + std::to_string(n_info) + " edge information values, the edge kinds need " + std::to_string(ninfo); return false; }
+    return true;
+}
+
 bool validate_graph(const G2oGraph &g, std::string &error) {
     if (g.vertex_kind.size() != g.vertex_id.size()) { error = "graph arrays: vertex_kind and vertex_id differ in length"; return false; }
     if (g.edge_from.size() != g.edge_kind.size() || g.edge_to.size() != g.edge_kind.size()) { error = "graph arrays: edge_kind / edge_from / edge_to differ in length"; return false; }
-    size_t nval = 0, nmeas = 0, ninfo = 0;
-    for (size_t i = 0; i < g.vertex_kind.size(); i++) {
-        if (g.vertex_kind[i] > 2) { error = "graph arrays: vertex_kind[" + std::to_string(i) + "] = " + std::to_string(g.vertex_kind[i]) + " (must be 0, 1 or 2)"; return false; }
-        nval += (size_t)NVAL[g.vertex_kind[i]];
-    }
-    for (size_t i = 0; i < g.edge_kind.size(); i++) {
-        if (g.edge_kind[i] > 2) { error = "graph arrays: edge_kind[" + std::to_string(i) + "] = " + std::to_string(g.edge_kind[i]) + " (must be 0, 1 or 2)"; return false; }
-        nmeas += (size_t)NMEAS[g.edge_kind[i]]; ninfo += (size_t)NINFO[g.edge_kind[i]];
-    }
-    if (g.vertex_values.size() != nval) { error = "graph arrays: " + std::to_string(g.vertex_values.size()) + " vertex values, the vertex kinds need " + std::to_string(nval); return false; }
-    if (g.edge_meas.size() != nmeas) { error = "graph arrays: " + std::to_string(g.edge_meas.size()) + " edge measurement values, the edge kinds need " + std::to_string(nmeas); return false; }
-    if (g.edge_info_upper.size() != ninfo) { error = "graph arrays: " + std::to_string(g.edge_info_upper.size()) + " edge information values, the edge kinds need " + std::to_string(ninfo); return false; }
-    return true;
+    return validate_graph_arrays(g.vertex_id.size(), g.vertex_kind.data(), g.vertex_values.size(), g.edge_kind.size(), g.edge_kind.data(),
+                                 g.edge_meas.size(), g.edge_info_upper.size(), error);
 }
 
 bool write_g2o(const std::string &filename, const G2oGraph &g, std::string &error) {

@@ -26,6 +26,9 @@ bool parse_g2o(const std::string &filename, G2oGraph &out, std::string &error);
 
 // the packed value arrays hold exactly what the per-kind counts say, kinds are 0..2 (what pgo_create reads on the device side)
 bool validate_graph(const G2oGraph &g, std::string &error);
+// the same check on bare arrays (lengths of the value arrays against what the kinds need)
+bool validate_graph_arrays(size_t n_vertices, const uint8_t *vertex_kind, size_t n_values, size_t n_edges, const uint8_t *edge_kind,
+                           size_t n_meas, size_t n_info, std::string &error);
 
 // writes the graph back in g2o text form with round-trip precision (%.17g)
 bool write_g2o(const std::string &filename, const G2oGraph &g, std::string &error);

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <future>
 #include <sys/stat.h>
 #include <utility>
 
@@ -44,6 +45,9 @@ PoseGraph::PoseGraph(G2oGraph &&graph, const std::string &name, PoseGraphSolver 
     : graph_(std::move(graph)), name_(name), solver_(solver) {
     init(options);
 }
+
+PoseGraph::PoseGraph(G2oGraph &&graph, const std::string &name, PoseGraphSolver solver, pgo_handle *adopted)
+    : graph_(std::move(graph)), name_(name), solver_(solver), h_(adopted) {}
 
 PoseGraph::~PoseGraph() { pgo_destroy(h_); }
 
@@ -160,14 +164,25 @@ void *pg_from_arrays(const char *name, int solver, const pgo_options *opt,
                      int64_t ne, const uint8_t *ekind, const uint32_t *efrom, const uint32_t *eto,
                      const double *emeas, int64_t n_meas, const double *einfo, int64_t n_info) {
     try {
-        G2oGraph g;
-        g.vertex_id.assign(vid, vid + nv); g.vertex_kind.assign(vkind, vkind + nv); g.vertex_values.assign(vval, vval + n_values);
-        g.edge_kind.assign(ekind, ekind + ne); g.edge_from.assign(efrom, efrom + ne); g.edge_to.assign(eto, eto + ne);
-        g.edge_meas.assign(emeas, emeas + n_meas); g.edge_info_upper.assign(einfo, einfo + n_info);
+        if (nv < 0 || ne < 0 || n_values < 0 || n_meas < 0 || n_info < 0) throw Error("graph arrays: negative length");
         std::string verr;
-        if (!validate_graph(g, verr)) throw Error(verr);
-        for (int64_t i = 0; i < nv; i++) g.len += vkind[i] == 0 ? 3 : vkind[i] == 1 ? 2 : 6;
-        return new PoseGraph(std::move(g), name ? name : "graph", solver ? PoseGraphSolver::LevenbergMarquardt : PoseGraphSolver::GaussNewton, opt);
+        if (!validate_graph_arrays((size_t)nv, vkind, (size_t)n_values, (size_t)ne, ekind, (size_t)n_meas, (size_t)n_info, verr)) throw Error(verr);
+        // the PoseGraph owns a copy of the graph (like the reference's, :157-159); the ~0.4 GB copy at 1M poses runs beside pgo_create
+        std::future<G2oGraph> copy = std::async(std::launch::async, [&]() {
+            G2oGraph g;
+            g.vertex_id.assign(vid, vid + nv); g.vertex_kind.assign(vkind, vkind + nv); g.vertex_values.assign(vval, vval + n_values);
+            g.edge_kind.assign(ekind, ekind + ne); g.edge_from.assign(efrom, efrom + ne); g.edge_to.assign(eto, eto + ne);
+            g.edge_meas.assign(emeas, emeas + n_meas); g.edge_info_upper.assign(einfo, einfo + n_info);
+            for (int64_t i = 0; i < nv; i++) g.len += vkind[i] == 0 ? 3 : vkind[i] == 1 ? 2 : 6;
+            return g;
+        });
+        pgo_handle *h = nullptr;
+        const int rc = pgo_create(&h, opt, nv, vid, vkind, vval, ne, ekind, efrom, eto, emeas, einfo);
+        G2oGraph g = copy.get();
+        if (rc != PGO_OK) throw Error(std::string("pgo_create: ") + pgo_last_error(nullptr));
+        try {
+            return new PoseGraph(std::move(g), name ? name : "graph", solver ? PoseGraphSolver::LevenbergMarquardt : PoseGraphSolver::GaussNewton, h);
+        } catch (...) { pgo_destroy(h); throw; }
     } catch (const std::exception &e) { g_err = e.what(); return nullptr; }
 }
 

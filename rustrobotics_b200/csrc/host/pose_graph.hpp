@@ -27,6 +27,9 @@ public:
     // same, from an already loaded graph (synthetic benchmarks)
     PoseGraph(const G2oGraph &graph, const std::string &name, PoseGraphSolver solver, const pgo_options *options = nullptr);
     PoseGraph(G2oGraph &&graph, const std::string &name, PoseGraphSolver solver, const pgo_options *options = nullptr);
+    // adopts a handle that pgo_create has already built from these very arrays (pg_from_arrays copies the caller's arrays into
+    // `graph` while the handle is being created)
+    PoseGraph(G2oGraph &&graph, const std::string &name, PoseGraphSolver solver, pgo_handle *adopted);
     ~PoseGraph();
     PoseGraph(const PoseGraph &) = delete;
     PoseGraph &operator=(const PoseGraph &) = delete;

@@ -1853,6 +1853,37 @@ __global__ void __launch_bounds__(128) k_build_hz(LevelDev L, const int32_t *__r
     }
 }
 
+// One-time (pgo_create): the edge-ordered measurement records `ed` ([NM][stride] planes; SE2 / XY: z = x y cos sin, Omega upper (6 | 3);
+// SE3: z = t(3) q(w,x,y,z) normalised, Omega upper (21)) from the caller's packed g2o-layout arrays (measurement x y theta | x y |
+// t(3) q(x,y,z,w); information upper triangle).  Record i is edge inc[i] (all edges in order when inc == nullptr); mofs / iofs are the
+// packed offsets of every edge, nullptr when all edges have the same kind.
+template <int NM>
+__global__ void __launch_bounds__(256) k_build_ed(int64_t n_rec, const int32_t *__restrict__ inc, const uint8_t *__restrict__ ekind,
+                                                   const int64_t *__restrict__ mofs, const int64_t *__restrict__ iofs, const double *__restrict__ emeas,
+                                                   const double *__restrict__ einfo, double *__restrict__ ed, int64_t stride) {
+    PDL_ENTER();
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_rec) return;
+    const int64_t k = inc ? inc[i] : i;
+    const int kind = ekind[k];
+    const int nmeas = kind == 2 ? 7 : (kind == 1 ? 2 : 3), ninfo = kind == 2 ? 21 : (kind == 1 ? 3 : 6);
+    const double *m = emeas + (mofs ? mofs[k] : k * nmeas), *w = einfo + (iofs ? iofs[k] : k * ninfo);
+    double *o = ed + i;
+    if (NM == 28) {
+        const double nq = sqrt(m[3] * m[3] + m[4] * m[4] + m[5] * m[5] + m[6] * m[6]);
+        o[0] = m[0]; o[stride] = m[1]; o[2 * stride] = m[2];
+        o[3 * stride] = m[6] / nq; o[4 * stride] = m[3] / nq; o[5 * stride] = m[4] / nq; o[6 * stride] = m[5] / nq;
+#pragma unroll
+        for (int c = 0; c < 21; c++) o[(int64_t)(7 + c) * stride] = w[c];
+    } else {
+        double cz = 0.0, sz = 0.0;
+        if (kind == 0) sincos(m[2], &sz, &cz);
+        o[0] = m[0]; o[stride] = m[1]; o[2 * stride] = cz; o[3 * stride] = sz;
+#pragma unroll
+        for (int c = 0; c < 6; c++) o[(int64_t)(4 + c) * stride] = c < ninfo ? w[c] : 0.0;
+    }
+}
+
 struct PP { double e[3]; double m11, m12, a0, a1; };
 
 __device__ __forceinline__ void pose_pose(const double *x1, const double *x2, const double *z, PP &o) {

@@ -806,6 +806,7 @@ void pgo_destroy(pgo_handle *h) {
 // multi-GPU handle): h->sym / h->opt / world / rank are set.  Runs on the thread that will own the shard's CUDA device.
 static int create_shard(pgo_handle *h, const double *vval, int64_t ne, const uint8_t *ekind, const double *emeas, const double *einfo) {
     Symbolic &S = h->sym;
+    double t_last = now_s();
     // per-dimension record sizes (kernels.cuh: Dim<D>)
     const int D = S.D, DD = D * D, VS = D == 6 ? 6 : 4, PS = D == 6 ? 8 : 4, NG = D == 6 ? 3 : 2, LS = D == 6 ? 4 : 2, NM = D == 6 ? 28 : 10;
 
@@ -820,6 +821,7 @@ static int create_shard(pgo_handle *h, const double *vval, int64_t ne, const uin
     for (auto &e : h->poll_ev) CKU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CKU(cudaHostAlloc((void **)&h->hS, 2 * sizeof(Scalars), cudaHostAllocDefault));
     std::memset(h->hS, 0, 2 * sizeof(Scalars));
+    TICK("shard: context + stream");
 
     const int rank = h->rank, world = h->world;
     const int nl = (int)S.levels.size();
@@ -986,6 +988,7 @@ static int create_shard(pgo_handle *h, const double *vval, int64_t ne, const uin
         B.ksteps = (B.kcycle && l <= k3) ? 3 : 2;
         B.vec_rows = max_pad;
     }
+    TICK("shard: level structures");
     {
         const size_t vec = (size_t)VS * h->lv[0].vec_rows;
         arena_request(h, &h->poses, (size_t)PS * h->lv[0].vec_rows);
@@ -999,6 +1002,7 @@ static int create_shard(pgo_handle *h, const double *vval, int64_t ne, const uin
         h->dense_m = (int)HL.n * D;
     }
     CKC(arena_commit(h));
+    TICK("shard: arena");
     if (max_stage > 0) CKC(dalloc(h, &h->gstage, (size_t)max_stage, false));
     if (h->use_amg && S.dense_coarsest) {
         const int m = h->dense_m;
@@ -1040,18 +1044,28 @@ static int create_shard(pgo_handle *h, const double *vval, int64_t ne, const uin
         CKU(cudaGetLastError());
         if (D == 6) h->lv[0].d.quat = h->poses;
     }
+    TICK("shard: vertex data");
     {
         const int64_t ag = S.anchor >= 0 ? S.iperm[S.anchor] : -1;
         h->anchor_row = (ag >= r0 && ag < r1) ? ag - r0 : -1;
     }
     // ---- measurements.  Edges incident to the rows of this rank: first the ones it owns (owner = the rank of `from`; these are the
-    // edges its chi2 kernel sums), then the ones it only sees from the `to` side.  Their records -- SE2: z = x y cos sin, Omega upper (6);
-    // SE3: z = t(3) q(w,x,y,z) normalised, Omega upper (21) -- go to the device once, edge-ordered ([NM][n_inc] planes, `ed`); the
-    // half-edge stream hz the assembly kernel reads is gathered from them ON the device (k_build_hz).
+    // edges its chi2 kernel sums), then the ones it only sees from the `to` side.  The caller's packed arrays go to the device as they
+    // are and the edge-ordered records `ed` ([NM][n_inc] planes) are built there (k_build_ed); the half-edge stream hz the assembly
+    // kernel reads is then gathered from them, also on the device (k_build_hz).
     {
-        std::vector<int64_t> mofs(ne + 1, 0), iofs(ne + 1, 0);
         static const int NMEAS[3] = {3, 2, 7}, NINFO[3] = {6, 3, 21};
-        for (int64_t k = 0; k < ne; k++) { mofs[k + 1] = mofs[k] + NMEAS[ekind[k]]; iofs[k + 1] = iofs[k] + NINFO[ekind[k]]; }
+        int64_t nkind[3] = {0, 0, 0};
+        for (int64_t k = 0; k < ne; k++) nkind[ekind[k]]++;
+        const bool mixed = (nkind[0] > 0) + (nkind[1] > 0) + (nkind[2] > 0) > 1;
+        const int64_t n_meas = nkind[0] * NMEAS[0] + nkind[1] * NMEAS[1] + nkind[2] * NMEAS[2];
+        const int64_t n_info = nkind[0] * NINFO[0] + nkind[1] * NINFO[1] + nkind[2] * NINFO[2];
+        std::vector<int64_t> mofs, iofs;               // packed offsets: only when the edge kinds are mixed (SE2 graphs with landmarks)
+        if (mixed) {
+            mofs.resize(ne); iofs.resize(ne);
+            int64_t mo = 0, io = 0;
+            for (int64_t k = 0; k < ne; k++) { mofs[k] = mo; iofs[k] = io; mo += NMEAS[ekind[k]]; io += NINFO[ekind[k]]; }
+        }
         std::vector<int32_t> inc, inc_of;
         int64_t nm = ne, n_inc = ne;
         if (world > 1) {
@@ -1069,30 +1083,42 @@ static int create_shard(pgo_handle *h, const double *vval, int64_t ne, const uin
         h->ed_stride = std::max<int64_t>(n_inc, 1);
         const int64_t stride = h->ed_stride;
         std::vector<uint2> ends(std::max<int64_t>(nm, 1));
-        std::vector<double> ed((size_t)NM * stride, 0.0);
-        parallel_for(n_inc, 16384, [&](int64_t i0, int64_t i1) {
+        parallel_for(nm, 65536, [&](int64_t i0, int64_t i1) {
             for (int64_t i = i0; i < i1; i++) {
                 const int64_t k = world > 1 ? inc[i] : i;
-                const double *m = emeas + mofs[k], *w = einfo + iofs[k];
-                double *o = ed.data() + i;
-                if (ekind[k] == 2) {
-                    const double nq = std::sqrt(m[3] * m[3] + m[4] * m[4] + m[5] * m[5] + m[6] * m[6]);
-                    o[0] = m[0]; o[stride] = m[1]; o[2 * stride] = m[2];
-                    o[3 * stride] = m[6] / nq; o[4 * stride] = m[3] / nq; o[5 * stride] = m[4] / nq; o[6 * stride] = m[5] / nq;
-                    for (int c = 0; c < 21; c++) o[(size_t)(7 + c) * stride] = w[c];
-                } else {
-                    o[0] = m[0]; o[stride] = m[1];
-                    if (ekind[k] == 0) { o[2 * stride] = std::cos(m[2]); o[3 * stride] = std::sin(m[2]); for (int c = 0; c < 6; c++) o[(size_t)(4 + c) * stride] = w[c]; }
-                    else { for (int c = 0; c < 3; c++) o[(size_t)(4 + c) * stride] = w[c]; }
-                }
-                if (i < nm) {
-                    const int64_t a = S.iperm[S.efrom[k]];
-                    ends[i] = make_uint2((uint32_t)(a - r0), h->to_index[k] | (ekind[k] == 1 ? COL_EDGE_XY : 0u));
-                }
+                const int64_t a = S.iperm[S.efrom[k]];
+                ends[i] = make_uint2((uint32_t)(a - r0), h->to_index[k] | (ekind[k] == 1 ? COL_EDGE_XY : 0u));
             }
         });
         CKC(upload(h, &h->ends, ends));
-        CKC(upload(h, &h->ed, ed));
+        CKC(dalloc(h, &h->ed, (size_t)NM * stride));
+        {
+            struct Tmp {                                // device copies of the caller's arrays: only needed until `ed` is built
+                void *p[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+                ~Tmp() { for (void *q : p) if (q) cudaFree(q); }
+            } tmp;
+            auto push = [&](int slot, const void *src, size_t bytes) -> cudaError_t {
+                if (bytes == 0) return cudaSuccess;
+                cudaError_t e = cudaMalloc(&tmp.p[slot], bytes);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(tmp.p[slot], src, bytes, cudaMemcpyHostToDevice, h->stream);
+                return e;
+            };
+            CKU(push(0, emeas, (size_t)n_meas * sizeof(double)));
+            CKU(push(1, einfo, (size_t)n_info * sizeof(double)));
+            CKU(push(2, ekind, (size_t)ne));
+            CKU(push(3, mofs.data(), mofs.size() * sizeof(int64_t)));
+            CKU(push(4, iofs.data(), iofs.size() * sizeof(int64_t)));
+            CKU(push(5, inc.data(), world > 1 ? inc.size() * sizeof(int32_t) : 0));
+            if (n_inc > 0) {
+                if (D == 6) launch_k(h, k_build_ed<28>, grid_for(n_inc, 256), 256, 0, n_inc, (const int32_t *)tmp.p[5], (const uint8_t *)tmp.p[2], (const int64_t *)tmp.p[3],
+                                     (const int64_t *)tmp.p[4], (const double *)tmp.p[0], (const double *)tmp.p[1], h->ed, stride);
+                else launch_k(h, k_build_ed<10>, grid_for(n_inc, 256), 256, 0, n_inc, (const int32_t *)tmp.p[5], (const uint8_t *)tmp.p[2], (const int64_t *)tmp.p[3],
+                              (const int64_t *)tmp.p[4], (const double *)tmp.p[0], (const double *)tmp.p[1], h->ed, stride);
+            }
+            CKU(cudaStreamSynchronize(h->stream));
+            CKU(h->launch_err);
+        }
+        TICK("shard: edge records");
         h->to_index.clear(); h->to_index.shrink_to_fit();
         max_grid = std::max<int64_t>(max_grid, grid_for(nm, 256));
         // slot -> index into `ed` of the edge the stored block comes from
@@ -1118,6 +1144,7 @@ static int create_shard(pgo_handle *h, const double *vval, int64_t ne, const uin
         cudaFree(dse);
         CKU(ce);
     }
+    TICK("shard: half-edge stream");
     CKC(dalloc(h, &h->S, 1));
     CKC(dalloc(h, &h->partials, (size_t)4 * max_grid + 8));
     {

@@ -2,7 +2,9 @@
 // Not part of the ABI (include/pgo_b200.h is).
 #pragma once
 #include <algorithm>
+#include <chrono>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <string>
 #include <thread>
@@ -127,6 +129,10 @@ template <typename F> inline void parallel_for(int64_t n, int64_t grain, F f) {
     }
     for (auto &x : th) x.join();
 }
+
+// PGO_SYM_TIMING=1: wall time of the phases of pgo_create on stderr (needs a `double t_last = now_s();` in scope)
+inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+#define TICK(name) do { if (std::getenv("PGO_SYM_TIMING")) { double t_ = pgo::now_s(); std::fprintf(stderr, "[sym] %-28s %.3f s\n", name, t_ - t_last); t_last = t_; } } while (0)
 
 // lazily computed (only the structure checks and pgo_get_system need them)
 bool build_canonical(Symbolic &sym);      // brow_ptr / bcol / edge_slots

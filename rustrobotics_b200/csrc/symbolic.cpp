@@ -7,7 +7,6 @@
 #include "pgo_internal.h"
 
 #include <algorithm>
-#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -90,8 +89,6 @@ static void build_csr(HostLevel &L) {
     for (size_t k = 0; k < L.part_off.size(); k++) L.part_slot[k] = L.adj_ptr[L.part_off[k]];
 }
 
-static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
-#define TICK(name) do { if (getenv("PGO_SYM_TIMING")) { double t_ = now_s(); fprintf(stderr, "[sym] %-28s %.3f s\n", name, t_ - t_last); t_last = t_; } } while (0)
 // ------------------------------------------------------------------------------------------------
 bool build_canonical(Symbolic &S) {
     if (!S.brow_ptr.empty()) return true;
@@ -168,51 +165,58 @@ static int32_t aggregate_partition(const HostLevel &F, int k, int max_size, std:
     bool mixed = false;
     if (landmark) for (int64_t i = 0; i < n && !mixed; i++) mixed = landmark[i] != 0;
     if (!mixed) landmark = nullptr;
-    std::vector<int64_t> ptr(n + 1, 0);
-    std::vector<int32_t> nbr;
-    nbr.reserve(F.adj_ptr[r0 + n] - F.adj_ptr[r0]);
-    for (int64_t i = 0; i < n; i++) {
-        const size_t start = nbr.size();
-        if (!(landmark && landmark[i]))
-            for (int64_t p = F.adj_ptr[r0 + i]; p < F.adj_ptr[r0 + i + 1]; p++) {
-                const int64_t j = F.adj_nbr[p] - r0;
-                if (j >= 0 && j < n && j != i && !(landmark && landmark[j])) nbr.push_back((int32_t)j);
-            }
-        std::sort(nbr.begin() + start, nbr.end());
-        nbr.erase(std::unique(nbr.begin() + start, nbr.end()), nbr.end());
-        ptr[i + 1] = (int64_t)nbr.size();
-    }
+    // sorted unique in-partition neighbours of every row: row i's list is nbr[ptr[i] .. end[i])
+    const int64_t a0 = F.adj_ptr[r0];
+    std::vector<int64_t> ptr(n), end(n);
+    std::vector<int32_t> nbr(std::max<int64_t>(F.adj_ptr[r0 + n] - a0, 1));
+    parallel_for(n, 4096, [&](int64_t i0, int64_t i1) {
+        for (int64_t i = i0; i < i1; i++) {
+            int32_t *b = nbr.data() + (F.adj_ptr[r0 + i] - a0), *e = b;
+            if (!(landmark && landmark[i]))
+                for (int64_t p = F.adj_ptr[r0 + i]; p < F.adj_ptr[r0 + i + 1]; p++) {
+                    const int64_t j = F.adj_nbr[p] - r0;
+                    if (j >= 0 && j < n && j != i && !(landmark && landmark[j])) *e++ = (int32_t)j;
+                }
+            std::sort(b, e);
+            e = std::unique(b, e);
+            ptr[i] = b - nbr.data(); end[i] = e - nbr.data();
+        }
+    });
     if (landmark) for (int64_t i = 0; i < n; i++) if (landmark[i]) agg[i] = -2;      // not a candidate in the three passes below
     int32_t nc = 0;
     for (int64_t i = 0; i < n; i++) {
         if (agg[i] != -1) continue;
         bool free_nb = true;
-        for (int64_t p = ptr[i]; p < ptr[i + 1] && free_nb; p++) free_nb = agg[nbr[p]] < 0;
+        for (int64_t p = ptr[i]; p < end[i] && free_nb; p++) free_nb = agg[nbr[p]] < 0;
         if (!free_nb) continue;
         agg[i] = nc;
         int sz = 1;
-        for (int64_t p = ptr[i]; p < ptr[i + 1] && sz < max_size; p++) { agg[nbr[p]] = nc; sz++; }
+        for (int64_t p = ptr[i]; p < end[i] && sz < max_size; p++) { agg[nbr[p]] = nc; sz++; }
         nc++;
     }
+    // a free row joins the root aggregate most of its neighbours are in (the state after the root pass: rows are independent)
     std::vector<int32_t> snap(agg), cand;
-    for (int64_t i = 0; i < n; i++) {
-        if (agg[i] != -1) continue;
-        cand.clear();
-        for (int64_t p = ptr[i]; p < ptr[i + 1]; p++) if (snap[nbr[p]] >= 0) cand.push_back(snap[nbr[p]]);
-        if (cand.empty()) continue;
-        std::sort(cand.begin(), cand.end());
-        int32_t best = cand[0]; int bc = 0, run = 0;
-        for (size_t q = 0; q < cand.size(); q++) {
-            run = (q > 0 && cand[q] == cand[q - 1]) ? run + 1 : 1;
-            if (run > bc) { bc = run; best = cand[q]; }
+    parallel_for(n, 8192, [&](int64_t i0, int64_t i1) {
+        std::vector<int32_t> cand;
+        for (int64_t i = i0; i < i1; i++) {
+            if (snap[i] != -1) continue;
+            cand.clear();
+            for (int64_t p = ptr[i]; p < end[i]; p++) if (snap[nbr[p]] >= 0) cand.push_back(snap[nbr[p]]);
+            if (cand.empty()) continue;
+            std::sort(cand.begin(), cand.end());
+            int32_t best = cand[0]; int bc = 0, run = 0;
+            for (size_t q = 0; q < cand.size(); q++) {
+                run = (q > 0 && cand[q] == cand[q - 1]) ? run + 1 : 1;
+                if (run > bc) { bc = run; best = cand[q]; }
+            }
+            agg[i] = best;
         }
-        agg[i] = best;
-    }
+    });
     for (int64_t i = 0; i < n; i++) {
         if (agg[i] >= 0 || agg[i] == -2) continue;
         agg[i] = nc;
         int sz = 1;
-        for (int64_t p = ptr[i]; p < ptr[i + 1] && sz < max_size; p++) if (agg[nbr[p]] == -1) { agg[nbr[p]] = nc; sz++; }
+        for (int64_t p = ptr[i]; p < end[i] && sz < max_size; p++) if (agg[nbr[p]] == -1) { agg[nbr[p]] = nc; sz++; }
         nc++;
     }
     if (!landmark) return nc;
@@ -223,7 +227,7 @@ static int32_t aggregate_partition(const HostLevel &F, int k, int max_size, std:
         std::vector<std::vector<int32_t>> cadj(nc);
         for (int64_t i = 0; i < n; i++) {
             if (landmark[i]) continue;
-            for (int64_t p = ptr[i]; p < ptr[i + 1]; p++) if (agg[nbr[p]] != agg[i]) cadj[agg[i]].push_back(agg[nbr[p]]);
+            for (int64_t p = ptr[i]; p < end[i]; p++) if (agg[nbr[p]] != agg[i]) cadj[agg[i]].push_back(agg[nbr[p]]);
         }
         std::vector<int32_t> pair(nc, -1);
         int32_t np = 0;
@@ -314,77 +318,69 @@ static void build_coarse_level(HostLevel &F, HostLevel &C, const std::vector<std
     if (jds) build_jds(C); else build_csr(C);
     TICK("  bcl: storage");
     // Galerkin targets of every fine block, local to the owning partition: element offset of component 0 of the coarse
-    // block inside the partition's val array + the stride between components (CSR: 9 s, 1 ; JDS: component-major)
+    // block inside the partition's val array + the stride between components (CSR: 9 s, 1 ; JDS: component-major).
+    // Contributor lists of the deterministic (atomics-free) Galerkin product (block CSR coarse levels): every fine block is first
+    // projected into a staging buffer in storage order (coalesced), then ONE group of lanes per coarse block sums its contributors
+    // in ascending stage order (stored blocks by slot, then the diagonal blocks by row).
+    // Both come out of walks over the COARSE rows: every contributor of the blocks of coarse row I (its diagonal block and its
+    // stored blocks) is a block of one of I's members, so a coarse row is counted, filled and sorted by one thread, without atomics.
     F.ctgt.assign(F.n_slots, 0);
     F.cstr.assign(F.n_slots, 1);
-    for (int k = 0; k < world; k++)
-        parallel_for(F.part_real[k], 4096, [&, k](int64_t i0, int64_t i1) {
-        for (int64_t r = F.part_off[k] + i0; r < F.part_off[k] + i1; r++) {
-            const int32_t I = F.agg[r];
-            for (int64_t p = F.adj_ptr[r]; p < F.adj_ptr[r + 1]; p++) {
-                const int32_t J = F.agg[F.adj_nbr[p]];
-                const int64_t slot = F.adj_slot[p];
-                const int kc = merge ? 0 : k;
-                if (I == J) { F.ctgt[slot] = (int32_t)(-1 - (I - C.part_off[kc])); continue; }
-                auto b = C.adj_nbr.begin() + C.adj_ptr[I], e = C.adj_nbr.begin() + C.adj_ptr[I + 1];
-                const int64_t q = std::lower_bound(b, e, J) - C.adj_nbr.begin();
-                const int64_t cs = C.adj_slot[q] - C.part_slot[kc];
-                if (jds) {
-                    const int64_t lane = I & 31;
-                    F.ctgt[slot] = (int32_t)((cs - lane) * DD + lane);
-                    F.cstr[slot] = C.adj_cnt[q];
-                } else F.ctgt[slot] = (int32_t)(cs * DD);
-            }
-        }
-        });
-    TICK("  bcl: galerkin targets");
-    // Contributor lists of the deterministic (atomics-free) Galerkin product: every fine block is first projected into a staging
-    // buffer in storage order (coalesced), then ONE group of lanes per coarse block sums its contributors in this fixed order.
     F.gal_ptr.assign(world, {});
     F.gal_src.assign(world, {});
-    if (!jds) {
-        {
-            for (int64_t k = 0; k < world; k++) {
-                const int kc = merge ? 0 : (int)k;
-                const int64_t crows = C.part_off[kc + 1] - C.part_off[kc], cslots = C.part_slot[kc + 1] - C.part_slot[kc];
-                const int64_t fr0 = F.part_off[k], fs0 = F.part_slot[k], fslots = F.part_slot[k + 1] - fs0;
-                const int64_t nblk = crows + cslots;
-                std::vector<int32_t> &ptr = F.gal_ptr[k], &src = F.gal_src[k];
-                ptr.assign(nblk + 1, 0);
-                auto target = [&](int32_t ct) -> int64_t { return ct < 0 ? (int64_t)(-1 - ct) : crows + ct / DD; };
-                // contributors of every coarse block in ascending stage order (stored blocks by slot, then the diagonal blocks by row):
-                // counted and scattered by all cores, then every segment is sorted, so the lists do not depend on the thread count
-                std::vector<int32_t> slot_tgt(fslots, -1);                 // padding slots of the sliced storage have no block
-                parallel_for(F.part_real[k], 8192, [&](int64_t a, int64_t b2) {
-                    for (int64_t r = fr0 + a; r < fr0 + b2; r++)
-                        for (int64_t q = F.adj_ptr[r]; q < F.adj_ptr[r + 1]; q++) slot_tgt[F.adj_slot[q] - fs0] = (int32_t)target(F.ctgt[F.adj_slot[q]]);
-                });
-                std::vector<std::atomic<int32_t>> cnt(nblk);
-                parallel_for(nblk, 65536, [&](int64_t a, int64_t b2) { for (int64_t q = a; q < b2; q++) cnt[q].store(0, std::memory_order_relaxed); });
-                parallel_for(fslots, 65536, [&](int64_t a, int64_t b2) {
-                    for (int64_t sl = a; sl < b2; sl++) if (slot_tgt[sl] >= 0) cnt[slot_tgt[sl]].fetch_add(1, std::memory_order_relaxed);
-                });
-                parallel_for(F.part_real[k], 65536, [&](int64_t a, int64_t b2) {
-                    for (int64_t i = a; i < b2; i++) cnt[F.agg[fr0 + i] - C.part_off[kc]].fetch_add(1, std::memory_order_relaxed);
-                });
-                for (int64_t q = 0; q < nblk; q++) ptr[q + 1] = ptr[q] + cnt[q].load(std::memory_order_relaxed);
-                src.resize(ptr[nblk]);
-                parallel_for(nblk, 65536, [&](int64_t a, int64_t b2) { for (int64_t q = a; q < b2; q++) cnt[q].store(0, std::memory_order_relaxed); });
-                parallel_for(fslots, 65536, [&](int64_t a, int64_t b2) {
-                    for (int64_t sl = a; sl < b2; sl++) {
-                        const int32_t t = slot_tgt[sl];
-                        if (t >= 0) src[ptr[t] + cnt[t].fetch_add(1, std::memory_order_relaxed)] = (int32_t)sl;
+    for (int k = 0; k < world; k++) {
+        const int kc = merge ? 0 : k;
+        const int64_t c0 = C.part_off[kc], crows = C.part_off[kc + 1] - c0, cs0 = C.part_slot[kc], cslots = C.part_slot[kc + 1] - cs0;
+        const int64_t I0 = merge ? C.src_off[k] : c0, I1 = merge ? C.src_off[k + 1] : c0 + C.part_real[kc];   // coarse rows built from partition k
+        const int64_t fr0 = F.part_off[k], fs0 = F.part_slot[k], fslots = F.part_slot[k + 1] - fs0;
+        const int64_t nblk = crows + cslots;
+        std::vector<int32_t> &ptr = F.gal_ptr[k], &src = F.gal_src[k];
+        if (!jds) ptr.assign(nblk + 1, 0);
+        // coarse block id (local to the coarse partition) of a target: [0, crows) diagonal blocks, crows + s stored block s
+        auto block_of = [&](int32_t ct) -> int64_t { return ct < 0 ? (int64_t)(-1 - ct) : crows + ct / DD; };
+        parallel_for(I1 - I0, 512, [&](int64_t a, int64_t b2) {
+            for (int64_t I = I0 + a; I < I0 + b2; I++) {
+                const auto cb = C.adj_nbr.begin() + C.adj_ptr[I], ce = C.adj_nbr.begin() + C.adj_ptr[I + 1];
+                for (int64_t m = C.mem_ptr[I]; m < C.mem_ptr[I + 1]; m++) {
+                    const int64_t r = C.mem_idx[m];
+                    if (!jds) ptr[(I - c0) + 1]++;                                      // the member's diagonal block
+                    for (int64_t p = F.adj_ptr[r]; p < F.adj_ptr[r + 1]; p++) {
+                        const int32_t J = F.agg[F.adj_nbr[p]];
+                        const int64_t slot = F.adj_slot[p];
+                        if (I == J) { F.ctgt[slot] = (int32_t)(-1 - (I - c0)); if (!jds) ptr[(I - c0) + 1]++; continue; }
+                        const int64_t q = std::lower_bound(cb, ce, J) - C.adj_nbr.begin();
+                        const int64_t cs = C.adj_slot[q] - cs0;
+                        if (jds) {
+                            const int64_t lane = I & 31;
+                            F.ctgt[slot] = (int32_t)((cs - lane) * DD + lane);
+                            F.cstr[slot] = C.adj_cnt[q];
+                        } else { F.ctgt[slot] = (int32_t)(cs * DD); ptr[crows + cs + 1]++; }
                     }
-                });
-                parallel_for(F.part_real[k], 65536, [&](int64_t a, int64_t b2) {
-                    for (int64_t i = a; i < b2; i++) {
-                        const int64_t t = F.agg[fr0 + i] - C.part_off[kc];
-                        src[ptr[t] + cnt[t].fetch_add(1, std::memory_order_relaxed)] = (int32_t)(fslots + i);
-                    }
-                });
-                parallel_for(nblk, 4096, [&](int64_t a, int64_t b2) { for (int64_t q = a; q < b2; q++) std::sort(src.begin() + ptr[q], src.begin() + ptr[q + 1]); });
+                }
             }
-        }
+        });
+        if (jds) continue;
+        for (int64_t q = 0; q < nblk; q++) ptr[q + 1] += ptr[q];
+        src.resize(ptr[nblk]);
+        parallel_for(I1 - I0, 512, [&](int64_t a, int64_t b2) {
+            std::vector<int32_t> cur;                                                   // fill position of row I's blocks: [0] diagonal, [1 + j] stored block j
+            for (int64_t I = I0 + a; I < I0 + b2; I++) {
+                const int64_t ns = C.adj_ptr[I + 1] - C.adj_ptr[I], sb = ns > 0 ? C.adj_slot[C.adj_ptr[I]] - cs0 : 0;      // block CSR: the row's slots are contiguous
+                cur.assign(1 + ns, 0);
+                cur[0] = ptr[I - c0];
+                for (int64_t j = 0; j < ns; j++) cur[1 + j] = ptr[crows + sb + j];
+                for (int64_t m = C.mem_ptr[I]; m < C.mem_ptr[I + 1]; m++) {
+                    const int64_t r = C.mem_idx[m];
+                    for (int64_t p = F.adj_ptr[r]; p < F.adj_ptr[r + 1]; p++) {
+                        const int64_t slot = F.adj_slot[p], t = block_of(F.ctgt[slot]);
+                        src[cur[t < crows ? 0 : 1 + (t - crows - sb)]++] = (int32_t)(slot - fs0);
+                    }
+                }
+                for (int64_t m = C.mem_ptr[I]; m < C.mem_ptr[I + 1]; m++) src[cur[0]++] = (int32_t)(fslots + (C.mem_idx[m] - fr0));
+                std::sort(src.begin() + ptr[I - c0], src.begin() + ptr[I - c0 + 1]);
+                for (int64_t j = 0; j < ns; j++) std::sort(src.begin() + ptr[crows + sb + j], src.begin() + ptr[crows + sb + j + 1]);
+            }
+        });
     }
     TICK("  bcl: galerkin contributor lists");
 }
@@ -502,11 +498,13 @@ bool build_symbolic(Symbolic &S, const SymbolicOptions &opt,
         for (int k = 0; k < world; k++) {
             idv.resize(counts[k]);
             std::iota(idv.begin(), idv.end(), (int32_t)S.vrange[k]);
-            for (int64_t w = 0; w < counts[k]; w += window) {
-                const int64_t e = std::min<int64_t>(counts[k], w + window);
-                std::stable_sort(idv.begin() + w, idv.begin() + e, [&](int32_t a, int32_t b) { return deg[a] > deg[b]; });
-            }
-            for (int64_t i = 0; i < counts[k]; i++) { S.perm[L0.part_off[k] + i] = idv[i]; S.iperm[idv[i]] = (int32_t)(L0.part_off[k] + i); }
+            parallel_for((counts[k] + window - 1) / window, 8, [&](int64_t w0, int64_t w1) {
+                for (int64_t w = w0 * window; w < std::min<int64_t>(w1 * window, counts[k]); w += window) {
+                    const int64_t e = std::min<int64_t>(counts[k], w + window);
+                    std::stable_sort(idv.begin() + w, idv.begin() + e, [&](int32_t a, int32_t b) { return deg[a] > deg[b]; });
+                    for (int64_t i = w; i < e; i++) { S.perm[L0.part_off[k] + i] = idv[i]; S.iperm[idv[i]] = (int32_t)(L0.part_off[k] + i); }
+                }
+            });
         }
         TICK("storage order");
         // half edges per storage row, sorted by neighbour row

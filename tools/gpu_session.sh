@@ -55,6 +55,10 @@ PY
 abgj)
   for v in 1 0; do PGO_GJ_OLD=$v timeout 300 python tools/quick_perf.py --opts pcg_rtol=1e-9 2>&1 | tail -1 | sed "s/^/GJ_OLD=$v /"; done | tee gpurun_out/gj_$tag.log
   for v in 1 0; do PGO_GJ_OLD=$v timeout 300 python tools/quick_perf.py --se3 --poses 250000 --opts pcg_rtol=1e-9 2>&1 | tail -1 | sed "s/^/SE3 GJ_OLD=$v /"; done | tee -a gpurun_out/gj_$tag.log;;
+create)
+  nproc | sed 's/^/host cores: /' | tee gpurun_out/create_$tag.log
+  PGO_SYM_TIMING=1 timeout 300 python tools/time_create.py --repeats 3 2>&1 | tail -42 | tee -a gpurun_out/create_$tag.log
+  PGO_HOST_THREADS=1 PGO_SYM_TIMING=1 timeout 300 python tools/time_create.py --repeats 2 2>&1 | tail -42 | sed 's/^/1 thread: /' | tee -a gpurun_out/create_$tag.log;;
 abcs_removed)
   for v in 0 1; do PGO_STREAM_CS=$v timeout 300 python tools/quick_perf.py --opts pcg_rtol=1e-9 2>&1 | tail -1 | sed "s/^/STREAM_CS=$v /"; done | tee gpurun_out/stream_cs_$tag.log;;
 bundled)  # the reference's own datasets (BASELINE configs[0..2]) + configs[4]
