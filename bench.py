@@ -406,8 +406,8 @@ def run_b200(args):
         new_opt5 = {"new_s": t_new, "new_plus_optimize5_s": t_all, "gn_iterations_run": len(errs) - 1, "final_chi2": errs[-1],
                     "what": "PoseGraph(graph) + optimize(5) through the public API, host symbolic pass and uploads included (reference benches/graph_slam.rs:7-11 shape)"}
         pg2.close()
-    # ---- the same step with pgo_options.refine = 1 (one refinement round on a double-double residual): the mode that pins the poses of
-    # this 1M-pose step to 1e-6 m (tests/test_gpu_parity.py::test_config4_refined_step_is_within_1e_6_m_of_the_golden)
+    # ---- the same step with pgo_options.refine = 1 (one refinement round on a double-double residual): the mode that solves the assembled
+    # system exactly (1.4e-8 m; tests/test_gpu_parity.py::test_config4_solver_error_is_separated_from_the_conditioning_of_the_step)
     refined = None
     if world == 1 and n_shards == 1 and args.workload == "manhattan" and not args.no_secondary:
         pg3 = PoseGraph(graph=g, options=Options(device=local, pcg_rtol=args.pcg_rtol, preconditioner=args.preconditioner, refine=1, **extra))

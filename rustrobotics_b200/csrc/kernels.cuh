@@ -1555,27 +1555,27 @@ __global__ void __launch_bounds__(128) k_dense_assemble(LevelDev L, DenseMap dm,
     }
 }
 
-// Inverse of the dense coarsest matrix (symmetric positive definite, m <= 6 * 1024): right-looking BLOCKED Gauss-Jordan without
-// pivoting, panel width 32, as a persistent cooperative kernel with ONE grid barrier per panel.  With pivot block P = A[pp] the
-// panel step is
-//     A[pp] <- P^-1        A[p,r] <- P^-1 A[p,r] (= R)        A[r,p] <- -A[r,p] P^-1        A[r,r] <- A[r,r] - A[r,p] R
-// Every CTA recomputes the slice of R its 64x64 tiles need, so nothing has to be exchanged inside a panel step; the step reads `src`
-// and writes the whole matrix to `dst` (ping-pong, both L2-resident), which removes every read-after-write hazard between tiles.
-// The matrix is treated as padded with an identity block up to a multiple of 32.  The host passes the buffers such that the result
-// of the last panel lands in the caller's Ainv.
-constexpr int GJ_W = 32, GJ_T = 64;
-constexpr size_t GJ_SMEM = sizeof(double) * (2 * GJ_W * (GJ_W + 1) + 2 * GJ_W * GJ_T + GJ_T * (GJ_W + 1));
-// Second generation (round 2; the first one ran 32 redundant elimination steps per CTA and panel and used grid.sync(): 2.13 ms for the
-// 1221^2 matrix of config 4, this one 1.20 ms): same panel algebra and ping-pong buffers, restructured for latency.
-//   * the 32x32 pivot inverse of panel p+1 is produced DURING panel p (look-ahead): the CTA that owns the diagonal tile holding the
-//     next pivot block updates that tile first, inverts the block right away and publishes it, so after the barrier every CTA only
-//     loads 8 KB instead of running 32 dependent elimination steps itself;
-//   * the grid barrier is one atomic arrive + an acquire spin on a counter (the cooperative launch only guarantees co-residency),
-//     ~1 us instead of the cooperative-groups grid.sync();
+// Inverse of the dense coarsest matrix (symmetric positive definite, m <= 6 * 1024): blocked SWEEP operator (the symmetric form of
+// Gauss-Jordan, no pivoting), panel width 32, as a persistent cooperative kernel with ONE grid barrier per panel.  With pivot block
+// P = S[pp], R = S[p,r] and X = P^-1 R the panel step is
+//     S[pp] <- -P^-1        S[p,r] <- X        S[r,p] <- X^T        S[r,r] <- S[r,r] - R^T X
+// which keeps S symmetric; after the last panel S = -A^-1.  Only the 64x64 tiles on or above the diagonal are stored and updated --
+// half the work of plain Gauss-Jordan -- and a tile reads the panel rows / columns it needs from the stored triangle (transposed when
+// they lie below it).  Every CTA recomputes the slice of X its tiles need, so nothing has to be exchanged inside a panel step; the
+// step reads `src` and writes every stored tile to `dst` (ping-pong, both L2-resident), which removes every read-after-write hazard
+// between tiles.  The last panel writes -S, mirrored, so the caller's Ainv is the full matrix.  The matrix is treated as padded with
+// an identity block up to a multiple of 32.  The host passes the buffers such that the result of the last panel lands in Ainv.
+//   * the 32x32 pivot inverse of panel p+1 is produced DURING panel p (look-ahead) by one CTA that does nothing else: it updates
+//     just that block, inverts it (gj_invert32_cols) and publishes it, so after the barrier every CTA only loads 8 KB;
+//   * the grid barrier is one atomic arrive + an acquire spin on a counter (the cooperative launch only guarantees co-residency);
 //   * the panel product is register-blocked (6 shared loads per 8 FMAs).
-// A two-phase variant (R = P^-1 A[p, :] computed once per column block instead of once per tile, a second barrier per panel) measured
-// the same (profiles/r03n_gj3.log): the step is bound by its barriers and dependent L2 loads, ~31 us per panel, not by the flops.
-constexpr size_t GJ2_SMEM = GJ_SMEM + sizeof(double) * 2 * GJ_W * (GJ_W + 1);
+// History (1221^2 matrix of config 4): 2.13 ms (redundant elimination per CTA, grid.sync()) -> 1.20 ms (look-ahead, own barrier;
+// every tile of the full matrix: 400 tiles on 296 CTAs = two rounds per panel) -> 1.04 ms (symmetric: 210 tiles, one round; timers
+// inside the kernel then showed 16.6 us of each 26 us panel in the 32x32 look-ahead inverse on the CTA that also owned a tile,
+// profiles/r04a_gj_phases.log) -> 8.5 us for that inverse, on its own CTA, beside the tile updates (~10 us).  A two-phase variant
+// (X computed once per column block, a second barrier per panel) measured the same as the second one (profiles/r03n_gj3.log).
+constexpr int GJ_W = 32, GJ_T = 64;
+constexpr size_t GJ_SMEM = sizeof(double) * (4 * GJ_W * (GJ_W + 1) + GJ_W * (GJ_T + 1) + GJ_W * GJ_T + GJ_T * (GJ_W + 1));
 
 __device__ __forceinline__ void gj_grid_barrier(unsigned *bar, unsigned target) {
     __syncthreads();
@@ -1610,22 +1610,75 @@ __device__ __forceinline__ void gj_invert32(double (*Pb)[GJ_W][GJ_W + 1]) {
     }
 }
 
-__global__ void __launch_bounds__(256) k_dense_invert2(int m, double *__restrict__ bufA, double *__restrict__ bufB, double *__restrict__ pnext,
-                                                        unsigned *bar, unsigned bar_base) {
+// The same inverse for the look-ahead block, which sits on the critical path of every panel (16.6 us with the version above: a
+// block barrier, dynamic indexing and an fp64 division chain per step; 8.5 us with this one).  Thread (warp w, lane i) keeps
+// P[i][4w .. 4w+3] in registers through the 32 unrolled steps; the pivot row reaches the other lanes by shuffles inside each warp, the
+// multiplier column and the pivot's reciprocal -- computed one step ahead by the thread that owns the next pivot -- go through a
+// double-buffered shared-memory line (Pb[1]).
+__device__ __forceinline__ void gj_invert32_cols(double (*Pb)[GJ_W][GJ_W + 1]) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int BS = GJ_W + 2;
+    double *bc = &Pb[1][0][0];
+    double r[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) r[c] = Pb[0][lane][4 * w + c];
+    double ipn = 1.0 / r[0];                      // warp 0, lane 0: reciprocal of the first pivot
+#pragma unroll
+    for (int k = 0; k < GJ_W; k++) {
+        const int wk = k >> 2, ck = k & 3;
+        double *b = bc + (k & 1) * BS;
+        if (w == wk) {
+            b[lane] = r[ck];
+            if (lane == k) b[GJ_W] = ipn;
+        }
+        __syncthreads();
+        const double ip = b[GJ_W];
+        const double f = b[lane] * ip;
+        double pk[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) pk[c] = __shfl_sync(0xffffffffu, r[c], k);
+        if (lane == k) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) r[c] = (w == wk && c == ck) ? ip : pk[c] * ip;
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; c++) r[c] = (w == wk && c == ck) ? -f : fma(-f, pk[c], r[c]);
+        }
+        if (k + 1 < GJ_W && w == ((k + 1) >> 2)) ipn = 1.0 / r[(k + 1) & 3];
+    }
+#pragma unroll
+    for (int c = 0; c < 4; c++) Pb[0][lane][4 * w + c] = r[c];
+    __syncthreads();
+}
+
+// number of stored tiles (on or above the diagonal) and the position of stored tile t, rows first
+__host__ __device__ inline int gj_num_tiles(int nt) { return nt * (nt + 1) / 2; }
+__device__ __forceinline__ void gj_tile_of(int t, int nt, int &I, int &J) {
+    I = 0;
+    while (t >= nt - I) { t -= nt - I; I++; }
+    J = I + t;
+}
+
+__global__ void __launch_bounds__(256) k_dense_invert_sym(int m, double *__restrict__ bufA, double *__restrict__ bufB, double *__restrict__ pnext,
+                                                           unsigned *bar, unsigned bar_base) {
     PDL_ENTER();
     extern __shared__ double gj_smem[];
-    double (*Pb)[GJ_W][GJ_W + 1] = reinterpret_cast<double (*)[GJ_W][GJ_W + 1]>(gj_smem);                      // [2][32][33] current pivot inverse
-    double (*Xr)[GJ_T] = reinterpret_cast<double (*)[GJ_T]>(gj_smem + 2 * GJ_W * (GJ_W + 1));                 // [32][64] raw panel rows
-    double (*Xb)[GJ_T] = reinterpret_cast<double (*)[GJ_T]>(gj_smem + 2 * GJ_W * (GJ_W + 1) + GJ_W * GJ_T);   // [32][64] R (or P^-1 columns)
-    double (*Cb)[GJ_W + 1] = reinterpret_cast<double (*)[GJ_W + 1]>(gj_smem + 2 * GJ_W * (GJ_W + 1) + 2 * GJ_W * GJ_T);   // [64][33]
-    double (*Pn)[GJ_W][GJ_W + 1] = reinterpret_cast<double (*)[GJ_W][GJ_W + 1]>(gj_smem + GJ_SMEM / sizeof(double));        // [2][32][33] look-ahead block
+    double *sp = gj_smem;
+    double (*Pb)[GJ_W][GJ_W + 1] = reinterpret_cast<double (*)[GJ_W][GJ_W + 1]>(sp); sp += 2 * GJ_W * (GJ_W + 1);     // [2][32][33] current pivot inverse
+    double (*Pn)[GJ_W][GJ_W + 1] = reinterpret_cast<double (*)[GJ_W][GJ_W + 1]>(sp); sp += 2 * GJ_W * (GJ_W + 1);     // [2][32][33] look-ahead block
+    double (*Xr)[GJ_T + 1] = reinterpret_cast<double (*)[GJ_T + 1]>(sp); sp += GJ_W * (GJ_T + 1);                     // [32][65] raw panel rows
+    double (*Xb)[GJ_T] = reinterpret_cast<double (*)[GJ_T]>(sp); sp += GJ_W * GJ_T;                                   // [32][64] X (P^-1 in the pivot columns)
+    double (*Cb)[GJ_W + 1] = reinterpret_cast<double (*)[GJ_W + 1]>(sp);                                              // [64][33] panel columns
     const int tid = threadIdx.x;
-    const int nt = (m + GJ_T - 1) / GJ_T, n_panels = (m + GJ_W - 1) / GJ_W;
+    const int nt = (m + GJ_T - 1) / GJ_T, n_panels = (m + GJ_W - 1) / GJ_W, n_tiles = gj_num_tiles(nt);
+    const int G = (int)gridDim.x - 1;                    // CTAs 0 .. G-1 update tiles, CTA G produces the pivot inverses
+    const bool pivot_cta = (int)blockIdx.x == G;
     const double *src = bufA;
     double *dst = bufB;
     for (int pi = 0; pi < n_panels; pi++) {
-        const int p0 = pi * GJ_W;
-        if (pi == 0) {
+        const int p0 = pi * GJ_W, Ip = p0 / GJ_T;
+        const bool last = pi + 1 == n_panels;
+        if (pi == 0) {                                   // the first pivot: every CTA inverts it for itself
             for (int t = tid; t < GJ_W * GJ_W; t += 256) {
                 const int i = t / GJ_W, j = t % GJ_W;
                 Pb[0][i][j] = (i < m && j < m) ? __ldcg(src + (int64_t)i * m + j) : (i == j ? 1.0 : 0.0);
@@ -1638,29 +1691,78 @@ __global__ void __launch_bounds__(256) k_dense_invert2(int m, double *__restrict
             __syncthreads();
         }
         const double (*Pinv)[GJ_W + 1] = Pb[0];
-        // the diagonal tile that holds the NEXT pivot block goes first on the CTA that owns it
-        const int np0 = p0 + GJ_W;
-        const bool has_next = pi + 1 < n_panels;
-        const int ntile = (np0 / GJ_T) * nt + np0 / GJ_T;
-        const int first = (has_next && ntile % (int)gridDim.x == (int)blockIdx.x) ? ntile : -1;
-        for (int k = first >= 0 ? -1 : 0; ; k++) {      // k = -1: the priority tile; then the CTA's other tiles in order
-            int tile = first;
-            if (k >= 0) {
-                tile = (int)blockIdx.x + k * (int)gridDim.x;
-                if (tile >= nt * nt) break;
-                if (tile == first) continue;
+        if (pivot_cta) {
+            // Look-ahead: the NEXT pivot block as this panel leaves it, S[nn] - S[p,n]^T P^-1 S[p,n], inverted and published while the
+            // other CTAs update their tiles (they recompute this block as part of its tile)
+            if (!last) {
+                const int np0 = p0 + GJ_W;
+                const int i = tid >> 3, jq = (tid & 7) * 4;
+                for (int t = tid; t < GJ_W * GJ_W; t += 256) {
+                    const int l = t / GJ_W, jj = t % GJ_W;
+                    const int gi = p0 + l, gj = np0 + jj;
+                    Xr[l][jj] = (gi < m && gj < m) ? __ldcg(src + (int64_t)gi * m + gj) : 0.0;      // S[p, n]: on or above the diagonal
+                }
+                double d[4];
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const int gi = np0 + i, gj = np0 + jq + c;
+                    d[c] = (gi < m && gj < m) ? __ldcg(src + (int64_t)gi * m + gj) : (gi == gj ? 1.0 : 0.0);
+                }
+                __syncthreads();
+                double x[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 8
+                for (int q = 0; q < GJ_W; q++) {
+                    const double pv = Pinv[i][q];
+#pragma unroll
+                    for (int c = 0; c < 4; c++) x[c] = fma(pv, Xr[q][jq + c], x[c]);
+                }
+#pragma unroll
+                for (int c = 0; c < 4; c++) Xb[i][jq + c] = x[c];
+                __syncthreads();
+#pragma unroll 8
+                for (int l = 0; l < GJ_W; l++) {
+                    const double rv = Xr[l][i];
+#pragma unroll
+                    for (int c = 0; c < 4; c++) d[c] = fma(-rv, Xb[l][jq + c], d[c]);
+                }
+#pragma unroll
+                for (int c = 0; c < 4; c++) Pn[0][i][jq + c] = d[c];
+                __syncthreads();
+                gj_invert32_cols(Pn);
+                double *pn = pnext + (size_t)((pi + 1) & 1) * GJ_W * GJ_W;
+                for (int t = tid; t < GJ_W * GJ_W; t += 256) pn[t] = Pn[0][t / GJ_W][t % GJ_W];
             }
-            const int i0 = (tile / nt) * GJ_T, j0 = (tile % nt) * GJ_T;
+        } else
+        for (int tile = (int)blockIdx.x; tile < n_tiles; tile += G) {
+            int I, J;
+            gj_tile_of(tile, nt, I, J);
+            const int i0 = I * GJ_T, j0 = J * GJ_T;
             __syncthreads();                              // the previous tile's shared arrays are free
-            for (int t = tid; t < GJ_W * GJ_T; t += 256) {       // panel rows of this column block
-                const int l = t / GJ_T, jj = t % GJ_T;
-                const int gi = p0 + l, gj = j0 + jj;
-                Xr[l][jj] = (gi < m && gj < m) ? __ldcg(src + (int64_t)gi * m + gj) : 0.0;
+            if (Ip <= J) {                                // panel rows of this column block: stored as they are ...
+                for (int t = tid; t < GJ_W * GJ_T; t += 256) {
+                    const int l = t / GJ_T, jj = t % GJ_T;
+                    const int gi = p0 + l, gj = j0 + jj;
+                    Xr[l][jj] = (gi < m && gj < m) ? __ldcg(src + (int64_t)gi * m + gj) : 0.0;
+                }
+            } else {                                      // ... or below the diagonal: read S[j, p] from the stored triangle
+                for (int t = tid; t < GJ_W * GJ_T; t += 256) {
+                    const int jj = t / GJ_W, l = t % GJ_W;
+                    const int gi = p0 + l, gj = j0 + jj;
+                    Xr[l][jj] = (gi < m && gj < m) ? __ldcg(src + (int64_t)gj * m + gi) : 0.0;
+                }
             }
-            for (int t = tid; t < GJ_T * GJ_W; t += 256) {       // panel columns of this row block
-                const int ii = t / GJ_W, l = t % GJ_W;
-                const int gi = i0 + ii, gj = p0 + l;
-                Cb[ii][l] = (gi < m && gj < m) ? __ldcg(src + (int64_t)gi * m + gj) : 0.0;
+            if (I <= Ip) {                                // panel columns of this row block
+                for (int t = tid; t < GJ_T * GJ_W; t += 256) {
+                    const int ii = t / GJ_W, l = t % GJ_W;
+                    const int gi = i0 + ii, gj = p0 + l;
+                    Cb[ii][l] = (gi < m && gj < m) ? __ldcg(src + (int64_t)gi * m + gj) : 0.0;
+                }
+            } else {
+                for (int t = tid; t < GJ_T * GJ_W; t += 256) {
+                    const int l = t / GJ_T, ii = t % GJ_T;
+                    const int gi = i0 + ii, gj = p0 + l;
+                    Cb[ii][l] = (gi < m && gj < m) ? __ldcg(src + (int64_t)gj * m + gi) : 0.0;
+                }
             }
             const int ty = tid >> 4, tx = tid & 15;
             double aij[4][4];                             // the tile's own entries: requested before the products need them
@@ -1672,7 +1774,7 @@ __global__ void __launch_bounds__(256) k_dense_invert2(int m, double *__restrict
                     aij[a][c] = (gi < m && gj < m) ? __ldcg(src + (int64_t)gi * m + gj) : 0.0;
                 }
             __syncthreads();
-            {   // X[l][j] = (P^-1 A[p, j])[l] outside the panel columns, P^-1[l][j - p0] inside.  Register-blocked: a warp owns four rows l
+            {   // X[l][j] = (P^-1 S[p, j])[l] outside the panel columns, P^-1[l][j - p0] inside.  Register-blocked: a warp owns four rows l
                 // (its P^-1 operands are warp-uniform shared-memory broadcasts), a lane two columns: 6 shared loads per 8 FMAs
                 const int l0 = (tid >> 5) * 4, jj0 = tid & 31;
                 double xa[4][2];
@@ -1723,19 +1825,17 @@ __global__ void __launch_bounds__(256) k_dense_invert2(int m, double *__restrict
                     const int gj = j0 + tx + 16 * c;
                     const bool jin = gj >= p0 && gj < p0 + GJ_W;
                     double v;
-                    if (iin) v = Xb[gi - p0][tx + 16 * c];            // P^-1 (jin) or R
-                    else if (jin) v = -acc[a][c];
+                    if (iin) v = jin ? -Xb[gi - p0][tx + 16 * c] : Xb[gi - p0][tx + 16 * c];     // -P^-1 or X
+                    else if (jin) v = acc[a][c];                                                   // X^T = S[r,p] P^-1
                     else v = aij[a][c] - acc[a][c];
-                    if (gi < m && gj < m) dst[(int64_t)gi * m + gj] = v;
-                    if (tile == first && gi >= np0 && gi < np0 + GJ_W && gj >= np0 && gj < np0 + GJ_W)     // the next pivot block, as updated by this panel
-                        Pn[0][gi - np0][gj - np0] = (gi < m && gj < m) ? v : (gi == gj ? 1.0 : 0.0);
+                    if (gi < m && gj < m) {
+                        if (!last) dst[(int64_t)gi * m + gj] = v;
+                        else {                            // A^-1 = -S, both triangles (a diagonal tile holds both of its own)
+                            dst[(int64_t)gi * m + gj] = -v;
+                            if (I != J) dst[(int64_t)gj * m + gi] = -v;
+                        }
+                    }
                 }
-            }
-            if (tile == first) {                          // look-ahead: invert the next pivot block now and publish it
-                __syncthreads();
-                gj_invert32(Pn);
-                double *pn = pnext + (size_t)((pi + 1) & 1) * GJ_W * GJ_W;
-                for (int t = tid; t < GJ_W * GJ_W; t += 256) pn[t] = Pn[0][t / GJ_W][t % GJ_W];
             }
         }
         gj_grid_barrier(bar, bar_base + (unsigned)(pi + 1) * gridDim.x);

@@ -587,7 +587,7 @@ template <int D> int amg_setup(pgo_handle *h) {
         else launch_k(h, k_dense_assemble<D, false>, C.grid128, 128, 0, C.d, h->dmap, 0, m, first);
         h->launch_count += 1;
         void *args[] = {(void *)&h->dense_m, (void *)&first, (void *)&second, (void *)&h->gj_pnext, (void *)&h->gj_bar, (void *)&h->gj_bar_base};
-        CK(cudaLaunchCooperativeKernel((void *)k_dense_invert2, dim3(h->invert_grid), dim3(256), args, GJ2_SMEM, h->stream));
+        CK(cudaLaunchCooperativeKernel((void *)k_dense_invert_sym, dim3(h->invert_grid), dim3(256), args, GJ_SMEM, h->stream));
         h->gj_bar_base += (unsigned)n_panels * (unsigned)h->invert_grid;
         h->launch_count += 1;
     }
@@ -1012,11 +1012,11 @@ static int create_shard(pgo_handle *h, const double *vval, int64_t ne, const uin
         int per_sm = 0, sms = 0;
         CKC(dalloc(h, &h->gj_pnext, (size_t)2 * GJ_W * GJ_W));
         CKC(dalloc(h, &h->gj_bar, 1));
-        CKU(cudaFuncSetAttribute(k_dense_invert2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GJ2_SMEM));
-        CKU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dense_invert2, 256, GJ2_SMEM));
+        CKU(cudaFuncSetAttribute(k_dense_invert_sym, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GJ_SMEM));
+        CKU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dense_invert_sym, 256, GJ_SMEM));
         CKU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
         const int nt = (m + GJ_T - 1) / GJ_T;
-        h->invert_grid = std::max(1, std::min(std::max(per_sm, 1) * sms, nt * nt));
+        h->invert_grid = std::max(2, std::min(std::max(per_sm, 1) * sms, gj_num_tiles(nt) + 1));      // + 1: the CTA that produces the pivot inverses
         CKU(cudaFuncSetAttribute(k_dense_apply<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (6 * 1024 + 8))));
         CKU(cudaFuncSetAttribute(k_dense_apply<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (6 * 1024 + 8))));
     }

@@ -59,6 +59,13 @@ create)
   nproc | sed 's/^/host cores: /' | tee gpurun_out/create_$tag.log
   PGO_SYM_TIMING=1 timeout 300 python tools/time_create.py --repeats 3 2>&1 | tail -42 | tee -a gpurun_out/create_$tag.log
   PGO_HOST_THREADS=1 PGO_SYM_TIMING=1 timeout 300 python tools/time_create.py --repeats 2 2>&1 | tail -42 | sed 's/^/1 thread: /' | tee -a gpurun_out/create_$tag.log;;
+sweep2)   # solver error (against this build's own refined solution) and error against the golden, around the bench tolerance
+  timeout 900 python tools/rtol_sweep.py 2e-9 1e-9 5e-10 2e-10 1e-10 3e-11 --own > gpurun_out/rtol_sweep2_$tag.log 2>&1; echo "sweep2 rc=$?"; cut -c1-420 gpurun_out/rtol_sweep2_$tag.log;;
+quick)
+  timeout 300 python tools/quick_perf.py --opts pcg_rtol=1e-9 2>&1 | tail -1 | tee gpurun_out/quick_$tag.log
+  timeout 300 python tools/quick_perf.py --se3 --poses 250000 --opts pcg_rtol=1e-9 2>&1 | tail -1 | sed "s/^/SE3 /" | tee -a gpurun_out/quick_$tag.log;;
+ncugj)    # one source-level capture of the dense coarsest inversion
+  timeout 600 ncu --set full --import-source on --clock-control none -k regex:k_dense_invert -c 1 -f -o gpurun_out/gj_$tag python tools/quick_perf.py --poses 100000 > gpurun_out/ncugj_$tag.log 2>&1; echo "ncu rc=$?"; tail -2 gpurun_out/ncugj_$tag.log;;
 abcs_removed)
   for v in 0 1; do PGO_STREAM_CS=$v timeout 300 python tools/quick_perf.py --opts pcg_rtol=1e-9 2>&1 | tail -1 | sed "s/^/STREAM_CS=$v /"; done | tee gpurun_out/stream_cs_$tag.log;;
 bundled)  # the reference's own datasets (BASELINE configs[0..2]) + configs[4]

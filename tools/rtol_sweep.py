@@ -27,6 +27,15 @@ s = gold["sample"]
 full = ROOT / "tests" / "golden" / "_manhattan_1m_step1_dx_full.npy"
 dx_full = np.load(full).reshape(-1, 3) if full.exists() else None
 print(f"truth: chi2_1 {float(gold['chi2_1']):.6f} |dx| {float(gold['norm_dx']):.6f}  fp64 noise floor xy {float(gold['fp64_noise_xy']):.2e} theta {float(gold['fp64_noise_theta']):.2e}", flush=True)
+# the solution of the system THIS build assembles (pgo_options.refine = 1: exact to ~1e-8 m): separates the solver's own error from
+# the distance between two fp64 assemblies of the step
+own = None
+if "--own" in flags and ngpu == 1:
+    pg = PoseGraph(graph=g, options=Options(pcg_rtol=1e-9, refine=1, **extra))
+    own = pg.linearize_and_solve()[0].reshape(-1, 3)
+    pg.close()
+    e = np.abs(own[s] - gold["dx_sample"])
+    print(f"own exact solution vs golden: xy {e[:, :2].max():.2e} theta {e[:, 2].max():.2e}", flush=True)
 for rtol in rtols:
     kw = dict(pcg_rtol=rtol, **extra)
     if ngpu > 1:
@@ -46,6 +55,9 @@ for rtol in rtols:
     row = dict(rtol=rtol, its=it, step_ms=sum(v[0] for k, v in tm.items() if k != "spmv_fine"), pcg_ms=tm["pcg"][0], wall_ms=wall * 1e3,
                chi2_rel=abs(c2 - float(gold["chi2_1"])) / float(gold["chi2_1"]), norm_dx_abs=abs(nd_ - float(gold["norm_dx"])),
                max_xy=float(e[:, :2].max()), max_theta=float(e[:, 2].max()), rms=float(np.sqrt((e ** 2).mean())))
+    if own is not None:
+        eo = np.abs(dx - own)
+        row.update(solver_err_xy=float(eo[:, :2].max()), solver_err_theta=float(eo[:, 2].max()))
     if dx_full is not None:
         ef = np.abs(dx - dx_full)
         row.update(full_max_xy=float(ef[:, :2].max()), full_max_theta=float(ef[:, 2].max()))
