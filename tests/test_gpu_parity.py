@@ -370,6 +370,25 @@ def test_config4_solver_error_is_separated_from_the_conditioning_of_the_step(bui
     assert d_gold[:, :2].max() <= max(POSE_ATOL, 10.0 * noise) and d_gold[:, 2].max() <= POSE_ATOL
 
 
+@pytest.mark.parametrize("case", ["simulation-pose-pose", "manhattan500", "sphere4x100"])
+def test_dense_coarsest_inverse_is_exact(built, case):
+    """A graph of at most 640 block rows has ONE level: the AMG preconditioner is the explicit inverse of H itself (k_dense_invert_sym:
+    blocked symmetric sweep over the upper-triangle tiles), so PCG converges in one iteration, two where cond(H) ~ 1e9 limits the
+    fp64 inverse to ~1e-8 relative (pcg_rtol is 1e-10 here) -- a direct check of that kernel on matrices of 1200^2 (19 tile rows),
+    1500^2 and 2400^2 (6x6 blocks)."""
+    from rustrobotics_b200.synthetic import manhattan_se2, sphere_se3
+    g = graph_of(load_golden(case)) if case.startswith("simulation") else manhattan_se2(500) if case == "manhattan500" else sphere_se3(4, 100)
+    pg = _pg(g, pcg_rtol=1e-10)
+    assert pg.level_sizes()[0] == [len(g["vertex_id"])]
+    dx, it = pg.linearize_and_solve()
+    assert it <= 2, it
+    import scipy.sparse as sp
+    cp, ri, vals, b = pg.system()
+    H = sp.csc_matrix((vals, ri, cp), shape=(len(b), len(b)))
+    assert np.abs(H @ dx - b).max() <= 1e-7 * np.abs(b).max()
+    pg.close()
+
+
 @pytest.mark.parametrize("n_gpus", [1, 2])
 def test_repeat_runs_are_bit_identical(built, n_gpus):
     """deterministic mode is the only mode: no atomics anywhere on the path (segmented assembly, single-writer Galerkin product,

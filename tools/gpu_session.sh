@@ -14,7 +14,7 @@ traffic)
   # PGO_WHILE=0: ncu does not see the kernels inside the body of a conditional (WHILE) graph node; the chunked graph runs the same kernels
   PGO_WHILE=0 timeout 1200 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --cache-control none \
       --profile-from-start off --csv --log-file gpurun_out/step_traffic_$tag.csv python tools/step_traffic.py > gpurun_out/step_traffic_$tag.log 2>&1; echo "traffic rc=$?"
-  tail -2 gpurun_out/step_traffic_$tag.log; python tools/summarize_traffic.py gpurun_out/step_traffic_$tag.csv gpurun_out/step_traffic_$tag.json | head -30;;
+  tail -2 gpurun_out/step_traffic_$tag.log; python tools/summarize_traffic.py gpurun_out/step_traffic_$tag.csv gpurun_out/step_traffic_$tag.json > gpurun_out/step_traffic_$tag.md; head -30 gpurun_out/step_traffic_$tag.md;;
 multi)   # on a box with N >= 2 GPUs:  gpurun --gpus N -- 'bash tools/gpu_session.sh TAG multi'
   N=$(nvidia-smi -L | wc -l)
   timeout 900 python -m pytest tests/test_multi_gpu.py tests/test_sharded.py -m gpu -q -rs > gpurun_out/pytest_multi_n${N}_$tag.log 2>&1; echo "pytest multi rc=$?"; tail -4 gpurun_out/pytest_multi_n${N}_$tag.log
