@@ -1144,27 +1144,29 @@ __device__ __forceinline__ void xfer_ptap(const double *h, const Xfer<6> &Pi, co
     }
 }
 
-// rc_I = sum_{i in I} P_i^T res_i   (one warp per coarse row; fixed summation order => deterministic)
+// rc_I = sum_{i in I} P_i^T res_i   (16 lanes per coarse row -- an aggregate has ~16 members --, two rows per warp; fixed summation
+// order => deterministic)
 template <int D>
 __device__ __forceinline__ void restrict_body(const LevelDev &F, const LevelDev &C, const double *__restrict__ res, double *__restrict__ rc, unsigned vb) {
     constexpr int VS = VecStride<D>::value;
-    const int lane = threadIdx.x & 31;
-    const int64_t I = (int64_t)vb * 8 + (threadIdx.x >> 5);
-    if (I >= C.n_pad) return;
+    const int sub = threadIdx.x & 15;
+    const int64_t I = (int64_t)vb * 16 + (threadIdx.x >> 4);
     double s[VS];
 #pragma unroll
     for (int a = 0; a < VS; a++) s[a] = 0.0;
     if (I < C.n) {
-        for (int64_t m = C.mem_ptr[I] + lane; m < C.mem_ptr[I + 1]; m += 32) {
+        for (int64_t m = C.mem_ptr[I] + sub; m < C.mem_ptr[I + 1]; m += 16) {
             const int64_t i = C.mem_idx[m];
             double r[VS];
             ld_vec<VS>(res + i * VS, r);
             xfer_restrict(xfer_own<D>(F, i), r, s);
         }
-#pragma unroll
-        for (int a = 0; a < D; a++) s[a] = warp_sum(s[a]);
     }
-    if (lane == 0) st_vec<VS>(rc + I * VS, s);
+#pragma unroll
+    for (int a = 0; a < D; a++)
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) s[a] += __shfl_xor_sync(0xffffffffu, s[a], o);
+    if (sub == 0 && I < C.n_pad) st_vec<VS>(rc + I * VS, s);
 }
 template <int D>
 __global__ void __launch_bounds__(256) k_restrict(LevelDev F, LevelDev C, const double *__restrict__ res, double *__restrict__ rc,

@@ -303,7 +303,7 @@ template <int D, int FINK, bool PRE = false> void cycle(pgo_handle *h, int l, co
     // no barrier behind this product: xa is only overwritten by the prolongation, and every path to it crosses a barrier (the
     // gather of the first replicated level's right-hand side, or the barriers inside a sharded coarse solve)
     spmv_any<D, 1, true>(h, l, B.xa, rhs, B.res, 0.0, 1);
-    launch_k(h, k_restrict<D>, C.gridw, 256, 0, B.d, C.d, B.res, C.rhs, h->S);
+    launch_k(h, k_restrict<D>, grid_for(C.d.n_pad, 16), 256, 0, B.d, C.d, B.res, C.rhs, h->S);
     h->launch_count += 1;
     if (C.first_repl) {                              // every rank restricted onto its own aggregates: all-gather the coarse rhs
         lbarrier(h, l);
