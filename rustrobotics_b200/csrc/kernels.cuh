@@ -875,9 +875,9 @@ __global__ void __launch_bounds__(256) k_to_float(int64_t n, const double *__res
 // x += alpha p ; r -= alpha q
 template <int D>
 __global__ void __launch_bounds__(256) k_update_xr(int64_t n_pad, double *__restrict__ x, double *__restrict__ r,
-                                                    const double *__restrict__ p, const double *__restrict__ q, const Scalars *S) {
+                                                    const double *__restrict__ p, const double *__restrict__ q, const Scalars *S, int check_done) {
     PDL_ENTER();
-    if (ld_done(S)) return;
+    if (check_done && ld_done(S)) return;
     constexpr int VS = VecStride<D>::value;
     const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 2;       // in doubles
     if (i >= n_pad * VS) return;
@@ -894,9 +894,9 @@ __global__ void __launch_bounds__(256) k_update_xr(int64_t n_pad, double *__rest
 // the new residual is used while it is still in registers)
 template <int D>
 __global__ void __launch_bounds__(128) k_update_xr_dinv(LevelDev L, double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p,
-                                                         const double *__restrict__ q, double *__restrict__ xa, double omega, const Scalars *S) {
+                                                         const double *__restrict__ q, double *__restrict__ xa, double omega, const Scalars *S, int check_done) {
     PDL_ENTER();
-    if (ld_done(S)) return;
+    if (check_done && ld_done(S)) return;
     constexpr int VS = VecStride<D>::value;
     const int64_t row = (int64_t)blockIdx.x * 128 + threadIdx.x;
     if (row >= L.n_pad) return;
@@ -934,17 +934,25 @@ __global__ void __launch_bounds__(128) k_update_xr_dinv(LevelDev L, double *__re
 
 // p = z + beta p
 template <int D>
-__global__ void __launch_bounds__(256) k_update_p(int64_t n_pad, double *__restrict__ p, const double *__restrict__ z, const Scalars *S) {
+__global__ void __launch_bounds__(256) k_update_p(int64_t n_pad, double *__restrict__ p, const double *__restrict__ z, const Scalars *S, int check_done) {
     PDL_ENTER();
-    if (ld_done(S)) return;
-    constexpr int VS = VecStride<D>::value;
-    const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 2;
-    if (i >= n_pad * VS) return;
+    if (check_done && ld_done(S)) return;
+    constexpr int VS = VecStride<D>::value, U = 4;          // four 16-byte pairs per thread, all loads in flight before the scalar arrives
+    const int64_t n2 = n_pad * VS / 2, i0 = (int64_t)blockIdx.x * 256 * U + threadIdx.x;
+    double2 *p2 = reinterpret_cast<double2 *>(p);
+    const double2 *z2 = reinterpret_cast<const double2 *>(z);
+    double2 pv[U], zv[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const int64_t i = i0 + u * 256;
+        if (i < n2) { pv[u] = p2[i]; zv[u] = z2[i]; }
+    }
     const double b = S->beta;
-    double2 pv = *reinterpret_cast<double2 *>(p + i);
-    const double2 zv = *reinterpret_cast<const double2 *>(z + i);
-    pv.x = fma(b, pv.x, zv.x); pv.y = fma(b, pv.y, zv.y);
-    *reinterpret_cast<double2 *>(p + i) = pv;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const int64_t i = i0 + u * 256;
+        if (i < n2) p2[i] = make_double2(fma(b, pv[u].x, zv[u].x), fma(b, pv[u].y, zv[u].y));
+    }
 }
 
 // K-cycle vector updates at level lvl:  WHICH 0: out = a - alpha_l b      WHICH 1: out = coef1_l a + coef2_l b
@@ -966,9 +974,9 @@ __device__ __forceinline__ void kcombine_body(int64_t n_doubles, const double *_
 }
 template <int WHICH>
 __global__ void __launch_bounds__(256) k_kcombine(int64_t n_doubles, const double *__restrict__ a, const double *__restrict__ b,
-                                                   double *__restrict__ out, const Scalars *S, int lvl, const double *__restrict__ third) {
+                                                   double *__restrict__ out, const Scalars *S, int lvl, const double *__restrict__ third, int check_done) {
     PDL_ENTER();
-    if (ld_done(S)) return;
+    if (check_done && ld_done(S)) return;
     kcombine_body<WHICH>(n_doubles, a, b, out, S, lvl, blockIdx.x, third);
 }
 
@@ -977,9 +985,9 @@ __global__ void __launch_bounds__(256) k_kcombine(int64_t n_doubles, const doubl
 // STEP 2 (three-step K-cycle): r2 = r1 - e2 v2 + e1 v1, in place (rhs == r1), with w = v2
 template <int D, int STEP>
 __global__ void __launch_bounds__(128) k_kresid_dinv(LevelDev L, const double *rhs, const double *__restrict__ v1, const double *__restrict__ w, double *r1,
-                                                      double *__restrict__ xa, double omega, const Scalars *S, int lvl) {
+                                                      double *__restrict__ xa, double omega, const Scalars *S, int lvl, int check_done) {
     PDL_ENTER();
-    if (ld_done(S)) return;
+    if (check_done && ld_done(S)) return;
     constexpr int VS = VecStride<D>::value;
     const int64_t row = (int64_t)blockIdx.x * 128 + threadIdx.x;
     if (row >= L.n_pad) return;
@@ -1170,9 +1178,9 @@ __device__ __forceinline__ void restrict_body(const LevelDev &F, const LevelDev 
 }
 template <int D>
 __global__ void __launch_bounds__(256) k_restrict(LevelDev F, LevelDev C, const double *__restrict__ res, double *__restrict__ rc,
-                                                   const Scalars *S) {
+                                                   const Scalars *S, int check_done) {
     PDL_ENTER();
-    if (ld_done(S)) return;
+    if (check_done && ld_done(S)) return;
     restrict_body<D>(F, C, res, rc, blockIdx.x);
 }
 
@@ -1192,9 +1200,9 @@ __device__ __forceinline__ void prolong_body(const LevelDev &F, const double *__
 // x_i += P_i (coef1 c1 + coef2 c2)_{agg(i)}: prolongation fused with the final combination of the coarse level's K-cycle
 template <int D>
 __global__ void __launch_bounds__(128) k_prolong_k(LevelDev F, const double *__restrict__ c1, const double *__restrict__ c2, const double *__restrict__ c3,
-                                                    double *__restrict__ x, const Scalars *S, int clvl) {
+                                                    double *__restrict__ x, const Scalars *S, int clvl, int check_done) {
     PDL_ENTER();
-    if (ld_done(S)) return;
+    if (check_done && ld_done(S)) return;
     constexpr int VS = VecStride<D>::value;
     const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
     if (i >= F.n) return;
@@ -1216,9 +1224,9 @@ __global__ void __launch_bounds__(128) k_prolong_k(LevelDev F, const double *__r
     st_vec<VS>(x + i * VS, xi);
 }
 template <int D>
-__global__ void __launch_bounds__(128) k_prolong(LevelDev F, const double *__restrict__ ec, double *__restrict__ x, const Scalars *S) {
+__global__ void __launch_bounds__(128) k_prolong(LevelDev F, const double *__restrict__ ec, double *__restrict__ x, const Scalars *S, int check_done) {
     PDL_ENTER();
-    if (ld_done(S)) return;
+    if (check_done && ld_done(S)) return;
     prolong_body<D, 128>(F, ec, x, blockIdx.x);
 }
 
@@ -1886,9 +1894,9 @@ __device__ __forceinline__ void dense_apply_body(int64_t n_local, const DenseMap
 }
 template <int D>
 __global__ void __launch_bounds__(256) k_dense_apply(int64_t n_local, DenseMap dm, int rank, int world, int m, const double *__restrict__ Ainv,
-                                                      const __grid_constant__ XRef rr, double *__restrict__ x, const Scalars *S) {
+                                                      const __grid_constant__ XRef rr, double *__restrict__ x, const Scalars *S, int check_done) {
     PDL_ENTER();
-    if (ld_done(S)) return;
+    if (check_done && ld_done(S)) return;
     dense_apply_body<D>(n_local, dm, rank, world, m, Ainv, rr, x, blockIdx.x);
 }
 

@@ -130,6 +130,8 @@ struct pgo_handle {
                                        // chunks of `chunk` iterations per launch, the host polling a pinned copy of the scalars)
     bool opt_while_sharded = false;    // PGO_WHILE=2
     bool pcg_while = false;            // ... and that is what pcg_graph holds
+    int chk = 1;                       // `check_done` argument of the kernels of a PCG iteration: 0 while the WHILE-loop body is captured (nothing
+                                       // runs behind the convergence flag there, and the flag's load is a dependent L2 round trip at the top of every kernel)
     int chunk = 8;
     int64_t launches_per_iter = 0;
     cudaEvent_t ev[PGO_NUM_PHASES + 2]{}, poll_ev[2]{};
@@ -271,7 +273,7 @@ template <int D> void coarse_solve(pgo_handle *h, int l, const double *rhs, doub
 template <int D> void dense_apply(pgo_handle *h, int l, const double *rhs, double *out) {
     LevelBuf &B = h->lv[l];      // always a local (single-GPU or replicated) level
     launch_k(h, k_dense_apply<D>, grid_for(B.d.n * D, 8), 256, sizeof(double) * h->dense_m, B.d.n, h->dmap, 0, 1, h->dense_m,
-                                                                                             h->Ainv, xref(h, rhs, true), out, h->S);
+                                                                                             h->Ainv, xref(h, rhs, true), out, h->S, h->chk);
     h->launch_count += 1;
 }
 
@@ -284,26 +286,26 @@ template <int D, int FINK, bool PRE = false> void cycle(pgo_handle *h, int l, co
         if (h->sym.dense_coarsest) dense_apply<D>(h, l, rhs, out);
         else {
             // no direct solve possible: a few damped block-Jacobi sweeps
-            launch_k(h, k_dinv_apply<D, FIN_NONE>, B.grid128, 128, 0, B.d, rhs, B.xa, B.omega, nullptr, h->S, h->partials, 1);
+            launch_k(h, k_dinv_apply<D, FIN_NONE>, B.grid128, 128, 0, B.d, rhs, B.xa, B.omega, nullptr, h->S, h->partials, h->chk);
             h->launch_count += 1;
             lbarrier(h, l);
-            spmv_any<D, 2, true>(h, l, B.xa, rhs, B.res, B.omega, 1);
+            spmv_any<D, 2, true>(h, l, B.xa, rhs, B.res, B.omega, h->chk);
             lbarrier(h, l);
-            spmv_any<D, 2, true>(h, l, B.res, rhs, out, B.omega, 1);
+            spmv_any<D, 2, true>(h, l, B.res, rhs, out, B.omega, h->chk);
             lbarrier(h, l);
         }
         return;
     }
     LevelBuf &C = h->lv[l + 1];
     if (!PRE) {
-        launch_k(h, k_dinv_apply<D, FIN_NONE>, B.grid128, 128, 0, B.d, rhs, B.xa, B.omega, nullptr, h->S, h->partials, 1);
+        launch_k(h, k_dinv_apply<D, FIN_NONE>, B.grid128, 128, 0, B.d, rhs, B.xa, B.omega, nullptr, h->S, h->partials, h->chk);
         h->launch_count += 1;
     }
     lbarrier(h, l);                                  // the peers' xa rows are final before the halo pull
     // no barrier behind this product: xa is only overwritten by the prolongation, and every path to it crosses a barrier (the
     // gather of the first replicated level's right-hand side, or the barriers inside a sharded coarse solve)
-    spmv_any<D, 1, true>(h, l, B.xa, rhs, B.res, 0.0, 1);
-    launch_k(h, k_restrict<D>, grid_for(C.d.n_pad, 16), 256, 0, B.d, C.d, B.res, C.rhs, h->S);
+    spmv_any<D, 1, true>(h, l, B.xa, rhs, B.res, 0.0, h->chk);
+    launch_k(h, k_restrict<D>, grid_for(C.d.n_pad, 16), 256, 0, B.d, C.d, B.res, C.rhs, h->S, h->chk);
     h->launch_count += 1;
     if (C.first_repl) {                              // every rank restricted onto its own aggregates: all-gather the coarse rhs
         lbarrier(h, l);
@@ -312,11 +314,11 @@ template <int D, int FINK, bool PRE = false> void cycle(pgo_handle *h, int l, co
     // a K-cycle level leaves its two search directions in C.c1 / C.c2; their final combination is folded into the prolongation
     const bool kfold = l + 1 != last && C.kcycle;
     coarse_solve<D>(h, l + 1, C.rhs, C.sol, kfold);
-    if (kfold) launch_k(h, k_prolong_k<D>, B.grid128, 128, 0, B.d, C.c1, C.c2, C.ksteps == 3 ? C.c3 : nullptr, B.xa, h->S, l + 1);
-    else launch_k(h, k_prolong<D>, B.grid128, 128, 0, B.d, C.sol, B.xa, h->S);
+    if (kfold) launch_k(h, k_prolong_k<D>, B.grid128, 128, 0, B.d, C.c1, C.c2, C.ksteps == 3 ? C.c3 : nullptr, B.xa, h->S, l + 1, h->chk);
+    else launch_k(h, k_prolong<D>, B.grid128, 128, 0, B.d, C.sol, B.xa, h->S, h->chk);
     h->launch_count += 1;
     lbarrier(h, l);                                  // the peers' xa rows are final before the halo pull
-    spmv<D, 2, FINK, true>(h, l, B.xa, rhs, out, B.omega, FINK == FIN_RZ ? h->q : nullptr, nullptr, 1);
+    spmv<D, 2, FINK, true>(h, l, B.xa, rhs, out, B.omega, FINK == FIN_RZ ? h->q : nullptr, nullptr, h->chk);
     if (FINK == FIN_NONE) lbarrier(h, l);            // `out` is final everywhere (FINK != NONE: the fused all-reduce is the barrier)
 }
 
@@ -326,23 +328,23 @@ template <int D> void coarse_solve(pgo_handle *h, int l, const double *rhs, doub
     const int last = (int)h->lv.size() - 1;
     if (l == last || !B.kcycle) { cycle<D, FIN_NONE>(h, l, rhs, out); return; }
     cycle<D, FIN_NONE>(h, l, rhs, B.c1);
-    spmv<D, 0, FIN_K1, true>(h, l, B.c1, nullptr, B.v1, 0.0, rhs, nullptr, 1);
+    spmv<D, 0, FIN_K1, true>(h, l, B.c1, nullptr, B.v1, 0.0, rhs, nullptr, h->chk);
     // r1 = rhs - alpha v1, fused with the pre-smoothing step of the second cycle
-    launch_k(h, k_kresid_dinv<D, 1>, B.grid128, 128, 0, B.d, rhs, B.v1, nullptr, B.r1, B.xa, B.omega, h->S, l);
+    launch_k(h, k_kresid_dinv<D, 1>, B.grid128, 128, 0, B.d, rhs, B.v1, nullptr, B.r1, B.xa, B.omega, h->S, l, h->chk);
     h->launch_count += 1;
     cycle<D, FIN_NONE, true>(h, l, B.r1, B.c2);
-    spmv<D, 0, FIN_K2, true>(h, l, B.c2, nullptr, B.v2, 0.0, B.v1, B.r1, 1);
+    spmv<D, 0, FIN_K2, true>(h, l, B.c2, nullptr, B.v2, 0.0, B.v1, B.r1, h->chk);
     const double *c3 = nullptr;
     if (B.ksteps == 3) {                             // third inner step: r2 = r1 - e2 v2 + e1 v1 (in place), c3 = M(r2), dots of c3
-        launch_k(h, k_kresid_dinv<D, 2>, B.grid128, 128, 0, B.d, B.r1, B.v1, B.v2, B.r1, B.xa, B.omega, h->S, l);
+        launch_k(h, k_kresid_dinv<D, 2>, B.grid128, 128, 0, B.d, B.r1, B.v1, B.v2, B.r1, B.xa, B.omega, h->S, l, h->chk);
         h->launch_count += 1;
         cycle<D, FIN_NONE, true>(h, l, B.r1, B.c3);
-        spmv<D, 0, FIN_K3, true>(h, l, B.c3, B.r1, B.res, 0.0, B.v1, B.v2, 1);
+        spmv<D, 0, FIN_K3, true>(h, l, B.c3, B.r1, B.res, 0.0, B.v1, B.v2, h->chk);
         c3 = B.c3;
     }
     if (!defer_combine) {                            // else: the caller's prolongation applies coef1 c1 + coef2 c2 (+ coef3 c3)
-        if (c3) launch_k(h, k_kcombine<2>, B.gridv, 256, 0, B.d.n_pad * VecStride<D>::value, B.c1, B.c2, out, h->S, l, c3);
-        else launch_k(h, k_kcombine<1>, B.gridv, 256, 0, B.d.n_pad * VecStride<D>::value, B.c1, B.c2, out, h->S, l, nullptr);
+        if (c3) launch_k(h, k_kcombine<2>, B.gridv, 256, 0, B.d.n_pad * VecStride<D>::value, B.c1, B.c2, out, h->S, l, c3, h->chk);
+        else launch_k(h, k_kcombine<1>, B.gridv, 256, 0, B.d.n_pad * VecStride<D>::value, B.c1, B.c2, out, h->S, l, nullptr, h->chk);
         h->launch_count += 1;
     }
 }
@@ -352,11 +354,11 @@ template <int D, int FINK, bool PRE = false> void precondition(pgo_handle *h) { 
     if (h->use_amg && h->lv.size() > 1) cycle<D, FINK, PRE>(h, 0, h->r, h->z);
     else if (h->use_amg && h->sym.dense_coarsest) {      // the whole system fits the direct solve
         dense_apply<D>(h, 0, h->r, h->z);
-        launch_k(h, k_dots<D, FINK>, B.grid128, 128, 0, B.d.n_pad, h->r, h->z, h->q, h->S, h->partials, 0, 1);
+        launch_k(h, k_dots<D, FINK>, B.grid128, 128, 0, B.d.n_pad, h->r, h->z, h->q, h->S, h->partials, 0, h->chk);
         h->launch_count += 1;
         xreduce<FINK>(h, 0, 1);
     } else {
-        launch_k(h, k_dinv_apply<D, FINK>, B.grid128, 128, 0, B.d, h->r, h->z, 1.0, h->q, h->S, h->partials, 1);
+        launch_k(h, k_dinv_apply<D, FINK>, B.grid128, 128, 0, B.d, h->r, h->z, 1.0, h->q, h->S, h->partials, h->chk);
         h->launch_count += 1;
         xreduce<FINK>(h, 0, 1);
     }
@@ -369,18 +371,18 @@ template <int D> void update_p(pgo_handle *h) {
     LevelBuf &B = h->lv[0];
     halo_pull(h, 0, h->z, VecStride<D>::value, 1);
     const int64_t rows = B.d.n_pad + (h->world > 1 ? B.n_halo : 0);
-    launch_k(h, k_update_p<D>, grid_for(rows * (VecStride<D>::value / 2), 256), 256, 0, rows, h->p, h->z, h->S);
+    launch_k(h, k_update_p<D>, grid_for(rows * (VecStride<D>::value / 2), 256 * 4), 256, 0, rows, h->p, h->z, h->S, h->chk);
     h->launch_count += 1;
 }
 
 template <int D> void pcg_iteration(pgo_handle *h) {
     LevelBuf &B = h->lv[0];
-    spmv<D, 0, FIN_PQ, false, false>(h, 0, h->p, nullptr, h->q, 0.0, nullptr, nullptr, 1);
+    spmv<D, 0, FIN_PQ, false, false>(h, 0, h->p, nullptr, h->q, 0.0, nullptr, nullptr, h->chk);
     if (h->use_amg && h->lv.size() > 1) {
-        launch_k(h, k_update_xr_dinv<D>, B.grid128, 128, 0, B.d, h->x, h->r, h->p, h->q, B.xa, B.omega, h->S);
+        launch_k(h, k_update_xr_dinv<D>, B.grid128, 128, 0, B.d, h->x, h->r, h->p, h->q, B.xa, B.omega, h->S, h->chk);
         precondition<D, FIN_RZ, true>(h);
     } else {
-        launch_k(h, k_update_xr<D>, B.gridv, 256, 0, B.d.n_pad, h->x, h->r, h->p, h->q, h->S);
+        launch_k(h, k_update_xr<D>, B.gridv, 256, 0, B.d.n_pad, h->x, h->r, h->p, h->q, h->S, h->chk);
         precondition<D, FIN_RZ>(h);
     }
     h->launch_count += 1;
@@ -399,27 +401,43 @@ template <int D> bool build_pcg_while(pgo_handle *h) {
         if (cudaGraphCreate(&g, 0) != cudaSuccess) break;
         cudaGraphConditionalHandle hnd;
         if (cudaGraphConditionalHandleCreate(&hnd, g, 1, cudaGraphCondAssignDefault) != cudaSuccess) break;
+        // the loop condition is evaluated once in FRONT of the loop (no iteration at all when the initial residual already set `done`) ...
+        if (cudaStreamBeginCaptureToGraph(h->stream, g, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) != cudaSuccess) break;
+        capturing = true;
+        launch_k(h, k_loop_cond, 1, 32, 0, hnd, (const Scalars *)h->S);
+        cudaGraph_t out = nullptr;
+        cudaError_t ce = cudaStreamEndCapture(h->stream, &out);
+        capturing = false;
+        if (ce != cudaSuccess || h->launch_err != cudaSuccess) break;
+        cudaGraphNode_t head[4];
+        size_t n_head = 4;
+        if (cudaGraphGetNodes(g, head, &n_head) != cudaSuccess || n_head != 1) break;
         cudaGraphNodeParams p = {cudaGraphNodeTypeConditional};
         p.type = cudaGraphNodeTypeConditional;
         p.conditional.handle = hnd;
         p.conditional.type = cudaGraphCondTypeWhile;
         p.conditional.size = 1;
         cudaGraphNode_t node;
-        if (cudaGraphAddNode(&node, g, nullptr, 0, &p) != cudaSuccess) break;
+        if (cudaGraphAddNode(&node, g, head, 1, &p) != cudaSuccess) break;
         cudaGraph_t body = p.conditional.phGraph_out[0];
         if (cudaStreamBeginCaptureToGraph(h->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) != cudaSuccess) break;
         capturing = true;
+        // ... and at the end of every iteration, so no kernel of the body ever runs behind the flag: they are captured without the
+        // check (a dependent L2 round trip at the top of each of the ~110 kernels of an iteration)
+        h->chk = 0;
         pcg_iteration<D>(h);
+        h->chk = 1;
         launch_k(h, k_loop_cond, 1, 32, 0, hnd, (const Scalars *)h->S);
         h->launch_count += 1;
-        cudaGraph_t out = nullptr;
-        const cudaError_t ce = cudaStreamEndCapture(h->stream, &out);
+        out = nullptr;
+        ce = cudaStreamEndCapture(h->stream, &out);
         capturing = false;
         if (ce != cudaSuccess || h->launch_err != cudaSuccess) break;
         if (cudaGraphInstantiate(&ge, g, 0) != cudaSuccess) break;
         ok = true;
     } while (false);
     if (capturing) { cudaGraph_t out = nullptr; cudaStreamEndCapture(h->stream, &out); }
+    h->chk = 1;
     if (g) cudaGraphDestroy(g);
     if (!ok) { (void)cudaGetLastError(); h->launch_err = cudaSuccess; h->launch_count = before; return false; }
     h->pcg_graph = ge;
