@@ -75,7 +75,7 @@ def log(*a):
 
 class TorchComm:
     """The launcher-side communicator of the process-per-GPU mode (torchrun): torch.distributed is only plumbing here -- one
-    all-gather of a 64-byte CUDA IPC handle per rank at start-up, and the merge of the ranks' pose spans for the getters.
+    all-gather of an 80-byte blob (CUDA IPC handle + GPU UUID) per rank at start-up, and the merge of the ranks' pose spans for the getters.
     The product package imports no torch; its single-process multi-GPU mode (Options(n_gpus=N)) needs none of this."""
 
     def __init__(self, group=None):

@@ -85,6 +85,7 @@ struct pgo_handle {
     explicit pgo_handle(std::shared_ptr<Symbolic> s = std::make_shared<Symbolic>()) : symp(std::move(s)), sym(*symp) {}
     MultiCtx *multi = nullptr;         // single-process multi-GPU handle (pgo_options.n_gpus > 1): this handle only dispatches to its shards
     bool ipc_peer[MAX_RANKS]{};        // peer_base[k] was opened with cudaIpcOpenMemHandle (process-per-GPU mode)
+    bool shares_device = false;        // another shard of this handle's graph runs on the same GPU (a test vehicle)
     pgo_options opt{};
     int device = 0, world = 1, rank = 0;
     bool connected = false;
@@ -450,10 +451,14 @@ template <int D> bool build_pcg_while(pgo_handle *h) {
 template <int D> int build_pcg_graph(pgo_handle *h) {
     if (h->pcg_graph) return PGO_OK;
     h->pcg_while = false;
-    // Sharded handles keep the chunked graph: with SHARDED coarse levels the combination "WHILE body + programmatic dependent launch +
-    // kernels that wait for another GPU's kernels" stalls (measured, r03 debug session: either ingredient alone is fine) -- not understood,
-    // so not used; per-iteration cross-GPU synchronisation dominates there anyway.  PGO_WHILE=2 forces it for experiments.
-    if (h->opt_while && (h->world == 1 || h->opt_while_sharded) && build_pcg_while<D>(h)) return PGO_OK;
+    // Sharded handles use the device-side loop too when every shard has a GPU of its own and every coarse level is replicated (the
+    // default up to ~2M poses per level-1 partition).  Shards that SHARE a GPU (tests on a one-GPU machine) stall with it -- WHILE body +
+    // programmatic dependent launch + kernels spinning on another shard's kernels that need the same SMs (r03f / r04q: peer time-out;
+    // either ingredient alone is fine) -- and with sharded coarse levels it has only been run for experiments (PGO_WHILE=2: green on two
+    // real GPUs, profiles/r04p_*): both keep the chunked graph.
+    bool sharded_coarse = false;
+    for (size_t l = 1; l < h->lv.size(); l++) sharded_coarse |= h->world > 1 && !h->lv[l].repl;
+    if (h->opt_while && ((!sharded_coarse && !h->shares_device) || h->opt_while_sharded) && build_pcg_while<D>(h)) return PGO_OK;
     cudaGraph_t g = nullptr;
     int64_t before = h->launch_count;
     CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
@@ -1373,6 +1378,7 @@ static int create_multi(pgo_handle **out, const pgo_options &opt_in, int64_t nv,
     for (int k = 0; k < n; k++) M->th.emplace_back(multi_worker, M, k);
     bool shared_device = false;
     for (int a = 0; a < n; a++) for (int b = a + 1; b < n; b++) shared_device |= dev[a] == dev[b];
+    for (int k = 0; k < n; k++) M->shard[k]->shares_device = shared_device;
     int rc = multi_run(h, [&](pgo_handle *s, int k) {
         const int rc1 = create_shard(s, vval, ne, ekind, emeas, einfo);
         if (rc1 != PGO_OK) return rc1;
@@ -1442,15 +1448,21 @@ int pgo_create(pgo_handle **out, const pgo_options *opt_in,
 }
 
 // ---- sharded handles: exchange of the peer-memory handles (the caller moves the bytes, e.g. with torch.distributed.all_gather)
-int pgo_shard_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+// a shard's blob: the CUDA IPC handle of its peer arena + the UUID of its GPU (shards that share a GPU must know it)
+struct ShardBlob { cudaIpcMemHandle_t mem; unsigned char uuid[16]; };
+int pgo_shard_handle_bytes(void) { return (int)sizeof(ShardBlob); }
 
 int pgo_shard_export(pgo_handle *h, void *buf, int64_t cap) {
-    if (!h || !buf || cap < (int64_t)sizeof(cudaIpcMemHandle_t)) return PGO_ERR_ARG;
+    if (!h || !buf || cap < (int64_t)sizeof(ShardBlob)) return PGO_ERR_ARG;
     if (h->multi) { h->err = "pgo_shard_export: a single-process multi-GPU handle (n_gpus) connects its shards itself"; return PGO_ERR_ARG; }
     if (!h->stream) { h->err = "structure-only handle"; return PGO_ERR_CUDA; }
-    cudaIpcMemHandle_t mh;
-    CK(cudaIpcGetMemHandle(&mh, h->arena));
-    std::memcpy(buf, &mh, sizeof(mh));
+    ShardBlob blob;
+    std::memset(&blob, 0, sizeof(blob));
+    CK(cudaIpcGetMemHandle(&blob.mem, h->arena));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, h->device));
+    std::memcpy(blob.uuid, prop.uuid.bytes, sizeof(blob.uuid));
+    std::memcpy(buf, &blob, sizeof(blob));
     return PGO_OK;
 }
 
@@ -1458,12 +1470,15 @@ int pgo_shard_connect(pgo_handle *h, const void *all_handles, int64_t n_handles)
     if (!h || !all_handles || n_handles != h->world) return PGO_ERR_ARG;
     if (h->multi) { h->err = "pgo_shard_connect: a single-process multi-GPU handle (n_gpus) connects its shards itself"; return PGO_ERR_ARG; }
     if (!h->stream) { h->err = "structure-only handle"; return PGO_ERR_CUDA; }
+    ShardBlob mine;
+    std::memcpy(&mine, (const char *)all_handles + (size_t)h->rank * sizeof(ShardBlob), sizeof(ShardBlob));
     for (int k = 0; k < h->world; k++) {
         if (k == h->rank) continue;
-        cudaIpcMemHandle_t mh;
-        std::memcpy(&mh, (const char *)all_handles + (size_t)k * sizeof(mh), sizeof(mh));
+        ShardBlob blob;
+        std::memcpy(&blob, (const char *)all_handles + (size_t)k * sizeof(blob), sizeof(blob));
+        if (std::memcmp(blob.uuid, mine.uuid, sizeof(mine.uuid)) == 0) h->shares_device = true;
         void *p = nullptr;
-        CK(cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+        CK(cudaIpcOpenMemHandle(&p, blob.mem, cudaIpcMemLazyEnablePeerAccess));
         h->peer_base[k] = (char *)p;
         h->ipc_peer[k] = true;
     }

@@ -104,7 +104,7 @@ class PoseGraph:
 
     # ---- process-per-GPU sharding (options.world > 1; the launcher supplies `comm`) -----------------------------
     def connect_shards(self):
-        """Exchange the ranks' peer-memory handles (one all-gather of 64 bytes per rank at start-up, moved by the launcher's
+        """Exchange the ranks' peer-memory handles (one all-gather of 80 bytes per rank at start-up, moved by the launcher's
         `comm`) and connect the shards.  Afterwards every computing call is collective."""
         if self._comm is None:
             raise PgoError("process-per-GPU PoseGraph (options.world > 1) needs comm=<launcher's communicator>; "
