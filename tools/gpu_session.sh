@@ -1,6 +1,6 @@
 #!/bin/bash
 # 1-GPU measurement session on the B200 box:  gpurun --timeout 2400 -- 'bash tools/gpu_session.sh TAG [parts]'
-# parts (default all): tests sweep bench traffic sanitize
+# parts (default: tests sweep bench traffic sanitize); others: multi strong scale create sweep2 quick ncugj bundled refine abwhile setup sanitize2
 tag=${1:-r03}; parts=${2:-"tests sweep bench traffic sanitize"}
 mkdir -p gpurun_out
 for part in $parts; do case $part in
@@ -52,9 +52,6 @@ for f in ("bench_tr_n${N}_$tag", "bench_weak_n${N}_$tag"):
         print(f, "unreadable:", e)
 PY
   ;;
-abgj)
-  for v in 1 0; do PGO_GJ_OLD=$v timeout 300 python tools/quick_perf.py --opts pcg_rtol=1e-9 2>&1 | tail -1 | sed "s/^/GJ_OLD=$v /"; done | tee gpurun_out/gj_$tag.log
-  for v in 1 0; do PGO_GJ_OLD=$v timeout 300 python tools/quick_perf.py --se3 --poses 250000 --opts pcg_rtol=1e-9 2>&1 | tail -1 | sed "s/^/SE3 GJ_OLD=$v /"; done | tee -a gpurun_out/gj_$tag.log;;
 create)
   nproc | sed 's/^/host cores: /' | tee gpurun_out/create_$tag.log
   PGO_SYM_TIMING=1 timeout 300 python tools/time_create.py --repeats 3 2>&1 | tail -42 | tee -a gpurun_out/create_$tag.log
@@ -66,8 +63,6 @@ quick)
   timeout 300 python tools/quick_perf.py --se3 --poses 250000 --opts pcg_rtol=1e-9 2>&1 | tail -1 | sed "s/^/SE3 /" | tee -a gpurun_out/quick_$tag.log;;
 ncugj)    # one source-level capture of the dense coarsest inversion
   timeout 600 ncu --set full --import-source on --clock-control none -k regex:k_dense_invert -c 1 -f -o gpurun_out/gj_$tag python tools/quick_perf.py --poses 100000 > gpurun_out/ncugj_$tag.log 2>&1; echo "ncu rc=$?"; tail -2 gpurun_out/ncugj_$tag.log;;
-abcs_removed)
-  for v in 0 1; do PGO_STREAM_CS=$v timeout 300 python tools/quick_perf.py --opts pcg_rtol=1e-9 2>&1 | tail -1 | sed "s/^/STREAM_CS=$v /"; done | tee gpurun_out/stream_cs_$tag.log;;
 bundled)  # the reference's own datasets (BASELINE configs[0..2]) + configs[4]
   : > gpurun_out/bench_bundled_$tag.jsonl
   for w in pose-pose pose-landmark intel dlr m3500 sphere2500 garage; do
@@ -80,12 +75,6 @@ for l in open("gpurun_out/bench_bundled_$tag.jsonl"):
     print(d["config"]["workload"][:60], "| ms/step %.3f | pcg its %.0f | cpu s/GN it %s" % (d["ms_per_step"], d["pcg_iterations_per_step"], c.get("s_per_gn_iteration")))
 PY
   ;;
-abgj3)
-  for v in 2 3; do PGO_GJ=$v timeout 300 python tools/quick_perf.py --opts pcg_rtol=1e-9 2>&1 | tail -1 | sed "s/^/GJ=$v /"; done | tee gpurun_out/gj3_$tag.log
-  for v in 2 3; do PGO_GJ=$v timeout 300 python tools/quick_perf.py --se3 --poses 250000 --opts pcg_rtol=1e-9 2>&1 | tail -1 | sed "s/^/SE3 GJ=$v /"; done | tee -a gpurun_out/gj3_$tag.log
-  PGO_GJ=3 timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_se3.py -m gpu -q -x 2>&1 | tail -3 | tee -a gpurun_out/gj3_$tag.log
-  PGO_GJ=3 timeout 300 python bench.py --workload dlr --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('dlr GJ=3 ms/step', d['ms_per_step'], d['phase_ms'])" | tee -a gpurun_out/gj3_$tag.log
-  timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1;;
 refine)
   timeout 300 python tools/rtol_sweep.py 1e-9 1e-8 --opts=refine=1 2>&1 | tee gpurun_out/refine_$tag.log
   timeout 300 python tools/rtol_sweep.py 1e-9 --opts=refine=1,refine_rtol=1e-3 2>&1 | tail -1 | tee -a gpurun_out/refine_$tag.log
