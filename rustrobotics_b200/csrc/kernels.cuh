@@ -169,7 +169,7 @@ template <int NT, int NV> __device__ bool block_sum_last(const double *v, double
 }
 
 // Cross-rank all-reduce / barrier over NVLink peer memory, executed by ONE CTA per rank (the last block of a reducing kernel, or
-// the single block of k_xreduce): thread t < world stores this rank's NV partial sums and then the new epoch into rank t's Comm
+// the single block of k_xbarrier): thread t < world stores this rank's NV partial sums and then the new epoch into rank t's Comm
 // block (st.release.sys), and spins on its own Comm until rank t's epoch arrives (ld.acquire.sys); thread 0 then adds the
 // partials in rank order (identical bits on every rank).  Kernels of one stream run in order, so every later kernel sees the
 // peers' earlier writes; no peer can be more than one epoch ahead (values are double-buffered by epoch parity).  A spin of
