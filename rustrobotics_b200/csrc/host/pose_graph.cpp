@@ -178,7 +178,8 @@ void *pg_from_arrays(const char *name, int solver, const pgo_options *opt,
         });
         pgo_handle *h = nullptr;
         const int rc = pgo_create(&h, opt, nv, vid, vkind, vval, ne, ekind, efrom, eto, emeas, einfo);
-        G2oGraph g = copy.get();
+        G2oGraph g;
+        try { g = copy.get(); } catch (...) { pgo_destroy(h); throw; }          // (out of memory in the copy)
         if (rc != PGO_OK) throw Error(std::string("pgo_create: ") + pgo_last_error(nullptr));
         try {
             return new PoseGraph(std::move(g), name ? name : "graph", solver ? PoseGraphSolver::LevenbergMarquardt : PoseGraphSolver::GaussNewton, h);
