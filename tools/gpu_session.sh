@@ -88,6 +88,11 @@ setup)   # what the hierarchy set-up of one GN step consists of (launch list of 
       -k regex:'galerkin|dense|to_float|coarse_pos|lever|invert_diag|assemble|build_hz|chi2|retract' \
       --log-file gpurun_out/setup_launches_$tag.csv python tools/step_traffic.py > gpurun_out/setup_launches_$tag.log 2>&1; echo "setup rc=$?"
   python tools/summarize_launches.py gpurun_out/setup_launches_$tag.csv | tee gpurun_out/setup_launches_$tag.md | head -40;;
+sanitizeq)   # quick: memcheck + racecheck on the AMG path of two synthetic graphs (after a change of the set-up kernels)
+  for tool in memcheck racecheck; do
+    PGO_WHILE=0 timeout 200 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize.py 1 quick > gpurun_out/sanitize_${tool}_quick_$tag.log 2>&1; echo "$tool quick rc=$?"
+    grep -E "sanitize |ERROR SUMMARY|RACECHECK SUMMARY|Error|hazard" gpurun_out/sanitize_${tool}_quick_$tag.log | head -8
+  done;;
 sanitize2)
   for tool in ${SAN_TOOLS:-memcheck racecheck}; do
     timeout 200 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize.py 2 > gpurun_out/sanitize_${tool}_n2_$tag.log 2>&1; echo "$tool n=2 rc=$?"
